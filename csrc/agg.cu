@@ -1,0 +1,359 @@
+// agg.cu — K1+K2: fused scan -> filter -> (GROUP BY) aggregate kernels for sm_100a.
+//
+// Replaces, for one column batch, the reference's hot loop
+//     AggNode::open:  do { child->get_next(batch); process_row_batch(batch); } while (!eos)
+//         /root/reference/src/exec/agg_node.cpp:447-485,507-545
+// with its per-row FilterNode::need_copy (src/exec/filter_node.cpp:726-734), ExecNode::encode_exprs_key
+// (src/exec/exec_node.cpp:555-571) and AggFnCall::update (src/expr/agg_fn_call.cpp:496-555).
+//
+// Data flow: every referenced column is read exactly once with 256-bit non-allocating loads
+// (8 rows per thread and load); the predicate is evaluated in registers; passing rows update a
+// per-CTA open-addressed hash table in shared memory (native 32-bit ATOMS for counts, CAS loop for
+// double sums); each CTA merges its table once into the global group table (RED.ADD.F64 / RED.ADD.64).
+// Rows whose group does not fit the shared table go straight to the global table, so any
+// cardinality is handled; the global table is also the per-GPU partial state that NCCL ships.
+#include "agg_kernels.cuh"
+
+namespace bk {
+
+// ------------------------------------------------------------------------------------------
+// generic path: the lowered expression program is interpreted per row (any predicate, computed
+// keys and arguments, multi-column keys).  Postfix bytecode, warp-uniform dispatch.
+// ------------------------------------------------------------------------------------------
+__device__ void run_program(const Program& p, const DevCol* cols, int64_t row, uint64_t* out, uint32_t& out_null) {
+    uint64_t st[STACK_DEPTH];
+    uint32_t nul = 0;  // bit d set = stack entry d is NULL
+    int sp = 0;
+    out_null = 0;
+#pragma unroll 1
+    for (int pc = 0; pc < p.n_instr; pc++) {
+        const Instr in = p.code[pc];
+        switch (in.op) {
+            case OP_LOAD_COL: {
+                const DevCol& c = cols[in.a];
+                st[sp] = load_elem(c, row);
+                nul = elem_is_null(c, row) ? (nul | (1u << sp)) : (nul & ~(1u << sp));
+                sp++;
+            } break;
+            case OP_CONST:
+                st[sp] = p.cbits[in.a];
+                nul = ((p.cnull >> in.a) & 1ull) ? (nul | (1u << sp)) : (nul & ~(1u << sp));
+                sp++;
+                break;
+            case OP_CAST:
+                if (!((nul >> (sp - 1)) & 1u)) st[sp - 1] = cast_prim(st[sp - 1], in.a, in.b);
+                break;
+            case OP_CMP: {
+                sp--;
+                const bool n = ((nul >> sp) | (nul >> (sp - 1))) & 1u;
+                st[sp - 1] = n ? 0 : (cmp_vals(in.a, in.b, st[sp - 1], st[sp]) ? 1ull : 0ull);
+                nul = n ? (nul | (1u << (sp - 1))) : (nul & ~(1u << (sp - 1)));
+            } break;
+            case OP_ARITH: {
+                sp--;
+                const bool n = ((nul >> sp) | (nul >> (sp - 1))) & 1u;
+                uint64_t x = st[sp - 1], y = st[sp], r;
+                if (in.b == VC_F64) {
+                    double dx = bits_f64(x), dy = bits_f64(y);
+                    r = f64_bits(in.a == BK_FT_ADD ? __dadd_rn(dx, dy) : (in.a == BK_FT_MINUS ? __dsub_rn(dx, dy) : __dmul_rn(dx, dy)));
+                } else r = in.a == BK_FT_ADD ? x + y : (in.a == BK_FT_MINUS ? x - y : x * y);
+                st[sp - 1] = r;
+                nul = n ? (nul | (1u << (sp - 1))) : (nul & ~(1u << (sp - 1)));
+            } break;
+            case OP_DIV_F64: {
+                sp--;
+                bool n = ((nul >> sp) | (nul >> (sp - 1))) & 1u;
+                const double dy = bits_f64(st[sp]);
+                if (!n && dy == 0.0) n = true;  // NULL on zero divisor
+                if (!n) st[sp - 1] = f64_bits(__ddiv_rn(bits_f64(st[sp - 1]), dy));
+                nul = n ? (nul | (1u << (sp - 1))) : (nul & ~(1u << (sp - 1)));
+            } break;
+            case OP_MOD: {
+                sp--;
+                bool n = ((nul >> sp) | (nul >> (sp - 1))) & 1u;
+                if (!n && st[sp] == 0) n = true;
+                if (!n) {
+                    if (in.b == VC_U64) st[sp - 1] = st[sp - 1] % st[sp];
+                    else { int64_t y = (int64_t)st[sp]; st[sp - 1] = y == -1 ? 0 : (uint64_t)((int64_t)st[sp - 1] % y); }
+                }
+                nul = n ? (nul | (1u << (sp - 1))) : (nul & ~(1u << (sp - 1)));
+            } break;
+            case OP_BIT: {
+                sp--;
+                const bool n = ((nul >> sp) | (nul >> (sp - 1))) & 1u;
+                uint64_t x = st[sp - 1], y = st[sp], r;
+                switch (in.a) {
+                    case BK_FT_BIT_AND: r = x & y; break;
+                    case BK_FT_BIT_OR: r = x | y; break;
+                    case BK_FT_BIT_XOR: r = x ^ y; break;
+                    case BK_FT_LS: r = y >= 64 ? 0 : x << y; break;
+                    default: r = y >= 64 ? 0 : x >> y; break;
+                }
+                st[sp - 1] = r;
+                nul = n ? (nul | (1u << (sp - 1))) : (nul & ~(1u << (sp - 1)));
+            } break;
+            case OP_BIT_NOT: st[sp - 1] = ~st[sp - 1]; break;
+            case OP_NEG:
+                st[sp - 1] = in.b == VC_F64 ? f64_bits(-bits_f64(st[sp - 1])) : (uint64_t)0 - st[sp - 1];
+                break;
+            case OP_LOGIC_NOT: case OP_NOT3: st[sp - 1] = st[sp - 1] ? 0ull : 1ull; break;  // NULL stays NULL
+            case OP_AND: case OP_OR: {
+                const int n = in.a;
+                bool any_null = false, hit = false;  // hit: a non-NULL false (AND) / true (OR)
+                for (int i = sp - n; i < sp; i++) {
+                    const bool isn = (nul >> i) & 1u;
+                    any_null |= isn;
+                    if (!isn && ((st[i] != 0) == (in.op == OP_OR))) hit = true;
+                }
+                sp -= n - 1;
+                const bool rn = !hit && any_null;
+                st[sp - 1] = in.op == OP_OR ? (hit ? 1ull : 0ull) : (hit ? 0ull : 1ull);
+                nul = rn ? (nul | (1u << (sp - 1))) : (nul & ~(1u << (sp - 1)));
+            } break;
+            case OP_XOR: {
+                sp--;
+                const bool n = ((nul >> sp) | (nul >> (sp - 1))) & 1u;
+                st[sp - 1] = ((st[sp - 1] != 0) != (st[sp] != 0)) ? 1ull : 0ull;
+                nul = n ? (nul | (1u << (sp - 1))) : (nul & ~(1u << (sp - 1)));
+            } break;
+            case OP_IS_NULL:
+                st[sp - 1] = ((nul >> (sp - 1)) & 1u) ? 1ull : 0ull;
+                nul &= ~(1u << (sp - 1));
+                break;
+            case OP_IS_TRUE:
+                st[sp - 1] = (!((nul >> (sp - 1)) & 1u) && st[sp - 1] != 0) ? 1ull : 0ull;
+                nul &= ~(1u << (sp - 1));
+                break;
+            case OP_IN: {
+                const bool n = (nul >> (sp - 1)) & 1u;
+                if (!n) {
+                    const int vc = in.c & 0xF;
+                    bool found = false;
+                    for (int i = 0; i < in.b; i++) found |= cmp_vals(BK_FT_EQ, vc, st[sp - 1], p.cbits[in.a + i]);
+                    st[sp - 1] = found ? 1ull : 0ull;
+                    if (!found && (in.c >> 4)) nul |= 1u << (sp - 1);  // not found and the list holds a NULL
+                }
+            } break;
+            case OP_OUT:
+                sp--;
+                out[in.a] = st[sp];
+                if ((nul >> sp) & 1u) out_null |= 1u << in.a;
+                break;
+            default: break;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_agg_interp(const AggArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const AggPlan& ap = a.plan;
+    const GroupTable& gt = a.gt;
+    const bool grouped = ap.n_keyw > 0;
+    const bool use_smem = grouped && a.smem_cap_log2 > 0;
+    SmemTable st;
+    if (use_smem) st = smem_table_init(smem_raw, a);
+    const uint32_t gcap = gt.cap_mask + 1;
+    uint32_t passed = 0;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.nrows; row += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t out[MAX_GROUP + MAX_AGG + 1];
+        uint32_t out_null;
+        run_program(a.prog, a.cols, row, out, out_null);
+        if (ap.pred_out >= 0 && (((out_null >> ap.pred_out) & 1u) || out[ap.pred_out] == 0)) continue;
+        passed++;
+        auto arg = [&](int i, uint64_t& v, bool& isnull) {
+            const int r = ap.agg[i].arg_out;
+            if (r == 0xFF) { v = 0; isnull = true; return; }
+            v = out[r]; isnull = (out_null >> r) & 1u;
+        };
+        if (!grouped) {  // single group: slot 0 of the global table
+            accumulate_row<false>(a, gt.lanes, gcap, 0, arg);
+            continue;
+        }
+        uint64_t key[MAX_KEYW];
+        for (int w = 0; w < ap.n_keyw; w++) key[w] = 0;
+        for (int g = 0; g < ap.n_group; g++) {
+            const int r = ap.key_out[g];
+            if ((out_null >> r) & 1u) key[ap.key_null_word[g]] |= 1ull << ap.key_null_shift[g];
+            else {
+                const uint64_t m = ap.key_bits[g] >= 64 ? ~0ull : ((1ull << ap.key_bits[g]) - 1ull);
+                key[ap.key_word[g]] |= (out[r] & m) << ap.key_shift[g];
+            }
+        }
+        const uint32_t h = ap.n_keyw == 1 ? hash_key1(key[0]) : hash_key(key, ap.n_keyw);
+        int slot = -1;
+        if (use_smem) slot = table_upsert<true, 0>(st.state, st.keys, st.cap_mask, key, ap.n_keyw, h >> 7, 16, nullptr);
+        if (slot >= 0) accumulate_row<true>(a, st.lanes, st.cap_mask + 1, slot, arg);
+        else {
+            slot = table_upsert<false, 0>(gt.state, gt.keys, gt.cap_mask, key, ap.n_keyw, h, (int)gcap, gt.n_groups);
+            if (slot < 0) atomicExch(gt.overflow, 1u);
+            else accumulate_row<false>(a, gt.lanes, gcap, slot, arg);
+        }
+    }
+    if (use_smem) smem_table_flush(st, a);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) passed += __shfl_xor_sync(0xFFFFFFFFu, passed, d);
+    if ((threadIdx.x & 31) == 0 && passed) atomicAdd((unsigned long long*)a.rows_passed, (unsigned long long)passed);
+}
+
+// ------------------------------------------------------------------------------------------
+// table maintenance: init, partial export / import (K3), result extraction + finalize
+// ------------------------------------------------------------------------------------------
+__global__ void k_table_init(GroupTable gt, AggPlan ap) {
+    const uint32_t cap = gt.cap_mask + 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        gt.state[i] = ap.n_keyw == 0 ? 2u : 0u;
+        for (int l = 0; l < ap.n_lanes; l++) gt.lanes[(size_t)l * cap + i] = lane_identity(ap.lane_op[l]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *gt.n_groups = 0; *gt.overflow = 0; }
+}
+
+// Partial state layout (fixed capacity `pcap` groups): [u64 n_groups][keys n_keyw x pcap][lanes n_lanes x pcap]
+__global__ void k_partial_export(GroupTable gt, AggPlan ap, uint64_t* dst, uint32_t pcap, uint32_t* cursor) {
+    const uint32_t cap = gt.cap_mask + 1;
+    uint64_t* dkeys = dst + 1;
+    uint64_t* dlanes = dkeys + (size_t)ap.n_keyw * pcap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        if (gt.state[i] != 2u) continue;
+        if (ap.n_keyw == 0 && gt.lanes[i] == 0) continue;  // no row reached the single group
+        const uint32_t pos = atomicAdd(cursor, 1u);
+        if (pos >= pcap) { atomicExch(gt.overflow, 1u); continue; }
+        for (int w = 0; w < ap.n_keyw; w++) dkeys[(size_t)w * pcap + pos] = gt.keys[(size_t)w * cap + i];
+        for (int l = 0; l < ap.n_lanes; l++) dlanes[(size_t)l * pcap + pos] = gt.lanes[(size_t)l * cap + i];
+    }
+}
+__global__ void k_partial_count(uint64_t* dst, const uint32_t* cursor) { dst[0] = *cursor; }
+
+// K3: fold `nranks` exported partials into the (re-initialised) global table
+__global__ void k_partial_merge(GroupTable gt, AggPlan ap, const uint64_t* src, size_t words_per_rank, uint32_t pcap, int nranks) {
+    for (int r = 0; r < nranks; r++) {
+        const uint64_t* base = src + (size_t)r * words_per_rank;
+        const uint32_t n = (uint32_t)base[0];
+        const uint64_t* skeys = base + 1;
+        const uint64_t* slanes = skeys + (size_t)ap.n_keyw * pcap;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            uint64_t key[MAX_KEYW];
+            for (int w = 0; w < ap.n_keyw; w++) key[w] = skeys[(size_t)w * pcap + i];
+            merge_group(ap, gt, key, [&](int l, uint64_t& v) { v = slanes[(size_t)l * pcap + i]; return true; });
+        }
+    }
+}
+
+// Result extraction: one output row per occupied slot.  Output columns (canonical 64-bit images +
+// one null byte each), in this order: group expressions, then per aggregate its final value and,
+// for AVG, the intermediate {sum, count} pair (AggFnCall::finalize, agg_fn_call.cpp:927-990).
+__global__ void k_extract(GroupTable gt, AggPlan ap, uint64_t* outv, uint8_t* outn, uint32_t out_cap, uint32_t* cursor, int emit_default) {
+    const uint32_t cap = gt.cap_mask + 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        if (gt.state[i] != 2u) continue;
+        const uint64_t nrows = gt.lanes[i];
+        if (ap.n_keyw == 0 && nrows == 0 && !emit_default) continue;
+        const uint32_t pos = atomicAdd(cursor, 1u);
+        if (pos >= out_cap) continue;
+        int c = 0;
+        for (int g = 0; g < ap.n_group; g++, c++) {
+            const bool isnull = ap.key_null_word[g] != 0xFF &&
+                                ((gt.keys[(size_t)ap.key_null_word[g] * cap + i] >> ap.key_null_shift[g]) & 1ull);
+            uint64_t v = gt.keys[(size_t)ap.key_word[g] * cap + i] >> ap.key_shift[g];
+            if (ap.key_bits[g] < 64) v &= (1ull << ap.key_bits[g]) - 1ull;
+            // sign-extend narrow signed keys back to their canonical image
+            if (ap.key_bits[g] == 32 && prim_class(ap.key_prim[g]) == VC_I64) v = (uint64_t)(int64_t)(int32_t)v;
+            outv[(size_t)c * out_cap + pos] = isnull ? 0 : v;
+            outn[(size_t)c * out_cap + pos] = isnull ? 1 : 0;
+        }
+        for (int k = 0; k < ap.n_agg; k++) {
+            const AggSpec a = ap.agg[k];
+            const uint64_t cnt = a.cnt_lane ? gt.lanes[(size_t)a.cnt_lane * cap + i] : nrows;
+            const uint64_t acc = gt.lanes[(size_t)a.acc_lane * cap + i];
+            uint64_t v = 0; uint8_t isnull = 0;
+            switch (a.kind) {
+                case AG_COUNT_STAR: v = nrows; break;
+                case AG_COUNT: v = cnt; break;
+                case AG_AVG:
+                    if (cnt == 0) isnull = 1; else v = f64_bits(__ddiv_rn(bits_f64(acc), (double)(int64_t)cnt));
+                    break;
+                default: if (cnt == 0) isnull = 1; else v = acc; break;  // SUM / MIN / MAX: NULL without input
+            }
+            outv[(size_t)c * out_cap + pos] = v; outn[(size_t)c * out_cap + pos] = isnull; c++;
+            if (a.kind == AG_AVG) {  // intermediate blob {double sum; int64 count}
+                outv[(size_t)c * out_cap + pos] = acc; outn[(size_t)c * out_cap + pos] = 0; c++;
+                outv[(size_t)c * out_cap + pos] = cnt; outn[(size_t)c * out_cap + pos] = 0; c++;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------
+size_t agg_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2) {
+    if (cap_log2 <= 0 || ap.n_keyw == 0) return 0;
+    return ((size_t)(ap.n_keyw + n_smem_lanes) * 8 + 4) << cap_log2;
+}
+
+template <class K>
+static int occupancy_grid(K kernel, size_t smem, int sm_count) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * sm_count;  // persistent grid: a whole number of CTAs per SM (148 SMs on B200)
+}
+
+cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t s, const char** kernel_name) {
+    const bool grouped = a.plan.n_keyw > 0;
+    const size_t smem = grouped ? agg_smem_bytes(a.plan, a.n_smem_lanes, a.smem_cap_log2) : 0;
+    if (a.nrows <= 0) return cudaSuccess;
+    if (direct) {
+        // grid: CTAs resident per SM x SM count, bounded by the work available
+        int per_sm = smem ? (int)((220 * 1024) / (smem + 1024)) : 4;
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        int64_t want = ((a.nrows + 7) / 8 + 255) / 256;
+        int grid = (int)(want < (int64_t)per_sm * sm_count ? want : (int64_t)per_sm * sm_count);
+        *kernel_name = grouped ? "k_agg_group_direct" : "k_agg_scalar_direct";
+        switch (a.direct.n_terms) {
+            case 0: return launch_direct_np0(a, a.direct.n_vals, grid, smem, s, grouped);
+            case 1: return launch_direct_np1(a, a.direct.n_vals, grid, smem, s, grouped);
+            default: return launch_direct_np2(a, a.direct.n_vals, grid, smem, s, grouped);
+        }
+    }
+    *kernel_name = "k_agg_interp";
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_agg_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int grid = occupancy_grid(k_agg_interp, smem, sm_count);
+    int64_t want = (a.nrows + 255) / 256;
+    if (want < grid) grid = (int)want;
+    k_agg_interp<<<grid, 256, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStream_t s) {
+    const uint32_t cap = gt.cap_mask + 1;
+    int grid = (int)((cap + 255) / 256); if (grid > 1184) grid = 1184;
+    k_table_init<<<grid, 256, 0, s>>>(gt, ap);
+    return cudaGetLastError();
+}
+cudaError_t launch_partial_export(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, uint32_t pcap, uint32_t* cursor, cudaStream_t s) {
+    const uint32_t cap = gt.cap_mask + 1;
+    int grid = (int)((cap + 255) / 256); if (grid > 1184) grid = 1184;
+    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    k_partial_export<<<grid, 256, 0, s>>>(gt, ap, dst, pcap, cursor);
+    k_partial_count<<<1, 1, 0, s>>>(dst, cursor);
+    return cudaGetLastError();
+}
+cudaError_t launch_partial_merge(const GroupTable& gt, const AggPlan& ap, const uint64_t* src, size_t words_per_rank, uint32_t pcap, int nranks, cudaStream_t s) {
+    int grid = (int)((pcap + 255) / 256); if (grid > 1184) grid = 1184; if (grid < 1) grid = 1;
+    k_partial_merge<<<grid, 256, 0, s>>>(gt, ap, src, words_per_rank, pcap, nranks);
+    return cudaGetLastError();
+}
+cudaError_t launch_extract(const GroupTable& gt, const AggPlan& ap, uint64_t* outv, uint8_t* outn, uint32_t out_cap, uint32_t* cursor, int emit_default, cudaStream_t s) {
+    const uint32_t cap = gt.cap_mask + 1;
+    int grid = (int)((cap + 255) / 256); if (grid > 1184) grid = 1184;
+    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    k_extract<<<grid, 256, 0, s>>>(gt, ap, outv, outn, out_cap, cursor, emit_default);
+    return cudaGetLastError();
+}
+
+}  // namespace bk

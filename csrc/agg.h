@@ -1,0 +1,33 @@
+// agg.h — kernel argument block and host launchers of the filter+aggregate kernels (agg.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "dev_types.h"
+
+namespace bk {
+
+struct AggArgs {
+    DevCol cols[MAX_COLS];   // direct kernels: ordered [predicate][key][value] columns
+    int32_t n_cols;
+    int32_t smem_cap_log2;   // log2 slots of the per-CTA shared table (0 = no shared table)
+    int64_t nrows;
+    AggPlan plan;
+    DirectPlan direct;
+    Program prog;            // generic path only
+    GroupTable gt;
+    uint64_t* rows_passed;   // device counter: rows that survived the filter
+    uint8_t smem_lane[MAX_LANES];  // global lane -> shared lane of this batch, 0xFF = not held in shared memory
+    int32_t n_smem_lanes;
+    uint32_t alias_mask;     // global lanes that receive the shared row count at flush time
+};
+
+size_t agg_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2);
+cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t s, const char** kernel_name);
+cudaError_t launch_direct_np0(const AggArgs& a, int na, int grid, size_t smem, cudaStream_t s, bool grouped);
+cudaError_t launch_direct_np1(const AggArgs& a, int na, int grid, size_t smem, cudaStream_t s, bool grouped);
+cudaError_t launch_direct_np2(const AggArgs& a, int na, int grid, size_t smem, cudaStream_t s, bool grouped);
+cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStream_t s);
+cudaError_t launch_partial_export(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, uint32_t pcap, uint32_t* cursor, cudaStream_t s);
+cudaError_t launch_partial_merge(const GroupTable& gt, const AggPlan& ap, const uint64_t* src, size_t words_per_rank, uint32_t pcap, int nranks, cudaStream_t s);
+cudaError_t launch_extract(const GroupTable& gt, const AggPlan& ap, uint64_t* outv, uint8_t* outn, uint32_t out_cap, uint32_t* cursor, int emit_default, cudaStream_t s);
+
+}  // namespace bk

@@ -1,0 +1,660 @@
+// api.cu — the C ABI of include/bkgpu.h: plan lifecycle (ExecNode::init/open/get_next/close
+// inverted into init/open/push/finish/get_next/close), batch staging, result materialisation.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <vector>
+#include "../include/bkgpu.h"
+#include "agg.h"
+#include "plan.h"
+#include "sort.h"
+#include "nccl_dl.h"
+
+using namespace bk;
+
+namespace {
+
+thread_local std::string g_thread_error;
+
+enum State { S_INIT = 0, S_OPEN = 1, S_FINISHED = 2, S_CLOSED = 3 };
+
+struct HostCol {  // one materialised result column (host memory owned by the plan)
+    OutCol desc;
+    int elem = 0;
+    std::vector<uint8_t> values;
+    std::vector<uint8_t> validity;  // LSB bitmap; empty = all valid
+    void* dev_values = nullptr;     // output_on_device
+};
+
+struct EventPair { cudaEvent_t a, b; int64_t bytes; };
+
+}  // namespace
+
+struct bkgpu_plan {
+    Compiled c;
+    int device = 0;
+    int sm_count = 148;
+    State state = S_INIT;
+    std::string last_error;
+    std::atomic<int> cancelled{0};
+    void* nccl_comm = nullptr;
+    int nranks = 1;
+    // options
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;
+    int group_cap_log2 = 20;
+    int smem_cap_log2 = -1;       // -1 = choose per batch
+    int64_t batch_capacity = 1 << 20;
+    int64_t chunk_rows = 8 << 20;
+    int64_t partial_cap = 1 << 16;
+    int force_generic = 0;
+    int output_on_device = 0;
+    int64_t topk_sample = 1;
+    // aggregate state
+    GroupTable gt{};
+    uint64_t* d_rows_passed = nullptr;
+    uint32_t* d_cursor = nullptr;
+    uint64_t* d_partial = nullptr;  // export buffer (this rank)
+    uint64_t* d_gather = nullptr;   // nranks export buffers
+    uint32_t known_groups = 0;
+    // sort / filter state
+    SortState* sort = nullptr;
+    // host staging for pageable / pinned pushes
+    std::vector<void*> stage[2];
+    std::vector<void*> stage_valid[2];
+    size_t stage_rows = 0;
+    cudaEvent_t stage_free[2] = {nullptr, nullptr}, stage_ready[2] = {nullptr, nullptr};
+    // results
+    std::vector<HostCol> result;
+    int64_t result_rows = 0, result_pos = 0;
+    // stats
+    bkgpu_stats stats{};
+    std::vector<EventPair> timed;
+    std::vector<EventPair> timed_coll;
+    std::vector<void*> dev_allocs;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        last_error = buf; g_thread_error = buf; return code;
+    }
+    int cuda_fail(cudaError_t e, const char* what) {
+        return fail(e == cudaErrorMemoryAllocation ? BKGPU_ENOMEM : BKGPU_ENODEV, "%s: %s", what, cudaGetErrorString(e));
+    }
+};
+
+#define CK(plan, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (plan)->cuda_fail(e__, #call); } while (0)
+
+static int thread_fail(int code, const char* msg) { g_thread_error = msg; return code; }
+
+// ------------------------------------------------------------------ library
+extern "C" const char* bkgpu_version(void) { return "bkgpu 0.1 (sm_100a)"; }
+
+extern "C" int bkgpu_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { g_thread_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e); return BKGPU_ENODEV; }
+    return n;
+}
+
+extern "C" const char* bkgpu_last_error(bkgpu_plan* p) { return p ? p->last_error.c_str() : g_thread_error.c_str(); }
+
+extern "C" int bkgpu_plan_explain(const uint8_t* desc, size_t len, char* text, size_t text_len) {
+    Compiled c; std::string err;
+    int rc = compile_plan(desc, len, c, err);
+    if (rc != BKGPU_OK) { if (text && text_len) snprintf(text, text_len, "%s", err.c_str()); return thread_fail(rc, err.c_str()); }
+    if (text && text_len) snprintf(text, text_len, "%s", c.explain.c_str());
+    return BKGPU_OK;
+}
+
+// ------------------------------------------------------------------ helpers
+static int dev_alloc(bkgpu_plan* p, void** out, size_t bytes) {
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 8);
+    if (e != cudaSuccess) return p->cuda_fail(e, "cudaMalloc");
+    p->dev_allocs.push_back(*out);
+    return BKGPU_OK;
+}
+static void dev_free(bkgpu_plan* p, void* ptr) {
+    if (!ptr) return;
+    auto it = std::find(p->dev_allocs.begin(), p->dev_allocs.end(), ptr);
+    if (it != p->dev_allocs.end()) p->dev_allocs.erase(it);
+    cudaFree(ptr);
+}
+static EventPair* timer_begin(bkgpu_plan* p, std::vector<EventPair>& v, int64_t bytes) {
+    EventPair ep{};
+    if (cudaEventCreate(&ep.a) != cudaSuccess || cudaEventCreate(&ep.b) != cudaSuccess) return nullptr;
+    ep.bytes = bytes;
+    cudaEventRecord(ep.a, p->stream);
+    v.push_back(ep);
+    return &v.back();
+}
+static void timer_end(bkgpu_plan* p, EventPair* ep) { if (ep) cudaEventRecord(ep->b, p->stream); }
+
+// ------------------------------------------------------------------ lifecycle
+extern "C" int bkgpu_init(bkgpu_plan** out, const uint8_t* desc, size_t len, int device, void* nccl_comm) {
+    if (!out) return thread_fail(BKGPU_EINVAL, "bkgpu_init: out is NULL");
+    *out = nullptr;
+    bkgpu_plan* p = new bkgpu_plan();
+    std::string err;
+    int rc = compile_plan(desc, len, p->c, err);
+    if (rc != BKGPU_OK) { g_thread_error = err; delete p; return rc; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        g_thread_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU fallback)";
+        delete p; return BKGPU_ENODEV;
+    }
+    if (device < 0 || device >= ndev) { g_thread_error = "bkgpu_init: bad device index"; delete p; return BKGPU_EINVAL; }
+    p->device = device;
+    p->nccl_comm = nccl_comm;
+    if (nccl_comm) {
+        int n = 0;
+        if (nccl_comm_count(nccl_comm, &n) != 0 || n < 1) { g_thread_error = std::string("NCCL: ") + nccl_last_error(); delete p; return BKGPU_ENCCL; }
+        p->nranks = n;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
+    *out = p;
+    return BKGPU_OK;
+}
+
+extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
+    if (!p || !key) return thread_fail(BKGPU_EINVAL, "bkgpu_set_option: NULL argument");
+    if (p->state != S_INIT) return p->fail(BKGPU_ESTATE, "options must be set before bkgpu_open");
+    std::string k = key;
+    if (k == "stream") { p->stream = (cudaStream_t)(uintptr_t)v; p->own_stream = false; }
+    else if (k == "group_capacity_log2") { if (v < 4 || v > 30) return p->fail(BKGPU_EINVAL, "group_capacity_log2 out of range"); p->group_cap_log2 = (int)v; }
+    else if (k == "smem_capacity_log2") { if (v < -1 || v > 13) return p->fail(BKGPU_EINVAL, "smem_capacity_log2 out of range"); p->smem_cap_log2 = (int)v; }
+    else if (k == "batch_capacity") { if (v < 1) return p->fail(BKGPU_EINVAL, "batch_capacity must be positive"); p->batch_capacity = v; }
+    else if (k == "chunk_rows") { if (v < 1024) return p->fail(BKGPU_EINVAL, "chunk_rows too small"); p->chunk_rows = (v + 7) & ~7ll; }
+    else if (k == "partial_capacity") { if (v < 1) return p->fail(BKGPU_EINVAL, "partial_capacity must be positive"); p->partial_cap = v; }
+    else if (k == "force_generic") p->force_generic = v != 0;
+    else if (k == "output_on_device") p->output_on_device = v != 0;
+    else if (k == "topk_sample") p->topk_sample = v;
+    else return p->fail(BKGPU_EINVAL, "unknown option '%s'", key);
+    return BKGPU_OK;
+}
+
+static int alloc_group_table(bkgpu_plan* p) {
+    const AggPlan& ap = p->c.ap;
+    GroupTable& gt = p->gt;
+    int log2 = ap.n_keyw == 0 ? 0 : p->group_cap_log2;
+    size_t cap = (size_t)1 << log2;
+    gt.cap_mask = (uint32_t)(cap - 1); gt.cap_log2 = (uint32_t)log2;
+    int rc;
+    if ((rc = dev_alloc(p, (void**)&gt.state, cap * 4))) return rc;
+    if ((rc = dev_alloc(p, (void**)&gt.keys, cap * 8 * (size_t)std::max(ap.n_keyw, 1)))) return rc;
+    if ((rc = dev_alloc(p, (void**)&gt.lanes, cap * 8 * (size_t)ap.n_lanes))) return rc;
+    if ((rc = dev_alloc(p, (void**)&gt.n_groups, 8))) return rc;
+    gt.overflow = gt.n_groups + 1;
+    if ((rc = dev_alloc(p, (void**)&p->d_rows_passed, 8))) return rc;
+    if ((rc = dev_alloc(p, (void**)&p->d_cursor, 8))) return rc;
+    CK(p, cudaMemsetAsync(p->d_rows_passed, 0, 8, p->stream));
+    CK(p, launch_table_init(gt, ap, p->stream));
+    p->stats.kernel_launches++;
+    return BKGPU_OK;
+}
+
+extern "C" int bkgpu_open(bkgpu_plan* p) {
+    if (!p) return thread_fail(BKGPU_EINVAL, "bkgpu_open: NULL plan");
+    if (p->state != S_INIT) return p->fail(BKGPU_ESTATE, "bkgpu_open called twice");
+    CK(p, cudaSetDevice(p->device));
+    if (!p->stream) { CK(p, cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)); p->own_stream = true; }
+    CK(p, cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CK(p, cudaEventCreateWithFlags(&p->stage_free[i], cudaEventDisableTiming));
+        CK(p, cudaEventCreateWithFlags(&p->stage_ready[i], cudaEventDisableTiming));
+    }
+    int rc = BKGPU_OK;
+    if (p->c.kind == PK_AGG || p->c.kind == PK_JOIN_AGG) rc = alloc_group_table(p);
+    if (!rc && (p->c.kind == PK_SORT || p->c.kind == PK_FILTER)) rc = sort_open(p->c, p->device, p->stream, p->topk_sample, &p->sort, p->last_error);
+    if (rc) { g_thread_error = p->last_error; return rc; }
+    p->state = S_OPEN;
+    return BKGPU_OK;
+}
+
+// choose the shared-table capacity for this batch: >= 2x the groups seen so far, 2048 slots when
+// nothing is known yet, 0 (straight to the global table) when the groups cannot fit one CTA's 227 KB
+static int pick_smem_log2(bkgpu_plan* p, int n_smem_lanes) {
+    if (p->c.ap.n_keyw == 0) return 0;
+    if (p->smem_cap_log2 >= 0) return p->smem_cap_log2;
+    uint32_t g = p->known_groups;
+    int log2 = 11;
+    while (((uint32_t)1 << log2) < 2 * g && log2 < 14) log2++;
+    while (log2 > 0 && agg_smem_bytes(p->c.ap, n_smem_lanes, log2) > 200 * 1024) log2--;
+    if (((uint32_t)1 << log2) < g) return 0;  // would mostly miss: skip the shared table
+    return log2;
+}
+
+static int launch_agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, bool vec_ok) {
+    const Compiled& c = p->c;
+    AggArgs a; memset(&a, 0, sizeof a);
+    a.plan = c.ap; a.prog = c.prog; a.direct = c.direct; a.gt = p->gt; a.rows_passed = p->d_rows_passed;
+    const bool direct = c.has_direct && vec_ok && !p->force_generic;
+    const int ncols = (int)c.cols.size();
+    if (direct) { for (size_t i = 0; i < c.direct_cols.size(); i++) a.cols[i] = cols[c.direct_cols[i]]; a.n_cols = (int)c.direct_cols.size(); }
+    else { for (int i = 0; i < ncols; i++) a.cols[i] = cols[i]; a.n_cols = ncols; }
+    // per-batch nullability -> which lanes need per-row work in the shared table
+    memset(a.smem_lane, 0xFF, sizeof a.smem_lane);
+    a.smem_lane[0] = 0; a.n_smem_lanes = 1; a.alias_mask = 0;
+    for (int k = 0; k < a.plan.n_agg; k++) {
+        AggSpec& s = a.plan.agg[k];
+        if (s.kind == AG_COUNT_STAR) continue;
+        bool nullable = c.arg_can_null[(size_t)k];
+        for (int i = 0; i < ncols; i++) if ((c.arg_cols_mask[(size_t)k] >> i) & 1) nullable = nullable || cols[i].validity != nullptr;
+        s.nullable = nullable ? 1 : 0;
+        if (s.cnt_lane) {
+            if (nullable) { if (a.smem_lane[s.cnt_lane] == 0xFF) a.smem_lane[s.cnt_lane] = (uint8_t)a.n_smem_lanes++; }
+            else a.alias_mask |= 1u << s.cnt_lane;
+        }
+        if (s.kind != AG_COUNT && a.smem_lane[s.acc_lane] == 0xFF) a.smem_lane[s.acc_lane] = (uint8_t)a.n_smem_lanes++;
+    }
+    for (int l = 1; l < a.plan.n_lanes; l++) if (a.smem_lane[l] != 0xFF) a.alias_mask &= ~(1u << l);
+    a.smem_cap_log2 = pick_smem_log2(p, a.n_smem_lanes);
+    const int64_t kMax = (int64_t)1 << 30;  // rows per launch (32-bit counters inside a CTA)
+    int64_t algo_bytes_per_row = 0;
+    for (int i = 0; i < a.n_cols; i++) algo_bytes_per_row += storage_bytes(a.cols[i].stype);
+    for (int64_t off = 0; off < nrows; off += kMax) {
+        AggArgs b = a;
+        b.nrows = std::min(kMax, nrows - off);
+        for (int i = 0; i < b.n_cols; i++) {
+            b.cols[i].values = (const uint8_t*)a.cols[i].values + (size_t)off * storage_bytes(a.cols[i].stype);
+            if (a.cols[i].validity) b.cols[i].validity = a.cols[i].validity + off / 8;
+        }
+        const char* name = "";
+        EventPair* ep = timer_begin(p, p->timed, b.nrows * algo_bytes_per_row);
+        cudaError_t e = launch_agg(b, direct, p->sm_count, p->stream, &name);
+        timer_end(p, ep);
+        if (e != cudaSuccess) return p->cuda_fail(e, "launch_agg");
+        snprintf(p->stats.main_kernel_name, sizeof p->stats.main_kernel_name, "%s", name);
+        p->stats.kernel_launches++;
+    }
+    return BKGPU_OK;
+}
+
+// resolve the plan's columns against one pushed batch
+static int bind_columns(bkgpu_plan* p, const std::vector<ColRef>& want, const bkgpu_column* cols, int ncols, int64_t nrows,
+                        std::vector<const bkgpu_column*>& bound) {
+    bound.assign(want.size(), nullptr);
+    for (size_t i = 0; i < want.size(); i++) {
+        for (int k = 0; k < ncols; k++) if (cols[k].tuple_id == want[i].tuple_id && cols[k].slot_id == want[i].slot_id) { bound[i] = &cols[k]; break; }
+        if (!bound[i]) return p->fail(BKGPU_EINVAL, "batch lacks column %d_%d", want[i].tuple_id, want[i].slot_id);
+        if (bound[i]->length != nrows) return p->fail(BKGPU_EINVAL, "column %d_%d has length %lld, batch has %lld rows", want[i].tuple_id,
+                                                      want[i].slot_id, (long long)bound[i]->length, (long long)nrows);
+        if (nrows > 0 && !bound[i]->values) return p->fail(BKGPU_EINVAL, "column %d_%d has no values buffer", want[i].tuple_id, want[i].slot_id);
+        if (prim_storage(bound[i]->prim_type) != prim_storage(want[i].prim))
+            return p->fail(BKGPU_EINVAL, "column %d_%d arrives as type %d but the plan declares %d", want[i].tuple_id, want[i].slot_id,
+                           bound[i]->prim_type, want[i].prim);
+    }
+    return BKGPU_OK;
+}
+
+static int ensure_stage(bkgpu_plan* p, const std::vector<ColRef>& want, size_t rows) {
+    if (p->stage_rows >= rows && p->stage[0].size() == want.size()) return BKGPU_OK;
+    for (int b = 0; b < 2; b++) {
+        for (void* q : p->stage[b]) dev_free(p, q);
+        for (void* q : p->stage_valid[b]) dev_free(p, q);
+        p->stage[b].assign(want.size(), nullptr); p->stage_valid[b].assign(want.size(), nullptr);
+        for (size_t i = 0; i < want.size(); i++) {
+            int rc;
+            if ((rc = dev_alloc(p, &p->stage[b][i], rows * (size_t)storage_bytes(prim_storage(want[i].prim))))) return rc;
+            if ((rc = dev_alloc(p, &p->stage_valid[b][i], rows / 8 + 8))) return rc;
+        }
+    }
+    p->stage_rows = rows;
+    return BKGPU_OK;
+}
+
+typedef int (*BatchFn)(bkgpu_plan*, const DevCol*, int64_t nrows, int64_t row_base, bool vec_ok);
+
+// feed a batch: device-resident columns go straight to the kernels; host columns stream through
+// two sets of device staging buffers (H2D of chunk i+1 overlaps the kernel on chunk i)
+static int feed(bkgpu_plan* p, const std::vector<ColRef>& want, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device, BatchFn fn) {
+    std::vector<const bkgpu_column*> bound;
+    int rc = bind_columns(p, want, cols, ncols, nrows, bound);
+    if (rc) return rc;
+    std::vector<DevCol> dc(std::max<size_t>(want.size(), 1));
+    if (on_device) {
+        bool vec_ok = true;
+        for (size_t i = 0; i < want.size(); i++) {
+            dc[i].values = bound[i]->values; dc[i].validity = bound[i]->validity;
+            dc[i].stype = prim_storage(want[i].prim); dc[i].prim = want[i].prim;
+            if (((uintptr_t)dc[i].values & 31) != 0) vec_ok = false;
+        }
+        return fn(p, dc.data(), nrows, 0, vec_ok);
+    }
+    const int64_t chunk = std::min<int64_t>(p->chunk_rows, std::max<int64_t>((nrows + 7) & ~7ll, 8));
+    if ((rc = ensure_stage(p, want, (size_t)chunk))) return rc;
+    int buf = 0;
+    for (int64_t off = 0; off < nrows; off += chunk, buf ^= 1) {
+        if (p->cancelled.load()) return p->fail(BKGPU_ECANCELLED, "cancelled");
+        const int64_t n = std::min(chunk, nrows - off);
+        CK(p, cudaStreamWaitEvent(p->copy_stream, p->stage_free[buf], 0));
+        for (size_t i = 0; i < want.size(); i++) {
+            const int st = prim_storage(want[i].prim);
+            const size_t eb = (size_t)storage_bytes(st);
+            CK(p, cudaMemcpyAsync(p->stage[buf][i], (const uint8_t*)bound[i]->values + (size_t)off * eb, (size_t)n * eb, cudaMemcpyHostToDevice, p->copy_stream));
+            p->stats.h2d_bytes += (int64_t)((size_t)n * eb);
+            dc[i].values = p->stage[buf][i]; dc[i].stype = st; dc[i].prim = want[i].prim; dc[i].validity = nullptr;
+            if (bound[i]->validity) {
+                CK(p, cudaMemcpyAsync(p->stage_valid[buf][i], bound[i]->validity + off / 8, (size_t)(n + 7) / 8, cudaMemcpyHostToDevice, p->copy_stream));
+                p->stats.h2d_bytes += (n + 7) / 8;
+                dc[i].validity = (const uint8_t*)p->stage_valid[buf][i];
+            }
+        }
+        CK(p, cudaEventRecord(p->stage_ready[buf], p->copy_stream));
+        CK(p, cudaStreamWaitEvent(p->stream, p->stage_ready[buf], 0));
+        if ((rc = fn(p, dc.data(), n, off, true))) return rc;
+        CK(p, cudaEventRecord(p->stage_free[buf], p->stream));
+    }
+    return BKGPU_OK;
+}
+
+static int agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, int64_t, bool vec_ok) { return launch_agg_batch(p, cols, nrows, vec_ok); }
+static int sort_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, int64_t, bool) {
+    int rc = sort_push(p->sort, cols, nrows, p->stream, &p->stats, p->last_error);
+    if (rc) g_thread_error = p->last_error;
+    return rc;
+}
+
+extern "C" int bkgpu_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device) {
+    if (!p) return thread_fail(BKGPU_EINVAL, "bkgpu_push: NULL plan");
+    if (p->state != S_OPEN) return p->fail(BKGPU_ESTATE, "bkgpu_push needs an open, unfinished plan");
+    if (p->cancelled.load()) return p->fail(BKGPU_ECANCELLED, "cancelled");
+    if (nrows < 0 || ncols < 0 || (ncols > 0 && !cols)) return p->fail(BKGPU_EINVAL, "bkgpu_push: bad arguments");
+    CK(p, cudaSetDevice(p->device));
+    p->stats.rows_scanned += nrows;
+    if (nrows == 0) return BKGPU_OK;
+    switch (p->c.kind) {
+        case PK_AGG: {
+            int rc = feed(p, p->c.cols, cols, ncols, nrows, on_device, agg_batch);
+            if (rc) return rc;
+            if (p->c.ap.n_keyw > 0 && p->smem_cap_log2 < 0) {  // learn the cardinality for the next batch's table size
+                CK(p, cudaMemcpyAsync(&p->known_groups, p->gt.n_groups, 4, cudaMemcpyDeviceToHost, p->stream));
+                CK(p, cudaStreamSynchronize(p->stream));
+            }
+            return BKGPU_OK;
+        }
+        case PK_SORT: case PK_FILTER: return feed(p, p->c.cols, cols, ncols, nrows, on_device, sort_batch);
+        default: return p->fail(BKGPU_EUNSUPPORTED, "plan kind %d has no push path yet", p->c.kind);
+    }
+}
+
+// ---- result materialisation: device images -> typed host columns ----
+static void put_value(HostCol& hc, int64_t row, uint64_t bits, bool isnull, int prim) {
+    uint8_t* dst = hc.values.data() + (size_t)row * (size_t)hc.elem;
+    if (isnull) { hc.validity[(size_t)row >> 3] &= (uint8_t)~(1u << (row & 7)); return; }
+    switch (prim_storage(prim)) {
+        case ST_I32: { int32_t v = (int32_t)(int64_t)bits; memcpy(dst, &v, 4); } break;
+        case ST_U32: { uint32_t v = (uint32_t)bits; memcpy(dst, &v, 4); } break;
+        case ST_F32: { double d; memcpy(&d, &bits, 8); float f = (float)d; memcpy(dst, &f, 4); } break;
+        case ST_U8: dst[0] = bits ? 1 : 0; break;
+        default: memcpy(dst, &bits, 8); break;
+    }
+}
+
+static int agg_finish(bkgpu_plan* p) {
+    const AggPlan& ap = p->c.ap;
+    GroupTable& gt = p->gt;
+    uint32_t host_counts[2] = {0, 0};
+    if (p->nccl_comm && p->nranks > 1) {
+        // regions -> one set per GPU; partial tables meet in ONE all-gather and are folded by K3
+        const uint32_t pcap = (uint32_t)p->partial_cap;
+        const size_t words = 1 + (size_t)(ap.n_keyw + ap.n_lanes) * pcap;
+        int rc;
+        if (!p->d_partial && (rc = dev_alloc(p, (void**)&p->d_partial, words * 8))) return rc;
+        if (!p->d_gather && (rc = dev_alloc(p, (void**)&p->d_gather, words * 8 * (size_t)p->nranks))) return rc;
+        EventPair* ep = timer_begin(p, p->timed_coll, 0);
+        CK(p, launch_partial_export(gt, ap, p->d_partial, pcap, p->d_cursor, p->stream));
+        if (nccl_all_gather(p->nccl_comm, p->d_partial, p->d_gather, words, p->stream) != 0) return p->fail(BKGPU_ENCCL, "ncclAllGather: %s", nccl_last_error());
+        CK(p, launch_table_init(gt, ap, p->stream));
+        CK(p, launch_partial_merge(gt, ap, p->d_gather, words, pcap, p->nranks, p->stream));
+        timer_end(p, ep);
+        p->stats.kernel_launches += 4;
+    }
+    CK(p, cudaMemcpyAsync(host_counts, gt.n_groups, 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(p, cudaStreamSynchronize(p->stream));
+    p->stats.d2h_bytes += 8;
+    if (host_counts[1]) return p->fail(BKGPU_ETOOBIG, "group table overflow (capacity 2^%d slots / partial_capacity %lld): raise group_capacity_log2",
+                                       (int)gt.cap_log2, (long long)p->partial_cap);
+    uint32_t n = ap.n_keyw == 0 ? 1 : host_counts[0];
+    // device images: one per group expr, per aggregate its final (+2 for an AVG blob)
+    int n_img = ap.n_group;
+    for (int k = 0; k < ap.n_agg; k++) n_img += ap.agg[k].kind == AG_AVG ? 3 : 1;
+    uint64_t* d_outv = nullptr; uint8_t* d_outn = nullptr;
+    const uint32_t out_cap = std::max<uint32_t>(n, 1);
+    int rc;
+    if ((rc = dev_alloc(p, (void**)&d_outv, (size_t)out_cap * 8 * (size_t)n_img))) return rc;
+    if ((rc = dev_alloc(p, (void**)&d_outn, (size_t)out_cap * (size_t)n_img))) return rc;
+    CK(p, launch_extract(gt, ap, d_outv, d_outn, out_cap, p->d_cursor, p->c.emit_default ? 1 : 0, p->stream));
+    p->stats.kernel_launches++;
+    std::vector<uint64_t> hv((size_t)out_cap * (size_t)n_img);
+    std::vector<uint8_t> hn((size_t)out_cap * (size_t)n_img);
+    uint32_t n_out = 0;
+    CK(p, cudaMemcpyAsync(&n_out, p->d_cursor, 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(p, cudaMemcpyAsync(hv.data(), d_outv, hv.size() * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(p, cudaMemcpyAsync(hn.data(), d_outn, hn.size(), cudaMemcpyDeviceToHost, p->stream));
+    CK(p, cudaStreamSynchronize(p->stream));
+    p->stats.d2h_bytes += (int64_t)(hv.size() * 8 + hn.size() + 4);
+    dev_free(p, d_outv); dev_free(p, d_outn);
+    if (n_out > out_cap) n_out = out_cap;
+    int64_t rows = n_out;
+    int64_t skip = p->c.offset > 0 ? std::min<int64_t>(p->c.offset, rows) : 0;
+    int64_t lim = p->c.agg_limit;   // AggNode::get_next stops at its limit (agg_node.cpp:555)
+    if (p->c.limit >= 0 && (lim < 0 || p->c.limit < lim)) lim = p->c.limit;
+    int64_t keep = rows - skip;
+    if (lim >= 0 && keep > lim) keep = lim;
+    p->result.clear();
+    int img = 0;
+    for (const OutCol& oc : p->c.out_cols) {
+        HostCol hc; hc.desc = oc;
+        hc.elem = oc.kind == 1 ? 16 : storage_bytes(prim_storage(oc.prim));
+        hc.values.assign((size_t)std::max<int64_t>(keep, 1) * (size_t)hc.elem, 0);
+        hc.validity.assign((size_t)(keep + 7) / 8 + 1, 0xFF);
+        bool any_null = false;
+        for (int64_t r = 0; r < keep; r++) {
+            const size_t src = (size_t)(r + skip);
+            if (oc.kind == 1) {
+                memcpy(hc.values.data() + (size_t)r * 16, &hv[(size_t)img * out_cap + src], 8);
+                memcpy(hc.values.data() + (size_t)r * 16 + 8, &hv[(size_t)(img + 1) * out_cap + src], 8);
+            } else {
+                bool isnull = hn[(size_t)img * out_cap + src] != 0;
+                any_null |= isnull;
+                put_value(hc, r, hv[(size_t)img * out_cap + src], isnull, oc.prim);
+            }
+        }
+        if (!any_null) hc.validity.clear();
+        img += oc.kind == 1 ? 2 : 1;
+        p->result.push_back(std::move(hc));
+    }
+    p->result_rows = keep; p->result_pos = 0;
+    return BKGPU_OK;
+}
+
+static void resolve_timers(bkgpu_plan* p) {
+    for (auto& ep : p->timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) { p->stats.main_kernel_ms += ms; p->stats.main_kernel_launches++; p->stats.main_kernel_bytes += ep.bytes; }
+        cudaEventDestroy(ep.a); cudaEventDestroy(ep.b);
+    }
+    p->timed.clear();
+    for (auto& ep : p->timed_coll) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) p->stats.collective_ms += ms;
+        cudaEventDestroy(ep.a); cudaEventDestroy(ep.b);
+    }
+    p->timed_coll.clear();
+}
+
+extern "C" int bkgpu_finish(bkgpu_plan* p) {
+    if (!p) return thread_fail(BKGPU_EINVAL, "bkgpu_finish: NULL plan");
+    if (p->state != S_OPEN) return p->fail(BKGPU_ESTATE, "bkgpu_finish needs an open plan");
+    if (p->cancelled.load()) return p->fail(BKGPU_ECANCELLED, "cancelled");
+    CK(p, cudaSetDevice(p->device));
+    int rc = BKGPU_OK;
+    switch (p->c.kind) {
+        case PK_AGG: case PK_JOIN_AGG: {
+            rc = agg_finish(p);
+            if (!rc) {
+                uint64_t passed = 0;
+                CK(p, cudaMemcpy(&passed, p->d_rows_passed, 8, cudaMemcpyDeviceToHost));
+                p->stats.rows_filtered = p->stats.rows_scanned - (int64_t)passed;
+            }
+        } break;
+        case PK_SORT: case PK_FILTER: {
+            std::vector<SortOutCol> cols; int64_t rows = 0;
+            rc = sort_finish(p->sort, p->nccl_comm, p->nranks, p->stream, &p->stats, cols, &rows, p->last_error);
+            if (rc) { g_thread_error = p->last_error; break; }
+            p->result.clear();
+            for (auto& sc : cols) {
+                HostCol hc; hc.desc = {sc.tuple_id, sc.slot_id, sc.prim, 0}; hc.elem = sc.elem;
+                hc.values = std::move(sc.values); hc.validity = std::move(sc.validity);
+                p->result.push_back(std::move(hc));
+            }
+            p->result_rows = rows; p->result_pos = 0;
+        } break;
+        default: rc = p->fail(BKGPU_EUNSUPPORTED, "plan kind %d cannot finish", p->c.kind);
+    }
+    cudaStreamSynchronize(p->stream);
+    resolve_timers(p);
+    if (rc) return rc;
+    p->stats.rows_returned = p->result_rows;
+    p->state = S_FINISHED;
+    return BKGPU_OK;
+}
+
+extern "C" int bkgpu_get_next(bkgpu_plan* p, bkgpu_column* out_cols, int* ncols, int64_t* nrows, int* eos) {
+    if (!p || !ncols || !nrows || !eos) return thread_fail(BKGPU_EINVAL, "bkgpu_get_next: NULL argument");
+    if (p->state != S_FINISHED) return p->fail(BKGPU_ESTATE, "bkgpu_get_next before bkgpu_finish");
+    if (p->cancelled.load()) { *eos = 1; *nrows = 0; *ncols = 0; return BKGPU_OK; }  // cancelled: eos, like the reference's operators
+    const int have = (int)p->result.size();
+    if (*ncols < have || (have > 0 && !out_cols)) return p->fail(BKGPU_EINVAL, "bkgpu_get_next: need room for %d columns", have);
+    const int64_t n = std::min(p->batch_capacity, p->result_rows - p->result_pos);
+    for (int i = 0; i < have; i++) {
+        HostCol& hc = p->result[(size_t)i];
+        bkgpu_column& o = out_cols[i];
+        o.tuple_id = hc.desc.tuple_id; o.slot_id = hc.desc.slot_id; o.prim_type = hc.desc.prim; o.elem_size = hc.elem;
+        o.values = hc.values.data() + (size_t)p->result_pos * (size_t)hc.elem;
+        o.length = n;
+        o.validity = nullptr;
+        if (!hc.validity.empty()) {
+            if (p->result_pos == 0) o.validity = hc.validity.data();
+            else {  // re-base the bitmap for a non-first batch (batch_capacity is normally a multiple of 8)
+                if (p->result_pos % 8 == 0) o.validity = hc.validity.data() + p->result_pos / 8;
+                else return p->fail(BKGPU_EINVAL, "batch_capacity must be a multiple of 8 when results hold NULLs");
+            }
+        }
+    }
+    *ncols = have; *nrows = n;
+    p->result_pos += n;
+    *eos = p->result_pos >= p->result_rows ? 1 : 0;
+    return BKGPU_OK;
+}
+
+extern "C" void bkgpu_cancel(bkgpu_plan* p) { if (p) p->cancelled.store(1); }
+
+extern "C" void bkgpu_close(bkgpu_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
+    resolve_timers(p);
+    if (p->sort) sort_close(p->sort);
+    for (void* q : p->dev_allocs) cudaFree(q);
+    for (int i = 0; i < 2; i++) { if (p->stage_free[i]) cudaEventDestroy(p->stage_free[i]); if (p->stage_ready[i]) cudaEventDestroy(p->stage_ready[i]); }
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+extern "C" int bkgpu_get_stats(bkgpu_plan* p, bkgpu_stats* out) {
+    if (!p || !out) return thread_fail(BKGPU_EINVAL, "bkgpu_get_stats: NULL argument");
+    *out = p->stats;
+    return BKGPU_OK;
+}
+
+// ------------------------------------------------------------------ partial state
+extern "C" int bkgpu_partial_capacity(bkgpu_plan* p, size_t* bytes) {
+    if (!p || !bytes) return thread_fail(BKGPU_EINVAL, "bkgpu_partial_capacity: NULL argument");
+    if (p->c.kind == PK_AGG || p->c.kind == PK_JOIN_AGG) { *bytes = 8 * (1 + (size_t)(p->c.ap.n_keyw + p->c.ap.n_lanes) * (size_t)p->partial_cap); return BKGPU_OK; }
+    if (p->c.kind == PK_SORT && p->sort) { *bytes = sort_partial_bytes(p->sort); return BKGPU_OK; }
+    return p->fail(BKGPU_EUNSUPPORTED, "plan kind %d has no partial state", p->c.kind);
+}
+extern "C" int bkgpu_partial_export(bkgpu_plan* p, void* dev_dst, size_t bytes) {
+    if (!p || !dev_dst) return thread_fail(BKGPU_EINVAL, "bkgpu_partial_export: NULL argument");
+    if (p->state != S_OPEN && p->state != S_FINISHED) return p->fail(BKGPU_ESTATE, "bkgpu_partial_export needs an open plan");
+    size_t need = 0; int rc = bkgpu_partial_capacity(p, &need);
+    if (rc) return rc;
+    if (bytes < need) return p->fail(BKGPU_EINVAL, "partial buffer too small: %zu < %zu", bytes, need);
+    CK(p, cudaSetDevice(p->device));
+    if (p->c.kind == PK_SORT) { rc = sort_partial_export(p->sort, dev_dst, p->stream, p->last_error); if (rc) g_thread_error = p->last_error; return rc; }
+    CK(p, launch_partial_export(p->gt, p->c.ap, (uint64_t*)dev_dst, (uint32_t)p->partial_cap, p->d_cursor, p->stream));
+    p->stats.kernel_launches += 2;
+    CK(p, cudaStreamSynchronize(p->stream));
+    uint32_t ov = 0; CK(p, cudaMemcpy(&ov, p->gt.overflow, 4, cudaMemcpyDeviceToHost));
+    if (ov) return p->fail(BKGPU_ETOOBIG, "more than partial_capacity=%lld groups on this rank", (long long)p->partial_cap);
+    return BKGPU_OK;
+}
+extern "C" int bkgpu_partial_merge(bkgpu_plan* p, const void* dev_src, size_t bytes_per_rank, int nranks) {
+    if (!p || !dev_src || nranks < 1) return thread_fail(BKGPU_EINVAL, "bkgpu_partial_merge: bad argument");
+    if (p->state != S_OPEN && p->state != S_FINISHED) return p->fail(BKGPU_ESTATE, "bkgpu_partial_merge needs an open plan");
+    size_t need = 0; int rc = bkgpu_partial_capacity(p, &need);
+    if (rc) return rc;
+    if (bytes_per_rank != need) return p->fail(BKGPU_EINVAL, "bytes_per_rank %zu != partial capacity %zu", bytes_per_rank, need);
+    CK(p, cudaSetDevice(p->device));
+    if (p->c.kind == PK_SORT) {
+        std::vector<SortOutCol> cols; int64_t rows = 0;
+        rc = sort_partial_merge(p->sort, dev_src, nranks, p->stream, cols, &rows, p->last_error);
+        if (rc) { g_thread_error = p->last_error; return rc; }
+        p->result.clear();
+        for (auto& sc : cols) { HostCol hc; hc.desc = {sc.tuple_id, sc.slot_id, sc.prim, 0}; hc.elem = sc.elem; hc.values = std::move(sc.values); hc.validity = std::move(sc.validity); p->result.push_back(std::move(hc)); }
+        p->result_rows = rows; p->result_pos = 0; p->stats.rows_returned = rows; p->state = S_FINISHED;
+        return BKGPU_OK;
+    }
+    CK(p, launch_table_init(p->gt, p->c.ap, p->stream));
+    CK(p, launch_partial_merge(p->gt, p->c.ap, (const uint64_t*)dev_src, need / 8, (uint32_t)p->partial_cap, nranks, p->stream));
+    p->stats.kernel_launches += 2;
+    void* comm = p->nccl_comm; int nr = p->nranks; p->nccl_comm = nullptr; p->nranks = 1;  // already merged: finalize locally
+    rc = agg_finish(p);
+    p->nccl_comm = comm; p->nranks = nr;
+    if (rc) return rc;
+    p->stats.rows_returned = p->result_rows; p->state = S_FINISHED;
+    return BKGPU_OK;
+}
+
+// ------------------------------------------------------------------ NCCL plumbing
+extern "C" int bkgpu_nccl_unique_id(uint8_t id_out[128]) {
+    if (!id_out) return thread_fail(BKGPU_EINVAL, "bkgpu_nccl_unique_id: NULL");
+    if (nccl_unique_id(id_out) != 0) return thread_fail(BKGPU_ENCCL, nccl_last_error());
+    return BKGPU_OK;
+}
+extern "C" int bkgpu_nccl_comm_create(void** comm_out, const uint8_t id[128], int nranks, int rank, int device) {
+    if (!comm_out || !id) return thread_fail(BKGPU_EINVAL, "bkgpu_nccl_comm_create: NULL");
+    if (cudaSetDevice(device) != cudaSuccess) return thread_fail(BKGPU_ENODEV, "cudaSetDevice failed");
+    if (nccl_comm_create(comm_out, id, nranks, rank) != 0) return thread_fail(BKGPU_ENCCL, nccl_last_error());
+    return BKGPU_OK;
+}
+extern "C" void bkgpu_nccl_comm_destroy(void* comm) { if (comm) nccl_comm_destroy(comm); }
+
+// ------------------------------------------------------------------ memory helpers
+extern "C" void* bkgpu_host_alloc(size_t bytes) { void* p = nullptr; return cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
+extern "C" void bkgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" void* bkgpu_device_alloc(int device, size_t bytes) {
+    void* p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    return cudaMalloc(&p, bytes ? bytes : 8) == cudaSuccess ? p : nullptr;
+}
+extern "C" void bkgpu_device_free(int device, void* p) { if (p && cudaSetDevice(device) == cudaSuccess) cudaFree(p); }
+extern "C" int bkgpu_memcpy_h2d(int device, void* dst, const void* src, size_t bytes) {
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return thread_fail(BKGPU_ENODEV, "cudaMemcpy H2D failed");
+    return BKGPU_OK;
+}
+extern "C" int bkgpu_memcpy_d2h(int device, void* dst, const void* src, size_t bytes) {
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return thread_fail(BKGPU_ENODEV, "cudaMemcpy D2H failed");
+    return BKGPU_OK;
+}
