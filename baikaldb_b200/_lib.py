@@ -41,6 +41,7 @@ SYMBOLS = [
     ("bkgpu_push", c_int, [c_void_p, POINTER(BkgpuColumn), c_int, c_int64, c_int]),
     ("bkgpu_finish", c_int, [c_void_p]),
     ("bkgpu_get_next", c_int, [c_void_p, POINTER(BkgpuColumn), POINTER(c_int), POINTER(c_int64), POINTER(c_int)]),
+    ("bkgpu_reset", c_int, [c_void_p]),
     ("bkgpu_cancel", None, [c_void_p]),
     ("bkgpu_close", None, [c_void_p]),
     ("bkgpu_get_stats", c_int, [c_void_p, POINTER(BkgpuStats)]),

@@ -144,7 +144,7 @@ __device__ void run_program(const Program& p, const DevCol* cols, int64_t row, u
     }
 }
 
-__global__ void __launch_bounds__(256) k_agg_interp(const AggArgs a) {
+__global__ void __launch_bounds__(256) k_agg_interp(const __grid_constant__ AggArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AggPlan& ap = a.plan;
     const GroupTable& gt = a.gt;
@@ -290,6 +290,13 @@ size_t agg_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2) {
     return ((size_t)(ap.n_keyw + n_smem_lanes) * 8 + 4) << cap_log2;
 }
 
+// shared memory of the direct GROUP BY kernel: the table plus one compaction queue per warp
+size_t direct_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2, int na) {
+    const size_t table = (agg_smem_bytes(ap, n_smem_lanes, cap_log2) + 15) & ~(size_t)15;
+    const size_t queue = ((size_t)(ap.n_keyw + na) * 128 + 16) * 8;  // QCAP = 128 entries per warp
+    return table + queue * 16;                                         // DIRECT_THREADS / 32 warps
+}
+
 template <class K>
 static int occupancy_grid(K kernel, size_t smem, int sm_count) {
     int per_sm = 0;
@@ -302,17 +309,12 @@ cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t
     const size_t smem = grouped ? agg_smem_bytes(a.plan, a.n_smem_lanes, a.smem_cap_log2) : 0;
     if (a.nrows <= 0) return cudaSuccess;
     if (direct) {
-        // grid: CTAs resident per SM x SM count, bounded by the work available
-        int per_sm = smem ? (int)((220 * 1024) / (smem + 1024)) : 4;
-        if (per_sm > 4) per_sm = 4;
-        if (per_sm < 1) per_sm = 1;
-        int64_t want = ((a.nrows + 7) / 8 + 255) / 256;
-        int grid = (int)(want < (int64_t)per_sm * sm_count ? want : (int64_t)per_sm * sm_count);
+        const size_t dsmem = grouped ? direct_smem_bytes(a.plan, a.n_smem_lanes, a.smem_cap_log2, a.direct.n_vals) : 0;
         *kernel_name = grouped ? "k_agg_group_direct" : "k_agg_scalar_direct";
         switch (a.direct.n_terms) {
-            case 0: return launch_direct_np0(a, a.direct.n_vals, grid, smem, s, grouped);
-            case 1: return launch_direct_np1(a, a.direct.n_vals, grid, smem, s, grouped);
-            default: return launch_direct_np2(a, a.direct.n_vals, grid, smem, s, grouped);
+            case 0: return launch_direct_np0(a, a.direct.n_vals, sm_count, dsmem, s, grouped);
+            case 1: return launch_direct_np1(a, a.direct.n_vals, sm_count, dsmem, s, grouped);
+            default: return launch_direct_np2(a, a.direct.n_vals, sm_count, dsmem, s, grouped);
         }
     }
     *kernel_name = "k_agg_interp";

@@ -61,6 +61,8 @@ struct bkgpu_plan {
     uint32_t* d_cursor = nullptr;
     uint64_t* d_partial = nullptr;  // export buffer (this rank)
     uint64_t* d_gather = nullptr;   // nranks export buffers
+    uint64_t* d_outv = nullptr; uint8_t* d_outn = nullptr; size_t out_cap_alloc = 0;  // extraction buffers (kept across resets)
+    std::vector<uint64_t> hv; std::vector<uint8_t> hn;
     uint32_t known_groups = 0;
     // sort / filter state
     SortState* sort = nullptr;
@@ -220,13 +222,15 @@ extern "C" int bkgpu_open(bkgpu_plan* p) {
 
 // choose the shared-table capacity for this batch: >= 2x the groups seen so far, 2048 slots when
 // nothing is known yet, 0 (straight to the global table) when the groups cannot fit one CTA's 227 KB
-static int pick_smem_log2(bkgpu_plan* p, int n_smem_lanes) {
+static int pick_smem_log2(bkgpu_plan* p, int n_smem_lanes, bool direct, int na) {
     if (p->c.ap.n_keyw == 0) return 0;
-    if (p->smem_cap_log2 >= 0) return p->smem_cap_log2;
+    const size_t budget = 220 * 1024;
+    auto bytes = [&](int log2) { return direct ? direct_smem_bytes(p->c.ap, n_smem_lanes, log2, na) : agg_smem_bytes(p->c.ap, n_smem_lanes, log2); };
+    if (p->smem_cap_log2 >= 0) { int l = p->smem_cap_log2; while (l > 0 && bytes(l) > budget) l--; return l; }
     uint32_t g = p->known_groups;
     int log2 = 11;
     while (((uint32_t)1 << log2) < 2 * g && log2 < 14) log2++;
-    while (log2 > 0 && agg_smem_bytes(p->c.ap, n_smem_lanes, log2) > 200 * 1024) log2--;
+    while (log2 > 0 && bytes(log2) > budget) log2--;
     if (((uint32_t)1 << log2) < g) return 0;  // would mostly miss: skip the shared table
     return log2;
 }
@@ -255,7 +259,22 @@ static int launch_agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, bo
         if (s.kind != AG_COUNT && a.smem_lane[s.acc_lane] == 0xFF) a.smem_lane[s.acc_lane] = (uint8_t)a.n_smem_lanes++;
     }
     for (int l = 1; l < a.plan.n_lanes; l++) if (a.smem_lane[l] != 0xFF) a.alias_mask &= ~(1u << l);
-    a.smem_cap_log2 = pick_smem_log2(p, a.n_smem_lanes);
+    a.smem_cap_log2 = pick_smem_log2(p, a.n_smem_lanes, direct, c.direct.n_vals);
+    if (direct) {  // per value column: the lane operations it feeds
+        memset(a.vops, 0, sizeof a.vops);
+        for (int v = 0; v < c.direct.n_vals; v++) { a.vops[v].cnt_smem = 0xFF; }
+        for (int k = 0; k < a.plan.n_agg; k++) {
+            const AggSpec& s = a.plan.agg[k];
+            if (s.kind == AG_COUNT_STAR) continue;
+            ValOps& vo = a.vops[c.direct.agg_val[k]];
+            vo.arg_class = s.arg_vclass;
+            if (s.cnt_lane && s.cnt_owner) { vo.cnt_glob = s.cnt_lane; vo.cnt_smem = s.nullable ? a.smem_lane[s.cnt_lane] : 0xFF; }
+            if (s.kind != AG_COUNT && s.acc_owner) {
+                const int n = vo.n_ops++;
+                vo.op[n] = a.plan.lane_op[s.acc_lane]; vo.lane_class[n] = s.vclass; vo.glob_lane[n] = s.acc_lane; vo.smem_lane[n] = a.smem_lane[s.acc_lane];
+            }
+        }
+    }
     const int64_t kMax = (int64_t)1 << 30;  // rows per launch (32-bit counters inside a CTA)
     int64_t algo_bytes_per_row = 0;
     for (int i = 0; i < a.n_cols; i++) algo_bytes_per_row += storage_bytes(a.cols[i].stype);
@@ -426,22 +445,26 @@ static int agg_finish(bkgpu_plan* p) {
     // device images: one per group expr, per aggregate its final (+2 for an AVG blob)
     int n_img = ap.n_group;
     for (int k = 0; k < ap.n_agg; k++) n_img += ap.agg[k].kind == AG_AVG ? 3 : 1;
-    uint64_t* d_outv = nullptr; uint8_t* d_outn = nullptr;
     const uint32_t out_cap = std::max<uint32_t>(n, 1);
     int rc;
-    if ((rc = dev_alloc(p, (void**)&d_outv, (size_t)out_cap * 8 * (size_t)n_img))) return rc;
-    if ((rc = dev_alloc(p, (void**)&d_outn, (size_t)out_cap * (size_t)n_img))) return rc;
+    if (p->out_cap_alloc < out_cap) {
+        dev_free(p, p->d_outv); dev_free(p, p->d_outn); p->d_outv = nullptr; p->d_outn = nullptr;
+        size_t cap = std::max<size_t>(out_cap, 4096);
+        if ((rc = dev_alloc(p, (void**)&p->d_outv, cap * 8 * (size_t)n_img))) return rc;
+        if ((rc = dev_alloc(p, (void**)&p->d_outn, cap * (size_t)n_img))) return rc;
+        p->out_cap_alloc = cap;
+    }
+    uint64_t* d_outv = p->d_outv; uint8_t* d_outn = p->d_outn;
     CK(p, launch_extract(gt, ap, d_outv, d_outn, out_cap, p->d_cursor, p->c.emit_default ? 1 : 0, p->stream));
     p->stats.kernel_launches++;
-    std::vector<uint64_t> hv((size_t)out_cap * (size_t)n_img);
-    std::vector<uint8_t> hn((size_t)out_cap * (size_t)n_img);
+    std::vector<uint64_t>& hv = p->hv; std::vector<uint8_t>& hn = p->hn;
+    hv.resize((size_t)out_cap * (size_t)n_img); hn.resize((size_t)out_cap * (size_t)n_img);
     uint32_t n_out = 0;
     CK(p, cudaMemcpyAsync(&n_out, p->d_cursor, 4, cudaMemcpyDeviceToHost, p->stream));
     CK(p, cudaMemcpyAsync(hv.data(), d_outv, hv.size() * 8, cudaMemcpyDeviceToHost, p->stream));
     CK(p, cudaMemcpyAsync(hn.data(), d_outn, hn.size(), cudaMemcpyDeviceToHost, p->stream));
     CK(p, cudaStreamSynchronize(p->stream));
     p->stats.d2h_bytes += (int64_t)(hv.size() * 8 + hn.size() + 4);
-    dev_free(p, d_outv); dev_free(p, d_outn);
     if (n_out > out_cap) n_out = out_cap;
     int64_t rows = n_out;
     int64_t skip = p->c.offset > 0 ? std::min<int64_t>(p->c.offset, rows) : 0;
@@ -553,6 +576,25 @@ extern "C" int bkgpu_get_next(bkgpu_plan* p, bkgpu_column* out_cols, int* ncols,
     *ncols = have; *nrows = n;
     p->result_pos += n;
     *eos = p->result_pos >= p->result_rows ? 1 : 0;
+    return BKGPU_OK;
+}
+
+// Re-arm an executed plan for the next request of the same fragment (prepared-statement reuse): tables
+// are cleared, allocations, streams and staging buffers are kept.
+extern "C" int bkgpu_reset(bkgpu_plan* p) {
+    if (!p) return thread_fail(BKGPU_EINVAL, "bkgpu_reset: NULL plan");
+    if (p->state != S_OPEN && p->state != S_FINISHED) return p->fail(BKGPU_ESTATE, "bkgpu_reset needs an opened plan");
+    CK(p, cudaSetDevice(p->device));
+    p->cancelled.store(0);
+    if (p->c.kind == PK_AGG || p->c.kind == PK_JOIN_AGG) {
+        CK(p, cudaMemsetAsync(p->d_rows_passed, 0, 8, p->stream));
+        CK(p, launch_table_init(p->gt, p->c.ap, p->stream));
+        p->stats.kernel_launches++;
+    }
+    if (p->sort) { int rc = sort_reset(p->sort, p->stream, p->last_error); if (rc) { g_thread_error = p->last_error; return rc; } }
+    p->result.clear(); p->result_rows = 0; p->result_pos = 0;
+    bkgpu_stats z{}; z.kernel_launches = p->stats.kernel_launches; p->stats = z;
+    p->state = S_OPEN;
     return BKGPU_OK;
 }
 

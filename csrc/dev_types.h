@@ -82,6 +82,8 @@ struct AggSpec {
     uint8_t out_prim;    // pb::PrimitiveType of the final slot
     uint8_t arg_vclass;  // class the argument VALUE arrives in (converted to `vclass` on update:
                          // AVG does sum += get_numberic<double>(x), agg_fn_call.cpp:525-535)
+    uint8_t cnt_owner;   // lanes can be shared by aggregates over the same argument (SUM(x), AVG(x), COUNT(x)):
+    uint8_t acc_owner;   // only the owner updates the lane, everyone reads it at finalize
 };
 
 struct AggPlan {
@@ -114,6 +116,19 @@ struct DirectPlan {
     uint8_t key_col[2];
     uint8_t val_col[8];
     uint8_t agg_val[MAX_AGG];     // per aggregate: index into val_col (0xFF = none)
+};
+
+// Per value column of the direct kernels, prepared by the host for each batch: which lanes the column
+// feeds (SUM / AVG / MIN / MAX over the same column share the load) and its non-NULL counter.
+struct ValOps {
+    uint8_t n_ops;        // lane operations fed by this column (<= 3)
+    uint8_t arg_class;    // VClass the column's canonical image is in
+    uint8_t cnt_glob;     // global lane counting non-NULL values (0 = none: shares the row count)
+    uint8_t cnt_smem;     // shared lane of that counter in this batch (0xFF = not updated per row)
+    uint8_t op[3];        // LaneOp
+    uint8_t lane_class[3];
+    uint8_t glob_lane[3];
+    uint8_t smem_lane[3];
 };
 
 // ---- open-addressed group table (global memory; the shared-memory tables use the same layout) ----

@@ -557,7 +557,7 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const HNode* f
         a.arg_vclass = (uint8_t)host_prim_class(arg.col_type);
         a.nullable = 1;
         int m = 0; expr_cols(arg, out, m); out.arg_cols_mask[(size_t)k] = m; out.arg_can_null[(size_t)k] = expr_makes_null(arg);
-        if (!cnt_lane_of.count(key)) { int l = new_lane(LN_ADD_I64); if (l < 0) return false; cnt_lane_of[key] = l; }
+        if (!cnt_lane_of.count(key)) { int l = new_lane(LN_ADD_I64); if (l < 0) return false; cnt_lane_of[key] = l; a.cnt_owner = 1; }
         a.cnt_lane = (uint8_t)cnt_lane_of[key];
         uint8_t op;
         if (f.name == "count") { a.kind = AG_COUNT; continue; }
@@ -569,7 +569,7 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const HNode* f
             op = a.vclass == VC_F64 ? (mn ? LN_MIN_F64 : LN_MAX_F64) : (a.vclass == VC_U64 ? (mn ? LN_MIN_U64 : LN_MAX_U64) : (mn ? LN_MIN_I64 : LN_MAX_I64));
         }
         std::string akey = key + "#" + std::to_string((int)op) + "#" + std::to_string((int)a.vclass);
-        if (!acc_lane_of.count(akey)) { int l = new_lane(op); if (l < 0) return false; acc_lane_of[akey] = l; }
+        if (!acc_lane_of.count(akey)) { int l = new_lane(op); if (l < 0) return false; acc_lane_of[akey] = l; a.acc_owner = 1; }
         a.acc_lane = (uint8_t)acc_lane_of[akey];
     }
     p.n_out = reg;
@@ -642,7 +642,13 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const HNode* f
             if (pos == vals.size()) vals.push_back(ci);
             d.agg_val[k] = (uint8_t)pos;
         }
-        if (!ok || vals.size() > 4 || ap.n_agg > DIRECT_MAX_AGG) break;
+        if (!ok || vals.size() > 4) break;
+        {   // at most 3 lane operations per value column (ValOps)
+            int ops[4] = {0, 0, 0, 0}; bool too_many = false;
+            for (int k = 0; k < ap.n_agg; k++)
+                if (ap.agg[k].kind != AG_COUNT_STAR && ap.agg[k].kind != AG_COUNT && ap.agg[k].acc_owner && ++ops[d.agg_val[k]] > 3) too_many = true;
+            if (too_many) break;
+        }
         d.n_vals = (int)vals.size();
         for (int v : vals) order.push_back(v);
         out.direct_cols = order;

@@ -8,5 +8,6 @@ int  sort_finish(SortState*, void*, int, cudaStream_t, bkgpu_stats*, std::vector
 size_t sort_partial_bytes(SortState*) { return 0; }
 int  sort_partial_export(SortState*, void*, cudaStream_t, std::string& err) { err = "unsupported"; return BKGPU_EUNSUPPORTED; }
 int  sort_partial_merge(SortState*, const void*, int, cudaStream_t, std::vector<SortOutCol>&, int64_t*, std::string& err) { err = "unsupported"; return BKGPU_EUNSUPPORTED; }
+int  sort_reset(SortState*, cudaStream_t, std::string&) { return 0; }
 void sort_close(SortState*) {}
 }  // namespace bk

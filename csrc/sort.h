@@ -25,6 +25,7 @@ size_t sort_partial_bytes(SortState* s);
 int  sort_partial_export(SortState* s, void* dev_dst, cudaStream_t stream, std::string& err);
 int  sort_partial_merge(SortState* s, const void* dev_src, int nranks, cudaStream_t stream,
                         std::vector<SortOutCol>& out, int64_t* nrows, std::string& err);
+int  sort_reset(SortState* s, cudaStream_t stream, std::string& err);
 void sort_close(SortState* s);
 
 }  // namespace bk

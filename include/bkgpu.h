@@ -115,6 +115,10 @@ int   bkgpu_finish(bkgpu_plan*);
  * *ncols (in: capacity of out_cols, out: columns written) columns of the next result
  * batch; buffers are owned by the plan until the next call / close. */
 int   bkgpu_get_next(bkgpu_plan*, bkgpu_column* out_cols, int* ncols, int64_t* nrows, int* eos);
+/* Re-arm an executed plan for the next request of the same fragment (the reference caches plans of
+ * prepared statements; a maintainer may instead init/close per request): tables are cleared,
+ * allocations and streams kept.  Valid after open or finish. */
+int   bkgpu_reset(bkgpu_plan*);
 /* state->cancel(); polled between launches like RuntimeState::is_cancelled. */
 void  bkgpu_cancel(bkgpu_plan*);
 /* ExecNode::close + destroy_tree. */
