@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, byref, c_char, c_char_p, c_double, c_int,
     c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbkgpu.so")
+LIB_PATH = os.environ.get("BKGPU_LIB") or os.path.join(_HERE, "libbkgpu.so")  # BKGPU_LIB: A/B builds while tuning
 
 OK, EINVAL, EUNSUPPORTED, ENODEV, ENOMEM, ESTATE, ECANCELLED, ETOOBIG, ENCCL = 0, -1, -2, -3, -4, -5, -6, -7, -8
 ERROR_NAMES = {EINVAL: "EINVAL", EUNSUPPORTED: "EUNSUPPORTED", ENODEV: "ENODEV", ENOMEM: "ENOMEM", ESTATE: "ESTATE",

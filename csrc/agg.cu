@@ -294,7 +294,7 @@ size_t agg_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2) {
 size_t direct_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2, int na) {
     const size_t table = (agg_smem_bytes(ap, n_smem_lanes, cap_log2) + 15) & ~(size_t)15;
     const size_t queue = ((size_t)(ap.n_keyw + na) * 128 + 16) * 8;  // QCAP = 128 entries per warp
-    return table + queue * 16;                                         // DIRECT_THREADS / 32 warps
+    return table + queue * (DIRECT_THREADS / 32);                                         // DIRECT_THREADS / 32 warps
 }
 
 template <class K>

@@ -19,6 +19,7 @@ struct AggArgs {
     int32_t n_smem_lanes;
     uint32_t alias_mask;     // global lanes that receive the shared row count at flush time
     ValOps vops[4];          // direct kernels: per value column
+    int32_t smem_sentinel;   // shared table of one-word keys: the key word doubles as slot state (EMPTY_KEY = free)
 };
 
 size_t agg_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2);

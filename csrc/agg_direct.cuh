@@ -4,102 +4,119 @@
 //   columns by the host, so every slot index below is a compile-time constant.
 //
 // Structure of one warp iteration (128 rows = 4 consecutive rows per lane):
-//   1. LOAD     one 128-bit (4-byte types) or 256-bit (8-byte types) non-allocating load per column
+//   1. LOAD     one 128-bit (4-byte types) or 256-bit (8-byte types) non-allocating load per column,
+//               issued one iteration AHEAD (software prefetch: loads fly while atomics run)
 //   2. FILTER   predicate in registers -> 4-bit pass mask per lane          (FilterNode::need_copy)
-//   3. COMPACT  warp prefix sum of popc(pass); surviving rows are written to a per-warp queue in
+//   3. COMPACT  four warp ballots give every surviving row its position in a per-warp queue in
 //               shared memory (key + NA values + null bits)                 [warp-ballot stream compaction]
-//   4. CONSUME  all 32 lanes drain the queue: hash-probe the per-CTA table, then shared-memory
+//   4. CONSUME  all 32 lanes drain the queue: probe the per-CTA hash table, then shared-memory
 //               atomics on the group's lanes                                (AggFnCall::update)
 // Step 3 removes the selectivity-dependent lane divergence from step 4 and keeps the kernel small
 // enough for the instruction cache (the first version unrolled the aggregate step 8x per thread,
-// grew to 15k SASS instructions and stalled 97% of its issue slots on instruction fetch: see
-// profiles/r01_agg_v1_summary.md).
+// grew to 15k SASS instructions and lost 97% of its issue slots to instruction fetch; see
+// profiles/r01_agg_kernel_history.md).  Everything the loop needs from the plan descriptors is
+// resolved into registers before the loop; uncommon shapes (min/max, float/bool/narrow columns,
+// NULL keys wider than 32 bits ...) take out-of-line routines so the hot loop stays lean.
 #pragma once
 #include "agg_kernels.cuh"
 
 namespace bk {
 
-constexpr int DIRECT_THREADS = 512;
 constexpr int ROWS_PER_LANE = 4;
 constexpr int QCAP = 32 * ROWS_PER_LANE;  // queue entries per warp
 
-struct alignas(16) U32x4 { uint32_t v[4]; };
-__device__ __forceinline__ U32x4 ldg128_u32(const void* p) {
-    U32x4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]) : "l"(p));
-    return r;
+// per-column decode flags, computed once per kernel
+enum : uint32_t { SF_IS8 = 1u, SF_SIGNED = 2u, SF_SPECIAL = 4u, SF_HASV = 8u };
+__device__ __forceinline__ uint32_t slot_flags(const DevCol& c) {
+    uint32_t f = 0;
+    if (c.stype == ST_I64 || c.stype == ST_U64 || c.stype == ST_F64) f |= SF_IS8;
+    if (c.stype == ST_I32) f |= SF_SIGNED;
+    if (c.stype == ST_F32 || c.stype == ST_U8 || c.prim == BK_INT8 || c.prim == BK_INT16 || c.prim == BK_UINT8 ||
+        c.prim == BK_UINT16 || c.prim == BK_BOOL) f |= SF_SPECIAL;
+    if (c.validity) f |= SF_HASV;
+    return f;
 }
 
-// ragged tail of a batch (fewer than four rows left): element loads, out of line
-static __device__ __noinline__ void load_quad_tail(const DevCol& c, int64_t row0, int64_t nrows, uint64_t* v, uint32_t* nm_out) {
-    uint32_t nm = 0;
-    for (int j = 0; j < 4; j++) {
-        v[j] = 0;
-        if (row0 + j < nrows) { v[j] = load_elem(c, row0 + j); if (elem_is_null(c, row0 + j)) nm |= 1u << j; }
-    }
-    *nm_out = nm;
-}
+struct RawQuad { uint32_t r[8]; uint32_t nm; };
 
-// four consecutive rows [4q, 4q+4) of one column -> canonical images + 4-bit null mask
-__device__ __forceinline__ void load_quad(const DevCol& c, int64_t q, int64_t nrows, uint64_t (&v)[4], uint32_t& nm) {
-    const int64_t row0 = q * 4;
-    if (row0 + 4 <= nrows) {
-        switch (c.stype) {
-            case ST_I32: { U32x4 r = ldg128_u32((const uint8_t*)c.values + q * 16);
-#pragma unroll
-                for (int j = 0; j < 4; j++) v[j] = (uint64_t)(int64_t)(int32_t)r.v[j]; } break;
-            case ST_U32: { U32x4 r = ldg128_u32((const uint8_t*)c.values + q * 16);
-#pragma unroll
-                for (int j = 0; j < 4; j++) v[j] = (uint64_t)r.v[j]; } break;
-            case ST_F32: { U32x4 r = ldg128_u32((const uint8_t*)c.values + q * 16);
-#pragma unroll
-                for (int j = 0; j < 4; j++) v[j] = f64_bits((double)__uint_as_float(r.v[j])); } break;
-            case ST_U8: { uint32_t r = __ldg((const uint32_t*)c.values + q);
-#pragma unroll
-                for (int j = 0; j < 4; j++) v[j] = (r >> (8 * j)) & 0xFFu; } break;
-            default: { U64x4 r = ldg256_u64((const uint8_t*)c.values + q * 32);
-#pragma unroll
-                for (int j = 0; j < 4; j++) v[j] = r.v[j]; } break;
-        }
-        nm = 0;
-        if (c.validity) nm = (~((uint32_t)__ldg(c.validity + (row0 >> 3)) >> (row0 & 4))) & 0xFu;
+// four consecutive rows [4q, 4q+4) of one column (full quads only: the <= 3 ragged rows at the end of a
+// batch are handled by direct_tail_row)
+__device__ __forceinline__ void raw_quad_load(const DevCol& c, uint32_t flags, int64_t q, RawQuad& out) {
+    if (flags & SF_IS8) {
+        asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(out.r[0]), "=r"(out.r[1]), "=r"(out.r[2]), "=r"(out.r[3]), "=r"(out.r[4]), "=r"(out.r[5]), "=r"(out.r[6]), "=r"(out.r[7])
+            : "l"((const uint8_t*)c.values + q * 32));
+    } else if (c.stype == ST_U8) {
+        out.r[0] = __ldg((const uint32_t*)c.values + q);
     } else {
-        load_quad_tail(c, row0, nrows, v, &nm);
-        return;
+        asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+            : "=r"(out.r[0]), "=r"(out.r[1]), "=r"(out.r[2]), "=r"(out.r[3]) : "l"((const uint8_t*)c.values + q * 16));
     }
-    if (c.prim == BK_INT8 || c.prim == BK_INT16 || c.prim == BK_UINT8 || c.prim == BK_UINT16 || c.prim == BK_BOOL) {
+    out.nm = 0;
+    if (flags & SF_HASV) out.nm = (~((uint32_t)__ldg(c.validity + (q >> 1)) >> ((q & 1) * 4))) & 0xFu;
+}
+// float / bool / narrow integer columns: rare, decoded through the general switch
+__device__ __forceinline__ uint64_t decode_special(uint32_t r, int j, int stype, int prim) {
+    uint64_t v;
+    switch (stype) {
+        case ST_F32: v = f64_bits((double)__uint_as_float(r)); break;
+        case ST_U8: v = (r >> (8 * j)) & 0xFFu; break;
+        case ST_I32: v = (uint64_t)(int64_t)(int32_t)r; break;
+        default: v = r; break;
+    }
+    return narrow_prim(v, prim);
+}
+__device__ __forceinline__ void raw_quad_decode(const RawQuad& in, uint32_t flags, const DevCol& c, uint64_t (&v)[4]) {
+    if (flags & SF_IS8) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = narrow_prim(v[j], c.prim);
+        for (int j = 0; j < 4; j++) v[j] = (uint64_t)in.r[2 * j] | ((uint64_t)in.r[2 * j + 1] << 32);
+    } else if (!(flags & SF_SPECIAL)) {  // int32 / uint32: branch-free sign or zero extension
+        const uint32_t sm = (flags & SF_SIGNED) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (uint64_t)in.r[j] | ((uint64_t)((uint32_t)((int32_t)in.r[j] >> 31) & sm) << 32);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = decode_special(c.stype == ST_U8 ? in.r[0] : in.r[j], j, c.stype, c.prim);
     }
 }
 
-// `column <cmp> constant` over four rows -> 4-bit mask.  The class switch is hoisted out of the row
-// loop; the operator is applied branch-free from (lt, eq, gt).  IEEE semantics for DOUBLE.
+// `column <cmp> constant` over four rows -> 4-bit mask; one switch per quad, tight loops inside.
+// IEEE semantics for DOUBLE (NaN fails every ordered compare, != holds): operators.cpp:84-100.
+#define BK_CMP4(T, EXPR)                                                                    \
+    {                                                                                       \
+        _Pragma("unroll") for (int j = 0; j < 4; j++) { const T x = (T)xs[j]; m |= ((EXPR) ? 1u : 0u) << j; } \
+    }                                                                                       \
+    break;
 __device__ __forceinline__ uint32_t term_mask(const DirectTerm& t, const uint64_t (&v)[4]) {
-    uint32_t lt = 0, eq = 0, gt = 0;
+    uint32_t m = 0;
     if (t.vclass == VC_F64) {
+        double xs[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) xs[j] = bits_f64(v[j]);
         const double y = bits_f64(t.cbits);
-#pragma unroll
-        for (int j = 0; j < 4; j++) { const double x = bits_f64(v[j]); lt |= (x < y ? 1u : 0u) << j; eq |= (x == y ? 1u : 0u) << j; gt |= (x > y ? 1u : 0u) << j; }
+        switch (t.cmp) {
+            case BK_FT_EQ: BK_CMP4(double, x == y) case BK_FT_NE: BK_CMP4(double, x != y)
+            case BK_FT_LT: BK_CMP4(double, x < y) case BK_FT_LE: BK_CMP4(double, x <= y)
+            case BK_FT_GT: BK_CMP4(double, x > y) default: BK_CMP4(double, x >= y)
+        }
     } else if (t.vclass == VC_U64) {
-        const uint64_t y = t.cbits;
-#pragma unroll
-        for (int j = 0; j < 4; j++) { lt |= (v[j] < y ? 1u : 0u) << j; eq |= (v[j] == y ? 1u : 0u) << j; gt |= (v[j] > y ? 1u : 0u) << j; }
+        const uint64_t* xs = v; const uint64_t y = t.cbits;
+        switch (t.cmp) {
+            case BK_FT_EQ: BK_CMP4(uint64_t, x == y) case BK_FT_NE: BK_CMP4(uint64_t, x != y)
+            case BK_FT_LT: BK_CMP4(uint64_t, x < y) case BK_FT_LE: BK_CMP4(uint64_t, x <= y)
+            case BK_FT_GT: BK_CMP4(uint64_t, x > y) default: BK_CMP4(uint64_t, x >= y)
+        }
     } else {
-        const int64_t y = (int64_t)t.cbits;
-#pragma unroll
-        for (int j = 0; j < 4; j++) { const int64_t x = (int64_t)v[j]; lt |= (x < y ? 1u : 0u) << j; eq |= (x == y ? 1u : 0u) << j; gt |= (x > y ? 1u : 0u) << j; }
+        const uint64_t* xs = v; const int64_t y = (int64_t)t.cbits;
+        switch (t.cmp) {
+            case BK_FT_EQ: BK_CMP4(int64_t, x == y) case BK_FT_NE: BK_CMP4(int64_t, x != y)
+            case BK_FT_LT: BK_CMP4(int64_t, x < y) case BK_FT_LE: BK_CMP4(int64_t, x <= y)
+            case BK_FT_GT: BK_CMP4(int64_t, x > y) default: BK_CMP4(int64_t, x >= y)
+        }
     }
-    switch (t.cmp) {
-        case BK_FT_EQ: return eq;
-        case BK_FT_NE: return ~eq & 0xFu;
-        case BK_FT_LT: return lt;
-        case BK_FT_LE: return lt | eq;
-        case BK_FT_GT: return gt;
-        default: return gt | eq;
-    }
+    return m;
 }
+#undef BK_CMP4
 
 // read-modify-write of one 8-byte lane in shared memory with a CAS loop (min / max of any class)
 static __device__ __noinline__ void smem_rmw(int op, uint64_t* p, uint64_t v) {
@@ -139,13 +156,16 @@ static __device__ __noinline__ uint64_t combine4_generic(int op, uint64_t acc, c
 // a row whose group does not fit the shared table (or when no shared table is in use): update the
 // global table directly.  Kept out of line: it is the rare path and must not bloat the hot loop.
 template <int NA>
-__device__ __noinline__ void global_update_row(const AggArgs& a, const uint64_t* key, const uint64_t* vals, uint32_t nullbits) {
+static __device__ __noinline__ void global_update_row(const AggArgs& a, const uint64_t* key, const uint64_t* vals, uint32_t nullbits) {
     const AggPlan& ap = a.plan;
     const GroupTable& gt = a.gt;
     const uint32_t gcap = gt.cap_mask + 1;
-    const int slot = table_upsert<false, 0>(gt.state, gt.keys, gt.cap_mask, key, ap.n_keyw,
-                                            ap.n_keyw == 1 ? hash_key1(key[0]) : hash_key(key, ap.n_keyw), (int)gcap, gt.n_groups);
-    if (slot < 0) { atomicExch(gt.overflow, 1u); return; }
+    int slot = 0;
+    if (ap.n_keyw > 0) {
+        slot = table_upsert<false, 0>(gt.state, gt.keys, gt.cap_mask, key, ap.n_keyw,
+                                      ap.n_keyw == 1 ? hash_key1(key[0]) : hash_key(key, ap.n_keyw), (int)gcap, gt.n_groups);
+        if (slot < 0) { atomicExch(gt.overflow, 1u); return; }
+    }
     atomicAdd((unsigned long long*)(gt.lanes + slot), 1ull);
 #pragma unroll
     for (int s = 0; s < NA; s++) {
@@ -157,15 +177,135 @@ __device__ __noinline__ void global_update_row(const AggArgs& a, const uint64_t*
     }
 }
 
+// uncommon value-column shapes (min / max, several aggregates over one column, int -> double
+// conversion): one out-of-line routine per queue entry
+template <int NA>
+static __device__ __noinline__ void smem_update_row_generic(const AggArgs& a, uint64_t* lanes, uint32_t cap, int slot, const uint64_t* vals, uint32_t nb) {
+#pragma unroll
+    for (int s = 0; s < NA; s++) {
+        if ((nb >> s) & 1u) continue;
+        const ValOps vo = a.vops[s];
+        if (vo.cnt_smem != 0xFF) atomicAdd((uint32_t*)(lanes + (size_t)vo.cnt_smem * cap + slot), 1u);
+        for (int k = 0; k < vo.n_ops; k++)
+            smem_lane_update(vo.op[k], lanes + (size_t)vo.smem_lane[k] * cap + slot, to_lane_class(vals[s], vo.arg_class, vo.lane_class[k]));
+    }
+}
+
+// one of the <= 3 ragged rows at the end of a batch: element loads, straight to the global table
+template <int NP, int NA>
+static __device__ __noinline__ uint32_t direct_tail_row(const AggArgs& a, int64_t row) {
+    const AggPlan& ap = a.plan;
+    for (int t = 0; t < NP; t++) {
+        if (elem_is_null(a.cols[t], row)) return 0;
+        if (!cmp_vals(a.direct.term[t].cmp, a.direct.term[t].vclass, load_elem(a.cols[t], row), a.direct.term[t].cbits)) return 0;
+    }
+    uint64_t key[2] = {0, 0};
+    int vbase = NP;
+    if (ap.n_keyw > 0) {
+        const uint64_t kmask = ap.key_bits[0] >= 64 ? ~0ull : ((1ull << ap.key_bits[0]) - 1ull);
+        if (elem_is_null(a.cols[NP], row)) key[ap.key_null_word[0] == 1 ? 1 : 0] |= 1ull << ap.key_null_shift[0];
+        else key[0] = load_elem(a.cols[NP], row) & kmask;
+        vbase = NP + 1;
+    }
+    uint64_t vals[NA > 0 ? NA : 1]; uint32_t nb = 0;
+    for (int s = 0; s < NA; s++) { vals[s] = load_elem(a.cols[vbase + s], row); if (elem_is_null(a.cols[vbase + s], row)) nb |= 1u << s; }
+    global_update_row<NA>(a, key, vals, nb);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory access with 32-bit shared-space addresses: generic pointers cost 64-bit address
+// arithmetic plus a generic->shared conversion per access in the hot loop
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t lds64(uint32_t a) { uint64_t v; asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_inc32(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_add32(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ uint64_t atoms_cas64(uint32_t a, uint64_t cmp, uint64_t nw) {
+    uint64_t o; asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(o) : "r"(a), "l"(cmp), "l"(nw) : "memory"); return o;
+}
+// double add: LDS + DADD + ATOMS.CAS loop (sm_100a has no native 64-bit floating add in shared memory)
+__device__ __forceinline__ void smem32_add_f64(uint32_t a, double v) {
+    uint64_t cur = lds64(a);
+    for (;;) {
+        const uint64_t nw = f64_bits(bits_f64(cur) + v);
+        const uint64_t prev = atoms_cas64(a, cur, nw);
+        if (prev == cur) break;
+        cur = prev;
+    }
+}
+// 64-bit integer add from native 32-bit atomics (wraps mod 2^64 like ExprValue::add on INT64)
+__device__ __forceinline__ void smem32_add_u64(uint32_t a, uint64_t v) {
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    const uint32_t old = atoms_add32(a, lo);
+    const uint32_t carry = (old + lo) < old ? 1u : 0u;
+    if (hi + carry) atoms_add32(a + 4, hi + carry);
+}
+// probe of a sentinel-mode shared table (one-word keys: EMPTY_KEY = free slot): a hit costs one
+// LDS.64 and one compare.  Returns the slot's byte offset * 1 (slot index) or -1 after 16 probes.
+__device__ __forceinline__ int smem32_upsert1(uint32_t keys_addr, uint32_t cap_mask, uint64_t key, uint32_t slot) {
+#pragma unroll 1
+    for (int probes = 0; probes < 16; probes++) {
+        const uint32_t a = keys_addr + slot * 8u;
+        const uint64_t k = lds64(a);
+        if (k == key) return (int)slot;
+        if (k == EMPTY_KEY) {
+            const uint64_t old = atoms_cas64(a, EMPTY_KEY, key);
+            if (old == EMPTY_KEY || old == key) return (int)slot;
+        }
+        slot = (slot + 1) & cap_mask;
+    }
+    return -1;
+}
+
+// `int32 column <cmp> constant` on the raw 32-bit values when the constant fits: no widening
+__device__ __forceinline__ uint32_t term_mask_i32(int cmp, int32_t y, const uint32_t (&r)[8]) {
+    uint32_t m = 0;
+    switch (cmp) {
+        case BK_FT_EQ:
+#pragma unroll
+            for (int j = 0; j < 4; j++) m |= ((int32_t)r[j] == y ? 1u : 0u) << j;
+            break;
+        case BK_FT_NE:
+#pragma unroll
+            for (int j = 0; j < 4; j++) m |= ((int32_t)r[j] != y ? 1u : 0u) << j;
+            break;
+        case BK_FT_LT:
+#pragma unroll
+            for (int j = 0; j < 4; j++) m |= ((int32_t)r[j] < y ? 1u : 0u) << j;
+            break;
+        case BK_FT_LE:
+#pragma unroll
+            for (int j = 0; j < 4; j++) m |= ((int32_t)r[j] <= y ? 1u : 0u) << j;
+            break;
+        case BK_FT_GT:
+#pragma unroll
+            for (int j = 0; j < 4; j++) m |= ((int32_t)r[j] > y ? 1u : 0u) << j;
+            break;
+        default:
+#pragma unroll
+            for (int j = 0; j < 4; j++) m |= ((int32_t)r[j] >= y ? 1u : 0u) << j;
+            break;
+    }
+    return m;
+}
+
 // ------------------------------------------------------------------------------------------
 // GROUP BY one column
 // ------------------------------------------------------------------------------------------
 template <int NP, int NA>
 __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __grid_constant__ AggArgs a) {
+    constexpr int NS = NP + 1 + NA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AggPlan& ap = a.plan;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane_lt = (1u << lane) - 1u;
     const bool use_smem = a.smem_cap_log2 > 0;
+    const int kw = ap.n_keyw;                                  // 1 or 2
+    const bool sentinel = use_smem && a.smem_sentinel != 0;    // kw == 1: keys double as slot state
     SmemTable st{};
     size_t table_bytes = 0;
     if (use_smem) {
@@ -173,91 +313,164 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
         table_bytes = (((size_t)(ap.n_keyw + a.n_smem_lanes) * 8 + 4) << a.smem_cap_log2);
     }
     // per-warp queue: [key words kw x QCAP][values NA x QCAP][null bits QCAP]
-    const int kw = ap.n_keyw;  // 1 or 2
     const size_t qwords = (size_t)(kw + NA) * QCAP;
     uint64_t* qbase = (uint64_t*)(smem_raw + ((table_bytes + 15) & ~(size_t)15)) + (size_t)warp * (qwords + QCAP / 8);
-    uint64_t* qkey = qbase;
-    uint64_t* qval = qbase + (size_t)kw * QCAP;
-    uint8_t* qnull = (uint8_t*)(qbase + qwords);
+    const uint32_t qkey = smem_addr(qbase);
+    const uint32_t qval = qkey + (uint32_t)kw * QCAP * 8u;
+    const uint32_t qnull = qkey + (uint32_t)qwords * 8u;
     const uint64_t kmask = ap.key_bits[0] >= 64 ? ~0ull : ((1ull << ap.key_bits[0]) - 1ull);
     const int null_word = ap.key_null_word[0] == 0xFF ? 0 : ap.key_null_word[0];
     const uint64_t null_bit = 1ull << ap.key_null_shift[0];
+    // everything the loops need from the descriptors, resolved once into registers
+    uint32_t sf[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) sf[s] = slot_flags(a.cols[s]);
+    const bool key_nullable = (sf[NP] & SF_HASV) != 0;
+    const bool key32 = !(sf[NP] & (SF_IS8 | SF_SPECIAL));      // 4-byte integer key: its word is the raw value
+    bool any_vnull = false;
+#pragma unroll
+    for (int s = 0; s < NA; s++) any_vnull = any_vnull || (sf[NP + 1 + s] & SF_HASV);
+    bool term32[NP > 0 ? NP : 1]; int32_t term_c32[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int t = 0; t < NP; t++) {  // int32 column against a constant that fits int32: compare raw values
+        const DirectTerm tm = a.direct.term[t];
+        const int64_t c = (int64_t)tm.cbits;
+        term32[t] = a.cols[t].stype == ST_I32 && !(sf[t] & SF_SPECIAL) && tm.vclass == VC_I64 && c >= -2147483648ll && c <= 2147483647ll;
+        term_c32[t] = (int32_t)c;
+    }
+    const uint32_t tcap = st.cap_mask + 1;
+    const uint32_t keys_addr = smem_addr(st.keys), lanes_addr = smem_addr(st.lanes);
+    const int hash_shift = 32 - a.smem_cap_log2;
+    bool simple = use_smem;            // every value column feeds at most one ADD lane of its own class
+    uint32_t acc_addr[NA > 0 ? NA : 1], cnt_addr[NA > 0 ? NA : 1]; bool acc_f64[NA > 0 ? NA : 1];
+#pragma unroll
+    for (int s = 0; s < NA; s++) {
+        const ValOps vo = a.vops[s];
+        acc_addr[s] = 0; cnt_addr[s] = 0; acc_f64[s] = false;
+        if (vo.n_ops > 1) simple = false;
+        if (vo.n_ops == 1) {
+            if (!(vo.op[0] == LN_ADD_F64 || vo.op[0] == LN_ADD_I64) || (vo.lane_class[0] == VC_F64) != (vo.arg_class == VC_F64)) simple = false;
+            acc_addr[s] = lanes_addr + (uint32_t)vo.smem_lane[0] * tcap * 8u; acc_f64[s] = vo.op[0] == LN_ADD_F64;
+        }
+        if (vo.cnt_smem != 0xFF) cnt_addr[s] = lanes_addr + (uint32_t)vo.cnt_smem * tcap * 8u;
+    }
     uint32_t passed = 0;
-    const int64_t nquads = (a.nrows + 3) >> 2;
+    const int64_t nquads = a.nrows >> 2;  // full quads; the ragged rows follow the main loop
     const int64_t stride = (int64_t)gridDim.x * DIRECT_THREADS;
+    int64_t q0 = (int64_t)blockIdx.x * DIRECT_THREADS + warp * 32;
+    RawQuad nxt[NS];
+    if (q0 + lane < nquads) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) raw_quad_load(a.cols[s], sf[s], q0 + lane, nxt[s]);
+    }
     // all lanes of a warp run the same number of iterations (the queue is warp-collective)
-    for (int64_t q0 = (int64_t)blockIdx.x * DIRECT_THREADS + warp * 32; q0 < nquads; q0 += stride) {
+#pragma unroll 1
+    for (; q0 < nquads; q0 += stride) {
         const int64_t q = q0 + lane;
         uint64_t kv[4]; uint32_t knm = 0;
-        uint64_t vv[NA > 0 ? NA : 1][4]; uint32_t vnm[NA > 0 ? NA : 1];
+        uint64_t vv[NA > 0 ? NA : 1][4]; uint32_t vnull[4] = {0, 0, 0, 0};
         uint32_t pass = 0;
         if (q < nquads) {
-            const int64_t left = a.nrows - q * 4;
-            pass = left >= 4 ? 0xFu : ((1u << left) - 1u);
+            pass = 0xFu;
 #pragma unroll
             for (int t = 0; t < NP; t++) {
-                uint64_t pv[4]; uint32_t pnm;
-                load_quad(a.cols[t], q, a.nrows, pv, pnm);
-                pass &= term_mask(a.direct.term[t], pv) & ~pnm;  // NULL or false drops the row
+                if (term32[t]) pass &= term_mask_i32(a.direct.term[t].cmp, term_c32[t], nxt[t].r);
+                else {
+                    uint64_t pv[4];
+                    raw_quad_decode(nxt[t], sf[t], a.cols[t], pv);
+                    pass &= term_mask(a.direct.term[t], pv);
+                }
+                pass &= ~nxt[t].nm;  // NULL or false drops the row
             }
-            load_quad(a.cols[NP], q, a.nrows, kv, knm);
+            if (key32) {
 #pragma unroll
-            for (int s = 0; s < NA; s++) load_quad(a.cols[NP + 1 + s], q, a.nrows, vv[s], vnm[s]);
+                for (int j = 0; j < 4; j++) kv[j] = nxt[NP].r[j];
+            } else raw_quad_decode(nxt[NP], sf[NP], a.cols[NP], kv);
+            knm = nxt[NP].nm;
+#pragma unroll
+            for (int s = 0; s < NA; s++) {
+                raw_quad_decode(nxt[NP + 1 + s], sf[NP + 1 + s], a.cols[NP + 1 + s], vv[s]);
+                if (any_vnull) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) vnull[j] |= ((nxt[NP + 1 + s].nm >> j) & 1u) << s;
+                }
+            }
         }
-        // ---- compact the surviving rows of this warp into its queue ----
-        const int cnt = __popc(pass);
-        int base = cnt;
+        // prefetch the next iteration's columns: they stay in flight while the queue is drained
+        if (q + stride < nquads) {
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, base, d); if (lane >= d) base += n; }
-        const int total = __shfl_sync(0xFFFFFFFFu, base, 31);
-        base -= cnt;
-        passed += cnt;
+            for (int s = 0; s < NS; s++) raw_quad_load(a.cols[s], sf[s], q + stride, nxt[s]);
+        }
+        // ---- compact the surviving rows of this warp into its queue: one ballot per row position ----
+        uint32_t bal[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) bal[j] = __ballot_sync(0xFFFFFFFFu, (pass >> j) & 1u);
+        int total = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (!((pass >> j) & 1u)) continue;
-            const bool knull = (knm >> j) & 1u;
-            qkey[base] = knull ? (null_word == 0 ? null_bit : 0ull) : (kv[j] & kmask);
-            if (kw == 2) qkey[QCAP + base] = knull && null_word == 1 ? null_bit : 0ull;
-            uint32_t nb = 0;
+            if ((pass >> j) & 1u) {
+                const uint32_t pos = (uint32_t)(total + __popc(bal[j] & lane_lt));
+                uint64_t kword = kv[j] & kmask;
+                if (key_nullable && ((knm >> j) & 1u)) {
+                    kword = null_word == 0 ? null_bit : 0ull;
+                    if (kw == 2) sts64(qkey + (QCAP + pos) * 8u, null_word == 1 ? null_bit : 0ull);
+                } else if (kw == 2) sts64(qkey + (QCAP + pos) * 8u, 0ull);
+                sts64(qkey + pos * 8u, kword);
 #pragma unroll
-            for (int s = 0; s < NA; s++) { qval[s * QCAP + base] = vv[s][j]; nb |= ((vnm[s] >> j) & 1u) << s; }
-            qnull[base] = (uint8_t)nb;
-            base++;
+                for (int s = 0; s < NA; s++) sts64(qval + (s * QCAP + pos) * 8u, vv[s][j]);
+                if (any_vnull) sts8(qnull + pos, vnull[j]);
+            }
+            total += __popc(bal[j]);
         }
+        passed += __popc(pass);
         __syncwarp();
         // ---- drain: every lane takes queue entries, full warps regardless of selectivity ----
-        for (int e = lane; e < total; e += 32) {
-            uint64_t key[2];
-            key[0] = qkey[e]; key[1] = kw == 2 ? qkey[QCAP + e] : 0ull;
-            const uint32_t nb = qnull[e];
+        // (warp-uniform trip count: lanes beyond the tail idle inside the iteration, so the warp is
+        //  converged again when it returns to the load / filter / ballot code)
+#pragma unroll 1
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            if (e >= total) continue;
+            const uint64_t k0 = lds64(qkey + e * 8u);
+            const uint32_t nb = any_vnull ? lds8(qnull + e) : 0u;
             int slot = -1;
-            if (use_smem) {
-                const uint32_t h = kw == 1 ? hash_key1(key[0]) : hash_key(key, 2);
-                slot = kw == 1 ? table_upsert<true, 1>(st.state, st.keys, st.cap_mask, key, 1, h >> 7, 16, nullptr)
-                               : table_upsert<true, 2>(st.state, st.keys, st.cap_mask, key, 2, h >> 7, 16, nullptr);
+            if (sentinel) {  // Fibonacci hashing: consecutive keys land in well separated slots
+                const uint32_t h = ((uint32_t)k0 ^ (uint32_t)(k0 >> 32)) * 0x9E3779B1u;
+                if (k0 != EMPTY_KEY) slot = smem32_upsert1(keys_addr, st.cap_mask, k0, h >> hash_shift);
+            } else if (use_smem) {
+                uint64_t key[2] = {k0, lds64(qkey + (QCAP + e) * 8u)};
+                slot = table_upsert<true, 2>(st.state, st.keys, st.cap_mask, key, 2, hash_key(key, 2) >> 7, 16, nullptr);
             }
             if (slot >= 0) {
-                const uint32_t cap = st.cap_mask + 1;
-                atomicAdd((uint32_t*)(st.lanes + slot), 1u);  // lane 0 = row count (< 2^32 rows per CTA and launch)
+                reds_inc32(lanes_addr + slot * 8u);  // lane 0 = row count (< 2^32 rows per CTA and launch)
+                if (simple) {
 #pragma unroll
-                for (int s = 0; s < NA; s++) {
-                    if ((nb >> s) & 1u) continue;
-                    const ValOps vo = a.vops[s];
-                    const uint64_t v = qval[s * QCAP + e];
-                    if (vo.cnt_smem != 0xFF) atomicAdd((uint32_t*)(st.lanes + (size_t)vo.cnt_smem * cap + slot), 1u);
-                    for (int k = 0; k < vo.n_ops; k++)
-                        smem_lane_update(vo.op[k], st.lanes + (size_t)vo.smem_lane[k] * cap + slot, to_lane_class(v, vo.arg_class, vo.lane_class[k]));
+                    for (int s = 0; s < NA; s++) {
+                        if ((nb >> s) & 1u) continue;
+                        if (cnt_addr[s]) reds_inc32(cnt_addr[s] + slot * 8u);
+                        if (acc_addr[s]) {
+                            const uint64_t v = lds64(qval + (s * QCAP + e) * 8u);
+                            if (acc_f64[s]) smem32_add_f64(acc_addr[s] + slot * 8u, bits_f64(v)); else smem32_add_u64(acc_addr[s] + slot * 8u, v);
+                        }
+                    }
+                } else {
+                    uint64_t vals[NA > 0 ? NA : 1];
+#pragma unroll
+                    for (int s = 0; s < NA; s++) vals[s] = lds64(qval + (s * QCAP + e) * 8u);
+                    smem_update_row_generic<NA>(a, st.lanes, tcap, slot, vals, nb);
                 }
             } else {
+                uint64_t key[2] = {k0, kw == 2 ? lds64(qkey + (QCAP + e) * 8u) : 0ull};
                 uint64_t vals[NA > 0 ? NA : 1];
 #pragma unroll
-                for (int s = 0; s < NA; s++) vals[s] = qval[s * QCAP + e];
+                for (int s = 0; s < NA; s++) vals[s] = lds64(qval + (s * QCAP + e) * 8u);
                 global_update_row<NA>(a, key, vals, nb);
             }
         }
         __syncwarp();
     }
     if (use_smem) smem_table_flush(st, a);
+    if (blockIdx.x == 0 && threadIdx.x < (a.nrows & 3)) passed += direct_tail_row<NP, NA>(a, (a.nrows & ~(int64_t)3) + threadIdx.x);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) passed += __shfl_xor_sync(0xFFFFFFFFu, passed, d);
     if (lane == 0 && passed) atomicAdd((unsigned long long*)a.rows_passed, (unsigned long long)passed);
@@ -269,6 +482,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 // ------------------------------------------------------------------------------------------
 template <int NP, int NA>
 __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_scalar_direct(const __grid_constant__ AggArgs a) {
+    constexpr int NS = NP + NA;
     const int lane = threadIdx.x & 31;
     uint64_t rows = 0;
     uint64_t acc[NA > 0 ? NA : 1][3], cnt[NA > 0 ? NA : 1];
@@ -278,22 +492,28 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_scalar_direct(const _
 #pragma unroll
         for (int k = 0; k < 3; k++) acc[s][k] = k < a.vops[s].n_ops ? lane_identity(a.vops[s].op[k]) : 0;
     }
-    const int64_t nquads = (a.nrows + 3) >> 2;
+    uint32_t sf[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int s = 0; s < NS; s++) sf[s] = slot_flags(a.cols[s]);
+    const int64_t nquads = a.nrows >> 2;
+#pragma unroll 1
     for (int64_t q = (int64_t)blockIdx.x * DIRECT_THREADS + threadIdx.x; q < nquads; q += (int64_t)gridDim.x * DIRECT_THREADS) {
-        const int64_t left = a.nrows - q * 4;
-        uint32_t pass = left >= 4 ? 0xFu : ((1u << left) - 1u);
+        RawQuad raw[NS > 0 ? NS : 1];
+#pragma unroll
+        for (int s = 0; s < NS; s++) raw_quad_load(a.cols[s], sf[s], q, raw[s]);
+        uint32_t pass = 0xFu;
 #pragma unroll
         for (int t = 0; t < NP; t++) {
-            uint64_t pv[4]; uint32_t pnm;
-            load_quad(a.cols[t], q, a.nrows, pv, pnm);
-            pass &= term_mask(a.direct.term[t], pv) & ~pnm;
+            uint64_t pv[4];
+            raw_quad_decode(raw[t], sf[t], a.cols[t], pv);
+            pass &= term_mask(a.direct.term[t], pv) & ~raw[t].nm;
         }
         rows += __popc(pass);
 #pragma unroll
         for (int s = 0; s < NA; s++) {
-            uint64_t v[4]; uint32_t nm;
-            load_quad(a.cols[NP + s], q, a.nrows, v, nm);
-            const uint32_t ok = pass & ~nm;
+            uint64_t v[4];
+            raw_quad_decode(raw[NP + s], sf[NP + s], a.cols[NP + s], v);
+            const uint32_t ok = pass & ~raw[NP + s].nm;
             cnt[s] += __popc(ok);
             const ValOps vo = a.vops[s];
 #pragma unroll
@@ -326,6 +546,10 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_scalar_direct(const _
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) acc[s][k] = lane_combine(vo.op[k], acc[s][k], __shfl_xor_sync(0xFFFFFFFFu, acc[s][k], d));
         }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (a.nrows & 3)) {
+        const uint32_t p1 = direct_tail_row<NP, NA>(a, (a.nrows & ~(int64_t)3) + threadIdx.x);
+        if (p1) atomicAdd((unsigned long long*)a.rows_passed, 1ull);
     }
     if (lane == 0) {  // the single group lives in slot 0 (capacity 1): lane l is gt.lanes[l]
         if (rows) { atomicAdd((unsigned long long*)gt.lanes, (unsigned long long)rows); atomicAdd((unsigned long long*)a.rows_passed, (unsigned long long)rows); }

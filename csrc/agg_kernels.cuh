@@ -62,6 +62,8 @@ __device__ __forceinline__ void merge_group(const AggPlan& ap, const GroupTable&
 // ------------------------------------------------------------------------------------------
 // shared-memory table carve-up: [keys n_keyw x cap][lanes n_smem_lanes x cap][state cap]
 // ------------------------------------------------------------------------------------------
+constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;  // "free slot" marker of sentinel-mode shared tables (one-word keys)
+
 struct SmemTable {
     uint32_t* state; uint64_t* keys; uint64_t* lanes; uint32_t cap_mask;
 };
@@ -73,7 +75,8 @@ __device__ __forceinline__ SmemTable smem_table_init(unsigned char* raw, const A
     t.keys = (uint64_t*)raw;
     t.lanes = t.keys + (size_t)ap.n_keyw * cap;
     t.state = (uint32_t*)(t.lanes + (size_t)args.n_smem_lanes * cap);
-    for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) t.state[i] = 0u;
+    if (args.smem_sentinel) { for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) t.keys[i] = EMPTY_KEY; }
+    else { for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) t.state[i] = 0u; }
     for (int l = 0; l < ap.n_lanes; l++) {
         const int sl = args.smem_lane[l];
         if (sl == 0xFF) continue;
@@ -88,7 +91,7 @@ __device__ __forceinline__ void smem_table_flush(const SmemTable& t, const AggAr
     const AggPlan& ap = args.plan;
     const uint32_t cap = t.cap_mask + 1;
     for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) {
-        if (t.state[i] != 2u) continue;
+        if (args.smem_sentinel ? (t.keys[i] == EMPTY_KEY) : (t.state[i] != 2u)) continue;
         uint64_t key[MAX_KEYW];
         for (int w = 0; w < ap.n_keyw; w++) key[w] = t.keys[(size_t)w * cap + i];
         merge_group(ap, args.gt, key, [&](int l, uint64_t& v) {

@@ -260,6 +260,7 @@ static int launch_agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, bo
     }
     for (int l = 1; l < a.plan.n_lanes; l++) if (a.smem_lane[l] != 0xFF) a.alias_mask &= ~(1u << l);
     a.smem_cap_log2 = pick_smem_log2(p, a.n_smem_lanes, direct, c.direct.n_vals);
+    a.smem_sentinel = direct && a.plan.n_keyw == 1 ? 1 : 0;
     if (direct) {  // per value column: the lane operations it feeds
         memset(a.vops, 0, sizeof a.vops);
         for (int v = 0; v < c.direct.n_vals; v++) { a.vops[v].cnt_smem = 0xFF; }

@@ -23,6 +23,10 @@ constexpr int MAX_AGG = 12;       // aggregate functions per AggNode
 constexpr int MAX_LANES = 26;     // accumulator lanes (8-byte) per group
 constexpr int STACK_DEPTH = 12;
 constexpr int DIRECT_MAX_AGG = 6; // aggregates the specialised kernels keep in registers
+#ifndef BK_DIRECT_THREADS
+#define BK_DIRECT_THREADS 512     // threads per CTA of the direct filter+aggregate kernels (one CTA per SM)
+#endif
+constexpr int DIRECT_THREADS = BK_DIRECT_THREADS;
 
 struct DevCol {
     const void* values;
