@@ -285,15 +285,15 @@ __global__ void k_extract(GroupTable gt, AggPlan ap, uint64_t* outv, uint8_t* ou
 // ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
-size_t agg_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2) {
-    if (cap_log2 <= 0 || ap.n_keyw == 0) return 0;
-    return ((size_t)(ap.n_keyw + n_smem_lanes) * 8 + 4) << cap_log2;
+size_t agg_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2) {
+    if (cap_log2 <= 0 || smem_keyw == 0) return 0;
+    return ((size_t)(smem_keyw + n_smem_lanes) * 8 + 4) << cap_log2;
 }
 
 // shared memory of the direct GROUP BY kernel: the table plus one compaction queue per warp
-size_t direct_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2, int na) {
-    const size_t table = (agg_smem_bytes(ap, n_smem_lanes, cap_log2) + 15) & ~(size_t)15;
-    const size_t queue = ((size_t)(ap.n_keyw + na) * 128 + 16) * 8;  // QCAP = 128 entries per warp
+size_t direct_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2, int na) {
+    const size_t table = (agg_smem_bytes(smem_keyw, n_smem_lanes, cap_log2) + 15) & ~(size_t)15;
+    const size_t queue = ((size_t)(2 + na) * 128 + 16) * 8;  // QCAP = 128 entries per warp, up to 2 key words
     return table + queue * (DIRECT_THREADS / 32);                                         // DIRECT_THREADS / 32 warps
 }
 
@@ -306,10 +306,10 @@ static int occupancy_grid(K kernel, size_t smem, int sm_count) {
 
 cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t s, const char** kernel_name) {
     const bool grouped = a.plan.n_keyw > 0;
-    const size_t smem = grouped ? agg_smem_bytes(a.plan, a.n_smem_lanes, a.smem_cap_log2) : 0;
+    const size_t smem = grouped ? agg_smem_bytes(a.smem_keyw, a.n_smem_lanes, a.smem_cap_log2) : 0;
     if (a.nrows <= 0) return cudaSuccess;
     if (direct) {
-        const size_t dsmem = grouped ? direct_smem_bytes(a.plan, a.n_smem_lanes, a.smem_cap_log2, a.direct.n_vals) : 0;
+        const size_t dsmem = grouped ? direct_smem_bytes(a.smem_keyw, a.n_smem_lanes, a.smem_cap_log2, a.direct.n_vals) : 0;
         *kernel_name = grouped ? "k_agg_group_direct" : "k_agg_scalar_direct";
         switch (a.direct.n_terms) {
             case 0: return launch_direct_np0(a, a.direct.n_vals, sm_count, dsmem, s, grouped);

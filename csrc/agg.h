@@ -19,15 +19,17 @@ struct AggArgs {
     int32_t n_smem_lanes;
     uint32_t alias_mask;     // global lanes that receive the shared row count at flush time
     ValOps vops[4];          // direct kernels: per value column
+    int32_t smem_keyw;       // key words per slot of the shared table (1 in sentinel mode, else plan.n_keyw)
+    int32_t lean;            // batch qualifies for k_agg_group_lean (see agg_direct.cuh)
     int32_t smem_sentinel;   // shared table of one-word keys: the key word doubles as slot state (EMPTY_KEY = free)
 };
 
-size_t agg_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2);
+size_t agg_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2);
 cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t s, const char** kernel_name);
 cudaError_t launch_direct_np0(const AggArgs& a, int na, int sm_count, size_t smem, cudaStream_t s, bool grouped);
 cudaError_t launch_direct_np1(const AggArgs& a, int na, int sm_count, size_t smem, cudaStream_t s, bool grouped);
 cudaError_t launch_direct_np2(const AggArgs& a, int na, int sm_count, size_t smem, cudaStream_t s, bool grouped);
-size_t direct_smem_bytes(const AggPlan& ap, int n_smem_lanes, int cap_log2, int na);
+size_t direct_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2, int na);
 cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStream_t s);
 cudaError_t launch_partial_export(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, uint32_t pcap, uint32_t* cursor, cudaStream_t s);
 cudaError_t launch_partial_merge(const GroupTable& gt, const AggPlan& ap, const uint64_t* src, size_t words_per_rank, uint32_t pcap, int nranks, cudaStream_t s);

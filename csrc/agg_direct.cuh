@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
     size_t table_bytes = 0;
     if (use_smem) {
         st = smem_table_init(smem_raw, a);
-        table_bytes = (((size_t)(ap.n_keyw + a.n_smem_lanes) * 8 + 4) << a.smem_cap_log2);
+        table_bytes = (((size_t)(a.smem_keyw + a.n_smem_lanes) * 8 + 4) << a.smem_cap_log2);
     }
     // per-warp queue: [key words kw x QCAP][values NA x QCAP][null bits QCAP]
     const size_t qwords = (size_t)(kw + NA) * QCAP;
@@ -477,6 +477,149 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 }
 
 // ------------------------------------------------------------------------------------------
+// GROUP BY one column, LEAN shape — what the headline query (config C2/C4) and most star-schema
+// aggregations look like: no NULLs in this batch, every predicate term is `int32 column <cmp> int32
+// constant`, the key is a 4- or 8-byte integer column, every value column is 8 bytes wide and feeds
+// exactly one SUM lane (double or int64) — COUNT(*) and AVG ride on the row count.  With all of that
+// fixed the hot loop has no descriptor interpretation left in it.  Everything else takes
+// k_agg_group_direct above (same results, more instructions per row).
+// ------------------------------------------------------------------------------------------
+template <int NP, int NA>
+__global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_lean(const __grid_constant__ AggArgs a) {
+    constexpr int NS = NP + 1 + NA;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const AggPlan& ap = a.plan;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    SmemTable st = smem_table_init(smem_raw, a);
+    const size_t table_bytes = (((size_t)(1 + a.n_smem_lanes) * 8 + 4) << a.smem_cap_log2);
+    const size_t qwords = (size_t)(1 + NA) * QCAP;
+    uint64_t* qbase = (uint64_t*)(smem_raw + ((table_bytes + 15) & ~(size_t)15)) + (size_t)warp * (qwords + QCAP / 8);
+    const uint32_t qkey = smem_addr(qbase);
+    const uint32_t qval = qkey + QCAP * 8u;
+    const uint64_t kmask = ap.key_bits[0] >= 64 ? ~0ull : ((1ull << ap.key_bits[0]) - 1ull);
+    const bool key8 = a.cols[NP].stype == ST_I64 || a.cols[NP].stype == ST_U64;
+    const uint32_t cap_mask = st.cap_mask, tcap = st.cap_mask + 1;
+    const uint32_t keys_addr = smem_addr(st.keys), lanes_addr = smem_addr(st.lanes);
+    const int hash_shift = 32 - a.smem_cap_log2;
+    int tcmp[NP > 0 ? NP : 1]; int32_t tconst[NP > 0 ? NP : 1];
+    const uint8_t* tptr[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int t = 0; t < NP; t++) { tcmp[t] = a.direct.term[t].cmp; tconst[t] = (int32_t)(int64_t)a.direct.term[t].cbits; tptr[t] = (const uint8_t*)a.cols[t].values; }
+    const uint8_t* kptr = (const uint8_t*)a.cols[NP].values;
+    const uint8_t* vptr[NA > 0 ? NA : 1]; uint32_t acc_addr[NA > 0 ? NA : 1]; bool acc_f64[NA > 0 ? NA : 1];
+#pragma unroll
+    for (int s = 0; s < NA; s++) {
+        vptr[s] = (const uint8_t*)a.cols[NP + 1 + s].values;
+        acc_addr[s] = lanes_addr + (uint32_t)a.vops[s].smem_lane[0] * tcap * 8u;
+        acc_f64[s] = a.vops[s].op[0] == LN_ADD_F64;
+    }
+    uint32_t passed = 0;
+    const int64_t nquads = a.nrows >> 2;
+    const int64_t stride = (int64_t)gridDim.x * DIRECT_THREADS;
+    int64_t q0 = (int64_t)blockIdx.x * DIRECT_THREADS + warp * 32;
+    uint32_t pr[NP > 0 ? NP : 1][4]; uint32_t kr[8]; uint64_t vr[NA > 0 ? NA : 1][4];
+    auto issue_loads = [&](int64_t q) {
+#pragma unroll
+        for (int t = 0; t < NP; t++) { const U32x4 r = ldg128_u32(tptr[t] + q * 16);
+#pragma unroll
+            for (int j = 0; j < 4; j++) pr[t][j] = r.v[j]; }
+        if (key8) { const U32x8 r = ldg256_u32(kptr + q * 32);
+#pragma unroll
+            for (int j = 0; j < 8; j++) kr[j] = r.v[j]; }
+        else { const U32x4 r = ldg128_u32(kptr + q * 16);
+#pragma unroll
+            for (int j = 0; j < 4; j++) kr[j] = r.v[j]; }
+#pragma unroll
+        for (int s = 0; s < NA; s++) { const U64x4 r = ldg256_u64(vptr[s] + q * 32);
+#pragma unroll
+            for (int j = 0; j < 4; j++) vr[s][j] = r.v[j]; }
+    };
+    if (q0 + lane < nquads) issue_loads(q0 + lane);
+#pragma unroll 1
+    for (; q0 < nquads; q0 += stride) {
+        const int64_t q = q0 + lane;
+        uint32_t pass = 0;
+        uint64_t kv[4]; uint64_t vv[NA > 0 ? NA : 1][4];
+        if (q < nquads) {
+            pass = 0xFu;
+#pragma unroll
+            for (int t = 0; t < NP; t++) {
+                uint32_t r8[8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) r8[j] = pr[t][j];
+                pass &= term_mask_i32(tcmp[t], tconst[t], r8);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) kv[j] = key8 ? ((uint64_t)kr[2 * j] | ((uint64_t)kr[2 * j + 1] << 32)) : ((uint64_t)kr[j] & kmask);
+#pragma unroll
+        for (int s = 0; s < NA; s++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) vv[s][j] = vr[s][j];
+        if (q + stride < nquads) issue_loads(q + stride);  // next iteration's columns fly while the queue drains
+        uint32_t bal[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) bal[j] = __ballot_sync(0xFFFFFFFFu, (pass >> j) & 1u);
+        int total = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if ((pass >> j) & 1u) {
+                const uint32_t pos = (uint32_t)(total + __popc(bal[j] & lane_lt));
+                sts64(qkey + pos * 8u, kv[j]);
+#pragma unroll
+                for (int s = 0; s < NA; s++) sts64(qval + (s * QCAP + pos) * 8u, vv[s][j]);
+            }
+            total += __popc(bal[j]);
+        }
+        passed += __popc(pass);
+        __syncwarp();
+        // (a two-entries-per-lane variant of this loop measured 17% slower: more registers, more idle
+        //  lanes in the last pass — profiles/r01_agg_kernel_history.md)
+#pragma unroll 1
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            if (e >= total) continue;
+            const uint64_t k0 = lds64(qkey + e * 8u);
+            uint64_t v[NA > 0 ? NA : 1];
+#pragma unroll
+            for (int s = 0; s < NA; s++) v[s] = lds64(qval + (s * QCAP + e) * 8u);
+            const uint32_t h = ((uint32_t)k0 ^ (uint32_t)(k0 >> 32)) * 0x9E3779B1u;
+            int slot = -1;
+            if (k0 != EMPTY_KEY) slot = smem32_upsert1(keys_addr, cap_mask, k0, h >> hash_shift);
+            if (slot >= 0) {
+                reds_inc32(lanes_addr + slot * 8u);
+                // the NA accumulations are independent: run their LDS -> add -> CAS chains interleaved
+                uint64_t cur[NA > 0 ? NA : 1]; uint32_t pending = 0;
+#pragma unroll
+                for (int s = 0; s < NA; s++) {
+                    if (acc_f64[s]) { cur[s] = lds64(acc_addr[s] + slot * 8u); pending |= 1u << s; }
+                    else smem32_add_u64(acc_addr[s] + slot * 8u, v[s]);
+                }
+                while (pending) {
+#pragma unroll
+                    for (int s = 0; s < NA; s++) {
+                        if (!((pending >> s) & 1u)) continue;
+                        const uint64_t nw = f64_bits(bits_f64(cur[s]) + bits_f64(v[s]));
+                        const uint64_t prev = atoms_cas64(acc_addr[s] + slot * 8u, cur[s], nw);
+                        if (prev == cur[s]) pending &= ~(1u << s); else cur[s] = prev;
+                    }
+                }
+            } else {
+                uint64_t key[2] = {k0, 0ull};
+                global_update_row<NA>(a, key, v, 0u);
+            }
+        }
+        __syncwarp();
+    }
+    smem_table_flush(st, a);
+    if (blockIdx.x == 0 && threadIdx.x < (a.nrows & 3)) passed += direct_tail_row<NP, NA>(a, (a.nrows & ~(int64_t)3) + threadIdx.x);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) passed += __shfl_xor_sync(0xFFFFFFFFu, passed, d);
+    if (lane == 0 && passed) atomicAdd((unsigned long long*)a.rows_passed, (unsigned long long)passed);
+}
+
+// ------------------------------------------------------------------------------------------
 // no GROUP BY: accumulate in registers (per value column up to 3 lane operations), warp shuffle
 // reduction, one set of global atomics per warp
 // ------------------------------------------------------------------------------------------
@@ -580,6 +723,13 @@ static inline cudaError_t launch_direct(const AggArgs& a, int sm_count, size_t s
             cudaError_t e = cudaFuncSetAttribute(k_agg_group_direct<NP, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
+        if (a.lean) {
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+            }
+            k_agg_group_lean<NP, NA><<<direct_grid(k_agg_group_lean<NP, NA>, smem, sm_count, a.nrows), DIRECT_THREADS, smem, s>>>(a);
+        } else
         k_agg_group_direct<NP, NA><<<direct_grid(k_agg_group_direct<NP, NA>, smem, sm_count, a.nrows), DIRECT_THREADS, smem, s>>>(a);
     } else {
         k_agg_scalar_direct<NP, NA><<<direct_grid(k_agg_scalar_direct<NP, NA>, 0, sm_count, a.nrows), DIRECT_THREADS, 0, s>>>(a);

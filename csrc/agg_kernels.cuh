@@ -73,7 +73,7 @@ __device__ __forceinline__ SmemTable smem_table_init(unsigned char* raw, const A
     const uint32_t cap = 1u << args.smem_cap_log2;
     t.cap_mask = cap - 1;
     t.keys = (uint64_t*)raw;
-    t.lanes = t.keys + (size_t)ap.n_keyw * cap;
+    t.lanes = t.keys + (size_t)args.smem_keyw * cap;
     t.state = (uint32_t*)(t.lanes + (size_t)args.n_smem_lanes * cap);
     if (args.smem_sentinel) { for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) t.keys[i] = EMPTY_KEY; }
     else { for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) t.state[i] = 0u; }
@@ -93,7 +93,7 @@ __device__ __forceinline__ void smem_table_flush(const SmemTable& t, const AggAr
     for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) {
         if (args.smem_sentinel ? (t.keys[i] == EMPTY_KEY) : (t.state[i] != 2u)) continue;
         uint64_t key[MAX_KEYW];
-        for (int w = 0; w < ap.n_keyw; w++) key[w] = t.keys[(size_t)w * cap + i];
+        for (int w = 0; w < ap.n_keyw; w++) key[w] = w < args.smem_keyw ? t.keys[(size_t)w * cap + i] : 0ull;  // sentinel mode: further words are 0
         merge_group(ap, args.gt, key, [&](int l, uint64_t& v) {
             const int sl = args.smem_lane[l];
             if (sl != 0xFF) { v = t.lanes[(size_t)sl * cap + i]; return true; }

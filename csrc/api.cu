@@ -53,6 +53,7 @@ struct bkgpu_plan {
     int64_t chunk_rows = 8 << 20;
     int64_t partial_cap = 1 << 16;
     int force_generic = 0;
+    int no_lean = 0;
     int output_on_device = 0;
     int64_t topk_sample = 1;
     // aggregate state
@@ -176,6 +177,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "chunk_rows") { if (v < 1024) return p->fail(BKGPU_EINVAL, "chunk_rows too small"); p->chunk_rows = (v + 7) & ~7ll; }
     else if (k == "partial_capacity") { if (v < 1) return p->fail(BKGPU_EINVAL, "partial_capacity must be positive"); p->partial_cap = v; }
     else if (k == "force_generic") p->force_generic = v != 0;
+    else if (k == "no_lean") p->no_lean = v != 0;
     else if (k == "output_on_device") p->output_on_device = v != 0;
     else if (k == "topk_sample") p->topk_sample = v;
     else return p->fail(BKGPU_EINVAL, "unknown option '%s'", key);
@@ -225,7 +227,7 @@ extern "C" int bkgpu_open(bkgpu_plan* p) {
 static int pick_smem_log2(bkgpu_plan* p, int n_smem_lanes, bool direct, int na) {
     if (p->c.ap.n_keyw == 0) return 0;
     const size_t budget = 220 * 1024;
-    auto bytes = [&](int log2) { return direct ? direct_smem_bytes(p->c.ap, n_smem_lanes, log2, na) : agg_smem_bytes(p->c.ap, n_smem_lanes, log2); };
+    auto bytes = [&](int log2) { return direct ? direct_smem_bytes(p->c.ap.n_keyw, n_smem_lanes, log2, na) : agg_smem_bytes(p->c.ap.n_keyw, n_smem_lanes, log2); };
     if (p->smem_cap_log2 >= 0) { int l = p->smem_cap_log2; while (l > 0 && bytes(l) > budget) l--; return l; }
     uint32_t g = p->known_groups;
     int log2 = 11;
@@ -261,6 +263,8 @@ static int launch_agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, bo
     for (int l = 1; l < a.plan.n_lanes; l++) if (a.smem_lane[l] != 0xFF) a.alias_mask &= ~(1u << l);
     a.smem_cap_log2 = pick_smem_log2(p, a.n_smem_lanes, direct, c.direct.n_vals);
     a.smem_sentinel = direct && a.plan.n_keyw == 1 ? 1 : 0;
+    a.smem_keyw = a.plan.n_keyw;
+
     if (direct) {  // per value column: the lane operations it feeds
         memset(a.vops, 0, sizeof a.vops);
         for (int v = 0; v < c.direct.n_vals; v++) { a.vops[v].cnt_smem = 0xFF; }
@@ -275,6 +279,29 @@ static int launch_agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, bo
                 vo.op[n] = a.plan.lane_op[s.acc_lane]; vo.lane_class[n] = s.vclass; vo.glob_lane[n] = s.acc_lane; vo.smem_lane[n] = a.smem_lane[s.acc_lane];
             }
         }
+    }
+    a.lean = 0;
+    // lean shape: one key word, or a 64-bit key whose second word only carries the (here unused) NULL flag
+    const bool lean_keyw = a.plan.n_keyw == 1 || (a.plan.n_keyw == 2 && a.plan.n_group == 1 && a.plan.key_bits[0] == 64 && a.plan.key_null_word[0] == 1);
+    if (direct && lean_keyw && a.smem_cap_log2 > 0 && !p->no_lean) {  // does this batch fit the lean kernel?
+        bool ok = true;
+        const int np = c.direct.n_terms, na = c.direct.n_vals;
+        for (int i = 0; i < a.n_cols; i++) if (a.cols[i].validity) ok = false;
+        for (int t = 0; t < np && ok; t++) {
+            const DirectTerm& tm = c.direct.term[t];
+            const int64_t cv = (int64_t)tm.cbits;
+            ok = a.cols[t].stype == ST_I32 && a.cols[t].prim == BK_INT32 && tm.vclass == VC_I64 && cv >= INT32_MIN && cv <= INT32_MAX;
+        }
+        const DevCol& kc = a.cols[np];
+        ok = ok && ((kc.stype == ST_I32 && kc.prim == BK_INT32) || (kc.stype == ST_U32 && kc.prim == BK_UINT32) || kc.stype == ST_I64 || kc.stype == ST_U64);
+        for (int v = 0; v < na && ok; v++) {
+            const DevCol& vc = a.cols[np + 1 + v];
+            const ValOps& vo = a.vops[v];
+            ok = (vc.stype == ST_F64 || vc.stype == ST_I64 || vc.stype == ST_U64) && vo.n_ops == 1 && vo.cnt_smem == 0xFF &&
+                 ((vo.op[0] == LN_ADD_F64 && vc.stype == ST_F64 && vo.lane_class[0] == VC_F64) || (vo.op[0] == LN_ADD_I64 && vc.stype != ST_F64));
+        }
+        a.lean = ok ? 1 : 0;
+        if (a.lean) { a.smem_sentinel = 1; a.smem_keyw = 1; }
     }
     const int64_t kMax = (int64_t)1 << 30;  // rows per launch (32-bit counters inside a CTA)
     int64_t algo_bytes_per_row = 0;
@@ -291,7 +318,7 @@ static int launch_agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, bo
         cudaError_t e = launch_agg(b, direct, p->sm_count, p->stream, &name);
         timer_end(p, ep);
         if (e != cudaSuccess) return p->cuda_fail(e, "launch_agg");
-        snprintf(p->stats.main_kernel_name, sizeof p->stats.main_kernel_name, "%s", name);
+        snprintf(p->stats.main_kernel_name, sizeof p->stats.main_kernel_name, "%s", b.lean && direct ? "k_agg_group_lean" : name);
         p->stats.kernel_launches++;
     }
     return BKGPU_OK;

@@ -12,9 +12,16 @@ namespace bk {
 // ------------------------------------------------------------------------------------------
 // streaming loads.  Column data is read exactly once: bypass L1 allocation.
 // ------------------------------------------------------------------------------------------
+struct alignas(16) U32x4 { uint32_t v[4]; };
 struct alignas(32) U32x8 { uint32_t v[8]; };
 struct alignas(32) U64x4 { uint64_t v[4]; };
 
+__device__ __forceinline__ U32x4 ldg128_u32(const void* p) {
+    U32x4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ U32x8 ldg256_u32(const void* p) {
     U32x8 r;
     asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

@@ -18,11 +18,27 @@ def test_c1_count_where():
     assert stats.main_kernel_name.decode() == "k_agg_scalar_direct"
 
 
-@pytest.mark.parametrize("n", [1, 7, 8, 9, 1000, 65537, 300_003])
-def test_c2_sizes(n):
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 127, 128, 129, 1000, 65537, 300_003])
+@pytest.mark.parametrize("no_lean", [0, 1])
+def test_c2_sizes(n, no_lean):
+    """ragged sizes around the 4-rows-per-lane / 128-rows-per-warp boundaries, lean and general direct kernels"""
     cols = datagen.c2_table(0, n, n_groups=50)
-    _, stats, _ = run_both(queries.c2_filter_groupby(), cols, keys=["0_1"])
-    assert stats.main_kernel_name.decode() == "k_agg_group_direct"
+    _, stats, _ = run_both(queries.c2_filter_groupby(), cols, keys=["0_1"], options={"no_lean": no_lean})
+    assert stats.main_kernel_name.decode() == ("k_agg_group_direct" if no_lean else "k_agg_group_lean")
+
+
+def test_lean_int64_key_and_integer_sums():
+    rng = np.random.default_rng(12)
+    n = 77_777
+    cols = [make_column(0, 1, T.INT32, rng.integers(-100, 100, n)), make_column(0, 2, T.INT64, rng.integers(-40, 40, n) * (1 << 35)),
+            make_column(0, 3, T.DOUBLE, rng.normal(size=n)), make_column(0, 4, T.INT64, rng.integers(-(1 << 62), 1 << 62, n))]
+    aggs = [P.agg_expr("count_star", 1, 1), P.agg_expr("sum", 1, 2, None, P.slot_ref(0, 3, T.DOUBLE)),
+            P.agg_expr("sum", 1, 3, None, P.slot_ref(0, 4, T.INT64)), P.agg_expr("avg", 1, 4, 5, P.slot_ref(0, 3, T.DOUBLE))]
+    root = P.agg(P.where(P.scan(0), P.ge(P.slot_ref(0, 1, T.INT32), P.int_lit(-50)), P.ne(P.slot_ref(0, 1, T.INT32), P.int_lit(7))), 1,
+                 [P.slot_ref(0, 2, T.INT64)], aggs)
+    pl = P.Plan(root, {0: [(1, T.INT32), (2, T.INT64), (3, T.DOUBLE), (4, T.INT64)], 1: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE, T.INT64, T.DOUBLE])})
+    _, stats, _ = run_both(pl, cols, keys=["0_2"])
+    assert stats.main_kernel_name.decode() == "k_agg_group_lean"
 
 
 @pytest.mark.parametrize("k", [0, 1, 10486, 1 << 19, 1038090, 1 << 20])
@@ -152,7 +168,7 @@ def test_single_int64_key_direct():
             make_column(0, 3, T.DOUBLE, rng.random(n)), make_column(0, 4, T.INT32, rng.integers(0, 100, n))]
     aggs = [P.agg_expr("count_star", 1, 1), P.agg_expr("sum", 1, 2, None, P.slot_ref(0, 3, T.DOUBLE))]
     _, stats, _ = run_both(_agg_plan([P.slot_ref(0, 2, T.INT64)], aggs, [T.INT64, T.DOUBLE]), cols, keys=["0_2"])
-    assert stats.main_kernel_name.decode() == "k_agg_group_direct"
+    assert stats.main_kernel_name.decode() == "k_agg_group_direct"  # nullable key column: not the lean shape
 
 
 def test_literal_takes_column_type_quirk():
