@@ -1,0 +1,226 @@
+"""Pins the oracle (oracle/bk_oracle.c) to the reference's own known-answer tests and fixtures
+(SURVEY.md §8c): test/test_expr_value.cpp:456-653 (ExprValue compare / cast) and the Arrow fixture of
+test/test_arrow_compute.cpp:51-277, plus cross-checks of the row-engine restatement against the Acero
+plan the reference's vectorized engine builds.  CPU only."""
+import struct
+
+import numpy as np
+import pytest
+
+from baikaldb_b200 import datagen, plan as P, queries
+from baikaldb_b200.column import make_column, rows_as_set
+from baikaldb_b200.plan import PrimitiveType as T
+from oracle import acero_oracle as A
+from oracle import oracle
+
+
+def _bits(fmt, v):
+    return struct.unpack("<Q", struct.pack(fmt, v).ljust(8, b"\0"))[0]
+
+
+def i64(v): return _bits("<q", v)
+def u64(v): return _bits("<Q", v & 0xFFFFFFFFFFFFFFFF)
+def i32(v): return _bits("<i", v)
+def u32(v): return _bits("<I", v & 0xFFFFFFFF)
+def f64(v): return _bits("<d", v)
+
+
+def cmp(ta, ba, tb, bb, diff=False):
+    return oracle.lib().bko_ev_compare(int(ta), ba, int(tb), bb, 1 if diff else 0)
+
+
+# ---- test/test_expr_value.cpp TEST(test_compare, case_all) ----
+def test_int64_1_equals_int32_1_after_promotion():      # :498-503
+    assert cmp(T.INT64, i64(1), T.INT32, i32(1), diff=True) == 0
+
+
+def test_int64_ordering():                               # :504-510
+    assert cmp(T.INT64, i64(65571188177), T.INT64, i64(72856896263)) < 0
+
+
+def test_uint64_ordering():                              # :511-524
+    assert cmp(T.UINT64, u64(65571188177), T.UINT64, u64(72856896263)) < 0
+    assert cmp(T.UINT64, u64(1), T.UINT64, u64(-1)) < 0   # 1 < 0xFFFF...FFFF
+
+
+def test_int32_compare_reads_int32_member_of_other():    # :525-531  v2 is typed INT64 but only int32_val is set
+    assert cmp(T.INT32, i32(2147483610), T.INT64, i32(-2147483610)) > 0
+
+
+def test_uint32_minus_one_is_large():                    # :532-538
+    assert cmp(T.UINT32, u32(-1), T.UINT32, u32(1)) > 0
+
+
+def test_datetime_compares_as_uint64():                  # :539-548
+    a = oracle.lib().bko_ev_cast(int(T.UINT64), u64(9223372036854775800), int(T.DATETIME))
+    b = oracle.lib().bko_ev_cast(int(T.UINT64), u64(9223372036854775810), int(T.DATETIME))
+    assert cmp(T.DATETIME, a, T.DATETIME, b) < 0
+
+
+def test_maxvalue_type():                                # :583-603
+    MAXV = 24
+    assert cmp(MAXV, 0, T.INT32, i32(2147483647)) > 0
+    assert cmp(MAXV, 0, MAXV, 0) == 0
+    assert cmp(T.INT32, i32(2147483647), MAXV, 0) < 0
+
+
+def test_int64_double_round_trip():                      # :468-476
+    d = oracle.lib().bko_ev_cast(int(T.INT64), i64(123372036854775800), int(T.DOUBLE))
+    assert struct.unpack("<d", struct.pack("<Q", d))[0] == float(123372036854775800)
+    back = oracle.lib().bko_ev_cast(int(T.DOUBLE), d, int(T.INT64))
+    assert struct.unpack("<q", struct.pack("<Q", back))[0] == int(float(123372036854775800))
+
+
+def test_cast_truncations():
+    L = oracle.lib()
+    assert L.bko_ev_cast(int(T.INT64), i64(3_000_000_000), int(T.INT32)) & 0xFFFFFFFF == u32(3_000_000_000 - (1 << 32))
+    assert L.bko_ev_cast(int(T.DOUBLE), f64(0.9), int(T.INT64)) == 0
+    assert L.bko_ev_cast(int(T.DOUBLE), f64(-1.5), int(T.INT64)) == i64(-1)
+    assert L.bko_ev_cast(int(T.INT32), i32(-1), int(T.UINT64)) == u64(-1)
+
+
+def test_nan_compares_equal():                           # expr_value.h:928-933
+    nan = f64(float("nan"))
+    assert cmp(T.DOUBLE, nan, T.DOUBLE, f64(1.0)) == 0
+    assert cmp(T.DOUBLE, f64(1.0), T.DOUBLE, nan) == 0
+
+
+def test_memcomparable_key_encoding():                   # mut_table_key.h:60-160, key_encoder.h:120-135
+    L = oracle.lib()
+    buf = bytes(8)
+
+    def enc(t, b):
+        out = bytearray(8)
+        c = (np.frombuffer(out, dtype=np.uint8)).ctypes
+        import ctypes
+        raw = ctypes.create_string_buffer(8)
+        n = L.bko_key_encode(int(t), b, raw)
+        return raw.raw[:n]
+    assert enc(T.INT32, i32(0)) == b"\x80\x00\x00\x00"
+    assert enc(T.INT32, i32(-1)) == b"\x7f\xff\xff\xff"
+    assert enc(T.INT64, i64(1)) == b"\x80" + b"\x00" * 6 + b"\x01"
+    assert enc(T.UINT32, u32(258)) == b"\x00\x00\x01\x02"
+    assert enc(T.INT32, i32(-5)) < enc(T.INT32, i32(3))       # memcomparable
+    assert enc(T.DOUBLE, f64(-2.5)) < enc(T.DOUBLE, f64(-1.0)) < enc(T.DOUBLE, f64(0.0)) < enc(T.DOUBLE, f64(1e300))
+
+
+# ---- test/test_arrow_compute.cpp:51-277: the 5-row, 14-column fixture and its 6-key hash_sum plan ----
+def _arrow_compute_fixture():
+    u, q = T.UINT32, T.UINT64
+    data = {
+        (0, 1, u): [0, 1, 0, 1, 0], (0, 9, u): [841665] * 5,
+        (0, 2, q): [134384483009, 100507578, 19687499137, 19687499137, 100507578],
+        (0, 3, u): [1381619] * 5, (0, 4, q): [920714] * 5, (0, 5, q): [105320959] * 5,
+        (0, 6, T.INT64): [1] * 5, (0, 7, T.INT64): [0] * 5, (0, 8, T.INT64): [0] * 5, (0, 10, u): [1] * 5,
+        (1, 1, T.INT64): [2, 5, 6, 1, 8], (1, 2, T.INT64): [0, 0, 0, 0, 2], (1, 3, T.INT64): [0, 0, 0, 0, 7664],
+    }
+    return [make_column(t, s, pt, v) for (t, s, pt), v in data.items()]
+
+
+def test_arrow_compute_fixture_six_key_group_by():
+    """keys 0_1,0_9,0_2,0_3,0_4,0_5; hash_sum over 1_1,1_2,1_3 (the reference prints the result; the five
+    key tuples are distinct, so every sum equals its row's value).  Row oracle == Acero == expected."""
+    cols = _arrow_compute_fixture()
+    keys = [(0, 1, T.UINT32), (0, 9, T.UINT32), (0, 2, T.UINT64), (0, 3, T.UINT32), (0, 4, T.UINT64), (0, 5, T.UINT64)]
+    aggs = [P.agg_expr("sum", 2, i + 1, None, P.slot_ref(1, i + 1, T.INT64)) for i in range(3)]
+    root = P.agg(P.scan(0), 2, [P.slot_ref(t, s, pt) for t, s, pt in keys], aggs)
+    tuples = {0: [(s, pt) for (t, s, pt) in [(c.tuple_id, c.slot_id, c.prim_type) for c in cols] if t == 0],
+              1: [(1, T.INT64), (2, T.INT64), (3, T.INT64)], 2: P.agg_tuple_slots(aggs, [T.INT64] * 3)}
+    res = oracle.execute(P.Plan(root, tuples).serialize(), cols)
+    got = rows_as_set(res.columns, ["0_1", "0_2"])
+    expected = {(0, 134384483009): (2, 0, 0), (1, 100507578): (5, 0, 0), (0, 19687499137): (6, 0, 0),
+                (1, 19687499137): (1, 0, 0), (0, 100507578): (8, 2, 7664)}
+    names = [c.name for c in res.columns]
+    assert set(got) == set(expected)
+    for k, sums in expected.items():
+        row = got[k]
+        assert tuple(row[names.index(n)] for n in ("2_1", "2_2", "2_3")) == sums
+    table = A.to_table(cols)
+    acero = A.filter_groupby(table, None, ["0_1", "0_9", "0_2", "0_3", "0_4", "0_5"],
+                             [("hash_sum", "1_1", "2_1"), ("hash_sum", "1_2", "2_2"), ("hash_sum", "1_3", "2_3")])
+    arows = A.table_rows(acero, ["0_1", "0_2"])
+    an = acero.column_names
+    for k, sums in expected.items():
+        assert tuple(arows[k][an.index(n)] for n in ("2_1", "2_2", "2_3")) == sums
+
+
+# ---- row-engine restatement == Acero plan on the BASELINE configs (small sizes) ----
+def test_c1_row_oracle_equals_acero_and_numpy():
+    cols = datagen.c1_table(0, 1_000_000)
+    res = oracle.execute(queries.c1_count_where().serialize(), cols)
+    want = int((cols[0].values < (1 << 19)).sum())
+    assert res.columns[0].to_list() == [want]
+    assert A.c1_count_where(A.to_table(cols), 1 << 19).column("1_1").to_pylist() == [want]
+    assert res.rows_scanned == 1_000_000 and res.rows_filtered == 1_000_000 - want
+
+
+@pytest.mark.parametrize("k", [1 << 19, 10486])
+def test_c2_row_oracle_equals_acero(k):
+    cols = datagen.c2_table(0, 300_000)
+    res = oracle.execute(queries.c2_filter_groupby(k).serialize(), cols)
+    got = rows_as_set(res.columns, ["0_1"])
+    names = [c.name for c in res.columns]
+    ac = A.c2_filter_groupby(A.to_table(cols), k)
+    arows = A.table_rows(ac, ["0_1"])
+    an = ac.column_names
+    assert set(got) == set(arows)
+    for key, row in got.items():
+        assert row[names.index("1_1")] == arows[key][an.index("1_1")]                      # COUNT(*) bit-exact
+        assert row[names.index("1_2")] == pytest.approx(arows[key][an.index("1_2")], rel=1e-9)   # SUM(double)
+        assert row[names.index("1_3")] == pytest.approx(arows[key][an.index("1_3")], rel=1e-9)   # AVG(double)
+        blob = row[names.index("1_4")]                                                     # AVG intermediate {sum, count}
+        s, c = struct.unpack("<dq", blob)
+        assert c == row[names.index("1_1")] and s / c == row[names.index("1_3")]
+
+
+def test_c3_row_oracle_equals_acero():
+    fact, dim = datagen.c3_fact(0, 200_000, 5000), datagen.c3_dim(0, 5000, 5000, n_groups=40)
+    assert sorted(dim[0].values.tolist()) == list(range(5000))  # the generator's permutation is a bijection
+    res = oracle.execute(queries.c3_join_groupby().serialize(), fact + dim)
+    got = rows_as_set(res.columns, ["1_2"])
+    names = [c.name for c in res.columns]
+    ac = A.c3_join_groupby(A.to_table(fact), A.to_table(dim))
+    arows = A.table_rows(ac, ["1_2"])
+    an = ac.column_names
+    assert set(got) == set(arows)
+    for key, row in got.items():
+        assert row[names.index("2_1")] == arows[key][an.index("2_1")]
+        assert row[names.index("2_2")] == pytest.approx(arows[key][an.index("2_2")], rel=1e-9)
+
+
+def test_c5_row_oracle_equals_acero_with_ties():
+    rng = np.random.default_rng(9)
+    n = 50_000
+    cols = [make_column(0, 1, T.INT64, rng.integers(0, 2000, n)), make_column(0, 2, T.INT32, np.arange(n))]
+    res = oracle.execute(queries.c5_topk(1000).serialize(), cols)
+    keys, payload = res.columns[0].to_list(), res.columns[1].to_list()
+    order = np.lexsort((np.arange(n), cols[0].values))[:1000]          # stable: ties by arrival index (topn_sorter.h:96-106)
+    assert keys == cols[0].values[order].tolist() and payload == order.tolist()
+    ac = A.c5_topk(A.to_table(cols), 1000)
+    assert ac.column("0_1").to_pylist() == keys                        # Acero's sort is not stable: keys only
+
+
+def test_empty_input_semantics():
+    empty = [make_column(0, 1, T.INT32, np.zeros(0, np.int32))]
+    assert oracle.execute(queries.c1_count_where().serialize(), empty).columns[0].to_list() == [0]   # under PACKET: COUNT=0 row
+    r = oracle.execute(queries.c2_filter_groupby().serialize(), datagen.c2_table(0, 0))
+    assert r.nrows == 0
+
+
+def test_three_valued_logic_and_null_arithmetic():
+    n = 6
+    a = make_column(0, 1, T.INT32, [1, 0, 1, 0, 5, 5], [True, True, False, False, True, True])
+    b = make_column(0, 2, T.INT64, [0, 0, 0, 0, 0, 2])
+    c = make_column(0, 3, T.DOUBLE, np.arange(n, dtype=float))
+    d = make_column(0, 4, T.INT32, np.arange(n))
+    s1, s2 = P.slot_ref(0, 1, T.INT32), P.slot_ref(0, 2, T.INT64)
+    # WHERE (a = 1 OR a IS NULL) AND NOT (b / b > 0)   -- b/0 is NULL, NOT NULL is NULL -> row dropped
+    aggs = [P.agg_expr("count_star", 1, 1)]
+    conj = [P.or_(P.eq(s1, P.int_lit(1)), P.is_null(s1)), P.not_(P.gt(P.divides(s2, s2), P.int_lit(0)))]
+    root = P.agg(P.where(P.scan(0), *conj), 1, [], aggs)
+    pl = P.Plan(P.packet(root), {0: [(1, T.INT32), (2, T.INT64), (3, T.DOUBLE), (4, T.INT32)], 1: P.agg_tuple_slots(aggs, [T.INT64])})
+    assert oracle.execute(pl.serialize(), [a, b, c, d]).columns[0].to_list() == [0]
+    conj2 = [P.or_(P.eq(s1, P.int_lit(1)), P.is_null(s1))]
+    root2 = P.agg(P.where(P.scan(0), *conj2), 1, [], aggs)
+    pl2 = P.Plan(P.packet(root2), pl.tuples)
+    assert oracle.execute(pl2.serialize(), [a, b, c, d]).columns[0].to_list() == [3]
