@@ -55,7 +55,7 @@ struct bkgpu_plan {
     int force_generic = 0;
     int no_lean = 0;
     int output_on_device = 0;
-    int64_t topk_sample = 1;
+    int64_t region_base = 0;      // arrival index of this plan's first row (ties across GPUs break by (region, row))
     // aggregate state
     GroupTable gt{};
     uint64_t* d_rows_passed = nullptr;
@@ -179,7 +179,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "force_generic") p->force_generic = v != 0;
     else if (k == "no_lean") p->no_lean = v != 0;
     else if (k == "output_on_device") p->output_on_device = v != 0;
-    else if (k == "topk_sample") p->topk_sample = v;
+    else if (k == "region_base") p->region_base = v;
     else return p->fail(BKGPU_EINVAL, "unknown option '%s'", key);
     return BKGPU_OK;
 }
@@ -216,7 +216,7 @@ extern "C" int bkgpu_open(bkgpu_plan* p) {
     }
     int rc = BKGPU_OK;
     if (p->c.kind == PK_AGG || p->c.kind == PK_JOIN_AGG) rc = alloc_group_table(p);
-    if (!rc && (p->c.kind == PK_SORT || p->c.kind == PK_FILTER)) rc = sort_open(p->c, p->device, p->stream, p->topk_sample, &p->sort, p->last_error);
+    if (!rc && (p->c.kind == PK_SORT || p->c.kind == PK_FILTER)) rc = sort_open(p->c, p->device, p->stream, p->region_base, &p->sort, p->last_error);
     if (rc) { g_thread_error = p->last_error; return rc; }
     p->state = S_OPEN;
     return BKGPU_OK;

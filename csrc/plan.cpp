@@ -319,6 +319,10 @@ static bool infer_expr(Infer& in, HExpr& e) {
 }
 
 // ---------------------------------------------------------------- lowering
+static bool is_filter(const HNode* n) {
+    return n && (n->node_type == BK_WHERE_FILTER_NODE || n->node_type == BK_TABLE_FILTER_NODE);
+}
+
 struct Lower {
     Compiled* out;
     Infer* in;
@@ -684,6 +688,10 @@ static void explain(Compiled& c) {
             }
         }
     }
+    if (c.kind == PK_SORT || c.kind == PK_FILTER) {
+        snprintf(buf, sizeof buf, "rows: pred_out=%d limit=%lld offset=%lld direct=%d\n", c.ap.pred_out, (long long)c.limit, (long long)c.offset, (int)c.has_direct); s += buf;
+        for (auto& k : c.sort_keys) { snprintf(buf, sizeof buf, "  order key: out=%d prim=%d asc=%d null_first=%d\n", k.out_reg, k.prim, (int)k.asc, (int)k.null_first); s += buf; }
+    }
     snprintf(buf, sizeof buf, "program: %d instr, %d outputs\n", c.prog.n_instr, c.prog.n_out); s += buf;
     for (int i = 0; i < c.prog.n_instr; i++) {
         const Instr& in = c.prog.code[i];
@@ -705,9 +713,6 @@ static bool infer_node(Infer& in, HNode& n) {
     for (auto& e : n.order_exprs) if (!infer_expr(in, e)) return false;
     for (auto& c : n.ch) if (!infer_node(in, c)) return false;
     return true;
-}
-static bool is_filter(const HNode* n) {
-    return n && (n->node_type == BK_WHERE_FILTER_NODE || n->node_type == BK_TABLE_FILTER_NODE);
 }
 
 int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& err) {
@@ -767,9 +772,88 @@ int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& er
     return BKGPU_OK;
 }
 
-// ---- stubs replaced as the corresponding kernels land ----
-bool lower_sort(Infer& in, Compiled&, const HNode&, const HNode*, const HNode&) { return in.fail(BKGPU_EUNSUPPORTED, "SORT_NODE not lowered yet"); }
-bool lower_filter(Infer& in, Compiled&, const HNode*, const HNode&, const HNode&) { return in.fail(BKGPU_EUNSUPPORTED, "filter-only fragment not lowered yet"); }
+// ---------------------------------------------------------------- SORT / filter-only fragments
+// Rows of the scan tuple are returned (all slots of its tuple descriptor), ordered / filtered.
+static bool intern_scan_tuple(Infer& in, Compiled& out, Lower& lw, int tuple_id) {
+    const HTuple* t = nullptr;
+    for (auto& x : out.tuples) if (x.tuple_id == tuple_id) t = &x;
+    if (!t || t->slots.empty()) return in.fail(BKGPU_EINVAL, "scan tuple %d has no descriptor", tuple_id);
+    for (auto& sl : t->slots) {
+        if (prim_storage(sl.second) < 0 || sl.second == BK_STRING)
+            return in.fail(BKGPU_EUNSUPPORTED, "column %d_%d has type %d: outside the GPU path", tuple_id, sl.first, sl.second);
+        int ci = lw.intern_col(tuple_id, sl.first, sl.second);
+        if (ci >= MAX_COLS) return in.fail(BKGPU_EUNSUPPORTED, "more than %d columns in the scan tuple", MAX_COLS);
+        out.out_cols.push_back({tuple_id, sl.first, sl.second, 0});
+    }
+    return true;
+}
+static bool lower_predicate(Infer& in, Lower& lw, const HNode* filter, AggPlan& ap, int& reg) {
+    ap.pred_out = -1;
+    if (!filter || filter->conjuncts.empty()) return true;
+    if (filter->conjuncts.size() > 8) return in.fail(BKGPU_EUNSUPPORTED, "more than 8 conjuncts");
+    for (auto& c : filter->conjuncts) { int depth = 0; if (!lw.expr(c, depth) || !lw.to_bool(c)) return false; }
+    if (filter->conjuncts.size() > 1 && !lw.emit(OP_AND, (uint8_t)filter->conjuncts.size())) return false;
+    ap.pred_out = reg;
+    return lw.out_reg(reg++);
+}
+
+bool lower_sort(Infer& in, Compiled& out, const HNode& sort, const HNode* filter, const HNode& scan) {
+    out.kind = PK_SORT;
+    out.scan_tuple = scan.tuple_id;
+    out.limit = sort.limit;
+    if (filter && filter->limit != -1) return in.fail(BKGPU_EUNSUPPORTED, "LIMIT on a filter below a sort is order dependent");
+    Program& p = out.prog; memset(&p, 0, sizeof p);
+    memset(&out.ap, 0, sizeof out.ap);
+    Lower lw{&out, &in, &p, {}};
+    if (!intern_scan_tuple(in, out, lw, scan.tuple_id)) return false;
+    int reg = 0;
+    if (!lower_predicate(in, lw, filter, out.ap, reg)) return false;
+    if (sort.order_exprs.empty()) return in.fail(BKGPU_EINVAL, "SORT node without order expressions");
+    if (sort.order_exprs.size() > 4) return in.fail(BKGPU_EUNSUPPORTED, "more than 4 ORDER BY expressions");
+    for (size_t i = 0; i < sort.order_exprs.size(); i++) {
+        const HExpr& e = sort.order_exprs[i];
+        if (e.col_type == BK_STRING) return in.fail(BKGPU_EUNSUPPORTED, "ORDER BY over a STRING key is outside the GPU path");
+        int depth = 0;
+        if (!lw.expr(e, depth)) return false;
+        out.sort_keys.push_back({reg, e.col_type, sort.is_asc[i] != 0, sort.is_null_first[i] != 0});
+        if (!lw.out_reg(reg++)) return false;
+    }
+    p.n_out = reg;
+    // direct shape: one plain column key, no filter (config C5)
+    out.has_direct = false;
+    if (!filter && sort.order_exprs.size() == 1 && sort.order_exprs[0].node_type == BK_SLOT_REF) {
+        const HExpr& e = sort.order_exprs[0];
+        int st = in.slot_type(e.tuple_id, e.slot_id);
+        if (st == e.col_type && (prim_storage(st) == ST_I64 || prim_storage(st) == ST_U64 || prim_storage(st) == ST_F64 ||
+                                 prim_storage(st) == ST_I32 || prim_storage(st) == ST_U32)) {
+            out.has_direct = true;
+            out.direct_cols = {lw.intern_col(e.tuple_id, e.slot_id, st)};
+        }
+    }
+    return true;
+}
+
+bool lower_filter(Infer& in, Compiled& out, const HNode* limit_node, const HNode& top, const HNode& scan) {
+    out.kind = PK_FILTER;
+    out.scan_tuple = scan.tuple_id;
+    const HNode* filter = is_filter(&top) ? &top : nullptr;
+    out.limit = filter ? filter->limit : scan.limit;   // FilterNode honours its own limit in input order (filter_node.cpp:786-791)
+    out.offset = 0;
+    if (limit_node) {
+        out.offset = limit_node->offset;
+        int64_t lim = limit_node->limit < 0 ? -1 : limit_node->limit + limit_node->offset;
+        if (lim >= 0 && (out.limit < 0 || lim < out.limit)) out.limit = lim;
+    }
+    Program& p = out.prog; memset(&p, 0, sizeof p);
+    memset(&out.ap, 0, sizeof out.ap);
+    Lower lw{&out, &in, &p, {}};
+    if (!intern_scan_tuple(in, out, lw, scan.tuple_id)) return false;
+    int reg = 0;
+    if (!lower_predicate(in, lw, filter, out.ap, reg)) return false;
+    p.n_out = reg;
+    return true;
+}
+
 bool lower_join_agg(Infer& in, Compiled&, const HNode&, const HNode&, bool) { return in.fail(BKGPU_EUNSUPPORTED, "JOIN_NODE not lowered yet"); }
 
 }  // namespace bk

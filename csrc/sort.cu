@@ -1,13 +1,962 @@
-// sort.cu — placeholder until K5 lands (next commit): every entry point reports "unsupported".
+// sort.cu — K5 (ORDER BY / top-k) and K1 (filter-only stream compaction) for sm_100a.
+//
+// Replaces SortNode::open + Sorter / TopNSorter (src/exec/sort_node.cpp:278-346, src/runtime/sorter.cpp:54-114,
+// src/runtime/topn_sorter.cpp:25-103) and the row-copy half of FilterNode::get_next (src/exec/filter_node.cpp:736-795).
+//
+// Ordering is the reference's MemRowCompare (src/mem_row/mem_row_compare.cpp:18-38) made total: every row
+// carries the composite (class, key image, arrival index) where class orders NULL keys first / last
+// (is_null_first), the key image is an order-preserving 64-bit transform (descending = complemented)
+// and the arrival index breaks ties the way TopNSorter does (include/runtime/topn_sorter.h:96-106).
+//
+// ORDER BY ... LIMIT k (one key): selection, not sorting.  Per batch:
+//   sample 4096 random positions -> threshold at a rank that leaves >= k rows below it with overwhelming
+//   probability -> ONE pass over the key column compacts the candidates (warp-ballot compaction, 8 B/row) ->
+//   the same step recurses on the shrinking candidate arrays until <= 8192 remain -> one CTA sorts them in
+//   shared memory together with the k rows kept from earlier batches -> payload columns are gathered for
+//   the k survivors only.
+// ORDER BY without LIMIT / several keys: LSD radix sort (8 bits per pass, stable) of (key image, row id),
+//   least significant ORDER BY key first, then a gather of every column.
+// Filter-only fragments: predicate -> ordered compaction (block scan) -> gather, honouring LIMIT in input order.
 #include "sort.h"
+#include <algorithm>
+#include <string.h>
+#include "dev_common.cuh"
+#include "interp.cuh"
+#include "nccl_dl.h"
+
 namespace bk {
-struct SortState { int dummy; };
-int  sort_open(const Compiled&, int, cudaStream_t, int64_t, SortState**, std::string& err) { err = "SORT/FILTER-only plans are not implemented yet"; return BKGPU_EUNSUPPORTED; }
-int  sort_push(SortState*, const DevCol*, int64_t, cudaStream_t, bkgpu_stats*, std::string& err) { err = "unsupported"; return BKGPU_EUNSUPPORTED; }
-int  sort_finish(SortState*, void*, int, cudaStream_t, bkgpu_stats*, std::vector<SortOutCol>&, int64_t*, std::string& err) { err = "unsupported"; return BKGPU_EUNSUPPORTED; }
-size_t sort_partial_bytes(SortState*) { return 0; }
-int  sort_partial_export(SortState*, void*, cudaStream_t, std::string& err) { err = "unsupported"; return BKGPU_EUNSUPPORTED; }
-int  sort_partial_merge(SortState*, const void*, int, cudaStream_t, std::vector<SortOutCol>&, int64_t*, std::string& err) { err = "unsupported"; return BKGPU_EUNSUPPORTED; }
-int  sort_reset(SortState*, cudaStream_t, std::string&) { return 0; }
-void sort_close(SortState*) {}
+
+namespace {
+
+constexpr int SMALL_N = 8192;        // one CTA sorts this many composite keys in shared memory
+constexpr int SAMPLE_N = 4096;
+
+struct KeySpec {       // how a row's sort key is obtained on the device
+    int direct;        // 1: plain column `col` of class `vclass`; 0: program output register `out_reg`
+    int col, vclass, out_reg;
+    int desc;          // ORDER BY ... DESC
+    int pred_out;      // predicate register (-1 = none); generic path only
+};
+
+struct RowArgs {
+    DevCol cols[MAX_COLS];
+    int32_t n_cols;
+    int64_t nrows;
+    uint64_t row_base;   // arrival index of row 0 of this batch
+    Program prog;
+    KeySpec key;
+};
+
+// order-preserving 64-bit image (ascending); DESC complements it
+__device__ __forceinline__ uint64_t key_image(uint64_t v, int vclass, int desc) {
+    uint64_t t;
+    if (vclass == VC_F64) t = (v >> 63) ? ~v : (v | 0x8000000000000000ull);
+    else if (vclass == VC_I64) t = v ^ 0x8000000000000000ull;
+    else t = v;
+    return desc ? ~t : t;
+}
+
+// cls: 0 = row filtered out, 1 = key present, 2 = key is NULL
+__device__ __forceinline__ int row_key(const RowArgs& a, int64_t row, uint64_t& image) {
+    if (a.key.direct) {
+        const DevCol& c = a.cols[a.key.col];
+        if (elem_is_null(c, row)) { image = 0; return 2; }
+        image = key_image(load_elem(c, row), a.key.vclass, a.key.desc);
+        return 1;
+    }
+    uint64_t out[8]; uint32_t out_null;
+    run_program(a.prog, a.cols, row, out, out_null);
+    if (a.key.pred_out >= 0 && (((out_null >> a.key.pred_out) & 1u) || out[a.key.pred_out] == 0)) return 0;
+    if ((out_null >> a.key.out_reg) & 1u) { image = 0; return 2; }
+    image = key_image(out[a.key.out_reg], a.key.vclass, a.key.desc);
+    return 1;
+}
+
+__device__ __forceinline__ bool comp_le(uint64_t k, uint64_t i, uint64_t tk, uint64_t ti) { return k < tk || (k == tk && i <= ti); }
+__device__ __forceinline__ bool comp_lt(uint64_t k, uint64_t i, uint64_t tk, uint64_t ti) { return k < tk || (k == tk && i < ti); }
+
+__device__ __forceinline__ uint64_t mix64d(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31);
+}
+
+// ---- level-1 kernels: straight from the batch columns ----
+// sample: position i of SAMPLE_N is drawn uniformly inside its stratum [i*n/S, (i+1)*n/S)
+__global__ void k_sample_rows(RowArgs a, int want_cls, uint64_t* skey, uint64_t* sidx, uint32_t* scount, uint64_t salt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= SAMPLE_N) return;
+    const int64_t lo = (int64_t)(((__int128)i * a.nrows) / SAMPLE_N), hi = (int64_t)(((__int128)(i + 1) * a.nrows) / SAMPLE_N);
+    if (hi <= lo) return;
+    const int64_t row = lo + (int64_t)(mix64d(salt + i) % (uint64_t)(hi - lo));
+    uint64_t img;
+    if (row_key(a, row, img) != want_cls) return;
+    const uint32_t pos = atomicAdd(scount, 1u);
+    skey[pos] = img; sidx[pos] = a.row_base + (uint64_t)row;
+}
+
+// compaction of the rows whose composite key is <= (tk, ti): warp-ballot positions, one atomic per warp
+__global__ void __launch_bounds__(256) k_collect_rows(RowArgs a, int want_cls, uint64_t tk, uint64_t ti, uint64_t* okey, uint64_t* oidx,
+                                                      uint32_t* ocount, uint32_t cap, uint32_t* class_count) {
+    const int lane = threadIdx.x & 31;
+    uint32_t seen = 0;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane); base < a.nrows; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = base + lane;
+        uint64_t img = 0; bool take = false;
+        if (row < a.nrows) {
+            const int cls = row_key(a, row, img);
+            if (cls == want_cls) { seen++; take = comp_le(img, a.row_base + (uint64_t)row, tk, ti); }
+        }
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, take);
+        if (b) {
+            uint32_t wbase = 0;
+            if (lane == 0) wbase = atomicAdd(ocount, (uint32_t)__popc(b));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            const uint32_t pos = wbase + __popc(b & ((1u << lane) - 1u));
+            if (take && pos < cap) { okey[pos] = img; oidx[pos] = a.row_base + (uint64_t)row; }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) seen += __shfl_xor_sync(0xFFFFFFFFu, seen, d);
+    if (lane == 0 && seen && class_count) atomicAdd(class_count, seen);
+}
+
+// ---- level >= 2 kernels: on (key, idx) candidate arrays ----
+__global__ void k_sample_pairs(const uint64_t* key, const uint64_t* idx, uint32_t n, uint64_t* skey, uint64_t* sidx, uint32_t* scount, uint64_t salt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= SAMPLE_N) return;
+    const uint64_t lo = (uint64_t)i * n / SAMPLE_N, hi = (uint64_t)(i + 1) * n / SAMPLE_N;
+    if (hi <= lo) return;
+    const uint64_t p = lo + mix64d(salt + i) % (hi - lo);
+    const uint32_t pos = atomicAdd(scount, 1u);
+    skey[pos] = key[p]; sidx[pos] = idx[p];
+}
+__global__ void __launch_bounds__(256) k_collect_pairs(const uint64_t* key, const uint64_t* idx, uint32_t n, uint64_t tk, uint64_t ti,
+                                                       uint64_t* okey, uint64_t* oidx, uint32_t* ocount, uint32_t cap) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        const bool take = i < n && comp_le(key[i], idx[i], tk, ti);
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, take);
+        if (b) {
+            uint32_t wbase = 0;
+            if (lane == 0) wbase = atomicAdd(ocount, (uint32_t)__popc(b));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            const uint32_t pos = wbase + __popc(b & ((1u << lane) - 1u));
+            if (take && pos < cap) { okey[pos] = key[i]; oidx[pos] = idx[i]; }
+        }
+    }
+}
+
+// one CTA: bitonic sort of n <= SMALL_N composite keys in shared memory (ascending); optionally reads a
+// second segment (the rows kept from earlier batches).  Writes the first `keep` entries and the r-th (0-based) one.
+__global__ void __launch_bounds__(1024) k_sort_small(const uint64_t* k1, const uint64_t* i1, const uint32_t* n1p, uint32_t n1max,
+                                                     const uint64_t* k2, const uint64_t* i2, uint32_t n2,
+                                                     uint64_t* okey, uint64_t* oidx, uint32_t keep, uint32_t* out_n,
+                                                     uint32_t rank, uint64_t* rank_out) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint64_t* sk = (uint64_t*)sm; uint64_t* si = sk + SMALL_N;
+    uint32_t n1 = n1p ? *n1p : n1max; if (n1 > n1max) n1 = n1max;
+    const uint32_t n = n1 + n2;
+    uint32_t m = 1; while (m < n) m <<= 1; if (m < 2) m = 2;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        if (i < n1) { sk[i] = k1[i]; si[i] = i1[i]; }
+        else if (i < n) { sk[i] = k2[i - n1]; si[i] = i2[i - n1]; }
+        else { sk[i] = ~0ull; si[i] = ~0ull; }
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= m; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+                const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint64_t ka = sk[lo], ia = si[lo], kb = sk[hi], ib = si[hi];
+                const bool a_gt_b = comp_lt(kb, ib, ka, ia);
+                if (a_gt_b == up) { sk[lo] = kb; si[lo] = ib; sk[hi] = ka; si[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t nk = n < keep ? n : keep;
+    if (okey) for (uint32_t i = threadIdx.x; i < nk; i += blockDim.x) { okey[i] = sk[i]; oidx[i] = si[i]; }
+    if (threadIdx.x == 0) {
+        if (out_n) *out_n = nk;
+        if (rank_out) { const uint32_t r = n == 0 ? 0 : (rank < n ? rank : n - 1); rank_out[0] = n ? sk[r] : ~0ull; rank_out[1] = n ? si[r] : ~0ull; rank_out[2] = n; }
+    }
+}
+
+// ---- payload: gather rows of the current batch / move rows kept from earlier batches ----
+struct GatherArgs {
+    DevCol cols[MAX_COLS]; int32_t n_cols; uint64_t row_base; int64_t nrows;
+    uint8_t* dst_vals[MAX_COLS]; uint8_t* dst_null[MAX_COLS];
+    const uint8_t* old_vals[MAX_COLS]; const uint8_t* old_null[MAX_COLS];
+    const uint64_t* old_idx; uint32_t old_n;
+};
+__global__ void k_gather_topk(GatherArgs g, const uint64_t* idx, const uint32_t* np) {
+    const uint32_t n = *np;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint64_t id = idx[i];
+        const bool from_batch = g.nrows > 0 && id >= g.row_base && id < g.row_base + (uint64_t)g.nrows;
+        int64_t src = -1;
+        if (from_batch) src = (int64_t)(id - g.row_base);
+        else {  // binary search in the previous survivors (sorted by composite key, not by idx): linear scan is fine for k rows
+            for (uint32_t j = 0; j < g.old_n; j++) if (g.old_idx[j] == id) { src = j; break; }
+        }
+        for (int c = 0; c < g.n_cols; c++) {
+            const int eb = g.cols[c].stype == ST_U8 ? 1 : ((g.cols[c].stype == ST_I32 || g.cols[c].stype == ST_U32 || g.cols[c].stype == ST_F32) ? 4 : 8);
+            const uint8_t* sv; uint8_t isnull;
+            if (from_batch) { sv = (const uint8_t*)g.cols[c].values + (size_t)src * eb; isnull = elem_is_null(g.cols[c], src) ? 1 : 0; }
+            else { sv = g.old_vals[c] + (size_t)src * eb; isnull = g.old_null[c][src]; }
+            uint8_t* dv = g.dst_vals[c] + (size_t)i * eb;
+            for (int b = 0; b < eb; b++) dv[b] = sv[b];
+            g.dst_null[c][i] = isnull;
+        }
+    }
+}
+
+// ---- filter-only: ordered compaction.  Pass 1 counts per block, pass 2 (after a scan of the counts) writes. ----
+__global__ void __launch_bounds__(256) k_filter_count(RowArgs a, uint32_t* block_counts, int64_t rows_per_block) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, a.nrows);
+    uint32_t cnt = 0;
+    for (int64_t row = r0 + threadIdx.x; row < r1; row += blockDim.x) {
+        uint64_t img; const int cls = a.key.pred_out < 0 ? 1 : row_key(a, row, img);
+        cnt += cls != 0;
+    }
+    __shared__ uint32_t s[8];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int i = 0; i < 8; i++) t += s[i]; block_counts[blockIdx.x] = t; }
+}
+__global__ void k_scan_counts(uint32_t* counts, uint32_t n, uint64_t* total) {  // single CTA exclusive scan (n <= a few thousand blocks)
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = i < n ? counts[i] : 0;
+        // inclusive warp scan
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        __shared__ uint32_t ws[32];
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0, xw = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xw, d); if (threadIdx.x >= d) xw += y; }
+            ws[threadIdx.x] = xw - w;
+        }
+        __syncthreads();
+        const uint64_t excl = carry + ws[threadIdx.x >> 5] + (x - v);
+        if (i < n) counts[i] = (uint32_t)excl;  // offsets fit 32 bits per launch (<= 2^31 rows)
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(256) k_filter_write(RowArgs a, const uint32_t* block_offsets, int64_t rows_per_block, uint32_t* sel, uint64_t out_base, uint64_t cap) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, a.nrows);
+    __shared__ uint32_t warp_cnt[8];
+    __shared__ uint32_t running;
+    if (threadIdx.x == 0) running = block_offsets[blockIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = r0; base < r1; base += blockDim.x) {
+        const int64_t row = base + threadIdx.x;
+        bool take = false;
+        if (row < r1) { uint64_t img; take = a.key.pred_out < 0 ? true : row_key(a, row, img) != 0; }
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, take);
+        if (lane == 0) warp_cnt[warp] = __popc(b);
+        __syncthreads();
+        uint32_t before = running;
+        for (int w = 0; w < warp; w++) before += warp_cnt[w];
+        const uint64_t pos = out_base + before + __popc(b & ((1u << lane) - 1u));
+        if (take && pos < cap) sel[pos] = (uint32_t)row;
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; w++) t += warp_cnt[w]; running += t; }
+        __syncthreads();
+    }
+}
+__global__ void k_gather_sel(GatherArgs g, const uint32_t* sel, uint64_t n, uint64_t dst_off) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t src = sel[i];
+        for (int c = 0; c < g.n_cols; c++) {
+            const int eb = g.cols[c].stype == ST_U8 ? 1 : ((g.cols[c].stype == ST_I32 || g.cols[c].stype == ST_U32 || g.cols[c].stype == ST_F32) ? 4 : 8);
+            const uint8_t* sv = (const uint8_t*)g.cols[c].values + (size_t)src * eb;
+            uint8_t* dv = g.dst_vals[c] + (size_t)(dst_off + i) * eb;
+            if (eb == 8) *(uint64_t*)dv = *(const uint64_t*)sv; else if (eb == 4) *(uint32_t*)dv = *(const uint32_t*)sv; else *dv = *sv;
+            g.dst_null[c][dst_off + i] = elem_is_null(g.cols[c], src) ? 1 : 0;
+        }
+    }
+}
+
+// ---- full sort: materialise (image, row id), LSD radix sort, gather ----
+// mode 0: order-preserving image of the key (NULL -> 0); mode 1: the NULL rank (0 sorts first) — sorted by one
+// extra radix pass AFTER the eight value passes so NULL keys come strictly first / last (is_null_first)
+__global__ void k_sort_images(RowArgs a, int key_reg, int vclass, int desc, int null_first, int mode, uint64_t* img, uint32_t* rid) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.nrows; row += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t out[8]; uint32_t out_null;
+        run_program(a.prog, a.cols, row, out, out_null);
+        const bool isnull = (out_null >> key_reg) & 1u;
+        if (mode == 0) img[row] = isnull ? 0ull : key_image(out[key_reg], vclass, desc);
+        else img[row] = isnull ? (null_first ? 0ull : 1ull) : (null_first ? 1ull : 0ull);
+        if (rid) rid[row] = (uint32_t)row;
+    }
+}
+// one radix pass over `digit_shift`: warp w of block b owns the contiguous sub-tile [tile0, tile1)
+constexpr int RS_TILE = 2048;  // elements per warp sub-tile
+__global__ void __launch_bounds__(256) k_radix_hist(const uint64_t* key, const uint32_t* perm, uint32_t n, int shift, uint32_t* hist, uint32_t ntiles) {
+    const uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    __shared__ uint32_t h[8][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = lane; i < 256; i += 32) h[w][i] = 0;
+    __syncwarp();
+    const uint32_t t0 = tile * RS_TILE, t1 = min(t0 + RS_TILE, n);
+    for (uint32_t i = t0 + lane; i < t1; i += 32) atomicAdd(&h[w][(key[perm ? perm[i] : i] >> shift) & 0xFF], 1u);
+    __syncwarp();
+    for (int i = lane; i < 256; i += 32) hist[(size_t)i * ntiles + tile] = h[w][i];  // digit-major: a scan over it yields scatter bases
+}
+__global__ void k_scan_u32(uint32_t* data, uint64_t n, uint32_t* block_sums, int phase) {
+    // phase 0: per-block (1024 elements per thread-block chunk of 256 threads x 4) inclusive->exclusive scan, write block sums
+    // phase 1: add scanned block sums
+    const uint64_t base = (uint64_t)blockIdx.x * 1024;
+    if (phase == 1) {
+        const uint32_t add = block_sums[blockIdx.x];
+        for (int k = 0; k < 4; k++) { const uint64_t i = base + threadIdx.x * 4 + k; if (i < n) data[i] += add; }
+        return;
+    }
+    uint32_t v[4]; uint32_t s = 0;
+    for (int k = 0; k < 4; k++) { const uint64_t i = base + threadIdx.x * 4 + k; v[k] = i < n ? data[i] : 0; s += v[k]; }
+    uint32_t x = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+    __shared__ uint32_t ws[8];
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t wpre = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) wpre += ws[w];
+    uint32_t run = wpre + x - s;
+    for (int k = 0; k < 4; k++) { const uint64_t i = base + threadIdx.x * 4 + k; if (i < n) data[i] = run; run += v[k]; }
+    if (threadIdx.x == 255) block_sums[blockIdx.x] = run;
+}
+__global__ void __launch_bounds__(256) k_radix_scatter(const uint64_t* key, const uint32_t* perm_in, uint32_t* perm_out, uint32_t n, int shift,
+                                                        const uint32_t* bases, uint32_t ntiles) {
+    const uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    __shared__ uint32_t cur[8][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = lane; i < 256; i += 32) cur[w][i] = bases[(size_t)i * ntiles + tile];
+    __syncwarp();
+    const uint32_t t0 = tile * RS_TILE, t1 = min(t0 + RS_TILE, n);
+    for (uint32_t b = t0; b < t1; b += 32) {   // in order: stability comes from processing the sub-tile front to back
+        const uint32_t i = b + lane;
+        const bool live = i < t1;
+        const uint32_t src = live ? (perm_in ? perm_in[i] : i) : 0;
+        const uint32_t d = live ? (uint32_t)((key[src] >> shift) & 0xFF) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        if (live) {
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            const uint32_t pos = cur[w][d] + rank;
+            perm_out[pos] = src;
+        }
+        __syncwarp();
+        if (live && lane == (31 - __clz(peers))) cur[w][d] += __popc(peers);  // the last lane of each digit group advances the cursor
+        __syncwarp();
+    }
+}
+__global__ void k_compact_perm(const uint32_t* perm, const uint8_t* keep, uint32_t n, uint32_t* out, uint32_t* count, int null_first, int want_nulls_sep) {
+    // ordered compaction of the sorted permutation by `keep` (1 = row, 2 = NULL key row); single CTA (results are being copied to the host anyway)
+    __shared__ uint32_t run;
+    if (threadIdx.x == 0) run = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const bool take = i < n && keep[perm[i]] != 0;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, take);
+        __shared__ uint32_t wc[32];
+        if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(b);
+        __syncthreads();
+        uint32_t before = run;
+        for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) before += wc[w];
+        if (take) out[before + __popc(b & ((1u << (threadIdx.x & 31)) - 1u))] = perm[i];
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t t = 0; for (uint32_t w = 0; w < (blockDim.x >> 5); w++) t += wc[w]; run += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = run;
+    (void)null_first; (void)want_nulls_sep;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+struct Pool {               // the k best rows seen so far of one class (keys present / NULL keys)
+    uint64_t* key[2] = {nullptr, nullptr}; uint64_t* idx[2] = {nullptr, nullptr};
+    uint8_t* vals[2][MAX_COLS] = {}; uint8_t* nulls[2][MAX_COLS] = {};
+    int cur = 0; uint32_t n = 0;
+};
+
+struct SortState {
+    Compiled c;
+    int device = 0, sm_count = 148;
+    int ncols = 0;
+    int64_t k = -1;                 // rows to keep; -1 = all
+    uint64_t row_base = 0, region_base = 0;
+    bool topk = false;              // single key + limit: selection path
+    Pool pool[2];
+    // scratch for selection
+    uint64_t *cand_key[2] = {nullptr, nullptr}, *cand_idx[2] = {nullptr, nullptr}; uint32_t cand_cap = 0;
+    uint64_t *samp_key = nullptr, *samp_idx = nullptr;
+    uint32_t* d_counts = nullptr;   // [0] sample count, [1] candidate count A, [2] candidate count B, [3] class count, [4] pool out n
+    uint64_t* d_rank = nullptr;     // {key, idx, n}
+    // full sort / filter-only: retained rows
+    std::vector<uint8_t*> ret_vals, ret_null; int64_t ret_rows = 0, ret_cap = 0;
+    std::vector<uint8_t*> key_img;  // per ORDER BY key: retained images (full sort)
+    uint8_t* ret_keep = nullptr;
+    std::vector<void*> allocs;
+    int64_t total_seen = 0;
+    std::vector<SortOutCol> pending_out; int64_t pending_rows = 0;
+};
+
+namespace {
+
+int fail(std::string& err, int code, const char* msg) { err = msg; return code; }
+int cuda_fail(std::string& err, cudaError_t e, const char* what) { err = std::string(what) + ": " + cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? BKGPU_ENOMEM : BKGPU_ENODEV; }
+#define SCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(err, e__, #call); } while (0)
+
+template <class T> int dalloc(SortState* s, T** p, size_t bytes, std::string& err) {
+    cudaError_t e = cudaMalloc((void**)p, bytes ? bytes : 8);
+    if (e != cudaSuccess) return cuda_fail(err, e, "cudaMalloc");
+    s->allocs.push_back(*p);
+    return 0;
+}
+void dfree(SortState* s, void* p) {
+    if (!p) return;
+    auto it = std::find(s->allocs.begin(), s->allocs.end(), p);
+    if (it != s->allocs.end()) s->allocs.erase(it);
+    cudaFree(p);
+}
+int elem_bytes_of(int prim) { return storage_bytes(prim_storage(prim)); }
+
+void fill_row_args(const SortState* s, const DevCol* cols, int64_t nrows, RowArgs& a) {
+    memset(&a, 0, sizeof a);
+    for (int i = 0; i < s->ncols; i++) a.cols[i] = cols[i];
+    a.n_cols = s->ncols; a.nrows = nrows; a.row_base = s->row_base; a.prog = s->c.prog;
+    a.key.pred_out = s->c.ap.pred_out;
+    if (!s->c.sort_keys.empty()) {
+        const SortKey& k = s->c.sort_keys[0];
+        a.key.out_reg = k.out_reg; a.key.vclass = host_prim_class(k.prim); a.key.desc = k.asc ? 0 : 1;
+        a.key.direct = s->c.has_direct ? 1 : 0; a.key.col = s->c.has_direct ? s->c.direct_cols[0] : 0;
+    }
+}
+
+int grid_for(int64_t n, int per_block, int sm) { int64_t g = (n + per_block - 1) / per_block; int64_t cap = (int64_t)sm * 8; return (int)std::max<int64_t>(1, std::min(g, cap)); }
+
+// ---- selection of the k smallest composite keys of one class out of the batch; result merged into the pool ----
+int select_topk_class(SortState* s, const RowArgs& ra, int cls, cudaStream_t st, bkgpu_stats* stats, std::string& err) {
+    Pool& P = s->pool[cls - 1];
+    const uint32_t k = (uint32_t)s->k;
+    uint32_t* cnt = s->d_counts;
+    // level 1: from the batch columns into cand[0]
+    uint64_t tk = ~0ull, ti = ~0ull;
+    uint32_t n_cand = 0;
+    bool collected = false;
+    uint32_t h_counts[8];
+    uint64_t h_rank[3];
+    if (P.n >= k) {   // threshold = the k-th composite key kept so far: later rows must beat it
+        SCK(cudaMemcpyAsync(&tk, P.key[P.cur] + (k - 1), 8, cudaMemcpyDeviceToHost, st));
+        SCK(cudaMemcpyAsync(&ti, P.idx[P.cur] + (k - 1), 8, cudaMemcpyDeviceToHost, st));
+        SCK(cudaStreamSynchronize(st));
+    } else if (ra.nrows > (int64_t)s->cand_cap / 2) {
+        // estimate a threshold from SAMPLE_N stratified random rows: the rank-r sample bounds ~ r * n / SAMPLE_N rows
+        for (int attempt = 0; attempt < 6 && !collected; attempt++) {
+            SCK(cudaMemsetAsync(cnt, 0, 32, st));
+            k_sample_rows<<<(SAMPLE_N + 255) / 256, 256, 0, st>>>(ra, cls, s->samp_key, s->samp_idx, cnt, 0x5bd1e995ull + attempt * 7919);
+            double frac = (double)SAMPLE_N / (double)ra.nrows;
+            double want = ((double)k * frac * 1.5 + 32.0) * (double)(1 << attempt);   // widen on every retry
+            uint32_t rank = (uint32_t)std::min<double>(want, SAMPLE_N - 1);
+            k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, rank, s->d_rank);
+            SCK(cudaMemcpyAsync(h_rank, s->d_rank, 24, cudaMemcpyDeviceToHost, st));
+            SCK(cudaStreamSynchronize(st));
+            stats->kernel_launches += 2;
+            if (h_rank[2] == 0) { tk = ~0ull; ti = ~0ull; }                       // no row of this class in the sample: take everything
+            else if (h_rank[2] <= rank) { tk = ~0ull; ti = ~0ull; }                // fewer sampled rows than the rank: threshold = +inf
+            else { tk = h_rank[0]; ti = h_rank[1]; }
+            SCK(cudaMemsetAsync(cnt + 1, 0, 12, st));
+            k_collect_rows<<<grid_for(ra.nrows, 256, s->sm_count), 256, 0, st>>>(ra, cls, tk, ti, s->cand_key[0], s->cand_idx[0], cnt + 1, s->cand_cap, cnt + 3);
+            SCK(cudaMemcpyAsync(h_counts, cnt, 32, cudaMemcpyDeviceToHost, st));
+            SCK(cudaStreamSynchronize(st));
+            stats->kernel_launches += 1;
+            const uint32_t class_rows = h_counts[3];
+            if (h_counts[1] > s->cand_cap) continue;                              // threshold too loose for the buffer (halve is implicit: new sample)
+            if (h_counts[1] < k && h_counts[1] < class_rows) continue;            // too tight: retry wider
+            n_cand = h_counts[1]; collected = true;
+        }
+        if (!collected) return fail(err, BKGPU_ETOOBIG, "top-k selection did not converge (candidate buffer too small for this key distribution)");
+    }
+    if (!collected) {
+        SCK(cudaMemsetAsync(cnt + 1, 0, 12, st));
+        k_collect_rows<<<grid_for(ra.nrows, 256, s->sm_count), 256, 0, st>>>(ra, cls, tk, ti, s->cand_key[0], s->cand_idx[0], cnt + 1, s->cand_cap, cnt + 3);
+        SCK(cudaMemcpyAsync(h_counts, cnt, 32, cudaMemcpyDeviceToHost, st));
+        SCK(cudaStreamSynchronize(st));
+        stats->kernel_launches += 1;
+        if (h_counts[1] > s->cand_cap) return fail(err, BKGPU_ETOOBIG, "top-k candidate buffer overflow");
+        n_cand = h_counts[1];
+    }
+    // levels >= 2: shrink the candidate arrays until one CTA can sort them together with the kept rows
+    int cur = 0;
+    const uint32_t room = SMALL_N - std::min<uint32_t>(P.n, k);
+    while (n_cand > room) {
+        bool ok = false;
+        for (int attempt = 0; attempt < 6 && !ok; attempt++) {
+            SCK(cudaMemsetAsync(cnt, 0, 32, st));
+            k_sample_pairs<<<(SAMPLE_N + 255) / 256, 256, 0, st>>>(s->cand_key[cur], s->cand_idx[cur], n_cand, s->samp_key, s->samp_idx, cnt, 0x9e3779b9ull + attempt * 104729);
+            double frac = (double)SAMPLE_N / (double)n_cand; if (frac > 1) frac = 1;
+            double want = ((double)k * frac * 1.5 + 32.0) * (double)(1 << attempt);
+            uint32_t rank = (uint32_t)std::min<double>(want, SAMPLE_N - 1);
+            k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, rank, s->d_rank);
+            SCK(cudaMemcpyAsync(h_rank, s->d_rank, 24, cudaMemcpyDeviceToHost, st));
+            SCK(cudaStreamSynchronize(st));
+            uint64_t tk2 = h_rank[2] > rank ? h_rank[0] : ~0ull, ti2 = h_rank[2] > rank ? h_rank[1] : ~0ull;
+            SCK(cudaMemsetAsync(cnt + 2, 0, 4, st));
+            k_collect_pairs<<<grid_for(n_cand, 256, s->sm_count), 256, 0, st>>>(s->cand_key[cur], s->cand_idx[cur], n_cand, tk2, ti2, s->cand_key[cur ^ 1], s->cand_idx[cur ^ 1], cnt + 2, s->cand_cap);
+            SCK(cudaMemcpyAsync(h_counts, cnt, 32, cudaMemcpyDeviceToHost, st));
+            SCK(cudaStreamSynchronize(st));
+            stats->kernel_launches += 3;
+            if (h_counts[2] < k && h_counts[2] < n_cand) continue;
+            if (h_counts[2] >= n_cand && n_cand > room) {   // threshold = +inf did not shrink anything: sample rank saturated
+                if (attempt < 5) continue;
+                return fail(err, BKGPU_ETOOBIG, "top-k refinement did not shrink the candidate set");
+            }
+            n_cand = h_counts[2]; cur ^= 1; ok = true;
+        }
+        if (!ok) return fail(err, BKGPU_ETOOBIG, "top-k refinement did not converge");
+    }
+    // final: sort candidates + kept rows in one CTA, keep k, then fetch the payload of the survivors
+    const int nxt = P.cur ^ 1;
+    const uint32_t old_n = std::min<uint32_t>(P.n, k);
+    SCK(cudaMemcpyAsync(cnt + 1, &n_cand, 4, cudaMemcpyHostToDevice, st));
+    k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->cand_key[cur], s->cand_idx[cur], cnt + 1, n_cand, P.key[P.cur], P.idx[P.cur], old_n,
+                                                P.key[nxt], P.idx[nxt], k, cnt + 4, 0, nullptr);
+    GatherArgs g; memset(&g, 0, sizeof g);
+    for (int i = 0; i < s->ncols; i++) { g.cols[i] = ra.cols[i]; g.dst_vals[i] = P.vals[nxt][i]; g.dst_null[i] = P.nulls[nxt][i]; g.old_vals[i] = P.vals[P.cur][i]; g.old_null[i] = P.nulls[P.cur][i]; }
+    g.n_cols = s->ncols; g.row_base = ra.row_base; g.nrows = ra.nrows; g.old_idx = P.idx[P.cur]; g.old_n = old_n;
+    k_gather_topk<<<std::max(1, (int)((k + 127) / 128)), 128, 0, st>>>(g, P.idx[nxt], cnt + 4);
+    uint32_t new_n = 0;
+    SCK(cudaMemcpyAsync(&new_n, cnt + 4, 4, cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
+    stats->kernel_launches += 2;
+    P.cur = nxt; P.n = new_n;
+    return 0;
+}
+
+int ensure_retained(SortState* s, int64_t need, cudaStream_t st, std::string& err) {
+    if (need <= s->ret_cap) return 0;
+    int64_t cap = std::max<int64_t>(need, std::max<int64_t>(s->ret_cap * 2, 1 << 16));
+    for (int c = 0; c < s->ncols; c++) {
+        const int eb = elem_bytes_of(s->c.cols[(size_t)c].prim);
+        uint8_t *nv = nullptr, *nn = nullptr; int rc;
+        if ((rc = dalloc(s, &nv, (size_t)cap * eb, err))) return rc;
+        if ((rc = dalloc(s, &nn, (size_t)cap, err))) return rc;
+        if (s->ret_rows) {
+            SCK(cudaMemcpyAsync(nv, s->ret_vals[(size_t)c], (size_t)s->ret_rows * eb, cudaMemcpyDeviceToDevice, st));
+            SCK(cudaMemcpyAsync(nn, s->ret_null[(size_t)c], (size_t)s->ret_rows, cudaMemcpyDeviceToDevice, st));
+        }
+        SCK(cudaStreamSynchronize(st));
+        dfree(s, s->ret_vals[(size_t)c]); dfree(s, s->ret_null[(size_t)c]);
+        s->ret_vals[(size_t)c] = nv; s->ret_null[(size_t)c] = nn;
+    }
+    s->ret_cap = cap;
+    return 0;
+}
+
+// rows that pass the predicate are appended, in input order, to the retained columns (filter-only and full sort)
+int retain_batch(SortState* s, const RowArgs& ra, cudaStream_t st, bkgpu_stats* stats, std::string& err) {
+    const int64_t limit_left = (s->c.kind == PK_FILTER && s->c.limit >= 0) ? std::max<int64_t>(s->c.limit - s->ret_rows, 0) : INT64_MAX;
+    if (limit_left == 0) return 0;   // FilterNode stops after `limit` passing rows (filter_node.cpp:786-791)
+    const int64_t rows_per_block = 4096;
+    const uint32_t nblocks = (uint32_t)((ra.nrows + rows_per_block - 1) / rows_per_block);
+    uint32_t* counts = nullptr; uint64_t* d_total = nullptr; uint32_t* sel = nullptr; int rc;
+    if ((rc = dalloc(s, &counts, (size_t)nblocks * 4, err))) return rc;
+    if ((rc = dalloc(s, &d_total, 8, err))) return rc;
+    k_filter_count<<<nblocks, 256, 0, st>>>(ra, counts, rows_per_block);
+    k_scan_counts<<<1, 1024, 0, st>>>(counts, nblocks, d_total);
+    uint64_t total = 0;
+    SCK(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
+    const uint64_t take = std::min<uint64_t>(total, (uint64_t)limit_left);
+    if (take > 0) {
+        if ((rc = dalloc(s, &sel, (size_t)take * 4, err))) return rc;
+        k_filter_write<<<nblocks, 256, 0, st>>>(ra, counts, rows_per_block, sel, 0, take);
+        if ((rc = ensure_retained(s, s->ret_rows + (int64_t)take, st, err))) return rc;
+        GatherArgs g; memset(&g, 0, sizeof g);
+        for (int i = 0; i < s->ncols; i++) { g.cols[i] = ra.cols[i]; g.dst_vals[i] = s->ret_vals[(size_t)i]; g.dst_null[i] = s->ret_null[(size_t)i]; }
+        g.n_cols = s->ncols;
+        k_gather_sel<<<grid_for((int64_t)take, 256, s->sm_count), 256, 0, st>>>(g, sel, take, (uint64_t)s->ret_rows);
+        SCK(cudaStreamSynchronize(st));
+        s->ret_rows += (int64_t)take;
+        stats->kernel_launches += 2;
+    }
+    stats->kernel_launches += 2;
+    stats->rows_filtered += ra.nrows - (int64_t)total;
+    dfree(s, counts); dfree(s, d_total); dfree(s, sel);
+    return 0;
+}
+
+int copy_out(SortState* s, uint8_t* const* vals, uint8_t* const* nulls, const uint32_t* perm_dev, int64_t n, int64_t skip, cudaStream_t st,
+             std::vector<SortOutCol>& out, std::string& err) {
+    // perm_dev == nullptr: rows [skip, skip+n) in place; else gather through a device permutation first
+    out.clear();
+    for (int c = 0; c < s->ncols; c++) {
+        const ColRef& cr = s->c.cols[(size_t)c];
+        SortOutCol oc; oc.tuple_id = cr.tuple_id; oc.slot_id = cr.slot_id; oc.prim = cr.prim; oc.elem = elem_bytes_of(cr.prim);
+        oc.values.assign((size_t)std::max<int64_t>(n, 1) * oc.elem, 0);
+        std::vector<uint8_t> nb((size_t)std::max<int64_t>(n, 1));
+        const uint8_t* sv = vals[c]; const uint8_t* sn = nulls[c];
+        uint8_t *tv = nullptr, *tn = nullptr;
+        if (perm_dev && n > 0) {
+            int rc;
+            if ((rc = dalloc(s, &tv, (size_t)n * oc.elem, err))) return rc;
+            if ((rc = dalloc(s, &tn, (size_t)n, err))) return rc;
+            GatherArgs g; memset(&g, 0, sizeof g);
+            g.cols[0].values = sv; g.cols[0].validity = nullptr; g.cols[0].stype = prim_storage(cr.prim); g.cols[0].prim = cr.prim;
+            g.n_cols = 1; g.dst_vals[0] = tv; g.dst_null[0] = tn;
+            k_gather_sel<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(g, perm_dev + skip, (uint64_t)n, 0);
+            // null bytes travel separately (k_gather_sel read validity bitmaps, retained columns hold null BYTES)
+            SCK(cudaMemcpyAsync(oc.values.data(), tv, (size_t)n * oc.elem, cudaMemcpyDeviceToHost, st));
+            SCK(cudaStreamSynchronize(st));
+            std::vector<uint8_t> all_nulls((size_t)s->ret_rows);
+            SCK(cudaMemcpy(all_nulls.data(), sn, (size_t)s->ret_rows, cudaMemcpyDeviceToHost));
+            std::vector<uint32_t> hp((size_t)n);
+            SCK(cudaMemcpy(hp.data(), perm_dev + skip, (size_t)n * 4, cudaMemcpyDeviceToHost));
+            for (int64_t i = 0; i < n; i++) nb[(size_t)i] = all_nulls[hp[(size_t)i]];
+            dfree(s, tv); dfree(s, tn);
+        } else if (n > 0) {
+            SCK(cudaMemcpyAsync(oc.values.data(), sv + (size_t)skip * oc.elem, (size_t)n * oc.elem, cudaMemcpyDeviceToHost, st));
+            SCK(cudaMemcpyAsync(nb.data(), sn + skip, (size_t)n, cudaMemcpyDeviceToHost, st));
+            SCK(cudaStreamSynchronize(st));
+        }
+        bool any = false;
+        for (int64_t i = 0; i < n; i++) any |= nb[(size_t)i] != 0;
+        if (any) {
+            oc.validity.assign((size_t)(n + 7) / 8 + 1, 0xFF);
+            for (int64_t i = 0; i < n; i++) if (nb[(size_t)i]) oc.validity[(size_t)i >> 3] &= (uint8_t)~(1u << (i & 7));
+        }
+        out.push_back(std::move(oc));
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+int sort_open(const Compiled& c, int device, cudaStream_t stream, int64_t region_base, SortState** out, std::string& err) {
+    (void)stream;
+    SortState* s = new SortState();
+    s->c = c; s->device = device; s->ncols = (int)c.cols.size();
+    s->row_base = s->region_base = (uint64_t)region_base;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+    s->k = c.kind == PK_SORT ? c.limit : -1;
+    s->topk = c.kind == PK_SORT && c.sort_keys.size() == 1 && s->k >= 0 && s->k <= 4096;
+    s->ret_vals.assign((size_t)s->ncols, nullptr); s->ret_null.assign((size_t)s->ncols, nullptr);
+    int rc = 0;
+    if (s->topk) {
+        s->cand_cap = 1u << 22;   // 4M candidate pairs (64 MB per array pair)
+        const size_t kk = (size_t)std::max<int64_t>(s->k, 1);
+        for (int b = 0; b < 2 && !rc; b++) {
+            if ((rc = dalloc(s, &s->cand_key[b], (size_t)s->cand_cap * 8, err))) break;
+            if ((rc = dalloc(s, &s->cand_idx[b], (size_t)s->cand_cap * 8, err))) break;
+        }
+        if (!rc) rc = dalloc(s, &s->samp_key, SAMPLE_N * 8, err);
+        if (!rc) rc = dalloc(s, &s->samp_idx, SAMPLE_N * 8, err);
+        if (!rc) rc = dalloc(s, &s->d_counts, 64, err);
+        if (!rc) rc = dalloc(s, &s->d_rank, 32, err);
+        for (int p = 0; p < 2 && !rc; p++) for (int b = 0; b < 2 && !rc; b++) {
+            if ((rc = dalloc(s, &s->pool[p].key[b], kk * 8, err))) break;
+            if ((rc = dalloc(s, &s->pool[p].idx[b], kk * 8, err))) break;
+            for (int ci = 0; ci < s->ncols && !rc; ci++) {
+                if ((rc = dalloc(s, &s->pool[p].vals[b][ci], kk * (size_t)elem_bytes_of(c.cols[(size_t)ci].prim), err))) break;
+                rc = dalloc(s, &s->pool[p].nulls[b][ci], kk, err);
+            }
+        }
+        if (!rc) { cudaError_t e = cudaFuncSetAttribute(k_sort_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_N * 16); if (e != cudaSuccess) rc = cuda_fail(err, e, "cudaFuncSetAttribute"); }
+    }
+    if (rc) { sort_close(s); return rc; }
+    *out = s;
+    return 0;
+}
+
+int sort_reset(SortState* s, cudaStream_t, std::string&) {
+    for (auto& p : s->pool) { p.n = 0; p.cur = 0; }
+    s->ret_rows = 0; s->total_seen = 0;
+    s->row_base = s->region_base;
+    return 0;
+}
+
+int sort_push(SortState* s, const DevCol* cols, int64_t nrows, cudaStream_t stream, bkgpu_stats* stats, std::string& err) {
+    if (nrows > 0x7FFFFFFFll) return fail(err, BKGPU_EUNSUPPORTED, "a single pushed batch of a SORT/FILTER plan is limited to 2^31-1 rows");
+    RowArgs ra; fill_row_args(s, cols, nrows, ra);
+    int rc = 0;
+    if (s->topk) {
+        if (s->k == 0) { s->row_base += (uint64_t)nrows; return 0; }
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, stream);
+        rc = select_topk_class(s, ra, 1, stream, stats, err);
+        const bool need_nulls = ra.key.direct ? cols[ra.key.col].validity != nullptr : true;
+        if (!rc && need_nulls) rc = select_topk_class(s, ra, 2, stream, stats, err);
+        cudaEventRecord(e1, stream); cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+        stats->main_kernel_ms += ms; stats->main_kernel_launches += 1;
+        stats->main_kernel_bytes += nrows * (ra.key.direct ? storage_bytes(cols[ra.key.col].stype) : 8);
+        snprintf(stats->main_kernel_name, sizeof stats->main_kernel_name, "topk_select(k_collect_rows)");
+    } else {
+        rc = retain_batch(s, ra, stream, stats, err);
+        snprintf(stats->main_kernel_name, sizeof stats->main_kernel_name, "%s", s->c.kind == PK_FILTER ? "k_filter_write" : "k_radix_scatter");
+    }
+    s->row_base += (uint64_t)nrows; s->total_seen += nrows;
+    return rc;
+}
+
+// layout of the exported partial (top-k): [u64 n][k keys][k idx][per column: k values (8-byte slots)][per column: k null bytes padded to 8]
+size_t sort_partial_bytes(SortState* s) {
+    if (!s->topk) return 0;
+    const size_t k = (size_t)std::max<int64_t>(s->k, 1);
+    return 8 * (1 + 2 * 2 * k) + (size_t)s->ncols * 2 * (k * 8 + ((k + 7) & ~(size_t)7));
+}
+
+static int pool_rows_to_host(SortState* s, int p, std::vector<uint64_t>& key, std::vector<uint64_t>& idx, std::vector<std::vector<uint8_t>>& vals,
+                             std::vector<std::vector<uint8_t>>& nulls, cudaStream_t st, std::string& err) {
+    Pool& P = s->pool[p];
+    const size_t n = P.n;
+    key.resize(n); idx.resize(n); vals.assign((size_t)s->ncols, {}); nulls.assign((size_t)s->ncols, {});
+    if (n) {
+        SCK(cudaMemcpyAsync(key.data(), P.key[P.cur], n * 8, cudaMemcpyDeviceToHost, st));
+        SCK(cudaMemcpyAsync(idx.data(), P.idx[P.cur], n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (int c = 0; c < s->ncols; c++) {
+        const int eb = elem_bytes_of(s->c.cols[(size_t)c].prim);
+        vals[(size_t)c].resize(n * eb + 1); nulls[(size_t)c].resize(n + 1);
+        if (n) {
+            SCK(cudaMemcpyAsync(vals[(size_t)c].data(), P.vals[P.cur][c], n * eb, cudaMemcpyDeviceToHost, st));
+            SCK(cudaMemcpyAsync(nulls[(size_t)c].data(), P.nulls[P.cur][c], n, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    SCK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// host image of the k best rows of this rank: class-tagged, ready to be merged with other ranks'
+struct HostRows {
+    std::vector<uint8_t> cls; std::vector<uint64_t> key, idx;
+    std::vector<std::vector<uint8_t>> vals, nulls;   // per column, row-major fixed width
+};
+
+static int topk_host_rows(SortState* s, HostRows& h, cudaStream_t st, std::string& err) {
+    h.vals.assign((size_t)s->ncols, {}); h.nulls.assign((size_t)s->ncols, {});
+    for (int p = 0; p < 2; p++) {
+        std::vector<uint64_t> key, idx; std::vector<std::vector<uint8_t>> vals, nulls;
+        int rc = pool_rows_to_host(s, p, key, idx, vals, nulls, st, err);
+        if (rc) return rc;
+        for (size_t i = 0; i < key.size(); i++) { h.cls.push_back((uint8_t)(p + 1)); h.key.push_back(key[i]); h.idx.push_back(idx[i]); }
+        for (int c = 0; c < s->ncols; c++) {
+            const int eb = elem_bytes_of(s->c.cols[(size_t)c].prim);
+            h.vals[(size_t)c].insert(h.vals[(size_t)c].end(), vals[(size_t)c].begin(), vals[(size_t)c].begin() + (ptrdiff_t)(key.size() * eb));
+            h.nulls[(size_t)c].insert(h.nulls[(size_t)c].end(), nulls[(size_t)c].begin(), nulls[(size_t)c].begin() + (ptrdiff_t)key.size());
+        }
+    }
+    return 0;
+}
+
+// order host rows by (class rank, key image, arrival index), apply offset / limit, build output columns
+static void finish_host_rows(SortState* s, const HostRows& h, std::vector<SortOutCol>& out, int64_t* nrows) {
+    const bool null_first = s->c.sort_keys[0].null_first;
+    std::vector<uint32_t> order(h.key.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const int ra = h.cls[a] == 2 ? (null_first ? 0 : 2) : 1, rb = h.cls[b] == 2 ? (null_first ? 0 : 2) : 1;
+        if (ra != rb) return ra < rb;
+        if (h.key[a] != h.key[b]) return h.key[a] < h.key[b];
+        return h.idx[a] < h.idx[b];
+    });
+    int64_t n = (int64_t)order.size();
+    if (s->k >= 0 && n > s->k) n = s->k;
+    int64_t skip = std::min<int64_t>(s->c.offset, n);
+    n -= skip;
+    out.clear();
+    for (int c = 0; c < s->ncols; c++) {
+        const ColRef& cr = s->c.cols[(size_t)c];
+        SortOutCol oc; oc.tuple_id = cr.tuple_id; oc.slot_id = cr.slot_id; oc.prim = cr.prim; oc.elem = elem_bytes_of(cr.prim);
+        oc.values.assign((size_t)std::max<int64_t>(n, 1) * oc.elem, 0);
+        bool any = false;
+        std::vector<uint8_t> valid((size_t)(n + 7) / 8 + 1, 0xFF);
+        for (int64_t i = 0; i < n; i++) {
+            const uint32_t src = order[(size_t)(i + skip)];
+            memcpy(oc.values.data() + (size_t)i * oc.elem, h.vals[(size_t)c].data() + (size_t)src * oc.elem, (size_t)oc.elem);
+            if (h.nulls[(size_t)c][src]) { any = true; valid[(size_t)i >> 3] &= (uint8_t)~(1u << (i & 7)); }
+        }
+        if (any) oc.validity = std::move(valid);
+        out.push_back(std::move(oc));
+    }
+    *nrows = n;
+}
+
+static void pack_rows(SortState* s, const HostRows& h, std::vector<uint64_t>& buf) {
+    const size_t k = (size_t)std::max<int64_t>(s->k, 1), kk = 2 * k;   // both classes
+    const size_t nullw = (k + 7) / 8;
+    buf.assign(sort_partial_bytes(s) / 8, 0);
+    const size_t n = std::min(h.key.size(), kk);
+    buf[0] = n;
+    uint64_t* keys = buf.data() + 1; uint64_t* idx = keys + kk;
+    uint64_t* col0 = idx + kk;
+    for (size_t i = 0; i < n; i++) { keys[i] = h.key[i]; idx[i] = h.idx[i] | ((uint64_t)(h.cls[i] == 2) << 63); }
+    for (int c = 0; c < s->ncols; c++) {
+        const int eb = elem_bytes_of(s->c.cols[(size_t)c].prim);
+        uint64_t* v = col0 + (size_t)c * 2 * (k + nullw);
+        uint8_t* nb = (uint8_t*)(v + kk);
+        for (size_t i = 0; i < n; i++) { memcpy(&v[i], h.vals[(size_t)c].data() + i * eb, (size_t)eb); nb[i] = h.nulls[(size_t)c][i]; }
+    }
+}
+static void unpack_rows(SortState* s, const uint64_t* buf, HostRows& h) {
+    const size_t k = (size_t)std::max<int64_t>(s->k, 1), kk = 2 * k, nullw = (k + 7) / 8;
+    const size_t n = (size_t)buf[0];
+    const uint64_t* keys = buf + 1; const uint64_t* idx = keys + kk; const uint64_t* col0 = idx + kk;
+    if (h.vals.empty()) { h.vals.assign((size_t)s->ncols, {}); h.nulls.assign((size_t)s->ncols, {}); }
+    for (size_t i = 0; i < n; i++) { h.key.push_back(keys[i]); h.idx.push_back(idx[i] & ~(1ull << 63)); h.cls.push_back((idx[i] >> 63) ? 2 : 1); }
+    for (int c = 0; c < s->ncols; c++) {
+        const int eb = elem_bytes_of(s->c.cols[(size_t)c].prim);
+        const uint64_t* v = col0 + (size_t)c * 2 * (k + nullw);
+        const uint8_t* nb = (const uint8_t*)(v + kk);
+        for (size_t i = 0; i < n; i++) {
+            const uint8_t* p = (const uint8_t*)&v[i];
+            h.vals[(size_t)c].insert(h.vals[(size_t)c].end(), p, p + eb);
+            h.nulls[(size_t)c].push_back(nb[i]);
+        }
+    }
+}
+
+int sort_partial_export(SortState* s, void* dev_dst, cudaStream_t st, std::string& err) {
+    if (!s->topk) return fail(err, BKGPU_EUNSUPPORTED, "only ORDER BY ... LIMIT plans have a partial state");
+    HostRows h; int rc = topk_host_rows(s, h, st, err);
+    if (rc) return rc;
+    std::vector<uint64_t> buf; pack_rows(s, h, buf);
+    SCK(cudaMemcpyAsync(dev_dst, buf.data(), buf.size() * 8, cudaMemcpyHostToDevice, st));
+    SCK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int sort_partial_merge(SortState* s, const void* dev_src, int nranks, cudaStream_t st, std::vector<SortOutCol>& out, int64_t* nrows, std::string& err) {
+    if (!s->topk) return fail(err, BKGPU_EUNSUPPORTED, "only ORDER BY ... LIMIT plans have a partial state");
+    const size_t words = sort_partial_bytes(s) / 8;
+    std::vector<uint64_t> all(words * (size_t)nranks);
+    SCK(cudaMemcpyAsync(all.data(), dev_src, all.size() * 8, cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
+    HostRows h;
+    for (int r = 0; r < nranks; r++) unpack_rows(s, all.data() + (size_t)r * words, h);
+    finish_host_rows(s, h, out, nrows);   // SelectManagerNode's merge of per-region sorted runs (select_manager_node.cpp:50-51)
+    return 0;
+}
+
+int sort_finish(SortState* s, void* nccl_comm, int nranks, cudaStream_t st, bkgpu_stats* stats, std::vector<SortOutCol>& out, int64_t* nrows, std::string& err) {
+    if (s->topk) {
+        HostRows h; int rc = topk_host_rows(s, h, st, err);
+        if (rc) return rc;
+        if (nccl_comm && nranks > 1) {   // per-GPU top-k rows meet in one all-gather; every rank finishes the merge
+            std::vector<uint64_t> buf; pack_rows(s, h, buf);
+            uint64_t *d_send = nullptr, *d_recv = nullptr;
+            if ((rc = dalloc(s, &d_send, buf.size() * 8, err))) return rc;
+            if ((rc = dalloc(s, &d_recv, buf.size() * 8 * (size_t)nranks, err))) return rc;
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            SCK(cudaMemcpyAsync(d_send, buf.data(), buf.size() * 8, cudaMemcpyHostToDevice, st));
+            cudaEventRecord(e0, st);
+            if (nccl_all_gather(nccl_comm, d_send, d_recv, buf.size(), st) != 0) { err = std::string("ncclAllGather: ") + nccl_last_error(); return BKGPU_ENCCL; }
+            cudaEventRecord(e1, st);
+            rc = sort_partial_merge(s, d_recv, nranks, st, out, nrows, err);
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1); stats->collective_ms += ms; cudaEventDestroy(e0); cudaEventDestroy(e1);
+            dfree(s, d_send); dfree(s, d_recv);
+            return rc;
+        }
+        finish_host_rows(s, h, out, nrows);
+        return 0;
+    }
+    if (nccl_comm && nranks > 1) return fail(err, BKGPU_EUNSUPPORTED, "multi-GPU merge is implemented for ORDER BY ... LIMIT (top-k) and aggregates");
+    if (s->c.kind == PK_FILTER) {
+        int64_t n = s->ret_rows;
+        int64_t skip = std::min<int64_t>(s->c.offset, n);
+        n -= skip;
+        *nrows = n;
+        return copy_out(s, s->ret_vals.data(), s->ret_null.data(), nullptr, n, skip, st, out, err);
+    }
+    // ---- full ORDER BY: LSD radix sort of the retained rows, least significant key first ----
+    const int64_t n = s->ret_rows;
+    if (n > 0xFFFFFFF0ll) return fail(err, BKGPU_EUNSUPPORTED, "full sort is limited to 2^32 rows per GPU");
+    if (n == 0) { *nrows = 0; return copy_out(s, s->ret_vals.data(), s->ret_null.data(), nullptr, 0, 0, st, out, err); }
+    uint64_t* img = nullptr; uint32_t *perm[2] = {nullptr, nullptr}, *hist = nullptr, *bsum = nullptr, *bsum2 = nullptr; int rc;
+    const uint32_t un = (uint32_t)n;
+    const uint32_t ntiles = (un + RS_TILE - 1) / RS_TILE;
+    const uint64_t hist_n = (uint64_t)ntiles * 256;
+    const uint32_t nb1 = (uint32_t)((hist_n + 1023) / 1024), nb2 = (nb1 + 1023) / 1024;
+    if ((rc = dalloc(s, &img, (size_t)n * 8, err))) return rc;
+    if ((rc = dalloc(s, &perm[0], (size_t)n * 4, err))) return rc;
+    if ((rc = dalloc(s, &perm[1], (size_t)n * 4, err))) return rc;
+    if ((rc = dalloc(s, &hist, (size_t)hist_n * 4, err))) return rc;
+    if ((rc = dalloc(s, &bsum, (size_t)(nb1 + 1024) * 4, err))) return rc;
+    if ((rc = dalloc(s, &bsum2, (size_t)(nb2 + 1024) * 4, err))) return rc;
+    if (nb2 > 1024) return fail(err, BKGPU_EUNSUPPORTED, "full sort: too many radix tiles");
+    RowArgs ra; memset(&ra, 0, sizeof ra);
+    for (int c = 0; c < s->ncols; c++) { ra.cols[c].values = s->ret_vals[(size_t)c]; ra.cols[c].validity = nullptr; ra.cols[c].stype = prim_storage(s->c.cols[(size_t)c].prim); ra.cols[c].prim = s->c.cols[(size_t)c].prim; }
+    // retained columns carry null BYTES: rebuild bitmaps so the program sees NULLs
+    std::vector<uint8_t*> bitmaps((size_t)s->ncols, nullptr);
+    for (int c = 0; c < s->ncols; c++) {
+        std::vector<uint8_t> nbytes((size_t)n);
+        SCK(cudaMemcpy(nbytes.data(), s->ret_null[(size_t)c], (size_t)n, cudaMemcpyDeviceToHost));
+        bool any = false; for (auto b : nbytes) any |= b != 0;
+        if (!any) continue;
+        std::vector<uint8_t> bm((size_t)(n + 7) / 8 + 8, 0xFF);
+        for (int64_t i = 0; i < n; i++) if (nbytes[(size_t)i]) bm[(size_t)i >> 3] &= (uint8_t)~(1u << (i & 7));
+        if ((rc = dalloc(s, &bitmaps[(size_t)c], bm.size(), err))) return rc;
+        SCK(cudaMemcpy(bitmaps[(size_t)c], bm.data(), bm.size(), cudaMemcpyHostToDevice));
+        ra.cols[c].validity = bitmaps[(size_t)c];
+    }
+    ra.n_cols = s->ncols; ra.nrows = n; ra.prog = s->c.prog; ra.key.pred_out = -1;
+    int cur = 0; bool first = true;
+    for (int ki = (int)s->c.sort_keys.size() - 1; ki >= 0; ki--) {
+        const SortKey& sk = s->c.sort_keys[(size_t)ki];
+      for (int mode = 0; mode < 2; mode++) {
+        k_sort_images<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(ra, sk.out_reg, host_prim_class(sk.prim), sk.asc ? 0 : 1, sk.null_first ? 1 : 0, mode, img, first ? perm[cur] : nullptr);
+        first = false;
+        for (int pass = 0; pass < (mode == 0 ? 8 : 1); pass++) {
+            k_radix_hist<<<(ntiles + 7) / 8, 256, 0, st>>>(img, perm[cur], un, pass * 8, hist, ntiles);
+            k_scan_u32<<<nb1, 256, 0, st>>>(hist, hist_n, bsum, 0);
+            k_scan_u32<<<nb2, 256, 0, st>>>(bsum, nb1, bsum2, 0);
+            if (nb2 > 1) { // third level on the host-sized tail (nb2 <= 1024): one block
+                k_scan_u32<<<1, 256, 0, st>>>(bsum2, nb2, bsum2 + 1024, 0);
+                k_scan_u32<<<nb2, 256, 0, st>>>(bsum, nb1, bsum2, 1);
+            }
+            k_scan_u32<<<nb1, 256, 0, st>>>(hist, hist_n, bsum, 1);
+            k_radix_scatter<<<(ntiles + 7) / 8, 256, 0, st>>>(img, perm[cur], perm[cur ^ 1], un, pass * 8, hist, ntiles);
+            cur ^= 1;
+            stats->kernel_launches += 5;
+        }
+      }
+    }
+    SCK(cudaStreamSynchronize(st));
+    int64_t keep = n; if (s->k >= 0 && keep > s->k) keep = s->k;
+    int64_t skip = std::min<int64_t>(s->c.offset, keep); keep -= skip;
+    *nrows = keep;
+    rc = copy_out(s, s->ret_vals.data(), s->ret_null.data(), perm[cur], keep, skip, st, out, err);
+    dfree(s, img); dfree(s, perm[0]); dfree(s, perm[1]); dfree(s, hist); dfree(s, bsum); dfree(s, bsum2);
+    for (auto b : bitmaps) dfree(s, b);
+    return rc;
+}
+
+void sort_close(SortState* s) {
+    if (!s) return;
+    for (void* p : s->allocs) cudaFree(p);
+    delete s;
+}
+
 }  // namespace bk

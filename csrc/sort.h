@@ -17,7 +17,7 @@ struct SortOutCol {
     std::vector<uint8_t> validity;  // LSB bitmap, empty = all valid
 };
 
-int  sort_open(const Compiled& c, int device, cudaStream_t stream, int64_t topk_sample, SortState** out, std::string& err);
+int  sort_open(const Compiled& c, int device, cudaStream_t stream, int64_t region_base, SortState** out, std::string& err);
 int  sort_push(SortState* s, const DevCol* cols, int64_t nrows, cudaStream_t stream, bkgpu_stats* stats, std::string& err);
 int  sort_finish(SortState* s, void* nccl_comm, int nranks, cudaStream_t stream, bkgpu_stats* stats,
                  std::vector<SortOutCol>& out, int64_t* nrows, std::string& err);

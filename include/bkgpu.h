@@ -99,8 +99,15 @@ int   bkgpu_plan_explain(const uint8_t* plan_desc, size_t len, char* text, size_
  * bkgpu_finish (regions -> one set per GPU; src/physical_plan/separate.cpp:249-258). */
 int   bkgpu_init(bkgpu_plan** out, const uint8_t* plan_desc, size_t len,
                  int device, void* nccl_comm_or_null);
-/* Tunables, before open: "stream" (cudaStream_t as int64), "group_capacity_log2",
- * "batch_capacity", "output_on_device", "topk_sample", "smem_agg" ... */
+/* Tunables, before open:
+ *   "stream"               cudaStream_t (as int64) the plan launches on (default: its own stream)
+ *   "group_capacity_log2"  slots of the global group table (default 20); overflow -> BKGPU_ETOOBIG
+ *   "smem_capacity_log2"   slots of the per-CTA shared table (-1 = chosen per batch, 0 = none)
+ *   "batch_capacity"       rows per bkgpu_get_next batch (RuntimeState::row_batch_capacity)
+ *   "chunk_rows"           rows per host->device staging chunk of a host push
+ *   "partial_capacity"     groups per rank in the exported partial state
+ *   "region_base"          arrival index of this plan's first row: ORDER BY ties across GPUs break by (region, row)
+ *   "force_generic" / "no_lean"   pin the kernel variant (tests, A/B measurements) */
 int   bkgpu_set_option(bkgpu_plan*, const char* key, int64_t value);
 /* ExecNode::open(RuntimeState*) (exec_node.h:140): allocate tables. */
 int   bkgpu_open(bkgpu_plan*);
