@@ -21,55 +21,88 @@ namespace bk {
 // generic path: the lowered expression program (interp.cuh) is interpreted per row (any predicate,
 // computed keys and arguments, multi-column keys).
 // ------------------------------------------------------------------------------------------
+// one (possibly joined) row through the program into the tables
+struct InterpCtx { SmemTable st; bool grouped, use_smem; uint32_t gcap; };
+__device__ __forceinline__ uint32_t interp_row(const AggArgs& a, const InterpCtx& cx, int64_t row, int64_t brow) {
+    const AggPlan& ap = a.plan;
+    const GroupTable& gt = a.gt;
+    uint64_t out[MAX_GROUP + MAX_AGG + 1];
+    uint32_t out_null;
+    run_program(a.prog, a.cols, row, out, out_null, brow);
+    if (ap.pred_out >= 0 && (((out_null >> ap.pred_out) & 1u) || out[ap.pred_out] == 0)) return 0;
+    auto arg = [&](int i, uint64_t& v, bool& isnull) {
+        const int r = ap.agg[i].arg_out;
+        if (r == 0xFF) { v = 0; isnull = true; return; }
+        v = out[r]; isnull = (out_null >> r) & 1u;
+    };
+    if (!cx.grouped) {  // single group: slot 0 of the global table
+        accumulate_row<false>(a, gt.lanes, cx.gcap, 0, arg);
+        return 1;
+    }
+    uint64_t key[MAX_KEYW];
+    for (int w = 0; w < ap.n_keyw; w++) key[w] = 0;
+    for (int g = 0; g < ap.n_group; g++) {
+        const int r = ap.key_out[g];
+        if ((out_null >> r) & 1u) key[ap.key_null_word[g]] |= 1ull << ap.key_null_shift[g];
+        else {
+            const uint64_t m = ap.key_bits[g] >= 64 ? ~0ull : ((1ull << ap.key_bits[g]) - 1ull);
+            key[ap.key_word[g]] |= (out[r] & m) << ap.key_shift[g];
+        }
+    }
+    const uint32_t h = ap.n_keyw == 1 ? hash_key1(key[0]) : hash_key(key, ap.n_keyw);
+    int slot = -1;
+    if (cx.use_smem) slot = table_upsert<true, 0>(cx.st.state, cx.st.keys, cx.st.cap_mask, key, ap.n_keyw, h >> 7, 16, nullptr);
+    if (slot >= 0) accumulate_row<true>(a, cx.st.lanes, cx.st.cap_mask + 1, slot, arg);
+    else {
+        slot = table_upsert<false, 0>(gt.state, gt.keys, gt.cap_mask, key, ap.n_keyw, h, (int)cx.gcap, gt.n_groups);
+        if (slot < 0) atomicExch(gt.overflow, 1u);
+        else accumulate_row<false>(a, gt.lanes, cx.gcap, slot, arg);
+    }
+    return 1;
+}
+
 __global__ void __launch_bounds__(256) k_agg_interp(const __grid_constant__ AggArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AggPlan& ap = a.plan;
-    const GroupTable& gt = a.gt;
-    const bool grouped = ap.n_keyw > 0;
-    const bool use_smem = grouped && a.smem_cap_log2 > 0;
-    SmemTable st;
-    if (use_smem) st = smem_table_init(smem_raw, a);
-    const uint32_t gcap = gt.cap_mask + 1;
+    InterpCtx cx;
+    cx.grouped = ap.n_keyw > 0;
+    cx.use_smem = cx.grouped && a.smem_cap_log2 > 0;
+    cx.gcap = a.gt.cap_mask + 1;
+    cx.st = SmemTable{};
+    if (cx.use_smem) cx.st = smem_table_init(smem_raw, a);
     uint32_t passed = 0;
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.nrows; row += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t out[MAX_GROUP + MAX_AGG + 1];
-        uint32_t out_null;
-        run_program(a.prog, a.cols, row, out, out_null);
-        if (ap.pred_out >= 0 && (((out_null >> ap.pred_out) & 1u) || out[ap.pred_out] == 0)) continue;
-        passed++;
-        auto arg = [&](int i, uint64_t& v, bool& isnull) {
-            const int r = ap.agg[i].arg_out;
-            if (r == 0xFF) { v = 0; isnull = true; return; }
-            v = out[r]; isnull = (out_null >> r) & 1u;
-        };
-        if (!grouped) {  // single group: slot 0 of the global table
-            accumulate_row<false>(a, gt.lanes, gcap, 0, arg);
-            continue;
-        }
-        uint64_t key[MAX_KEYW];
-        for (int w = 0; w < ap.n_keyw; w++) key[w] = 0;
-        for (int g = 0; g < ap.n_group; g++) {
-            const int r = ap.key_out[g];
-            if ((out_null >> r) & 1u) key[ap.key_null_word[g]] |= 1ull << ap.key_null_shift[g];
-            else {
-                const uint64_t m = ap.key_bits[g] >= 64 ? ~0ull : ((1ull << ap.key_bits[g]) - 1ull);
-                key[ap.key_word[g]] |= (out[r] & m) << ap.key_shift[g];
-            }
-        }
-        const uint32_t h = ap.n_keyw == 1 ? hash_key1(key[0]) : hash_key(key, ap.n_keyw);
-        int slot = -1;
-        if (use_smem) slot = table_upsert<true, 0>(st.state, st.keys, st.cap_mask, key, ap.n_keyw, h >> 7, 16, nullptr);
-        if (slot >= 0) accumulate_row<true>(a, st.lanes, st.cap_mask + 1, slot, arg);
-        else {
-            slot = table_upsert<false, 0>(gt.state, gt.keys, gt.cap_mask, key, ap.n_keyw, h, (int)gcap, gt.n_groups);
-            if (slot < 0) atomicExch(gt.overflow, 1u);
-            else accumulate_row<false>(a, gt.lanes, gcap, slot, arg);
+        if (!a.join.enabled) { passed += interp_row(a, cx, row, -1); continue; }
+        // K4 probe: every build row whose cast key equals this row's (Joiner::encode_hash_key + FlatMap seek,
+        // src/exec/joiner.cpp:608-622, join_node.cpp:1290-1292); a NULL key never matches (SQL / Acero hashjoin)
+        const DevCol& pc = a.cols[a.join.probe_col];
+        if (elem_is_null(pc, row)) continue;
+        const uint64_t img = cast_prim(load_elem(pc, row), a.join.probe_prim, a.join.cast_prim);
+        uint32_t slot = hash_key1(img) & a.join.cap_mask;
+        for (;;) {
+            const uint32_t br = a.join.rows[slot];
+            if (br == 0xFFFFFFFFu) break;
+            if (a.join.keys[slot] == img) passed += interp_row(a, cx, row, (int64_t)br);
+            slot = (slot + 1) & a.join.cap_mask;
         }
     }
-    if (use_smem) smem_table_flush(st, a);
+    if (cx.use_smem) smem_table_flush(cx.st, a);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) passed += __shfl_xor_sync(0xFFFFFFFFu, passed, d);
     if ((threadIdx.x & 31) == 0 && passed) atomicAdd((unsigned long long*)a.rows_passed, (unsigned long long)passed);
+}
+
+// K4 build: insert (cast key image, row) of every non-NULL build row (Joiner::construct_hash_map, joiner.cpp:624-631)
+__global__ void k_join_build(DevCol key, int from_prim, int cast_to, int64_t nrows, uint64_t* keys, uint32_t* rows, uint32_t cap_mask) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        if (elem_is_null(key, r)) continue;
+        const uint64_t img = cast_prim(load_elem(key, r), from_prim, cast_to);
+        uint32_t slot = hash_key1(img) & cap_mask;
+        for (;;) {
+            if (atomicCAS(rows + slot, 0xFFFFFFFFu, (uint32_t)r) == 0xFFFFFFFFu) { keys[slot] = img; break; }
+            slot = (slot + 1) & cap_mask;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -206,6 +239,37 @@ cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t
     return cudaGetLastError();
 }
 
+__global__ void k_unpack_validity(const uint8_t* bitmap, int64_t n, uint8_t* null_bytes) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        null_bytes[i] = bitmap ? (((bitmap[i >> 3] >> (i & 7)) & 1) ? 0 : 1) : 0;
+}
+__global__ void k_pack_validity(const uint8_t* null_bytes, int64_t n, uint8_t* bitmap) {
+    const int64_t nbytes = (n + 7) >> 3;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbytes; b += (int64_t)gridDim.x * blockDim.x) {
+        uint8_t v = 0;
+        for (int j = 0; j < 8; j++) { const int64_t i = b * 8 + j; if (i >= n || !null_bytes[i]) v |= (uint8_t)(1u << j); }
+        bitmap[b] = v;
+    }
+}
+cudaError_t launch_unpack_validity(const uint8_t* bitmap, int64_t n, uint8_t* null_bytes, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    int grid = (int)((n + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    k_unpack_validity<<<grid, 256, 0, s>>>(bitmap, n, null_bytes);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_validity(const uint8_t* null_bytes, int64_t n, uint8_t* bitmap, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    int grid = (int)(((n + 7) / 8 + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    k_pack_validity<<<grid, 256, 0, s>>>(null_bytes, n, bitmap);
+    return cudaGetLastError();
+}
+cudaError_t launch_join_build(const DevCol& key, int from_prim, int cast_prim_, int64_t nrows, uint64_t* keys, uint32_t* rows, uint32_t cap_mask, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(rows, 0xFF, (size_t)(cap_mask + 1) * 4, s);
+    if (e != cudaSuccess || nrows == 0) return e;
+    int grid = (int)((nrows + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    k_join_build<<<grid, 256, 0, s>>>(key, from_prim, cast_prim_, nrows, keys, rows, cap_mask);
+    return cudaGetLastError();
+}
 cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStream_t s) {
     const uint32_t cap = gt.cap_mask + 1;
     int grid = (int)((cap + 255) / 256); if (grid > 1184) grid = 1184;

@@ -5,6 +5,16 @@
 
 namespace bk {
 
+// hash join (K4): open-addressed multimap from the cast build key image to the build row
+struct JoinArgs {
+    const uint64_t* keys;    // [cap] key images
+    const uint32_t* rows;    // [cap] build row, 0xFFFFFFFF = free slot
+    uint32_t cap_mask;
+    int32_t enabled;
+    int32_t probe_col;       // index into cols of the probe key
+    int32_t probe_prim, cast_prim;
+};
+
 struct AggArgs {
     DevCol cols[MAX_COLS];   // direct kernels: ordered [predicate][key][value] columns
     int32_t n_cols;
@@ -15,6 +25,7 @@ struct AggArgs {
     Program prog;            // generic path only
     GroupTable gt;
     uint64_t* rows_passed;   // device counter: rows that survived the filter
+    JoinArgs join;
     uint8_t smem_lane[MAX_LANES];  // global lane -> shared lane of this batch, 0xFF = not held in shared memory
     int32_t n_smem_lanes;
     uint32_t alias_mask;     // global lanes that receive the shared row count at flush time
@@ -30,6 +41,9 @@ cudaError_t launch_direct_np0(const AggArgs& a, int na, int sm_count, size_t sme
 cudaError_t launch_direct_np1(const AggArgs& a, int na, int sm_count, size_t smem, cudaStream_t s, bool grouped);
 cudaError_t launch_direct_np2(const AggArgs& a, int na, int sm_count, size_t smem, cudaStream_t s, bool grouped);
 size_t direct_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2, int na);
+cudaError_t launch_join_build(const DevCol& key, int from_prim, int cast_prim, int64_t nrows, uint64_t* keys, uint32_t* rows, uint32_t cap_mask, cudaStream_t s);
+cudaError_t launch_unpack_validity(const uint8_t* bitmap, int64_t n, uint8_t* null_bytes, cudaStream_t s);
+cudaError_t launch_pack_validity(const uint8_t* null_bytes, int64_t n, uint8_t* bitmap, cudaStream_t s);
 cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStream_t s);
 cudaError_t launch_partial_export(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, uint32_t pcap, uint32_t* cursor, cudaStream_t s);
 cudaError_t launch_partial_merge(const GroupTable& gt, const AggPlan& ap, const uint64_t* src, size_t words_per_rank, uint32_t pcap, int nranks, cudaStream_t s);

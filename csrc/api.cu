@@ -65,6 +65,12 @@ struct bkgpu_plan {
     uint64_t* d_outv = nullptr; uint8_t* d_outn = nullptr; size_t out_cap_alloc = 0;  // extraction buffers (kept across resets)
     std::vector<uint64_t> hv; std::vector<uint8_t> hn;
     uint32_t known_groups = 0;
+    // hash join (K4): retained build side + multimap
+    std::vector<uint8_t*> jb_vals, jb_nullbytes, jb_bitmap;   // per plan column (side 1 only)
+    std::vector<bool> jb_has_null;
+    int64_t jb_rows = 0, jb_cap = 0;
+    uint64_t* jt_keys = nullptr; uint32_t* jt_rows = nullptr; uint32_t jt_mask = 0; bool jt_built = false;
+    std::vector<ColRef> probe_want; std::vector<int> probe_map;   // probe-side columns and their index in c.cols
     // sort / filter state
     SortState* sort = nullptr;
     // host staging for pageable / pinned pushes
@@ -241,7 +247,11 @@ static int launch_agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, bo
     const Compiled& c = p->c;
     AggArgs a; memset(&a, 0, sizeof a);
     a.plan = c.ap; a.prog = c.prog; a.direct = c.direct; a.gt = p->gt; a.rows_passed = p->d_rows_passed;
-    const bool direct = c.has_direct && vec_ok && !p->force_generic;
+    if (c.kind == PK_JOIN_AGG) {
+        a.join.enabled = 1; a.join.keys = p->jt_keys; a.join.rows = p->jt_rows; a.join.cap_mask = p->jt_mask;
+        a.join.probe_col = c.probe_key_col; a.join.probe_prim = c.cols[(size_t)c.probe_key_col].prim; a.join.cast_prim = c.join_key_prim;
+    }
+    const bool direct = c.has_direct && vec_ok && !p->force_generic && c.kind == PK_AGG;
     const int ncols = (int)c.cols.size();
     if (direct) { for (size_t i = 0; i < c.direct_cols.size(); i++) a.cols[i] = cols[c.direct_cols[i]]; a.n_cols = (int)c.direct_cols.size(); }
     else { for (int i = 0; i < ncols; i++) a.cols[i] = cols[i]; a.n_cols = ncols; }
@@ -409,6 +419,105 @@ static int sort_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, int64_t,
     return rc;
 }
 
+// ---- K4: retain the build (outer / driver) table, build the multimap at the first probe batch ----
+static int join_retain_build(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device) {
+    const Compiled& c = p->c;
+    if (p->jt_built) return p->fail(BKGPU_ESTATE, "build-side rows arrived after probing started (the reference fetches the whole driver table first, join_node.cpp:920-1022)");
+    const size_t nc = c.cols.size();
+    if (p->jb_vals.empty()) { p->jb_vals.assign(nc, nullptr); p->jb_nullbytes.assign(nc, nullptr); p->jb_bitmap.assign(nc, nullptr); p->jb_has_null.assign(nc, false); }
+    std::vector<ColRef> want; std::vector<int> idx;
+    for (size_t i = 0; i < nc; i++) if (c.col_side[i] == 1) { want.push_back(c.cols[i]); idx.push_back((int)i); }
+    std::vector<const bkgpu_column*> bound;
+    int rc = bind_columns(p, want, cols, ncols, nrows, bound);
+    if (rc) return rc;
+    if (p->jb_rows + nrows > 0xFFFFFFF0ll) return p->fail(BKGPU_EUNSUPPORTED, "build side larger than 2^32 rows");
+    if (p->jb_rows + nrows > p->jb_cap) {
+        const int64_t cap = std::max<int64_t>(p->jb_rows + nrows, std::max<int64_t>(p->jb_cap * 2, 1 << 16));
+        for (int i : idx) {
+            const size_t eb = (size_t)storage_bytes(prim_storage(c.cols[(size_t)i].prim));
+            uint8_t *nv = nullptr, *nn = nullptr;
+            if ((rc = dev_alloc(p, (void**)&nv, (size_t)cap * eb))) return rc;
+            if ((rc = dev_alloc(p, (void**)&nn, (size_t)cap))) return rc;
+            if (p->jb_rows) {
+                CK(p, cudaMemcpyAsync(nv, p->jb_vals[(size_t)i], (size_t)p->jb_rows * eb, cudaMemcpyDeviceToDevice, p->stream));
+                CK(p, cudaMemcpyAsync(nn, p->jb_nullbytes[(size_t)i], (size_t)p->jb_rows, cudaMemcpyDeviceToDevice, p->stream));
+                CK(p, cudaStreamSynchronize(p->stream));
+            }
+            dev_free(p, p->jb_vals[(size_t)i]); dev_free(p, p->jb_nullbytes[(size_t)i]);
+            p->jb_vals[(size_t)i] = nv; p->jb_nullbytes[(size_t)i] = nn;
+        }
+        p->jb_cap = cap;
+    }
+    for (size_t w = 0; w < want.size(); w++) {
+        const int i = idx[w];
+        const size_t eb = (size_t)storage_bytes(prim_storage(c.cols[(size_t)i].prim));
+        uint8_t* dv = p->jb_vals[(size_t)i] + (size_t)p->jb_rows * eb;
+        uint8_t* dn = p->jb_nullbytes[(size_t)i] + p->jb_rows;
+        if (on_device) {
+            CK(p, cudaMemcpyAsync(dv, bound[w]->values, (size_t)nrows * eb, cudaMemcpyDeviceToDevice, p->stream));
+            CK(p, launch_unpack_validity(bound[w]->validity, nrows, dn, p->stream));
+            p->stats.kernel_launches++;
+        } else {
+            CK(p, cudaMemcpyAsync(dv, bound[w]->values, (size_t)nrows * eb, cudaMemcpyHostToDevice, p->stream));
+            std::vector<uint8_t> nb((size_t)nrows, 0);
+            if (bound[w]->validity) for (int64_t r = 0; r < nrows; r++) nb[(size_t)r] = ((bound[w]->validity[r >> 3] >> (r & 7)) & 1) ? 0 : 1;
+            CK(p, cudaMemcpyAsync(dn, nb.data(), (size_t)nrows, cudaMemcpyHostToDevice, p->stream));
+            CK(p, cudaStreamSynchronize(p->stream));
+            p->stats.h2d_bytes += (int64_t)((size_t)nrows * (eb + 1));
+        }
+        if (bound[w]->validity) p->jb_has_null[(size_t)i] = true;
+    }
+    p->jb_rows += nrows;
+    return BKGPU_OK;
+}
+
+static int join_build_table(bkgpu_plan* p) {
+    const Compiled& c = p->c;
+    const size_t nc = c.cols.size();
+    if (p->jb_vals.empty()) { p->jb_vals.assign(nc, nullptr); p->jb_nullbytes.assign(nc, nullptr); p->jb_bitmap.assign(nc, nullptr); p->jb_has_null.assign(nc, false); }
+    int rc;
+    for (size_t i = 0; i < nc; i++) {
+        if (c.col_side[i] != 1 || !p->jb_has_null[i]) continue;
+        dev_free(p, p->jb_bitmap[i]); p->jb_bitmap[i] = nullptr;
+        if ((rc = dev_alloc(p, (void**)&p->jb_bitmap[i], (size_t)(p->jb_rows + 7) / 8 + 8))) return rc;
+        CK(p, launch_pack_validity(p->jb_nullbytes[i], p->jb_rows, p->jb_bitmap[i], p->stream));
+        p->stats.kernel_launches++;
+    }
+    uint32_t cap = 1024;
+    while ((int64_t)cap < 2 * p->jb_rows) cap <<= 1;
+    dev_free(p, p->jt_keys); dev_free(p, p->jt_rows);
+    if ((rc = dev_alloc(p, (void**)&p->jt_keys, (size_t)cap * 8))) return rc;
+    if ((rc = dev_alloc(p, (void**)&p->jt_rows, (size_t)cap * 4))) return rc;
+    p->jt_mask = cap - 1;
+    DevCol key{};
+    const size_t ki = (size_t)c.build_key_col;
+    key.values = p->jb_vals[ki]; key.validity = p->jb_bitmap[ki]; key.stype = prim_storage(c.cols[ki].prim); key.prim = c.cols[ki].prim;
+    CK(p, launch_join_build(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, p->jt_keys, p->jt_rows, p->jt_mask, p->stream));
+    p->stats.kernel_launches++;
+    p->jt_built = true;
+    return BKGPU_OK;
+}
+
+static int join_probe_batch(bkgpu_plan* p, const DevCol* probe_cols, int64_t nrows, int64_t, bool) {
+    const Compiled& c = p->c;
+    std::vector<DevCol> all(c.cols.size());
+    for (size_t i = 0; i < c.cols.size(); i++) {
+        if (c.col_side[i] == 1) { all[i].values = p->jb_vals[i]; all[i].validity = p->jb_bitmap[i]; all[i].stype = prim_storage(c.cols[i].prim); all[i].prim = c.cols[i].prim; }
+    }
+    for (size_t w = 0; w < p->probe_map.size(); w++) all[(size_t)p->probe_map[w]] = probe_cols[w];
+    return launch_agg_batch(p, all.data(), nrows, false);
+}
+
+static int join_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device) {
+    const Compiled& c = p->c;
+    bool is_build = false;
+    for (int k = 0; k < ncols; k++) if (cols[k].tuple_id == c.build_tuple) is_build = true;
+    if (is_build) return join_retain_build(p, cols, ncols, nrows, on_device);
+    if (!p->jt_built) { int rc = join_build_table(p); if (rc) return rc; }
+    if (p->probe_want.empty()) for (size_t i = 0; i < c.cols.size(); i++) if (c.col_side[i] == 0) { p->probe_want.push_back(c.cols[i]); p->probe_map.push_back((int)i); }
+    return feed(p, p->probe_want, cols, ncols, nrows, on_device, join_probe_batch);
+}
+
 extern "C" int bkgpu_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device) {
     if (!p) return thread_fail(BKGPU_EINVAL, "bkgpu_push: NULL plan");
     if (p->state != S_OPEN) return p->fail(BKGPU_ESTATE, "bkgpu_push needs an open, unfinished plan");
@@ -427,6 +536,7 @@ extern "C" int bkgpu_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, in
             }
             return BKGPU_OK;
         }
+        case PK_JOIN_AGG: return join_push(p, cols, ncols, nrows, on_device);
         case PK_SORT: case PK_FILTER: return feed(p, p->c.cols, cols, ncols, nrows, on_device, sort_batch);
         default: return p->fail(BKGPU_EUNSUPPORTED, "plan kind %d has no push path yet", p->c.kind);
     }
@@ -619,6 +729,7 @@ extern "C" int bkgpu_reset(bkgpu_plan* p) {
         CK(p, launch_table_init(p->gt, p->c.ap, p->stream));
         p->stats.kernel_launches++;
     }
+    p->jb_rows = 0; p->jt_built = false; std::fill(p->jb_has_null.begin(), p->jb_has_null.end(), false);
     if (p->sort) { int rc = sort_reset(p->sort, p->stream, p->last_error); if (rc) { g_thread_error = p->last_error; return rc; } }
     p->result.clear(); p->result_rows = 0; p->result_pos = 0;
     bkgpu_stats z{}; z.kernel_launches = p->stats.kernel_launches; p->stats = z;

@@ -9,7 +9,9 @@ namespace bk {
 // generic path: the lowered expression program is interpreted per row (any predicate, computed
 // keys and arguments, multi-column keys).  Postfix bytecode, warp-uniform dispatch.
 // ------------------------------------------------------------------------------------------
-static __device__ __noinline__ void run_program(const Program& p, const DevCol* cols, int64_t row, uint64_t* out, uint32_t& out_null) {
+// `brow`: row of the join's build side; LOAD_COL instructions with c == 1 read there (the joined row of
+// Joiner::construct_result_batch, src/exec/joiner.cpp:633-685, without materialising it)
+static __device__ __noinline__ void run_program(const Program& p, const DevCol* cols, int64_t row, uint64_t* out, uint32_t& out_null, int64_t brow = -1) {
     uint64_t st[STACK_DEPTH];
     uint32_t nul = 0;  // bit d set = stack entry d is NULL
     int sp = 0;
@@ -20,8 +22,9 @@ static __device__ __noinline__ void run_program(const Program& p, const DevCol* 
         switch (in.op) {
             case OP_LOAD_COL: {
                 const DevCol& c = cols[in.a];
-                st[sp] = load_elem(c, row);
-                nul = elem_is_null(c, row) ? (nul | (1u << sp)) : (nul & ~(1u << sp));
+                const int64_t r = in.c ? brow : row;
+                st[sp] = load_elem(c, r);
+                nul = elem_is_null(c, r) ? (nul | (1u << sp)) : (nul & ~(1u << sp));
                 sp++;
             } break;
             case OP_CONST:

@@ -332,6 +332,7 @@ struct Lower {
         auto& cols = out->cols;
         for (size_t i = 0; i < cols.size(); i++) if (cols[i].tuple_id == tuple_id && cols[i].slot_id == slot_id) return (int)i;
         cols.push_back({tuple_id, slot_id, prim});
+        out->col_side.push_back(out->build_tuple >= 0 && tuple_id == out->build_tuple ? 1 : 0);
         return (int)cols.size() - 1;
     }
     bool emit(uint8_t op, uint8_t a = 0, uint8_t b = 0, uint8_t c = 0) {
@@ -364,7 +365,7 @@ struct Lower {
                 if (st == BK_STRING) return in->fail(BKGPU_EUNSUPPORTED, "STRING column %d_%d used in an expression", e.tuple_id, e.slot_id);
                 int ci = intern_col(e.tuple_id, e.slot_id, st);
                 if (ci >= MAX_COLS) return in->fail(BKGPU_EUNSUPPORTED, "more than %d columns referenced", MAX_COLS);
-                if (!emit(OP_LOAD_COL, (uint8_t)ci)) return false;
+                if (!emit(OP_LOAD_COL, (uint8_t)ci, 0, (uint8_t)out->col_side[(size_t)ci])) return false;  // c = 1: read at the matched build row
                 depth++;
                 return cast(st, e.col_type);
             }
@@ -485,9 +486,9 @@ static const HNode* skip_passthrough(const HNode* n, bool* under_packet) {
     return n;
 }
 
-static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const HNode* filter, const HNode& scan, bool under_packet) {
+static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vector<const HExpr*>& conjuncts, int scan_tuple, bool under_packet, bool allow_direct) {
     out.kind = PK_AGG;
-    out.scan_tuple = scan.tuple_id;
+    out.scan_tuple = scan_tuple;
     out.is_merge = agg.node_type == BK_MERGE_AGG_NODE;
     out.emit_default = agg.group_exprs.empty() && (under_packet || out.is_merge);
     out.agg_limit = agg.limit;
@@ -500,10 +501,10 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const HNode* f
     int reg = 0, depth = 0;
     // ---- predicate: all conjuncts non-NULL true (filter_node.cpp:726-734) ----
     ap.pred_out = -1;
-    if (filter && !filter->conjuncts.empty()) {
-        if (filter->conjuncts.size() > 8) return in.fail(BKGPU_EUNSUPPORTED, "more than 8 conjuncts");
-        for (auto& c : filter->conjuncts) { depth = 0; if (!lw.expr(c, depth) || !lw.to_bool(c)) return false; }
-        if (filter->conjuncts.size() > 1 && !lw.emit(OP_AND, (uint8_t)filter->conjuncts.size())) return false;
+    if (!conjuncts.empty()) {
+        if (conjuncts.size() > 8) return in.fail(BKGPU_EUNSUPPORTED, "more than 8 conjuncts");
+        for (auto* c : conjuncts) { depth = 0; if (!lw.expr(*c, depth) || !lw.to_bool(*c)) return false; }
+        if (conjuncts.size() > 1 && !lw.emit(OP_AND, (uint8_t)conjuncts.size())) return false;
         ap.pred_out = reg;
         if (!lw.out_reg(reg++)) return false;
     }
@@ -597,10 +598,12 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const HNode* f
     DirectPlan& d = out.direct; memset(&d, 0, sizeof d); memset(d.agg_val, 0xFF, sizeof d.agg_val);
     do {
         std::vector<int> order;  // cols indices in [terms][key][values] order
-        if (filter) {
-            if (filter->conjuncts.size() > 2) break;
+        if (!allow_direct) break;
+        if (!conjuncts.empty()) {
+            if (conjuncts.size() > 2) break;
             bool ok = true;
-            for (auto& c : filter->conjuncts) {
+            for (auto* cp : conjuncts) {
+                const HExpr& c = *cp;
                 if (c.node_type != BK_FUNCTION_CALL || c.fn_op < BK_FT_EQ || c.fn_op > BK_FT_LE || c.ch.size() != 2 || c.col_type != BK_BOOL) { ok = false; break; }
                 const HExpr *col = &c.ch[0], *lit = &c.ch[1]; int op = c.fn_op;
                 if (is_literal_node(col->node_type) && lit->node_type == BK_SLOT_REF) {
@@ -749,7 +752,9 @@ int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& er
         if (is_filter(c)) { filter = c; c = c->ch.empty() ? nullptr : skip_passthrough(&c->ch[0], nullptr); }
         if (c && c->node_type == BK_SCAN_NODE) {
             if (filter && filter->limit != -1) { err = "LIMIT on a filter below an aggregate is order dependent: outside the GPU path"; return BKGPU_EUNSUPPORTED; }
-            ok = lower_agg(in, out, *top, filter, *c, under_packet);
+            std::vector<const HExpr*> conj;
+            if (filter) for (auto& e : filter->conjuncts) conj.push_back(&e);
+            ok = lower_agg(in, out, *top, conj, c->tuple_id, under_packet, true);
             if (ok && limit_node) { out.limit = limit_node->limit; out.offset = limit_node->offset; }
         } else if (c && c->node_type == BK_JOIN_NODE && !filter) {
             ok = lower_join_agg(in, out, *top, *c, under_packet);
@@ -854,6 +859,53 @@ bool lower_filter(Infer& in, Compiled& out, const HNode* limit_node, const HNode
     return true;
 }
 
-bool lower_join_agg(Infer& in, Compiled&, const HNode&, const HNode&, bool) { return in.fail(BKGPU_EUNSUPPORTED, "JOIN_NODE not lowered yet"); }
+// AGG over an equi-join (config C3).  The reference builds its hash map on the OUTER (driver) child and probes
+// with the inner child's rows (JoinNode::hash_join, src/exec/join_node.cpp:920-1022; Joiner::construct_hash_map,
+// src/exec/joiner.cpp:624-631); the key is the cast equal-slot value (strip_out_equal_slots, joiner.cpp:166-217).
+// Filters of both children and the residual join conditions become one predicate over the joined row — for an
+// INNER join that is the same set of rows.
+bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& join, bool under_packet) {
+    if (join.join_type != BK_INNER_JOIN) return in.fail(BKGPU_EUNSUPPORTED, "only INNER JOIN is fused with the aggregate on the GPU path");
+    if (join.ch.size() != 2) return in.fail(BKGPU_EINVAL, "JOIN node needs two children");
+    const HNode* side[2]; const HNode* filt[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++) {
+        const HNode* c = skip_passthrough(&join.ch[(size_t)i], nullptr);
+        if (is_filter(c)) { filt[i] = c; c = c->ch.empty() ? nullptr : skip_passthrough(&c->ch[0], nullptr); }
+        if (!c || c->node_type != BK_SCAN_NODE) return in.fail(BKGPU_EUNSUPPORTED, "JOIN children must be [FILTER ->] SCAN");
+        if (filt[i] && filt[i]->limit != -1) return in.fail(BKGPU_EUNSUPPORTED, "LIMIT below a join is order dependent");
+        side[i] = c;
+    }
+    const int build_tuple = side[0]->tuple_id, probe_tuple = side[1]->tuple_id;
+    out.build_tuple = build_tuple;
+    std::vector<const HExpr*> conj;
+    const HExpr *bk = nullptr, *pk = nullptr;
+    for (auto& e : join.conjuncts) {
+        bool taken = false;
+        if (!bk && e.node_type == BK_FUNCTION_CALL && e.fn_op == BK_FT_EQ && e.ch.size() == 2 && e.ch[0].node_type == BK_SLOT_REF && e.ch[1].node_type == BK_SLOT_REF) {
+            const HExpr *a = &e.ch[0], *b = &e.ch[1];
+            if (a->tuple_id == build_tuple && b->tuple_id == probe_tuple) { bk = a; pk = b; taken = true; }
+            else if (b->tuple_id == build_tuple && a->tuple_id == probe_tuple) { bk = b; pk = a; taken = true; }
+        }
+        if (!taken) conj.push_back(&e);
+    }
+    if (!bk) return in.fail(BKGPU_EUNSUPPORTED, "join without an equality between the two tables (nested loop) is outside the GPU path");
+    for (int i = 0; i < 2; i++) if (filt[i]) for (auto& e : filt[i]->conjuncts) conj.push_back(&e);
+    int ot = bk->col_type, it = pk->col_type, cast;
+    auto is_signed_t = [](int t) { return t >= BK_INT8 && t <= BK_INT64; };
+    if (ot == it) cast = ot;
+    else if (is_signed_t(ot) && is_signed_t(it)) cast = BK_INT64;
+    else if (is_uint_t(ot) && is_uint_t(it)) cast = BK_UINT64;
+    else return in.fail(BKGPU_EUNSUPPORTED, "join keys of types %d and %d are compared as STRING in the reference: outside the GPU path", ot, it);
+    if (cast == BK_STRING || is_double_t(cast)) return in.fail(BKGPU_EUNSUPPORTED, "join key type %d is outside the GPU path", cast);
+    if (!lower_agg(in, out, agg, conj, probe_tuple, under_packet, false)) return false;
+    out.kind = PK_JOIN_AGG;
+    out.join_type = join.join_type; out.join_key_prim = cast;
+    Program dummy; memset(&dummy, 0, sizeof dummy);
+    Lower lw{&out, &in, &dummy, {}};
+    out.build_key_col = lw.intern_col(bk->tuple_id, bk->slot_id, in.slot_type(bk->tuple_id, bk->slot_id));
+    out.probe_key_col = lw.intern_col(pk->tuple_id, pk->slot_id, in.slot_type(pk->tuple_id, pk->slot_id));
+    if ((int)out.cols.size() > MAX_COLS) return in.fail(BKGPU_EUNSUPPORTED, "more than %d columns referenced", MAX_COLS);
+    return true;
+}
 
 }  // namespace bk

@@ -58,6 +58,7 @@ struct Compiled {
     // main (probe-side / only) scan
     int scan_tuple = -1;
     std::vector<ColRef> cols;          // columns the device program references (index = DevCol index)
+    std::vector<int> col_side;         // per column: 0 = probe / only scan tuple, 1 = build side of a join
     Program prog;                      // outputs: [predicate][keys...][agg args...] / sort keys
     int n_const = 0;
     // aggregate
@@ -75,8 +76,7 @@ struct Compiled {
     std::vector<SortKey> sort_keys;
     // hash join (build side = outer child, probe side = inner child; join_node.cpp:920-1022)
     int build_tuple = -1;
-    std::vector<ColRef> build_cols;    // [0] = build key column, rest = payload columns referenced above the join
-    int build_key_col = -1;            // index into build_cols
+    int build_key_col = -1;            // index into cols (side 1)
     int probe_key_col = -1;            // index into cols
     int join_type = 0;
     int join_key_prim = 0;

@@ -1,0 +1,62 @@
+"""GPU parity: hash join fused with the aggregate (K4, config C3) vs the row-engine oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from baikaldb_b200 import datagen, plan as P, queries
+from baikaldb_b200.column import make_column
+from baikaldb_b200.plan import PrimitiveType as T
+from tests.util import run_both
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c3_join_groupby():
+    fact, dim = datagen.c3_fact(0, 400_000, 20_000), datagen.c3_dim(0, 20_000, 20_000, n_groups=100)
+    got, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact])
+    assert len(got[0]) == 100
+
+
+def test_c3_streamed_in_several_batches_host_and_build_first_rule():
+    fact, dim = datagen.c3_fact(0, 90_000, 5_000), datagen.c3_dim(0, 5_000, 5_000, n_groups=17)
+    sl = lambda cols, a, b: [make_column(c.tuple_id, c.slot_id, c.prim_type, c.values[a:b]) for c in cols]
+    batches = [sl(dim, 0, 1234), sl(dim, 1234, 5_000), sl(fact, 0, 50_000), sl(fact, 50_000, 90_000)]
+    run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=batches)
+    from baikaldb_b200._lib import BkgpuError, ESTATE
+    from baikaldb_b200.exec_node import execute
+    with pytest.raises(BkgpuError) as e:   # the driver table must be complete before probing (join_node.cpp:920-1022)
+        execute(queries.c3_join_groupby(), [sl(dim, 0, 10), sl(fact, 0, 10), sl(dim, 10, 20)])
+    assert e.value.code == ESTATE
+
+
+def test_join_duplicate_build_keys_null_keys_and_residual_conditions():
+    """multi-match probes, NULL keys on both sides never match, child filters and a residual (non-equality) join
+    condition are evaluated on the joined row; mixed INT32 / INT64 keys meet in INT64 (joiner.cpp:191-200)"""
+    rng = np.random.default_rng(31)
+    nd, nf = 3_000, 60_000
+    dim = [make_column(1, 1, T.INT64, rng.integers(0, 800, nd), rng.random(nd) > 0.05), make_column(1, 2, T.INT32, rng.integers(0, 9, nd)),
+           make_column(1, 3, T.DOUBLE, rng.normal(size=nd))]
+    fact = [make_column(0, 1, T.INT32, rng.integers(-50, 900, nf), rng.random(nf) > 0.05), make_column(0, 2, T.DOUBLE, rng.random(nf), rng.random(nf) > 0.1),
+            make_column(0, 3, T.INT32, rng.integers(0, 100, nf))]
+    aggs = [P.agg_expr("count_star", 2, 1), P.agg_expr("sum", 2, 2, None, P.multiplies(P.slot_ref(0, 2, T.DOUBLE), P.slot_ref(1, 3, T.DOUBLE))),
+            P.agg_expr("max", 2, 3, None, P.slot_ref(0, 3, T.INT32)), P.agg_expr("avg", 2, 4, 5, P.slot_ref(1, 3, T.DOUBLE))]
+    outer = P.where(P.scan(1), P.ne(P.slot_ref(1, 2, T.INT32), P.int_lit(4)))
+    inner = P.where(P.scan(0), P.lt(P.slot_ref(0, 3, T.INT32), P.int_lit(80)))
+    j = P.join(outer, inner, [P.eq(P.slot_ref(0, 1, T.INT32), P.slot_ref(1, 1, T.INT64)),
+                              P.gt(P.add(P.slot_ref(0, 3, T.INT32), P.slot_ref(1, 2, T.INT32)), P.int_lit(10))])
+    root = P.agg(j, 2, [P.slot_ref(1, 2, T.INT32)], aggs)
+    pl = P.Plan(root, {0: [(1, T.INT32), (2, T.DOUBLE), (3, T.INT32)], 1: [(1, T.INT64), (2, T.INT32), (3, T.DOUBLE)],
+                       2: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE, T.INT32, T.DOUBLE])})
+    got, _, _ = run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact])
+    assert 4 not in got[0].to_list()
+
+
+def test_join_without_group_by_and_empty_sides():
+    fact, dim = datagen.c3_fact(0, 10_000, 100), datagen.c3_dim(0, 100, 100, n_groups=5)
+    aggs = [P.agg_expr("count_star", 2, 1), P.agg_expr("sum", 2, 2, None, P.slot_ref(0, 2, T.DOUBLE))]
+    j = P.join(P.scan(1), P.scan(0), [P.eq(P.slot_ref(1, 1, T.INT32), P.slot_ref(0, 1, T.INT32))])
+    pl = P.Plan(P.packet(P.agg(j, 2, [], aggs)), {0: [(1, T.INT32), (2, T.DOUBLE)], 1: [(1, T.INT32), (2, T.INT32)], 2: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE])})
+    got, _, _ = run_both(pl, fact + dim, keys=[], batches=[dim, fact])
+    assert got[0].to_list() == [10_000]
+    empty_dim = [make_column(c.tuple_id, c.slot_id, c.prim_type, c.values[:0]) for c in dim]
+    got, _, _ = run_both(pl, fact + empty_dim, keys=[], batches=[empty_dim, fact])
+    assert got[0].to_list() == [0] and got[1].to_list() == [None]
