@@ -65,6 +65,7 @@ struct bkgpu_plan {
     uint64_t* d_outv = nullptr; uint8_t* d_outn = nullptr; size_t out_cap_alloc = 0;  // extraction buffers (kept across resets)
     std::vector<uint64_t> hv; std::vector<uint8_t> hn;
     uint32_t known_groups = 0;
+    uint32_t* h_pinned = nullptr;   // [0] groups seen (async copy after every aggregate launch), pinned
     // hash join (K4): retained build side + multimap
     std::vector<uint8_t*> jb_vals, jb_nullbytes, jb_bitmap;   // per plan column (side 1 only)
     std::vector<bool> jb_has_null;
@@ -216,6 +217,7 @@ extern "C" int bkgpu_open(bkgpu_plan* p) {
     CK(p, cudaSetDevice(p->device));
     if (!p->stream) { CK(p, cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)); p->own_stream = true; }
     CK(p, cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    if (cudaHostAlloc((void**)&p->h_pinned, 64, cudaHostAllocDefault) == cudaSuccess) p->h_pinned[0] = 0; else p->h_pinned = nullptr;
     for (int i = 0; i < 2; i++) {
         CK(p, cudaEventCreateWithFlags(&p->stage_free[i], cudaEventDisableTiming));
         CK(p, cudaEventCreateWithFlags(&p->stage_ready[i], cudaEventDisableTiming));
@@ -235,6 +237,7 @@ static int pick_smem_log2(bkgpu_plan* p, int n_smem_lanes, bool direct, int na) 
     const size_t budget = 220 * 1024;
     auto bytes = [&](int log2) { return direct ? direct_smem_bytes(p->c.ap.n_keyw, n_smem_lanes, log2, na) : agg_smem_bytes(p->c.ap.n_keyw, n_smem_lanes, log2); };
     if (p->smem_cap_log2 >= 0) { int l = p->smem_cap_log2; while (l > 0 && bytes(l) > budget) l--; return l; }
+    if (p->h_pinned && p->h_pinned[0] > p->known_groups) p->known_groups = p->h_pinned[0];
     uint32_t g = p->known_groups;
     int log2 = 11;
     while (((uint32_t)1 << log2) < 2 * g && log2 < 14) log2++;
@@ -530,10 +533,8 @@ extern "C" int bkgpu_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, in
         case PK_AGG: {
             int rc = feed(p, p->c.cols, cols, ncols, nrows, on_device, agg_batch);
             if (rc) return rc;
-            if (p->c.ap.n_keyw > 0 && p->smem_cap_log2 < 0) {  // learn the cardinality for the next batch's table size
-                CK(p, cudaMemcpyAsync(&p->known_groups, p->gt.n_groups, 4, cudaMemcpyDeviceToHost, p->stream));
-                CK(p, cudaStreamSynchronize(p->stream));
-            }
+            if (p->c.ap.n_keyw > 0 && p->smem_cap_log2 < 0 && p->h_pinned)   // learn the cardinality for later batches' table size;
+                CK(p, cudaMemcpyAsync(p->h_pinned, p->gt.n_groups, 4, cudaMemcpyDeviceToHost, p->stream));  // no sync: a stale value only costs speed
             return BKGPU_OK;
         }
         case PK_JOIN_AGG: return join_push(p, cols, ncols, nrows, on_device);
@@ -574,35 +575,39 @@ static int agg_finish(bkgpu_plan* p) {
         timer_end(p, ep);
         p->stats.kernel_launches += 4;
     }
-    CK(p, cudaMemcpyAsync(host_counts, gt.n_groups, 8, cudaMemcpyDeviceToHost, p->stream));
-    CK(p, cudaStreamSynchronize(p->stream));
-    p->stats.d2h_bytes += 8;
-    if (host_counts[1]) return p->fail(BKGPU_ETOOBIG, "group table overflow (capacity 2^%d slots / partial_capacity %lld): raise group_capacity_log2",
-                                       (int)gt.cap_log2, (long long)p->partial_cap);
-    uint32_t n = ap.n_keyw == 0 ? 1 : host_counts[0];
     // device images: one per group expr, per aggregate its final (+2 for an AVG blob)
     int n_img = ap.n_group;
     for (int k = 0; k < ap.n_agg; k++) n_img += ap.agg[k].kind == AG_AVG ? 3 : 1;
-    const uint32_t out_cap = std::max<uint32_t>(n, 1);
     int rc;
-    if (p->out_cap_alloc < out_cap) {
-        dev_free(p, p->d_outv); dev_free(p, p->d_outn); p->d_outv = nullptr; p->d_outn = nullptr;
-        size_t cap = std::max<size_t>(out_cap, 4096);
-        if ((rc = dev_alloc(p, (void**)&p->d_outv, cap * 8 * (size_t)n_img))) return rc;
-        if ((rc = dev_alloc(p, (void**)&p->d_outn, cap * (size_t)n_img))) return rc;
-        p->out_cap_alloc = cap;
-    }
-    uint64_t* d_outv = p->d_outv; uint8_t* d_outn = p->d_outn;
-    CK(p, launch_extract(gt, ap, d_outv, d_outn, out_cap, p->d_cursor, p->c.emit_default ? 1 : 0, p->stream));
-    p->stats.kernel_launches++;
+    uint32_t n_out = 0, out_cap = 0;
     std::vector<uint64_t>& hv = p->hv; std::vector<uint8_t>& hn = p->hn;
-    hv.resize((size_t)out_cap * (size_t)n_img); hn.resize((size_t)out_cap * (size_t)n_img);
-    uint32_t n_out = 0;
-    CK(p, cudaMemcpyAsync(&n_out, p->d_cursor, 4, cudaMemcpyDeviceToHost, p->stream));
-    CK(p, cudaMemcpyAsync(hv.data(), d_outv, hv.size() * 8, cudaMemcpyDeviceToHost, p->stream));
-    CK(p, cudaMemcpyAsync(hn.data(), d_outn, hn.size(), cudaMemcpyDeviceToHost, p->stream));
-    CK(p, cudaStreamSynchronize(p->stream));
-    p->stats.d2h_bytes += (int64_t)(hv.size() * 8 + hn.size() + 4);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        // speculative extraction into the buffers kept from earlier runs: counts, cursor and rows come back
+        // in ONE synchronisation; only a result larger than the buffers costs a second round
+        uint32_t want = std::max<uint32_t>(std::max<uint32_t>(p->known_groups, 1), attempt ? std::max<uint32_t>(host_counts[0], 1) : 1);
+        if (ap.n_keyw == 0) want = 1;
+        if (p->out_cap_alloc < want) {
+            dev_free(p, p->d_outv); dev_free(p, p->d_outn); p->d_outv = nullptr; p->d_outn = nullptr;
+            size_t cap = std::max<size_t>(want, 2048);
+            if ((rc = dev_alloc(p, (void**)&p->d_outv, cap * 8 * (size_t)n_img))) return rc;
+            if ((rc = dev_alloc(p, (void**)&p->d_outn, cap * (size_t)n_img))) return rc;
+            p->out_cap_alloc = cap;
+        }
+        out_cap = (uint32_t)p->out_cap_alloc;
+        CK(p, launch_extract(gt, ap, p->d_outv, p->d_outn, out_cap, p->d_cursor, p->c.emit_default ? 1 : 0, p->stream));
+        p->stats.kernel_launches++;
+        hv.resize((size_t)out_cap * (size_t)n_img); hn.resize((size_t)out_cap * (size_t)n_img);
+        CK(p, cudaMemcpyAsync(host_counts, gt.n_groups, 8, cudaMemcpyDeviceToHost, p->stream));
+        CK(p, cudaMemcpyAsync(&n_out, p->d_cursor, 4, cudaMemcpyDeviceToHost, p->stream));
+        CK(p, cudaMemcpyAsync(hv.data(), p->d_outv, hv.size() * 8, cudaMemcpyDeviceToHost, p->stream));
+        CK(p, cudaMemcpyAsync(hn.data(), p->d_outn, hn.size(), cudaMemcpyDeviceToHost, p->stream));
+        CK(p, cudaStreamSynchronize(p->stream));
+        p->stats.d2h_bytes += (int64_t)(hv.size() * 8 + hn.size() + 12);
+        if (host_counts[1]) return p->fail(BKGPU_ETOOBIG, "group table overflow (capacity 2^%d slots / partial_capacity %lld): raise group_capacity_log2",
+                                           (int)gt.cap_log2, (long long)p->partial_cap);
+        if (host_counts[0] > p->known_groups) p->known_groups = host_counts[0];
+        if (n_out <= out_cap) break;   // everything fitted
+    }
     if (n_out > out_cap) n_out = out_cap;
     int64_t rows = n_out;
     int64_t skip = p->c.offset > 0 ? std::min<int64_t>(p->c.offset, rows) : 0;
@@ -748,6 +753,7 @@ extern "C" void bkgpu_close(bkgpu_plan* p) {
     if (p->sort) sort_close(p->sort);
     for (void* q : p->dev_allocs) cudaFree(q);
     for (int i = 0; i < 2; i++) { if (p->stage_free[i]) cudaEventDestroy(p->stage_free[i]); if (p->stage_ready[i]) cudaEventDestroy(p->stage_ready[i]); }
+    if (p->h_pinned) cudaFreeHost(p->h_pinned);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;

@@ -1,0 +1,82 @@
+"""Worker of the multi-GPU parity tests (launched by torch.distributed.run, one rank per GPU):
+regions -> one set per GPU, partial results merged inside bkgpu_finish by ONE ncclAllGather (+ merge kernel for
+aggregates, host merge of the k rows for top-k).  Rank 0 checks the merged result against the oracle run over
+the WHOLE table."""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from baikaldb_b200 import _lib, datagen, queries
+from baikaldb_b200.column import make_column
+from baikaldb_b200.exec_node import ColumnSource, GpuExecNode, RowBatch, RuntimeState
+from tests.util import assert_same_rows
+from oracle import oracle
+
+
+def make_comm(rank, world, dev):
+    L = _lib.lib()
+    idbuf = (ctypes.c_uint8 * 128)()
+    if rank == 0:
+        _lib.check(L.bkgpu_nccl_unique_id(idbuf))
+    t = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    idbuf = (ctypes.c_uint8 * 128)(*t.cpu().tolist())
+    comm = ctypes.c_void_p()
+    _lib.check(L.bkgpu_nccl_comm_create(ctypes.byref(comm), idbuf, world, rank, dev))
+    return comm
+
+
+def run_plan(plan, cols, comm, dev, options):
+    st = RuntimeState(device=dev, nccl_comm=comm.value, options=options)
+    node = GpuExecNode()
+    node.init(plan)
+    node.add_child(ColumnSource([cols]))
+    assert node.open(st) == 0, st.error_msg
+    out, rb, eos = [], RowBatch(), False
+    while not eos:
+        rc, eos = node.get_next(st, rb)
+        assert rc == 0, st.error_msg
+        out = rb.columns if not out else out
+    stats = node.stats()
+    node.close(st)
+    return out, stats
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dev = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    comm = make_comm(rank, world, dev)
+    n_region = 150_000
+    # ---- C4: GROUP BY over `world` regions ----
+    region = datagen.c2_table(rank * n_region, n_region, n_groups=500)
+    got, stats = run_plan(queries.c2_filter_groupby(), region, comm, dev, {})
+    assert stats.collective_ms > 0
+    whole = datagen.c2_table(0, n_region * world, n_groups=500)
+    want = oracle.execute(queries.c2_filter_groupby().serialize(), whole)
+    assert_same_rows(got, want.columns, ["0_1"])      # every rank holds the merged result
+    # ---- C5: ORDER BY ... LIMIT over regions; duplicates across regions break ties by (region, row) ----
+    rng = np.random.default_rng(77)
+    keys = rng.integers(0, 5000, n_region * world)
+    whole5 = [make_column(0, 1, 6, keys), make_column(0, 2, 5, np.arange(n_region * world, dtype=np.int32))]
+    mine = [make_column(0, 1, 6, keys[rank * n_region:(rank + 1) * n_region]), make_column(0, 2, 5, whole5[1].values[rank * n_region:(rank + 1) * n_region])]
+    got5, _ = run_plan(queries.c5_topk(1000), mine, comm, dev, {"region_base": rank * n_region})
+    want5 = oracle.execute(queries.c5_topk(1000).serialize(), whole5)
+    assert_same_rows(got5, want5.columns, None)
+    dist.barrier()
+    _lib.lib().bkgpu_nccl_comm_destroy(comm)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_OK", world)
+
+
+if __name__ == "__main__":
+    main()
