@@ -356,7 +356,9 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))
-        traffic = prof.get(r["stats"].main_kernel_name.decode())
+        entry = prof.get(r["stats"].main_kernel_name.decode())
+        if entry:  # DRAM bytes per launch, scaled from the committed ncu capture to this launch's row count
+            traffic = entry["dram_bytes_per_row"] * rows
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
