@@ -239,6 +239,105 @@ cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t
     return cudaGetLastError();
 }
 
+// ---- FK -> PK fast path (see JoinFast in agg.h) ----
+__global__ void k_join_minmax(DevCol key, int from_prim, int cast_to, int64_t nrows, uint64_t bias, uint64_t* mm) {
+    uint64_t lo = ~0ull, hi = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        if (elem_is_null(key, r)) continue;
+        const uint64_t v = cast_prim(load_elem(key, r), from_prim, cast_to) ^ bias;
+        lo = v < lo ? v : lo; hi = v > hi ? v : hi;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const uint64_t l2 = __shfl_xor_sync(0xFFFFFFFFu, lo, d), h2 = __shfl_xor_sync(0xFFFFFFFFu, hi, d);
+        lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin((unsigned long long*)mm, (unsigned long long)lo); atomicMax((unsigned long long*)(mm + 1), (unsigned long long)hi); }
+}
+__global__ void k_join_build_fast(DevCol key, int from_prim, int cast_to, int64_t nrows, JoinFast jf, uint32_t* dense_w, uint64_t* packed_w, uint32_t* dup_flag) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        if (elem_is_null(key, r)) continue;   // a NULL key never matches
+        const uint64_t img = cast_prim(load_elem(key, r), from_prim, cast_to);
+        if (jf.mode == 1) {
+            if (atomicExch(dense_w + ((img ^ jf.bias) - jf.dense_min), (uint32_t)r) != 0xFFFFFFFFu) atomicExch(dup_flag, 1u);
+        } else {
+            const uint32_t k32 = (uint32_t)img;
+            const uint64_t v = ((uint64_t)k32 << 32) | (uint32_t)r;
+            uint32_t slot = (k32 * 0x9E3779B1u) & jf.packed_mask;
+            for (;;) {
+                const uint64_t old = atomicCAS((unsigned long long*)(packed_w + slot), ~0ull, (unsigned long long)v);
+                if (old == ~0ull) break;
+                if ((uint32_t)(old >> 32) == k32) { atomicExch(dup_flag, 1u); break; }   // duplicate key: not a PK
+                slot = (slot + 1) & jf.packed_mask;
+            }
+        }
+    }
+}
+__device__ __forceinline__ uint32_t join_lookup(const JoinFast& jf, uint64_t img) {
+    if (jf.mode == 1) {
+        const uint64_t off = (img ^ jf.bias) - jf.dense_min;
+        return off < jf.dense_size ? __ldg(jf.dense + off) : 0xFFFFFFFFu;
+    }
+    const uint32_t k32 = (uint32_t)img;
+    uint32_t slot = (k32 * 0x9E3779B1u) & jf.packed_mask;
+    for (;;) {
+        const uint64_t v = __ldg((const unsigned long long*)(jf.packed + slot));
+        if (v == ~0ull) return 0xFFFFFFFFu;
+        if ((uint32_t)(v >> 32) == k32) return (uint32_t)v;
+        slot = (slot + 1) & jf.packed_mask;
+    }
+}
+// gather the build-side columns to probe-row alignment; four independent rows per thread keep the random
+// lookups and gathers in flight together
+__global__ void __launch_bounds__(256) k_join_gather(DevCol pk, int from_prim, int cast_to, int64_t nrows, JoinFast jf, GatherCols gc, uint32_t* miss_flag) {
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    bool miss = false;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < nrows; base += 4 * T) {
+        uint32_t br[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t r = base + u * T;
+            br[u] = 0xFFFFFFFEu;   // beyond the batch
+            if (r < nrows) br[u] = elem_is_null(pk, r) ? 0xFFFFFFFFu : join_lookup(jf, cast_prim(load_elem(pk, r), from_prim, cast_to));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t r = base + u * T;
+            if (br[u] == 0xFFFFFFFEu) continue;
+            if (br[u] == 0xFFFFFFFFu) { miss = true; continue; }
+            for (int c = 0; c < gc.n; c++) {
+                if (gc.elem[c] == 8) ((uint64_t*)gc.dst[c])[r] = __ldg((const unsigned long long*)gc.src[c] + br[u]);
+                else if (gc.elem[c] == 4) ((uint32_t*)gc.dst[c])[r] = __ldg((const uint32_t*)gc.src[c] + br[u]);
+                else gc.dst[c][r] = __ldg(gc.src[c] + br[u]);
+            }
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, miss) && (threadIdx.x & 31) == 0) atomicExch(miss_flag, 1u);
+}
+cudaError_t launch_join_minmax(const DevCol& key, int from_prim, int cast_prim_, int64_t nrows, uint64_t bias, uint64_t* mm, cudaStream_t s) {
+    const uint64_t init[2] = {~0ull, 0ull};
+    cudaError_t e = cudaMemcpyAsync(mm, init, 16, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess || nrows == 0) return e;
+    int grid = (int)((nrows + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
+    k_join_minmax<<<grid, 256, 0, s>>>(key, from_prim, cast_prim_, nrows, bias, mm);
+    return cudaGetLastError();
+}
+cudaError_t launch_join_build_fast(const DevCol& key, int from_prim, int cast_prim_, int64_t nrows, const JoinFast& jf, uint32_t* dense_w, uint64_t* packed_w, uint32_t* dup_flag, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(dup_flag, 0, 4, s);
+    if (e != cudaSuccess) return e;
+    if (jf.mode == 1) e = cudaMemsetAsync(dense_w, 0xFF, jf.dense_size * 4, s); else e = cudaMemsetAsync(packed_w, 0xFF, ((size_t)jf.packed_mask + 1) * 8, s);
+    if (e != cudaSuccess || nrows == 0) return e;
+    int grid = (int)((nrows + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    k_join_build_fast<<<grid, 256, 0, s>>>(key, from_prim, cast_prim_, nrows, jf, dense_w, packed_w, dup_flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_join_gather(const DevCol& probe_key, int from_prim, int cast_prim_, int64_t nrows, const JoinFast& jf, const GatherCols& gc, uint32_t* miss_flag, cudaStream_t s) {
+    if (nrows == 0) return cudaSuccess;
+    int grid = (int)((nrows + 1023) / 1024); if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
+    k_join_gather<<<grid, 256, 0, s>>>(probe_key, from_prim, cast_prim_, nrows, jf, gc, miss_flag);
+    return cudaGetLastError();
+}
+
 __global__ void k_unpack_validity(const uint8_t* bitmap, int64_t n, uint8_t* null_bytes) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         null_bytes[i] = bitmap ? (((bitmap[i >> 3] >> (i & 7)) & 1) ? 0 : 1) : 0;

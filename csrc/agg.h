@@ -42,6 +42,17 @@ cudaError_t launch_direct_np1(const AggArgs& a, int na, int sm_count, size_t sme
 cudaError_t launch_direct_np2(const AggArgs& a, int na, int sm_count, size_t smem, cudaStream_t s, bool grouped);
 size_t direct_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2, int na);
 cudaError_t launch_join_build(const DevCol& key, int from_prim, int cast_prim, int64_t nrows, uint64_t* keys, uint32_t* rows, uint32_t cap_mask, cudaStream_t s);
+// FK -> PK join fast path: unique build keys, looked up through a dense array (small key range) or a packed
+// (key32 << 32 | row) table; build-side columns are gathered to probe-row alignment
+struct JoinFast {
+    int32_t mode;               // 0 = none, 1 = dense array, 2 = packed 32-bit-key table
+    const uint32_t* dense; uint64_t dense_min; uint64_t dense_size; uint64_t bias;
+    const uint64_t* packed; uint32_t packed_mask;
+};
+struct GatherCols { int32_t n; const uint8_t* src[MAX_COLS]; uint8_t* dst[MAX_COLS]; int32_t elem[MAX_COLS]; };
+cudaError_t launch_join_minmax(const DevCol& key, int from_prim, int cast_prim, int64_t nrows, uint64_t bias, uint64_t* mm, cudaStream_t s);
+cudaError_t launch_join_build_fast(const DevCol& key, int from_prim, int cast_prim, int64_t nrows, const JoinFast& jf, uint32_t* dense_w, uint64_t* packed_w, uint32_t* dup_flag, cudaStream_t s);
+cudaError_t launch_join_gather(const DevCol& probe_key, int from_prim, int cast_prim, int64_t nrows, const JoinFast& jf, const GatherCols& gc, uint32_t* miss_flag, cudaStream_t s);
 cudaError_t launch_unpack_validity(const uint8_t* bitmap, int64_t n, uint8_t* null_bytes, cudaStream_t s);
 cudaError_t launch_pack_validity(const uint8_t* null_bytes, int64_t n, uint8_t* bitmap, cudaStream_t s);
 cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStream_t s);

@@ -70,7 +70,9 @@ struct bkgpu_plan {
     std::vector<uint8_t*> jb_vals, jb_nullbytes, jb_bitmap;   // per plan column (side 1 only)
     std::vector<bool> jb_has_null;
     int64_t jb_rows = 0, jb_cap = 0;
-    uint64_t* jt_keys = nullptr; uint32_t* jt_rows = nullptr; uint32_t jt_mask = 0; bool jt_built = false;
+    uint64_t* jt_keys = nullptr; uint32_t* jt_rows = nullptr; uint32_t jt_mask = 0; bool jt_built = false, jt_generic = false;
+    JoinFast jf{}; uint32_t* jf_dense = nullptr; uint64_t* jf_packed = nullptr;   // FK -> PK fast path (unique build keys)
+    std::vector<uint8_t*> jg_buf; int64_t jg_rows = 0;                            // gathered build columns, one chunk
     std::vector<ColRef> probe_want; std::vector<int> probe_map;   // probe-side columns and their index in c.cols
     // sort / filter state
     SortState* sort = nullptr;
@@ -246,15 +248,14 @@ static int pick_smem_log2(bkgpu_plan* p, int n_smem_lanes, bool direct, int na) 
     return log2;
 }
 
-static int launch_agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, bool vec_ok) {
-    const Compiled& c = p->c;
+static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols, int64_t nrows, bool vec_ok) {
     AggArgs a; memset(&a, 0, sizeof a);
     a.plan = c.ap; a.prog = c.prog; a.direct = c.direct; a.gt = p->gt; a.rows_passed = p->d_rows_passed;
     if (c.kind == PK_JOIN_AGG) {
         a.join.enabled = 1; a.join.keys = p->jt_keys; a.join.rows = p->jt_rows; a.join.cap_mask = p->jt_mask;
         a.join.probe_col = c.probe_key_col; a.join.probe_prim = c.cols[(size_t)c.probe_key_col].prim; a.join.cast_prim = c.join_key_prim;
     }
-    const bool direct = c.has_direct && vec_ok && !p->force_generic && c.kind == PK_AGG;
+    const bool direct = c.has_direct && vec_ok && !p->force_generic && c.kind == PK_AGG;   // (the join's fast-path plan is lowered as PK_AGG)
     const int ncols = (int)c.cols.size();
     if (direct) { for (size_t i = 0; i < c.direct_cols.size(); i++) a.cols[i] = cols[c.direct_cols[i]]; a.n_cols = (int)c.direct_cols.size(); }
     else { for (int i = 0; i < ncols; i++) a.cols[i] = cols[i]; a.n_cols = ncols; }
@@ -415,7 +416,7 @@ static int feed(bkgpu_plan* p, const std::vector<ColRef>& want, const bkgpu_colu
     return BKGPU_OK;
 }
 
-static int agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, int64_t, bool vec_ok) { return launch_agg_batch(p, cols, nrows, vec_ok); }
+static int agg_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, int64_t, bool vec_ok) { return launch_agg_batch(p, p->c, cols, nrows, vec_ok); }
 static int sort_batch(bkgpu_plan* p, const DevCol* cols, int64_t nrows, int64_t, bool) {
     int rc = sort_push(p->sort, cols, nrows, p->stream, &p->stats, p->last_error);
     if (rc) g_thread_error = p->last_error;
@@ -486,6 +487,56 @@ static int join_build_table(bkgpu_plan* p) {
         CK(p, launch_pack_validity(p->jb_nullbytes[i], p->jb_rows, p->jb_bitmap[i], p->stream));
         p->stats.kernel_launches++;
     }
+    DevCol key{};
+    const size_t ki = (size_t)c.build_key_col;
+    key.values = p->jb_vals[ki]; key.validity = p->jb_bitmap[ki]; key.stype = prim_storage(c.cols[ki].prim); key.prim = c.cols[ki].prim;
+    p->jt_built = true; p->jt_generic = false;   // the multimap of the general probe is built on first use (join_generic_table)
+    // ---- FK -> PK fast path: are the build keys unique, and is their range dense or their type <= 32 bits? ----
+    p->jf = JoinFast{};
+    if (p->jg_buf.empty()) p->jg_buf.assign(nc, nullptr);
+    bool build_nulls = false;
+    for (size_t i = 0; i < nc; i++) if (c.col_side[i] == 1 && p->jb_has_null[i]) build_nulls = true;   // gathered columns must be NULL-free
+    if (c.jfast && !build_nulls && p->jb_rows > 0) {
+        const int cls = host_prim_class(c.join_key_prim);
+        const uint64_t bias = cls == VC_I64 ? 0x8000000000000000ull : 0ull;
+        uint64_t* mm = nullptr; uint32_t* dup = nullptr;
+        if ((rc = dev_alloc(p, (void**)&mm, 16))) return rc;
+        if ((rc = dev_alloc(p, (void**)&dup, 8))) return rc;
+        CK(p, launch_join_minmax(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, bias, mm, p->stream));
+        uint64_t h_mm[2];
+        CK(p, cudaMemcpyAsync(h_mm, mm, 16, cudaMemcpyDeviceToHost, p->stream));
+        CK(p, cudaStreamSynchronize(p->stream));
+        JoinFast jf{}; jf.bias = bias;
+        const uint64_t range = h_mm[1] >= h_mm[0] ? h_mm[1] - h_mm[0] + 1 : 0;
+        const int kb = storage_bytes(prim_storage(c.join_key_prim));
+        if (range > 0 && range <= (uint64_t)4 * (uint64_t)p->jb_rows + 1024 && range <= (1ull << 30)) {
+            jf.mode = 1; jf.dense_min = h_mm[0]; jf.dense_size = range;
+            dev_free(p, p->jf_dense); if ((rc = dev_alloc(p, (void**)&p->jf_dense, (size_t)range * 4))) return rc;
+            jf.dense = p->jf_dense;
+        } else if (kb <= 4) {
+            uint32_t pc = 1024; while ((int64_t)pc < 2 * p->jb_rows) pc <<= 1;
+            jf.mode = 2; jf.packed_mask = pc - 1;
+            dev_free(p, p->jf_packed); if ((rc = dev_alloc(p, (void**)&p->jf_packed, (size_t)pc * 8))) return rc;
+            jf.packed = p->jf_packed;
+        }
+        if (jf.mode) {
+            CK(p, launch_join_build_fast(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, jf, p->jf_dense, p->jf_packed, dup, p->stream));
+            uint32_t h_dup = 0;
+            CK(p, cudaMemcpyAsync(&h_dup, dup, 4, cudaMemcpyDeviceToHost, p->stream));
+            CK(p, cudaStreamSynchronize(p->stream));
+            p->stats.kernel_launches += 2;
+            if (!h_dup) p->jf = jf;   // unique keys: the gather path is valid
+        }
+        dev_free(p, mm); dev_free(p, dup);
+    }
+    return BKGPU_OK;
+}
+
+// the general probe's multimap (duplicate build keys, unmatched probe rows): built only when a batch needs it
+static int join_generic_table(bkgpu_plan* p) {
+    if (p->jt_generic) return BKGPU_OK;
+    const Compiled& c = p->c;
+    int rc;
     uint32_t cap = 1024;
     while ((int64_t)cap < 2 * p->jb_rows) cap <<= 1;
     dev_free(p, p->jt_keys); dev_free(p, p->jt_rows);
@@ -497,7 +548,7 @@ static int join_build_table(bkgpu_plan* p) {
     key.values = p->jb_vals[ki]; key.validity = p->jb_bitmap[ki]; key.stype = prim_storage(c.cols[ki].prim); key.prim = c.cols[ki].prim;
     CK(p, launch_join_build(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, p->jt_keys, p->jt_rows, p->jt_mask, p->stream));
     p->stats.kernel_launches++;
-    p->jt_built = true;
+    p->jt_generic = true;
     return BKGPU_OK;
 }
 
@@ -508,7 +559,58 @@ static int join_probe_batch(bkgpu_plan* p, const DevCol* probe_cols, int64_t nro
         if (c.col_side[i] == 1) { all[i].values = p->jb_vals[i]; all[i].validity = p->jb_bitmap[i]; all[i].stype = prim_storage(c.cols[i].prim); all[i].prim = c.cols[i].prim; }
     }
     for (size_t w = 0; w < p->probe_map.size(); w++) all[(size_t)p->probe_map[w]] = probe_cols[w];
-    return launch_agg_batch(p, all.data(), nrows, false);
+    // ---- FK -> PK fast path: gather the build columns next to the probe rows, then the ordinary (lean) aggregate ----
+    if (p->jf.mode != 0 && c.jfast && !p->force_generic) {
+        const Compiled& f = *c.jfast;
+        const int64_t chunk = 16 << 20;   // the gathered chunk is re-read immediately: keep it L2-sized
+        for (int64_t off = 0; off < nrows; off += chunk) {
+            const int64_t n = std::min(chunk, nrows - off);
+            GatherCols gc{}; std::vector<DevCol> fc(f.cols.size());
+            int rc;
+            for (size_t i = 0; i < f.cols.size(); i++) {
+                const size_t m = (size_t)c.jfast_of_main[i];
+                const size_t eb = (size_t)storage_bytes(prim_storage(c.cols[m].prim));
+                if (c.col_side[m] == 1) {
+                    if (!p->jg_buf[m] || p->jg_rows < n) {
+                        dev_free(p, p->jg_buf[m]); p->jg_buf[m] = nullptr;
+                        if ((rc = dev_alloc(p, (void**)&p->jg_buf[m], (size_t)chunk * eb))) return rc;
+                    }
+                    gc.src[gc.n] = p->jb_vals[m]; gc.dst[gc.n] = p->jg_buf[m]; gc.elem[gc.n] = (int32_t)eb; gc.n++;
+                    fc[i].values = p->jg_buf[m]; fc[i].validity = nullptr; fc[i].stype = prim_storage(c.cols[m].prim); fc[i].prim = c.cols[m].prim;
+                } else {
+                    fc[i] = all[m];
+                    fc[i].values = (const uint8_t*)all[m].values + (size_t)off * eb;
+                    if (all[m].validity) fc[i].validity = all[m].validity + off / 8;
+                }
+            }
+            p->jg_rows = chunk;
+            DevCol pk = all[(size_t)c.probe_key_col];
+            pk.values = (const uint8_t*)pk.values + (size_t)off * (size_t)storage_bytes(pk.stype);
+            if (pk.validity) pk.validity += off / 8;
+            CK(p, cudaMemsetAsync(p->d_cursor + 1, 0, 4, p->stream));
+            CK(p, launch_join_gather(pk, c.cols[(size_t)c.probe_key_col].prim, c.join_key_prim, n, p->jf, gc, p->d_cursor + 1, p->stream));
+            p->stats.kernel_launches++;
+            uint32_t miss = 0;
+            CK(p, cudaMemcpyAsync(&miss, p->d_cursor + 1, 4, cudaMemcpyDeviceToHost, p->stream));
+            CK(p, cudaStreamSynchronize(p->stream));
+            if (miss) {   // some probe row has no partner (or a NULL key): this chunk takes the general probe
+                std::vector<DevCol> sl(all);
+                for (size_t i = 0; i < sl.size(); i++) if (c.col_side[i] == 0) {
+                    sl[i].values = (const uint8_t*)all[i].values + (size_t)off * (size_t)storage_bytes(all[i].stype);
+                    if (all[i].validity) sl[i].validity = all[i].validity + off / 8;
+                }
+                if ((rc = join_generic_table(p))) return rc;
+                if ((rc = launch_agg_batch(p, c, sl.data(), n, false))) return rc;
+            } else {
+                bool vec_ok = true;
+                for (auto& d : fc) if (((uintptr_t)d.values & 31) != 0) vec_ok = false;
+                if ((rc = launch_agg_batch(p, f, fc.data(), n, vec_ok))) return rc;
+            }
+        }
+        return BKGPU_OK;
+    }
+    { int rc = join_generic_table(p); if (rc) return rc; }
+    return launch_agg_batch(p, c, all.data(), nrows, false);
 }
 
 static int join_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device) {
@@ -734,7 +836,7 @@ extern "C" int bkgpu_reset(bkgpu_plan* p) {
         CK(p, launch_table_init(p->gt, p->c.ap, p->stream));
         p->stats.kernel_launches++;
     }
-    p->jb_rows = 0; p->jt_built = false; std::fill(p->jb_has_null.begin(), p->jb_has_null.end(), false);
+    p->jb_rows = 0; p->jt_built = false; p->jt_generic = false; std::fill(p->jb_has_null.begin(), p->jb_has_null.end(), false);
     if (p->sort) { int rc = sort_reset(p->sort, p->stream, p->last_error); if (rc) { g_thread_error = p->last_error; return rc; } }
     p->result.clear(); p->result_rows = 0; p->result_pos = 0;
     bkgpu_stats z{}; z.kernel_launches = p->stats.kernel_launches; p->stats = z;

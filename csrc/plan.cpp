@@ -905,6 +905,23 @@ bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& joi
     out.build_key_col = lw.intern_col(bk->tuple_id, bk->slot_id, in.slot_type(bk->tuple_id, bk->slot_id));
     out.probe_key_col = lw.intern_col(pk->tuple_id, pk->slot_id, in.slot_type(pk->tuple_id, pk->slot_id));
     if ((int)out.cols.size() > MAX_COLS) return in.fail(BKGPU_EUNSUPPORTED, "more than %d columns referenced", MAX_COLS);
+    // fast path: lower the same aggregate again with every column treated as a column of ONE (virtual, joined) tuple
+    {
+        auto jf = std::make_shared<Compiled>();
+        jf->tuples = out.tuples; jf->build_tuple = -1;
+        Infer in2{&jf->tuples};
+        if (lower_agg(in2, *jf, agg, conj, probe_tuple, under_packet, true) && memcmp(&jf->ap.n_keyw, &out.ap.n_keyw, sizeof(int32_t) * 4) == 0 &&
+            jf->ap.n_lanes == out.ap.n_lanes) {
+            bool ok = true;
+            for (auto& c : jf->cols) {
+                int m = -1;
+                for (size_t i = 0; i < out.cols.size(); i++) if (out.cols[i].tuple_id == c.tuple_id && out.cols[i].slot_id == c.slot_id) m = (int)i;
+                if (m < 0) ok = false;
+                out.jfast_of_main.push_back(m);
+            }
+            if (ok) out.jfast = jf; else out.jfast_of_main.clear();
+        }
+    }
     return true;
 }
 

@@ -3,6 +3,7 @@
 // bkgpu_plan_explain() works on a machine without a GPU.
 #pragma once
 #include <stdint.h>
+#include <memory>
 #include <string>
 #include <vector>
 #include "dev_types.h"
@@ -80,6 +81,10 @@ struct Compiled {
     int probe_key_col = -1;            // index into cols
     int join_type = 0;
     int join_key_prim = 0;
+    // FK -> PK fast path: the same aggregate lowered over the virtual joined tuple (build-side columns are gathered
+    // to probe-row alignment first); usable while every probe row has exactly one match
+    std::shared_ptr<Compiled> jfast;
+    std::vector<int> jfast_of_main;    // for every column of jfast->cols: index of the same column in this->cols
     std::string explain;
 };
 

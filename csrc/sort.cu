@@ -94,9 +94,10 @@ __global__ void k_sample_rows(RowArgs a, int want_cls, uint64_t* skey, uint64_t*
 }
 
 // compaction of the rows whose composite key is <= (tk, ti): warp-ballot positions, one atomic per warp
-__global__ void __launch_bounds__(256) k_collect_rows(RowArgs a, int want_cls, uint64_t tk, uint64_t ti, uint64_t* okey, uint64_t* oidx,
+__global__ void __launch_bounds__(256) k_collect_rows(RowArgs a, int want_cls, const uint64_t* thr, uint64_t* okey, uint64_t* oidx,
                                                       uint32_t* ocount, uint32_t cap, uint32_t* class_count) {
     const int lane = threadIdx.x & 31;
+    const uint64_t tk = thr[0], ti = thr[1];   // threshold produced on the device by k_sort_small: no host round trip
     uint32_t seen = 0;
     for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane); base < a.nrows; base += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = base + lane;
@@ -119,19 +120,85 @@ __global__ void __launch_bounds__(256) k_collect_rows(RowArgs a, int want_cls, u
     if (lane == 0 && seen && class_count) atomicAdd(class_count, seen);
 }
 
+// level 1 for the direct shape (plain NULL-free key column, config C5): four keys per lane and load (LDG.256 / LDG.128),
+// two loads in flight; candidates are rare (~1 % of the rows), so the compaction slow path is off the hot loop
+template <int KEY_BYTES>
+__global__ void __launch_bounds__(256) k_collect_rows_vec(RowArgs a, const uint64_t* thr, uint64_t* okey, uint64_t* oidx, uint32_t* ocount,
+                                                          uint32_t cap, uint32_t* class_count) {
+    // candidates are staged per CTA in shared memory and leave with ONE global atomic per CTA: ~1M candidates
+    // hammering a single global counter cost 0.8 ms on their own (profiles/r01_topk_history.md)
+    constexpr uint32_t STAGE = 2048;
+    __shared__ uint64_t s_key[STAGE], s_idx[STAGE];
+    __shared__ uint32_t s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const uint64_t tk = thr[0], ti = thr[1];
+    const DevCol& c = a.cols[a.key.col];
+    const int vclass = a.key.vclass, desc = a.key.desc;
+    const bool sext = c.stype == ST_I32;
+    const int64_t nquads = a.nrows >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto emit = [&](uint64_t img, uint64_t idx) {
+        const uint32_t pos = atomicAdd(&s_n, 1u);
+        if (pos < STAGE) { s_key[pos] = img; s_idx[pos] = idx; }
+        else { const uint32_t g = atomicAdd(ocount, 1u); if (g < cap) { okey[g] = img; oidx[g] = idx; } }   // stage full: rare
+    };
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += 2 * stride) {
+        uint64_t v[8];
+        const bool second = q + stride < nquads;
+        if (KEY_BYTES == 8) {
+            const U64x4 r0 = ldg256_u64((const uint8_t*)c.values + q * 32);
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = r0.v[j];
+            if (second) { const U64x4 r1 = ldg256_u64((const uint8_t*)c.values + (q + stride) * 32);
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[4 + j] = r1.v[j]; }
+        } else {
+            const U32x4 r0 = ldg128_u32((const uint8_t*)c.values + q * 16);
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = sext ? (uint64_t)(int64_t)(int32_t)r0.v[j] : (uint64_t)r0.v[j];
+            if (second) { const U32x4 r1 = ldg128_u32((const uint8_t*)c.values + (q + stride) * 16);
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[4 + j] = sext ? (uint64_t)(int64_t)(int32_t)r1.v[j] : (uint64_t)r1.v[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j >= 4 && !second) break;
+            const uint64_t img = key_image(v[j], vclass, desc);
+            if (img > tk) continue;                                    // the common case: not a candidate
+            const uint64_t idx = a.row_base + (uint64_t)((j < 4 ? q : q + stride) * 4 + (j & 3));
+            if (comp_le(img, idx, tk, ti)) emit(img, idx);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (a.nrows & 3)) {   // ragged tail
+        const int64_t row = (a.nrows & ~(int64_t)3) + threadIdx.x;
+        const uint64_t img = key_image(load_elem(c, row), vclass, desc);
+        if (comp_le(img, a.row_base + (uint64_t)row, tk, ti)) emit(img, a.row_base + (uint64_t)row);
+    }
+    __syncthreads();
+    const uint32_t n = min(s_n, STAGE);
+    if (threadIdx.x == 0) s_base = n ? atomicAdd(ocount, n) : 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t g = s_base + i; if (g < cap) { okey[g] = s_key[i]; oidx[g] = s_idx[i]; } }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && class_count) atomicAdd(class_count, (uint32_t)min(a.nrows, (int64_t)0xFFFFFFFFll));  // no NULLs, no filter: every row is of this class
+}
+
 // ---- level >= 2 kernels: on (key, idx) candidate arrays ----
-__global__ void k_sample_pairs(const uint64_t* key, const uint64_t* idx, uint32_t n, uint64_t* skey, uint64_t* sidx, uint32_t* scount, uint64_t salt) {
+__global__ void k_sample_pairs(const uint64_t* key, const uint64_t* idx, const uint32_t* n_ptr, uint32_t cap, uint64_t* skey, uint64_t* sidx, uint32_t* scount, uint64_t salt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= SAMPLE_N) return;
+    const uint32_t n = min(*n_ptr, cap);
     const uint64_t lo = (uint64_t)i * n / SAMPLE_N, hi = (uint64_t)(i + 1) * n / SAMPLE_N;
     if (hi <= lo) return;
     const uint64_t p = lo + mix64d(salt + i) % (hi - lo);
     const uint32_t pos = atomicAdd(scount, 1u);
     skey[pos] = key[p]; sidx[pos] = idx[p];
 }
-__global__ void __launch_bounds__(256) k_collect_pairs(const uint64_t* key, const uint64_t* idx, uint32_t n, uint64_t tk, uint64_t ti,
+__global__ void __launch_bounds__(256) k_collect_pairs(const uint64_t* key, const uint64_t* idx, const uint32_t* n_ptr, const uint64_t* thr,
                                                        uint64_t* okey, uint64_t* oidx, uint32_t* ocount, uint32_t cap) {
     const int lane = threadIdx.x & 31;
+    const uint32_t n = min(*n_ptr, cap);
+    const uint64_t tk = thr[0], ti = thr[1];
     for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + lane;
         const bool take = i < n && comp_le(key[i], idx[i], tk, ti);
@@ -151,7 +218,8 @@ __global__ void __launch_bounds__(256) k_collect_pairs(const uint64_t* key, cons
 __global__ void __launch_bounds__(1024) k_sort_small(const uint64_t* k1, const uint64_t* i1, const uint32_t* n1p, uint32_t n1max,
                                                      const uint64_t* k2, const uint64_t* i2, uint32_t n2,
                                                      uint64_t* okey, uint64_t* oidx, uint32_t keep, uint32_t* out_n,
-                                                     uint32_t rank, uint64_t* rank_out) {
+                                                     uint32_t rank, uint64_t* rank_out,
+                                                     const uint32_t* pop_ptr, uint32_t k_want, uint32_t widen, uint32_t room, const uint64_t* cap_thr) {
     extern __shared__ __align__(16) unsigned char sm[];
     uint64_t* sk = (uint64_t*)sm; uint64_t* si = sk + SMALL_N;
     uint32_t n1 = n1p ? *n1p : n1max; if (n1 > n1max) n1 = n1max;
@@ -179,7 +247,21 @@ __global__ void __launch_bounds__(1024) k_sort_small(const uint64_t* k1, const u
     if (okey) for (uint32_t i = threadIdx.x; i < nk; i += blockDim.x) { okey[i] = sk[i]; oidx[i] = si[i]; }
     if (threadIdx.x == 0) {
         if (out_n) *out_n = nk;
-        if (rank_out) { const uint32_t r = n == 0 ? 0 : (rank < n ? rank : n - 1); rank_out[0] = n ? sk[r] : ~0ull; rank_out[1] = n ? si[r] : ~0ull; rank_out[2] = n; }
+        if (rank_out) {
+            // threshold for the next compaction: the sample (n entries of a population of *pop_ptr) at a rank that
+            // leaves >= k_want population members below it with overwhelming probability; +inf when the population
+            // already fits `room` or the sample is too small to say anything
+            uint64_t tk = ~0ull, ti = ~0ull;
+            uint32_t r = rank;
+            if (pop_ptr) {
+                const double pop = (double)*pop_ptr;
+                if (pop <= (double)room) r = 0xFFFFFFFFu;
+                else { double w = ((double)k_want * (double)SAMPLE_N / pop * 1.5 + 32.0) * (double)widen; r = w >= (double)(SAMPLE_N - 1) ? 0xFFFFFFFFu : (uint32_t)w; }
+            }
+            if (n > 0 && r < n) { tk = sk[r]; ti = si[r]; }
+            if (cap_thr && comp_lt(cap_thr[0], cap_thr[1], tk, ti)) { tk = cap_thr[0]; ti = cap_thr[1]; }   // never looser than the k-th row kept so far
+            rank_out[0] = tk; rank_out[1] = ti; rank_out[2] = n;
+        }
     }
 }
 
@@ -406,6 +488,7 @@ struct SortState {
     int64_t k = -1;                 // rows to keep; -1 = all
     uint64_t row_base = 0, region_base = 0;
     bool topk = false;              // single key + limit: selection path
+    bool used_vec = false;
     Pool pool[2];
     // scratch for selection
     uint64_t *cand_key[2] = {nullptr, nullptr}, *cand_idx[2] = {nullptr, nullptr}; uint32_t cand_cap = 0;
@@ -459,98 +542,75 @@ int grid_for(int64_t n, int per_block, int sm) { int64_t g = (n + per_block - 1)
 int select_topk_class(SortState* s, const RowArgs& ra, int cls, cudaStream_t st, bkgpu_stats* stats, std::string& err) {
     Pool& P = s->pool[cls - 1];
     const uint32_t k = (uint32_t)s->k;
-    uint32_t* cnt = s->d_counts;
-    // level 1: from the batch columns into cand[0]
-    uint64_t tk = ~0ull, ti = ~0ull;
-    uint32_t n_cand = 0;
-    bool collected = false;
-    uint32_t h_counts[8];
-    uint64_t h_rank[3];
-    if (P.n >= k) {   // threshold = the k-th composite key kept so far: later rows must beat it
-        SCK(cudaMemcpyAsync(&tk, P.key[P.cur] + (k - 1), 8, cudaMemcpyDeviceToHost, st));
-        SCK(cudaMemcpyAsync(&ti, P.idx[P.cur] + (k - 1), 8, cudaMemcpyDeviceToHost, st));
-        SCK(cudaStreamSynchronize(st));
-    } else if (ra.nrows > (int64_t)s->cand_cap / 2) {
-        // estimate a threshold from SAMPLE_N stratified random rows: the rank-r sample bounds ~ r * n / SAMPLE_N rows
-        for (int attempt = 0; attempt < 6 && !collected; attempt++) {
-            SCK(cudaMemsetAsync(cnt, 0, 32, st));
-            k_sample_rows<<<(SAMPLE_N + 255) / 256, 256, 0, st>>>(ra, cls, s->samp_key, s->samp_idx, cnt, 0x5bd1e995ull + attempt * 7919);
-            double frac = (double)SAMPLE_N / (double)ra.nrows;
-            double want = ((double)k * frac * 1.5 + 32.0) * (double)(1 << attempt);   // widen on every retry
-            uint32_t rank = (uint32_t)std::min<double>(want, SAMPLE_N - 1);
-            k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, rank, s->d_rank);
-            SCK(cudaMemcpyAsync(h_rank, s->d_rank, 24, cudaMemcpyDeviceToHost, st));
-            SCK(cudaStreamSynchronize(st));
-            stats->kernel_launches += 2;
-            if (h_rank[2] == 0) { tk = ~0ull; ti = ~0ull; }                       // no row of this class in the sample: take everything
-            else if (h_rank[2] <= rank) { tk = ~0ull; ti = ~0ull; }                // fewer sampled rows than the rank: threshold = +inf
-            else { tk = h_rank[0]; ti = h_rank[1]; }
-            SCK(cudaMemsetAsync(cnt + 1, 0, 12, st));
-            k_collect_rows<<<grid_for(ra.nrows, 256, s->sm_count), 256, 0, st>>>(ra, cls, tk, ti, s->cand_key[0], s->cand_idx[0], cnt + 1, s->cand_cap, cnt + 3);
-            SCK(cudaMemcpyAsync(h_counts, cnt, 32, cudaMemcpyDeviceToHost, st));
-            SCK(cudaStreamSynchronize(st));
-            stats->kernel_launches += 1;
-            const uint32_t class_rows = h_counts[3];
-            if (h_counts[1] > s->cand_cap) continue;                              // threshold too loose for the buffer (halve is implicit: new sample)
-            if (h_counts[1] < k && h_counts[1] < class_rows) continue;            // too tight: retry wider
-            n_cand = h_counts[1]; collected = true;
-        }
-        if (!collected) return fail(err, BKGPU_ETOOBIG, "top-k selection did not converge (candidate buffer too small for this key distribution)");
-    }
-    if (!collected) {
-        SCK(cudaMemsetAsync(cnt + 1, 0, 12, st));
-        k_collect_rows<<<grid_for(ra.nrows, 256, s->sm_count), 256, 0, st>>>(ra, cls, tk, ti, s->cand_key[0], s->cand_idx[0], cnt + 1, s->cand_cap, cnt + 3);
-        SCK(cudaMemcpyAsync(h_counts, cnt, 32, cudaMemcpyDeviceToHost, st));
-        SCK(cudaStreamSynchronize(st));
-        stats->kernel_launches += 1;
-        if (h_counts[1] > s->cand_cap) return fail(err, BKGPU_ETOOBIG, "top-k candidate buffer overflow");
-        n_cand = h_counts[1];
-    }
-    // levels >= 2: shrink the candidate arrays until one CTA can sort them together with the kept rows
-    int cur = 0;
-    const uint32_t room = SMALL_N - std::min<uint32_t>(P.n, k);
-    while (n_cand > room) {
-        bool ok = false;
-        for (int attempt = 0; attempt < 6 && !ok; attempt++) {
-            SCK(cudaMemsetAsync(cnt, 0, 32, st));
-            k_sample_pairs<<<(SAMPLE_N + 255) / 256, 256, 0, st>>>(s->cand_key[cur], s->cand_idx[cur], n_cand, s->samp_key, s->samp_idx, cnt, 0x9e3779b9ull + attempt * 104729);
-            double frac = (double)SAMPLE_N / (double)n_cand; if (frac > 1) frac = 1;
-            double want = ((double)k * frac * 1.5 + 32.0) * (double)(1 << attempt);
-            uint32_t rank = (uint32_t)std::min<double>(want, SAMPLE_N - 1);
-            k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, rank, s->d_rank);
-            SCK(cudaMemcpyAsync(h_rank, s->d_rank, 24, cudaMemcpyDeviceToHost, st));
-            SCK(cudaStreamSynchronize(st));
-            uint64_t tk2 = h_rank[2] > rank ? h_rank[0] : ~0ull, ti2 = h_rank[2] > rank ? h_rank[1] : ~0ull;
-            SCK(cudaMemsetAsync(cnt + 2, 0, 4, st));
-            k_collect_pairs<<<grid_for(n_cand, 256, s->sm_count), 256, 0, st>>>(s->cand_key[cur], s->cand_idx[cur], n_cand, tk2, ti2, s->cand_key[cur ^ 1], s->cand_idx[cur ^ 1], cnt + 2, s->cand_cap);
-            SCK(cudaMemcpyAsync(h_counts, cnt, 32, cudaMemcpyDeviceToHost, st));
-            SCK(cudaStreamSynchronize(st));
-            stats->kernel_launches += 3;
-            if (h_counts[2] < k && h_counts[2] < n_cand) continue;
-            if (h_counts[2] >= n_cand && n_cand > room) {   // threshold = +inf did not shrink anything: sample rank saturated
-                if (attempt < 5) continue;
-                return fail(err, BKGPU_ETOOBIG, "top-k refinement did not shrink the candidate set");
-            }
-            n_cand = h_counts[2]; cur ^= 1; ok = true;
-        }
-        if (!ok) return fail(err, BKGPU_ETOOBIG, "top-k refinement did not converge");
-    }
-    // final: sort candidates + kept rows in one CTA, keep k, then fetch the payload of the survivors
-    const int nxt = P.cur ^ 1;
+    uint32_t* cnt = s->d_counts;     // [0] sample count  [1] level-1 candidates  [2] level-2  [3] rows of this class  [4] kept rows  [5] level-3
+    uint64_t* thr = s->d_rank;       // three {key, idx, n} triples: thresholds of the three levels
     const uint32_t old_n = std::min<uint32_t>(P.n, k);
-    SCK(cudaMemcpyAsync(cnt + 1, &n_cand, 4, cudaMemcpyHostToDevice, st));
-    k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->cand_key[cur], s->cand_idx[cur], cnt + 1, n_cand, P.key[P.cur], P.idx[P.cur], old_n,
-                                                P.key[nxt], P.idx[nxt], k, cnt + 4, 0, nullptr);
-    GatherArgs g; memset(&g, 0, sizeof g);
-    for (int i = 0; i < s->ncols; i++) { g.cols[i] = ra.cols[i]; g.dst_vals[i] = P.vals[nxt][i]; g.dst_null[i] = P.nulls[nxt][i]; g.old_vals[i] = P.vals[P.cur][i]; g.old_null[i] = P.nulls[P.cur][i]; }
-    g.n_cols = s->ncols; g.row_base = ra.row_base; g.nrows = ra.nrows; g.old_idx = P.idx[P.cur]; g.old_n = old_n;
-    k_gather_topk<<<std::max(1, (int)((k + 127) / 128)), 128, 0, st>>>(g, P.idx[nxt], cnt + 4);
-    uint32_t new_n = 0;
-    SCK(cudaMemcpyAsync(&new_n, cnt + 4, 4, cudaMemcpyDeviceToHost, st));
-    SCK(cudaStreamSynchronize(st));
-    stats->kernel_launches += 2;
-    P.cur = nxt; P.n = new_n;
-    return 0;
+    const uint32_t room = SMALL_N - old_n;
+    const int nxt = P.cur ^ 1;
+    const uint64_t* pool_thr = nullptr;
+    if (P.n >= k) {   // later rows must beat the k-th composite key kept so far
+        SCK(cudaMemcpyAsync(thr + 12, P.key[P.cur] + (k - 1), 8, cudaMemcpyDeviceToDevice, st));
+        SCK(cudaMemcpyAsync(thr + 13, P.idx[P.cur] + (k - 1), 8, cudaMemcpyDeviceToDevice, st));
+        pool_thr = thr + 12;
+    }
+    uint32_t h[8];
+    // The whole chain (sample -> threshold -> compact, three times, then the one-CTA sort and the payload gather)
+    // is enqueued without a host round trip; counts are checked once at the end.  A statistically unlucky
+    // threshold (too tight / too loose) repeats the chain with wider ranks.
+    for (int attempt = 0; attempt < 6; attempt++) {
+        const uint32_t widen = 1u << attempt;
+        SCK(cudaMemsetAsync(cnt, 0, 32, st));
+        const bool big = ra.nrows > (int64_t)s->cand_cap / 2;
+        if (big) {
+            k_sample_rows<<<(SAMPLE_N + 255) / 256, 256, 0, st>>>(ra, cls, s->samp_key, s->samp_idx, cnt, 0x5bd1e995ull + attempt * 7919);
+            double w = ((double)k * (double)SAMPLE_N / (double)ra.nrows * 1.5 + 32.0) * (double)widen;
+            uint32_t rank = w >= (double)(SAMPLE_N - 1) ? 0xFFFFFFFFu : (uint32_t)w;
+            k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr,
+                                                        rank, thr, nullptr, 0, 0, 0, pool_thr);
+            stats->kernel_launches += 2;
+        } else if (pool_thr) {
+            SCK(cudaMemcpyAsync(thr, pool_thr, 16, cudaMemcpyDeviceToDevice, st));
+        } else SCK(cudaMemsetAsync(thr, 0xFF, 16, st));
+        const DevCol& kc = ra.cols[ra.key.col];
+        const bool vec = cls == 1 && ra.key.direct && !kc.validity && (((uintptr_t)kc.values & 31) == 0) && kc.prim != BK_INT8 && kc.prim != BK_INT16 &&
+                         kc.prim != BK_UINT8 && kc.prim != BK_UINT16 && (kc.stype == ST_I64 || kc.stype == ST_U64 || kc.stype == ST_F64 || kc.stype == ST_I32 || kc.stype == ST_U32);
+        s->used_vec = vec;
+        if (vec) {
+            const int g = std::max(1, std::min(s->sm_count * 8, (int)((ra.nrows / 4 + 511) / 512)));
+            if (kc.stype == ST_I32 || kc.stype == ST_U32) k_collect_rows_vec<4><<<g, 256, 0, st>>>(ra, thr, s->cand_key[0], s->cand_idx[0], cnt + 1, s->cand_cap, cnt + 3);
+            else k_collect_rows_vec<8><<<g, 256, 0, st>>>(ra, thr, s->cand_key[0], s->cand_idx[0], cnt + 1, s->cand_cap, cnt + 3);
+        } else
+        k_collect_rows<<<grid_for(ra.nrows, 256, s->sm_count), 256, 0, st>>>(ra, cls, thr, s->cand_key[0], s->cand_idx[0], cnt + 1, s->cand_cap, cnt + 3);
+        // level 2: cand[0] (cnt[1]) -> cand[1] (cnt[2]);  level 3: cand[1] (cnt[2]) -> cand[0] (cnt[5])
+        const int src_cnt[2] = {1, 2}, dst_cnt[2] = {2, 5};
+        for (int lvl = 0; lvl < 2; lvl++) {
+            const int from = lvl, to = lvl ^ 1;
+            SCK(cudaMemsetAsync(cnt, 0, 4, st));
+            k_sample_pairs<<<(SAMPLE_N + 255) / 256, 256, 0, st>>>(s->cand_key[from], s->cand_idx[from], cnt + src_cnt[lvl], s->cand_cap, s->samp_key, s->samp_idx, cnt,
+                                                                   0x9e3779b9ull + attempt * 104729 + lvl);
+            k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr,
+                                                        0, thr + 3 * (lvl + 1), cnt + src_cnt[lvl], k, widen, room, nullptr);
+            k_collect_pairs<<<grid_for(lvl == 0 ? (int64_t)s->cand_cap / 4 : 65536, 256, s->sm_count), 256, 0, st>>>(
+                s->cand_key[from], s->cand_idx[from], cnt + src_cnt[lvl], thr + 3 * (lvl + 1), s->cand_key[to], s->cand_idx[to], cnt + dst_cnt[lvl], s->cand_cap);
+            stats->kernel_launches += 3;
+        }
+        // final: candidates + kept rows sorted by one CTA, keep k, fetch the payload of the survivors
+        k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->cand_key[0], s->cand_idx[0], cnt + 5, room, P.key[P.cur], P.idx[P.cur], old_n,
+                                                    P.key[nxt], P.idx[nxt], k, cnt + 4, 0, nullptr, nullptr, 0, 0, 0, nullptr);
+        GatherArgs g; memset(&g, 0, sizeof g);
+        for (int i = 0; i < s->ncols; i++) { g.cols[i] = ra.cols[i]; g.dst_vals[i] = P.vals[nxt][i]; g.dst_null[i] = P.nulls[nxt][i]; g.old_vals[i] = P.vals[P.cur][i]; g.old_null[i] = P.nulls[P.cur][i]; }
+        g.n_cols = s->ncols; g.row_base = ra.row_base; g.nrows = ra.nrows; g.old_idx = P.idx[P.cur]; g.old_n = old_n;
+        k_gather_topk<<<std::max(1, (int)((k + 127) / 128)), 128, 0, st>>>(g, P.idx[nxt], cnt + 4);
+        stats->kernel_launches += 3;
+        SCK(cudaMemcpyAsync(h, cnt, 32, cudaMemcpyDeviceToHost, st));
+        SCK(cudaStreamSynchronize(st));
+        const uint32_t c1 = h[1], c2 = h[2], cls_rows = h[3], c3 = h[5];
+        const bool ok1 = c1 <= s->cand_cap && (c1 >= k || c1 >= cls_rows || pool_thr != nullptr);
+        const bool ok2 = c2 <= s->cand_cap && (c2 >= std::min(k, c1));
+        const bool ok3 = c3 <= room && (c3 >= std::min(k, c2));
+        if (ok1 && ok2 && ok3) { P.cur = nxt; P.n = h[4]; return 0; }
+    }
+    return fail(err, BKGPU_ETOOBIG, "top-k selection did not converge (candidate buffers too small for this key distribution)");
 }
 
 int ensure_retained(SortState* s, int64_t need, cudaStream_t st, std::string& err) {
@@ -674,7 +734,7 @@ int sort_open(const Compiled& c, int device, cudaStream_t stream, int64_t region
         if (!rc) rc = dalloc(s, &s->samp_key, SAMPLE_N * 8, err);
         if (!rc) rc = dalloc(s, &s->samp_idx, SAMPLE_N * 8, err);
         if (!rc) rc = dalloc(s, &s->d_counts, 64, err);
-        if (!rc) rc = dalloc(s, &s->d_rank, 32, err);
+        if (!rc) rc = dalloc(s, &s->d_rank, 128, err);
         for (int p = 0; p < 2 && !rc; p++) for (int b = 0; b < 2 && !rc; b++) {
             if ((rc = dalloc(s, &s->pool[p].key[b], kk * 8, err))) break;
             if ((rc = dalloc(s, &s->pool[p].idx[b], kk * 8, err))) break;
@@ -712,7 +772,7 @@ int sort_push(SortState* s, const DevCol* cols, int64_t nrows, cudaStream_t stre
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
         stats->main_kernel_ms += ms; stats->main_kernel_launches += 1;
         stats->main_kernel_bytes += nrows * (ra.key.direct ? storage_bytes(cols[ra.key.col].stype) : 8);
-        snprintf(stats->main_kernel_name, sizeof stats->main_kernel_name, "topk_select(k_collect_rows)");
+        snprintf(stats->main_kernel_name, sizeof stats->main_kernel_name, "%s", s->used_vec ? "topk_select(k_collect_rows_vec)" : "topk_select(k_collect_rows)");
     } else {
         rc = retain_batch(s, ra, stream, stats, err);
         snprintf(stats->main_kernel_name, sizeof stats->main_kernel_name, "%s", s->c.kind == PK_FILTER ? "k_filter_write" : "k_radix_scatter");

@@ -14,6 +14,27 @@ def test_c3_join_groupby():
     fact, dim = datagen.c3_fact(0, 400_000, 20_000), datagen.c3_dim(0, 20_000, 20_000, n_groups=100)
     got, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact])
     assert len(got[0]) == 100
+    # unique build keys, every probe row matched: the FK -> PK gather path feeds the lean aggregate kernel
+    assert stats.main_kernel_name.decode() == "k_agg_group_lean"
+    _, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact], options={"force_generic": 1})
+    assert stats.main_kernel_name.decode() == "k_agg_interp"
+
+
+def test_join_fast_path_sparse_keys_and_unmatched_rows():
+    """unique but sparse build keys (packed table instead of the dense array) and probe rows without a partner:
+    those chunks fall back to the general probe; results stay identical"""
+    rng = np.random.default_rng(41)
+    nd, nf = 5_000, 120_000
+    pk = rng.permutation(1 << 24)[:nd].astype(np.int32) * 97          # sparse: range >> 4 * n
+    dim = [make_column(1, 1, T.INT32, pk), make_column(1, 2, T.INT32, rng.integers(0, 30, nd))]
+    fk = pk[rng.integers(0, nd, nf)]
+    fact_all = [make_column(0, 1, T.INT32, fk), make_column(0, 2, T.DOUBLE, rng.random(nf))]
+    _, stats, _ = run_both(queries.c3_join_groupby(), fact_all + dim, keys=["1_2"], batches=[dim, fact_all])
+    assert stats.main_kernel_name.decode() == "k_agg_group_lean"
+    fk2 = fk.copy(); fk2[::1000] = 5                                   # 5 is not a build key
+    fact_miss = [make_column(0, 1, T.INT32, fk2), make_column(0, 2, T.DOUBLE, fact_all[1].values)]
+    _, stats, _ = run_both(queries.c3_join_groupby(), fact_miss + dim, keys=["1_2"], batches=[dim, fact_miss])
+    assert stats.main_kernel_name.decode() == "k_agg_interp"
 
 
 def test_c3_streamed_in_several_batches_host_and_build_first_rule():
