@@ -31,6 +31,7 @@ struct AggArgs {
     uint32_t alias_mask;     // global lanes that receive the shared row count at flush time
     ValOps vops[4];          // direct kernels: per value column
     int32_t smem_keyw;       // key words per slot of the shared table (1 in sentinel mode, else plan.n_keyw)
+    int32_t smem_paired;     // shared lanes are interleaved in 16-byte pairs {lane 2p, lane 2p+1} per slot (lean kernel: ATOMS.CAS.128)
     int32_t lean;            // batch qualifies for k_agg_group_lean (see agg_direct.cuh)
     int32_t smem_sentinel;   // shared table of one-word keys: the key word doubles as slot state (EMPTY_KEY = free)
 };

@@ -64,6 +64,12 @@ __device__ __forceinline__ void merge_group(const AggPlan& ap, const GroupTable&
 // ------------------------------------------------------------------------------------------
 constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;  // "free slot" marker of sentinel-mode shared tables (one-word keys)
 
+// word index of shared lane `sl` of `slot`: SoA, or 16-byte pairs so that two lanes of a group sit in one
+// 128-bit word (updated together by one ATOMS.CAS.128 in the lean kernel)
+__device__ __forceinline__ size_t smem_lane_word(const AggArgs& a, int sl, uint32_t slot, uint32_t cap) {
+    return a.smem_paired ? (((size_t)(sl >> 1) * cap + slot) * 2 + (size_t)(sl & 1)) : ((size_t)sl * cap + slot);
+}
+
 struct SmemTable {
     uint32_t* state; uint64_t* keys; uint64_t* lanes; uint32_t cap_mask;
 };
@@ -81,7 +87,7 @@ __device__ __forceinline__ SmemTable smem_table_init(unsigned char* raw, const A
         const int sl = args.smem_lane[l];
         if (sl == 0xFF) continue;
         const uint64_t id = lane_identity(ap.lane_op[l]);
-        for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) t.lanes[(size_t)sl * cap + i] = id;
+        for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) t.lanes[smem_lane_word(args, sl, i, cap)] = id;
     }
     __syncthreads();
     return t;
@@ -96,8 +102,8 @@ __device__ __forceinline__ void smem_table_flush(const SmemTable& t, const AggAr
         for (int w = 0; w < ap.n_keyw; w++) key[w] = w < args.smem_keyw ? t.keys[(size_t)w * cap + i] : 0ull;  // sentinel mode: further words are 0
         merge_group(ap, args.gt, key, [&](int l, uint64_t& v) {
             const int sl = args.smem_lane[l];
-            if (sl != 0xFF) { v = t.lanes[(size_t)sl * cap + i]; return true; }
-            if ((args.alias_mask >> l) & 1u) { v = t.lanes[i]; return true; }  // counter that follows the row count
+            if (sl != 0xFF) { v = t.lanes[smem_lane_word(args, sl, i, cap)]; return true; }
+            if ((args.alias_mask >> l) & 1u) { v = t.lanes[smem_lane_word(args, 0, i, cap)]; return true; }  // counter that follows the row count
             return false;
         });
     }

@@ -315,7 +315,25 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
                  ((vo.op[0] == LN_ADD_F64 && vc.stype == ST_F64 && vo.lane_class[0] == VC_F64) || (vo.op[0] == LN_ADD_I64 && vc.stype != ST_F64));
         }
         a.lean = ok ? 1 : 0;
-        if (a.lean) { a.smem_sentinel = 1; a.smem_keyw = 1; }
+        if (a.lean) {
+            a.smem_sentinel = 1; a.smem_keyw = 1; a.smem_paired = 1;
+            // lane placement for 128-bit shared CAS: ONE double sum shares a 16-byte word with the row count
+            // ({rows, sum}: a single atomic per row); otherwise double sums sit in pairs {sumA, sumB}
+            memset(a.smem_lane, 0xFF, sizeof a.smem_lane);
+            a.smem_lane[0] = 0;
+            int nf64 = 0;
+            for (int v = 0; v < na; v++) if (a.vops[v].op[0] == LN_ADD_F64) nf64++;
+            int next_f = nf64 == 1 ? 1 : 2, next_i = nf64 == 1 ? 2 : 2 + ((nf64 + 1) & ~1);
+            for (int v = 0; v < na; v++) {
+                ValOps& vo = a.vops[v];
+                const int sl = vo.op[0] == LN_ADD_F64 ? next_f++ : next_i++;
+                vo.smem_lane[0] = (uint8_t)sl; a.smem_lane[vo.glob_lane[0]] = (uint8_t)sl;
+            }
+            a.n_smem_lanes = (std::max(next_f, next_i) + 1) & ~1;
+            if (a.n_smem_lanes < 2) a.n_smem_lanes = 2;
+            a.smem_cap_log2 = pick_smem_log2(p, a.n_smem_lanes, true, na);
+            if (a.smem_cap_log2 <= 0) { a.lean = 0; a.smem_paired = 0; return p->fail(BKGPU_ENOMEM, "lean kernel: shared table does not fit"); }
+        }
     }
     const int64_t kMax = (int64_t)1 << 30;  // rows per launch (32-bit counters inside a CTA)
     int64_t algo_bytes_per_row = 0;
