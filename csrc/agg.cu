@@ -204,7 +204,8 @@ size_t agg_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2) {
 size_t direct_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2, int na) {
     const size_t table = (agg_smem_bytes(smem_keyw, n_smem_lanes, cap_log2) + 15) & ~(size_t)15;
     const size_t queue = ((size_t)(2 + na) * 128 + 16) * 8;  // QCAP = 128 entries per warp, up to 2 key words
-    return table + queue * (DIRECT_THREADS / 32);                                         // DIRECT_THREADS / 32 warps
+    const int warps = (DIRECT_THREADS > LEAN_THREADS ? DIRECT_THREADS : LEAN_THREADS) / 32;   // sized for the larger of the two CTA shapes
+    return table + queue * warps;
 }
 
 template <class K>

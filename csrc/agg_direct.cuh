@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 // k_agg_group_direct above (same results, more instructions per row).
 // ------------------------------------------------------------------------------------------
 template <int NP, int NA>
-__global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_lean(const __grid_constant__ AggArgs a) {
+__global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid_constant__ AggArgs a) {
     constexpr int NS = NP + 1 + NA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AggPlan& ap = a.plan;
@@ -528,8 +528,8 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_lean(const __gr
     const bool pair2 = NA >= 2 && acc_f64[0] && acc_f64[NA > 1 ? 1 : 0] && a.vops[0].smem_lane[0] == 2 && a.vops[NA > 1 ? 1 : 0].smem_lane[0] == 3;
     uint32_t passed = 0;
     const int64_t nquads = a.nrows >> 2;
-    const int64_t stride = (int64_t)gridDim.x * DIRECT_THREADS;
-    int64_t q0 = (int64_t)blockIdx.x * DIRECT_THREADS + warp * 32;
+    const int64_t stride = (int64_t)gridDim.x * LEAN_THREADS;
+    int64_t q0 = (int64_t)blockIdx.x * LEAN_THREADS + warp * 32;
     uint32_t pr[NP > 0 ? NP : 1][4]; uint32_t kr[8]; uint64_t vr[NA > 0 ? NA : 1][4];
     auto issue_loads = [&](int64_t q) {
 #pragma unroll
@@ -552,7 +552,6 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_lean(const __gr
     for (; q0 < nquads; q0 += stride) {
         const int64_t q = q0 + lane;
         uint32_t pass = 0;
-        uint64_t kv[4]; uint64_t vv[NA > 0 ? NA : 1][4];
         if (q < nquads) {
             pass = 0xFu;
 #pragma unroll
@@ -563,13 +562,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_lean(const __gr
                 pass &= term_mask_i32(tcmp[t], tconst[t], r8);
             }
         }
-#pragma unroll
-        for (int j = 0; j < 4; j++) kv[j] = key8 ? ((uint64_t)kr[2 * j] | ((uint64_t)kr[2 * j + 1] << 32)) : ((uint64_t)kr[j] & kmask);
-#pragma unroll
-        for (int s = 0; s < NA; s++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) vv[s][j] = vr[s][j];
-        if (q + stride < nquads) issue_loads(q + stride);  // next iteration's columns fly while the queue drains
+        // compact the surviving rows of this warp into its queue (straight from the load registers) ...
         uint32_t bal[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) bal[j] = __ballot_sync(0xFFFFFFFFu, (pass >> j) & 1u);
@@ -578,12 +571,14 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_lean(const __gr
         for (int j = 0; j < 4; j++) {
             if ((pass >> j) & 1u) {
                 const uint32_t pos = (uint32_t)(total + __popc(bal[j] & lane_lt));
-                sts64(qkey + pos * 8u, kv[j]);
+                sts64(qkey + pos * 8u, key8 ? ((uint64_t)kr[2 * j] | ((uint64_t)kr[2 * j + 1] << 32)) : ((uint64_t)kr[j] & kmask));
 #pragma unroll
-                for (int s = 0; s < NA; s++) sts64(qval + (s * QCAP + pos) * 8u, vv[s][j]);
+                for (int s = 0; s < NA; s++) sts64(qval + (s * QCAP + pos) * 8u, vr[s][j]);
             }
             total += __popc(bal[j]);
         }
+        // ... then reuse those registers for the next iteration's columns: they fly while the queue drains
+        if (q + stride < nquads) issue_loads(q + stride);
         passed += __popc(pass);
         __syncwarp();
         // (a two-entries-per-lane variant of this loop measured 17% slower: more registers, more idle
@@ -734,10 +729,10 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_scalar_direct(const _
 
 // ------------------------------------------------------------------------------------------
 template <class K>
-static inline int direct_grid(K kernel, size_t smem, int sm_count, int64_t nrows) {
+static inline int direct_grid(K kernel, size_t smem, int sm_count, int64_t nrows, int threads = DIRECT_THREADS) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DIRECT_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const int64_t want = ((nrows + 3) / 4 + DIRECT_THREADS - 1) / DIRECT_THREADS;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int64_t want = ((nrows + 3) / 4 + threads - 1) / threads;
     const int64_t full = (int64_t)per_sm * sm_count;  // persistent grid: whole CTAs per SM x 148 SMs
     return (int)(want < full ? want : full);
 }
@@ -754,7 +749,7 @@ static inline cudaError_t launch_direct(const AggArgs& a, int sm_count, size_t s
                 cudaError_t e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
             }
-            k_agg_group_lean<NP, NA><<<direct_grid(k_agg_group_lean<NP, NA>, smem, sm_count, a.nrows), DIRECT_THREADS, smem, s>>>(a);
+            k_agg_group_lean<NP, NA><<<direct_grid(k_agg_group_lean<NP, NA>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
         } else
         k_agg_group_direct<NP, NA><<<direct_grid(k_agg_group_direct<NP, NA>, smem, sm_count, a.nrows), DIRECT_THREADS, smem, s>>>(a);
     } else {

@@ -27,6 +27,10 @@ constexpr int DIRECT_MAX_AGG = 6; // aggregates the specialised kernels keep in 
 #define BK_DIRECT_THREADS 512     // threads per CTA of the direct filter+aggregate kernels (one CTA per SM)
 #endif
 constexpr int DIRECT_THREADS = BK_DIRECT_THREADS;
+#ifndef BK_LEAN_THREADS
+#define BK_LEAN_THREADS 640       // the lean kernel fits 96 registers: 20 warps per SM measured best (512: -2 %, 768: spills)
+#endif
+constexpr int LEAN_THREADS = BK_LEAN_THREADS;
 
 struct DevCol {
     const void* values;
