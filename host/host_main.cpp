@@ -1,0 +1,168 @@
+// host_main.cpp — drives the GPU path from C++ the way Region::select drives an ExecNode tree
+// (src/store/region.cpp:3069-3216), with plans built like the planner's and tables from the
+// counter-based generator of baikaldb_b200/datagen.py restated in C++ (bit-identical, so tests/ can check the
+// printed rows against the oracle on the same table).
+//
+//   bkgpu_host plan    <c1|c2|c3|c5>                       hex of the serialized plan (compared with plan.py's bytes)
+//   bkgpu_host explain <c1|c2|c3|c5>                       bkgpu_plan_explain of it (no GPU needed)
+//   bkgpu_host run     <c1|c2|c3|c5> <rows> [batch_rows]   executes on cuda:0 and prints one result row per line
+#include <cinttypes>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include "bkgpu_host.hpp"
+
+using namespace bkgpu;
+
+// ------------------------------------------------------------------ generator (datagen.py)
+static const uint64_t GOLDEN = 0x9E3779B97F4A7C15ull, C1 = 0xD1B54A32D192ED03ull, C2 = 0x8CB92BA72F3D8DD7ull;
+static uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31);
+}
+static uint64_t stream_key(uint64_t seed, uint64_t column_id, uint64_t k) { return mix64(seed + column_id * C1 + k * C2); }
+static uint64_t raw64(uint64_t key, int64_t row) { return mix64(key + (uint64_t)(row + 1) * GOLDEN); }
+static double u01(uint64_t r) { return (double)(r >> 11) * (1.0 / 9007199254740992.0); }
+
+static std::vector<int32_t> gen_uniform_i32(uint64_t seed, int cid, int64_t row0, int64_t n, int64_t lo, int64_t hi) {
+    std::vector<int32_t> v((size_t)n); uint64_t key = stream_key(seed, cid, 0);
+    for (int64_t i = 0; i < n; i++) v[(size_t)i] = (int32_t)(lo + (int64_t)(raw64(key, row0 + i) % (uint64_t)(hi - lo)));
+    return v;
+}
+static std::vector<double> gen_u01(uint64_t seed, int cid, int64_t row0, int64_t n) {
+    std::vector<double> v((size_t)n); uint64_t key = stream_key(seed, cid, 0);
+    for (int64_t i = 0; i < n; i++) v[(size_t)i] = u01(raw64(key, row0 + i));
+    return v;
+}
+static std::vector<double> gen_normal(uint64_t seed, int cid, int64_t row0, int64_t n, double scale) {
+    std::vector<double> v((size_t)n); uint64_t k[4];
+    for (int j = 0; j < 4; j++) k[j] = stream_key(seed, cid, j);
+    for (int64_t i = 0; i < n; i++) {
+        double s = u01(raw64(k[0], row0 + i));
+        for (int j = 1; j < 4; j++) s = s + u01(raw64(k[j], row0 + i));
+        v[(size_t)i] = (s - 2.0) * scale;
+    }
+    return v;
+}
+static std::vector<int64_t> gen_i64_full(uint64_t seed, int cid, int64_t row0, int64_t n) {
+    std::vector<int64_t> v((size_t)n); uint64_t key = stream_key(seed, cid, 0);
+    for (int64_t i = 0; i < n; i++) v[(size_t)i] = (int64_t)raw64(key, row0 + i);
+    return v;
+}
+static std::vector<int32_t> gen_permutation_i32(uint64_t seed, int cid, int64_t row0, int64_t n, int64_t domain) {
+    int bits = 0; while (((int64_t)1 << bits) < domain) bits++;     // bit_length(domain - 1)
+    if (bits < 2) bits = 2;
+    bits += bits & 1;
+    const int half = bits / 2; const uint64_t mask = ((uint64_t)1 << half) - 1;
+    uint64_t keys[4]; for (int r = 0; r < 4; r++) keys[r] = stream_key(seed, cid, 16 + r);
+    std::vector<int32_t> v((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t x = (uint64_t)(row0 + i);
+        do {
+            uint64_t left = x >> half, right = x & mask;
+            for (int r = 0; r < 4; r++) { uint64_t f = mix64(right + keys[r]) & mask; uint64_t nl = right; right = left ^ f; left = nl; }
+            x = (left << half) | right;
+        } while (x >= (uint64_t)domain);
+        v[(size_t)i] = (int32_t)x;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------ plans (queries.py)
+static Expr cmp(int op, const char* name, Expr a, Expr b) { return Expr::fn(op, name, {std::move(a), std::move(b)}); }
+static PlanNode scan(int tuple) { PlanNode n; n.node_type = BK_SCAN_NODE; n.tuple_id = tuple; return n; }
+static PlanNode where(PlanNode child, Expr c) { PlanNode n; n.node_type = BK_WHERE_FILTER_NODE; n.children.push_back(std::move(child)); n.conjuncts.push_back(std::move(c)); return n; }
+static PlanNode agg(PlanNode child, int agg_tuple, std::vector<Expr> groups, std::vector<Expr> fns) {
+    PlanNode n; n.node_type = BK_AGG_NODE; n.children.push_back(std::move(child)); n.agg_tuple_id = agg_tuple; n.group_exprs = std::move(groups); n.agg_fn_calls = std::move(fns); return n;
+}
+
+static Plan plan_c1() {   // SELECT COUNT(*) FROM t WHERE `0_1` < 2^19
+    Plan p; PlanNode packet; packet.node_type = BK_PACKET_NODE;
+    packet.children.push_back(agg(where(scan(0), cmp(BK_FT_LT, "lt", Expr::slot_ref(0, 1, BK_INT32), Expr::int_literal(1 << 19))), 1, {}, {Expr::agg("count_star", 1, 1, 1, {})}));
+    p.root = std::move(packet);
+    p.tuples = {{0, {{1, BK_INT32}}}, {1, {{1, BK_INT64}}}};
+    return p;
+}
+static Plan plan_c2() {   // SELECT `0_1`, COUNT(*), SUM(`0_3`), AVG(`0_4`) FROM t WHERE `0_2` < 2^19 GROUP BY `0_1`
+    Plan p;
+    p.root = agg(where(scan(0), cmp(BK_FT_LT, "lt", Expr::slot_ref(0, 2, BK_INT32), Expr::int_literal(1 << 19))), 1, {Expr::slot_ref(0, 1, BK_INT32)},
+                 {Expr::agg("count_star", 1, 1, 1, {}), Expr::agg("sum", 1, 2, 2, {Expr::slot_ref(0, 3, BK_DOUBLE)}), Expr::agg("avg", 1, 3, 4, {Expr::slot_ref(0, 4, BK_DOUBLE)})});
+    p.tuples = {{0, {{1, BK_INT32}, {2, BK_INT32}, {3, BK_DOUBLE}, {4, BK_DOUBLE}}}, {1, {{1, BK_INT64}, {2, BK_DOUBLE}, {3, BK_DOUBLE}, {4, BK_STRING}}}};
+    return p;
+}
+static Plan plan_c3() {   // SELECT `1_2`, COUNT(*), SUM(`0_2`) FROM fact JOIN dim ON `0_1` = `1_1` GROUP BY `1_2`; dim = outer (driver) child
+    Plan p; PlanNode j; j.node_type = BK_JOIN_NODE; j.join_type = BK_INNER_JOIN;
+    j.children.push_back(scan(1)); j.children.push_back(scan(0));
+    j.conjuncts.push_back(cmp(BK_FT_EQ, "eq", Expr::slot_ref(1, 1, BK_INT32), Expr::slot_ref(0, 1, BK_INT32)));
+    p.root = agg(std::move(j), 2, {Expr::slot_ref(1, 2, BK_INT32)}, {Expr::agg("count_star", 2, 1, 1, {}), Expr::agg("sum", 2, 2, 2, {Expr::slot_ref(0, 2, BK_DOUBLE)})});
+    p.tuples = {{0, {{1, BK_INT32}, {2, BK_DOUBLE}}}, {1, {{1, BK_INT32}, {2, BK_INT32}}}, {2, {{1, BK_INT64}, {2, BK_DOUBLE}}}};
+    return p;
+}
+static Plan plan_c5() {   // SELECT `0_1`, `0_2` FROM t ORDER BY `0_1` ASC LIMIT 1000
+    Plan p; PlanNode s; s.node_type = BK_SORT_NODE; s.tuple_id = 0; s.limit = 1000; s.children.push_back(scan(0));
+    s.order_exprs.push_back(Expr::slot_ref(0, 1, BK_INT64)); s.is_asc.push_back(true); s.is_null_first.push_back(true);
+    p.root = std::move(s);
+    p.tuples = {{0, {{1, BK_INT64}, {2, BK_INT32}}}};
+    return p;
+}
+
+// ------------------------------------------------------------------ scans over the synthetic tables, in batches (regions)
+static std::unique_ptr<ExecNode> scan_of(const std::string& cfg, int tuple, int64_t rows, int64_t batch_rows) {
+    std::vector<RowBatch> batches;
+    for (int64_t r0 = 0; r0 < rows; r0 += batch_rows) {
+        int64_t n = rows - r0 < batch_rows ? rows - r0 : batch_rows; RowBatch b;
+        if (cfg == "c1") b.columns = {Column::from(0, 1, BK_INT32, gen_uniform_i32(1, 1, r0, n, 0, 1 << 20))};
+        else if (cfg == "c2") b.columns = {Column::from(0, 1, BK_INT32, gen_uniform_i32(2, 1, r0, n, 0, 1000)), Column::from(0, 2, BK_INT32, gen_uniform_i32(2, 2, r0, n, 0, 1 << 20)),
+                                           Column::from(0, 3, BK_DOUBLE, gen_u01(2, 3, r0, n)), Column::from(0, 4, BK_DOUBLE, gen_normal(2, 4, r0, n, 1000.0 * 1.7320508075688772))};
+        else if (cfg == "c5") b.columns = {Column::from(0, 1, BK_INT64, gen_i64_full(5, 1, r0, n)), Column::from(0, 2, BK_INT32, gen_uniform_i32(5, 2, r0, n, 0, 1 << 30))};
+        else if (cfg == "c3" && tuple == 0) b.columns = {Column::from(0, 1, BK_INT32, gen_uniform_i32(3, 1, r0, n, 0, rows / 10)), Column::from(0, 2, BK_DOUBLE, gen_u01(3, 2, r0, n))};
+        else b.columns = {Column::from(1, 1, BK_INT32, gen_permutation_i32(3, 11, r0, n, rows)), Column::from(1, 2, BK_INT32, gen_uniform_i32(3, 12, r0, n, 0, 1000))};
+        batches.push_back(std::move(b));
+    }
+    return std::unique_ptr<ExecNode>(new ColumnScanNode(std::move(batches)));
+}
+
+static void print_value(const Column& c, int64_t i) {
+    if (c.is_null(i)) { printf("NULL"); return; }
+    switch (c.prim_type) {
+        case BK_INT32: printf("%d", c.at<int32_t>(i)); break;
+        case BK_INT64: printf("%" PRId64, c.at<int64_t>(i)); break;
+        case BK_UINT64: printf("%" PRIu64, c.at<uint64_t>(i)); break;
+        case BK_DOUBLE: printf("%.17g", c.at<double>(i)); break;
+        case BK_STRING: if (c.elem_size == 16) { printf("blob(%.17g,%" PRId64 ")", c.at<double>(2 * i), c.at<int64_t>(2 * i + 1)); break; }   // AVG intermediate {sum,count}
+            /* fallthrough */
+        default: printf("?"); break;
+    }
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) { fprintf(stderr, "usage: %s plan|explain|run c1|c2|c3|c5 [rows] [batch_rows]\n", argv[0]); return 2; }
+    std::string mode = argv[1], cfg = argv[2];
+    Plan plan = cfg == "c1" ? plan_c1() : cfg == "c2" ? plan_c2() : cfg == "c3" ? plan_c3() : plan_c5();
+    if (mode == "plan") { for (uint8_t b : plan.serialize()) printf("%02x", b); printf("\n"); return 0; }
+    if (mode == "explain") {
+        std::vector<uint8_t> d = plan.serialize(); std::vector<char> text(1 << 16);
+        int rc = bkgpu_plan_explain(d.data(), d.size(), text.data(), text.size());
+        if (rc != 0) { fprintf(stderr, "explain failed (%d): %s\n", rc, bkgpu_last_error(nullptr)); return 1; }
+        fputs(text.data(), stdout); return 0;
+    }
+    int64_t rows = argc > 3 ? atoll(argv[3]) : 1 << 20, batch_rows = argc > 4 ? atoll(argv[4]) : rows;
+    RuntimeState state; state.row_batch_capacity = 4096;
+    GpuExecNode root;
+    if (root.init(plan) < 0) return 1;
+    if (cfg == "c3") { root.add_child(scan_of(cfg, 1, rows / 10, batch_rows)); root.add_child(scan_of(cfg, 0, rows, batch_rows)); }   // driver (dim) first
+    else root.add_child(scan_of(cfg, 0, rows, batch_rows));
+    if (root.open(&state) < 0) { fprintf(stderr, "open failed (%d): %s\n", state.error_code, state.error_msg.c_str()); return 1; }
+    bool eos = false; int64_t total = 0;
+    while (!eos) {
+        RowBatch batch;
+        if (root.get_next(&state, &batch, &eos) < 0) { fprintf(stderr, "get_next failed (%d): %s\n", state.error_code, state.error_msg.c_str()); return 1; }
+        for (int64_t i = 0; i < batch.size(); i++) {
+            for (size_t c = 0; c < batch.columns.size(); c++) { if (c) printf(" "); printf("%d_%d=", batch.columns[c].tuple_id, batch.columns[c].slot_id); print_value(batch.columns[c], i); }
+            printf("\n");
+        }
+        total += batch.size();
+    }
+    root.close(&state);
+    fprintf(stderr, "rows_returned=%" PRId64 " scan_rows=%" PRId64 " filter_rows=%" PRId64 "\n", total, state.num_scan_rows, state.num_filter_rows);
+    return 0;
+}
