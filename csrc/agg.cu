@@ -172,12 +172,14 @@ __global__ void k_extract(GroupTable gt, AggPlan ap, uint64_t* outv, uint8_t* ou
         }
         for (int k = 0; k < ap.n_agg; k++) {
             const AggSpec a = ap.agg[k];
+            if (a.hidden) continue;
             const uint64_t cnt = a.cnt_lane ? gt.lanes[(size_t)a.cnt_lane * cap + i] : nrows;
             const uint64_t acc = gt.lanes[(size_t)a.acc_lane * cap + i];
             uint64_t v = 0; uint8_t isnull = 0;
             switch (a.kind) {
                 case AG_COUNT_STAR: v = nrows; break;
                 case AG_COUNT: v = cnt; break;
+                case AG_COUNT_MERGE: v = acc; break;
                 case AG_AVG:
                     if (cnt == 0) isnull = 1; else v = f64_bits(__ddiv_rn(bits_f64(acc), (double)(int64_t)cnt));
                     break;
@@ -185,7 +187,8 @@ __global__ void k_extract(GroupTable gt, AggPlan ap, uint64_t* outv, uint8_t* ou
             }
             outv[(size_t)c * out_cap + pos] = v; outn[(size_t)c * out_cap + pos] = isnull; c++;
             if (a.kind == AG_AVG) {  // intermediate blob {double sum; int64 count}
-                outv[(size_t)c * out_cap + pos] = acc; outn[(size_t)c * out_cap + pos] = 0; c++;
+                // the blank row of an empty scalar aggregate initialises only its counts (agg_node.cpp:489-503): blob stays NULL
+                outv[(size_t)c * out_cap + pos] = acc; outn[(size_t)c * out_cap + pos] = (ap.n_keyw == 0 && nrows == 0) ? 1 : 0; c++;
                 outv[(size_t)c * out_cap + pos] = cnt; outn[(size_t)c * out_cap + pos] = 0; c++;
             }
         }

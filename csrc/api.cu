@@ -268,7 +268,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
         bool nullable = c.arg_can_null[(size_t)k];
         for (int i = 0; i < ncols; i++) if ((c.arg_cols_mask[(size_t)k] >> i) & 1) nullable = nullable || cols[i].validity != nullptr;
         s.nullable = nullable ? 1 : 0;
-        if (s.cnt_lane) {
+        if (s.cnt_lane && s.cnt_owner) {
             if (nullable) { if (a.smem_lane[s.cnt_lane] == 0xFF) a.smem_lane[s.cnt_lane] = (uint8_t)a.n_smem_lanes++; }
             else a.alias_mask |= 1u << s.cnt_lane;
         }
@@ -697,7 +697,7 @@ static int agg_finish(bkgpu_plan* p) {
     }
     // device images: one per group expr, per aggregate its final (+2 for an AVG blob)
     int n_img = ap.n_group;
-    for (int k = 0; k < ap.n_agg; k++) n_img += ap.agg[k].kind == AG_AVG ? 3 : 1;
+    for (int k = 0; k < ap.n_agg; k++) if (!ap.agg[k].hidden) n_img += ap.agg[k].kind == AG_AVG ? 3 : 1;
     int rc;
     uint32_t n_out = 0, out_cap = 0;
     std::vector<uint64_t>& hv = p->hv; std::vector<uint8_t>& hn = p->hn;
@@ -746,6 +746,7 @@ static int agg_finish(bkgpu_plan* p) {
         for (int64_t r = 0; r < keep; r++) {
             const size_t src = (size_t)(r + skip);
             if (oc.kind == 1) {
+                if (hn[(size_t)img * out_cap + src]) { any_null = true; hc.validity[(size_t)r >> 3] &= (uint8_t)~(1u << (r & 7)); }
                 memcpy(hc.values.data() + (size_t)r * 16, &hv[(size_t)img * out_cap + src], 8);
                 memcpy(hc.values.data() + (size_t)r * 16 + 8, &hv[(size_t)(img + 1) * out_cap + src], 8);
             } else {

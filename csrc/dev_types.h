@@ -42,7 +42,7 @@ struct DevCol {
 // ---- expression bytecode (postfix).  One instruction = 4 bytes. ----
 enum Op : uint8_t {
     OP_END = 0,
-    OP_LOAD_COL,     // a = column index                      -> push value (class by storage), null from bitmap
+    OP_LOAD_COL,     // a = column index, b = 0 | 1 | 2: whole value | {sum | count} half of a 16-byte AVG blob                      -> push value (class by storage), null from bitmap
     OP_CONST,        // a = constant index                    -> push constant
     OP_CAST,         // a = from prim, b = to prim            ExprValue::cast_to (expr_value.h:502-611)
     OP_CMP,          // a = FuncType (EQ..LE), b = VClass     operators.cpp:84-100
@@ -77,7 +77,8 @@ struct Program {
 // count (COUNT(*) and the "first row seen" marker).  An aggregate names the lane its value
 // accumulates in and the lane that counts its non-NULL inputs (0 when the argument cannot be NULL,
 // so several aggregates share one counter).
-enum AggKind : uint8_t { AG_COUNT_STAR = 0, AG_COUNT = 1, AG_SUM = 2, AG_AVG = 3, AG_MIN = 4, AG_MAX = 5 };
+enum AggKind : uint8_t { AG_COUNT_STAR = 0, AG_COUNT = 1, AG_SUM = 2, AG_AVG = 3, AG_MIN = 4, AG_MAX = 5,
+                         AG_COUNT_MERGE = 6 };   // MERGE_AGG_NODE: counts shipped by the stores are summed (AggFnCall::merge, agg_fn_call.cpp:779-790)
 enum LaneOp : uint8_t { LN_ADD_I64 = 0, LN_ADD_F64 = 1, LN_MIN_I64, LN_MAX_I64, LN_MIN_U64, LN_MAX_U64, LN_MIN_F64, LN_MAX_F64 };
 
 struct AggSpec {
@@ -92,6 +93,7 @@ struct AggSpec {
                          // AVG does sum += get_numberic<double>(x), agg_fn_call.cpp:525-535)
     uint8_t cnt_owner;   // lanes can be shared by aggregates over the same argument (SUM(x), AVG(x), COUNT(x)):
     uint8_t acc_owner;   // only the owner updates the lane, everyone reads it at finalize
+    uint8_t hidden;      // helper accumulator without an output column (the count half of a merged AVG blob)
 };
 
 struct AggPlan {

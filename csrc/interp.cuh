@@ -23,7 +23,7 @@ static __device__ __noinline__ void run_program(const Program& p, const DevCol* 
             case OP_LOAD_COL: {
                 const DevCol& c = cols[in.a];
                 const int64_t r = in.c ? brow : row;
-                st[sp] = load_elem(c, r);
+                st[sp] = in.b ? __ldg((const unsigned long long*)c.values + 2 * r + (in.b - 1)) : load_elem(c, r);
                 nul = elem_is_null(c, r) ? (nul | (1u << sp)) : (nul & ~(1u << sp));
                 sp++;
             } break;

@@ -492,7 +492,6 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
     out.is_merge = agg.node_type == BK_MERGE_AGG_NODE;
     out.emit_default = agg.group_exprs.empty() && (under_packet || out.is_merge);
     out.agg_limit = agg.limit;
-    if (out.is_merge) return in.fail(BKGPU_EUNSUPPORTED, "MERGE_AGG_NODE over rows: use bkgpu_partial_merge (device partials) — row merge not lowered yet");
     if (agg.group_exprs.size() > MAX_GROUP) return in.fail(BKGPU_EUNSUPPORTED, "more than %d GROUP BY expressions", MAX_GROUP);
     if (agg.agg_fns.size() > MAX_AGG) return in.fail(BKGPU_EUNSUPPORTED, "more than %d aggregate functions", MAX_AGG);
     Program& p = out.prog; memset(&p, 0, sizeof p);
@@ -501,6 +500,26 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
     int reg = 0, depth = 0;
     // ---- predicate: all conjuncts non-NULL true (filter_node.cpp:726-734) ----
     ap.pred_out = -1;
+    if (out.is_merge && !conjuncts.empty()) return in.fail(BKGPU_EUNSUPPORTED, "filter below MERGE_AGG_NODE");
+    if (out.is_merge && agg.group_exprs.empty() && !agg.agg_fns.empty()) {
+        // a scalar merger skips input rows whose aggregates are all still "initial" (AggFnCall::all_is_initialize,
+        // agg_node.cpp:519-522): pass = OR_k (count_k <> 0 | value_k IS NOT NULL), three-valued, NULL = skip
+        for (size_t k = 0; k < agg.agg_fns.size(); k++) {
+            const HExpr& f = agg.agg_fns[k];
+            const int st = in.slot_type(f.tuple_id, f.inter_slot);
+            if (st == BK_INVALID_TYPE) return in.fail(BKGPU_EINVAL, "MERGE_AGG: slot %d_%d is not declared", f.tuple_id, f.inter_slot);
+            const int ci = lw.intern_col(f.tuple_id, f.inter_slot, st);
+            if (ci >= MAX_COLS) return in.fail(BKGPU_EUNSUPPORTED, "more than %d columns referenced", MAX_COLS);
+            if (!lw.emit(OP_LOAD_COL, (uint8_t)ci, st == BK_STRING ? 1 : 0, 0)) return false;
+            if (f.name == "count" || f.name == "count_star") {
+                const int z = lw.add_const(0, false); if (z < 0) return false;
+                if (!lw.emit(OP_CONST, (uint8_t)z) || !lw.emit(OP_CMP, (uint8_t)BK_FT_NE, (uint8_t)host_prim_class(st))) return false;
+            } else if (!lw.emit(OP_IS_NULL) || !lw.emit(OP_NOT3)) return false;
+            if (k > 0 && !lw.emit(OP_OR, 2)) return false;
+        }
+        ap.pred_out = reg;
+        if (!lw.out_reg(reg++)) return false;
+    }
     if (!conjuncts.empty()) {
         if (conjuncts.size() > 8) return in.fail(BKGPU_EUNSUPPORTED, "more than 8 conjuncts");
         for (auto* c : conjuncts) { depth = 0; if (!lw.expr(*c, depth) || !lw.to_bool(*c)) return false; }
@@ -533,10 +552,12 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
     ap.n_keyw = n_words;
     // ---- aggregates and lanes ----
     ap.n_agg = (int)agg.agg_fns.size();
+    const int n_visible = ap.n_agg;
+    int n_hidden = 0;
     ap.n_lanes = 1; ap.lane_op[0] = LN_ADD_I64;
     std::map<std::string, int> cnt_lane_of, acc_lane_of, arg_reg_of;
-    out.arg_cols_mask.assign((size_t)ap.n_agg, 0);
-    out.arg_can_null.assign((size_t)ap.n_agg, false);
+    out.arg_cols_mask.assign((size_t)MAX_AGG, 0);
+    out.arg_can_null.assign((size_t)MAX_AGG, false);
     auto new_lane = [&](uint8_t op) -> int {
         if (ap.n_lanes >= MAX_LANES) { in.fail(BKGPU_EUNSUPPORTED, "more than %d accumulator lanes", MAX_LANES); return -1; }
         ap.lane_op[ap.n_lanes] = op; return ap.n_lanes++;
@@ -545,6 +566,51 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
         const HExpr& f = agg.agg_fns[(size_t)k];
         AggSpec& a = ap.agg[k]; memset(&a, 0, sizeof a);
         a.arg_out = 0xFF; a.out_prim = (uint8_t)f.col_type;
+        if (out.is_merge) {
+            // MERGE_AGG_NODE: the input rows carry the stores' intermediate slots; AggFnCall::merge (agg_fn_call.cpp:719-822)
+            // adds counts and sums, folds MIN/MAX, and adds both halves of an AVG blob.  NULL intermediates are skipped.
+            const int st = in.slot_type(f.tuple_id, f.inter_slot);
+            if (st == BK_INVALID_TYPE) return in.fail(BKGPU_EINVAL, "MERGE_AGG: slot %d_%d is not declared", f.tuple_id, f.inter_slot);
+            const bool blob = f.name == "avg";
+            if (blob != (st == BK_STRING)) return in.fail(BKGPU_EUNSUPPORTED, "MERGE_AGG: %s over an intermediate slot of type %d", f.name.c_str(), st);
+            const int ci = lw.intern_col(f.tuple_id, f.inter_slot, st);
+            if (ci >= MAX_COLS) return in.fail(BKGPU_EUNSUPPORTED, "more than %d columns referenced", MAX_COLS);
+            out.arg_cols_mask[(size_t)k] = 1 << ci;
+            if (!lw.emit(OP_LOAD_COL, (uint8_t)ci, blob ? 1 : 0, 0)) return false;
+            a.arg_out = (uint8_t)reg; a.nullable = 1;
+            if (!lw.out_reg(reg++)) return false;
+            const uint8_t cls = (uint8_t)(blob ? VC_F64 : host_prim_class(st));
+            a.vclass = a.arg_vclass = cls;
+            uint8_t op = cls == VC_F64 ? LN_ADD_F64 : LN_ADD_I64;
+            if (blob) {
+                a.kind = AG_AVG;
+                if (n_visible + n_hidden >= MAX_AGG) return in.fail(BKGPU_EUNSUPPORTED, "more than %d aggregate accumulators", MAX_AGG);
+                const int hk = n_visible + n_hidden++;
+                AggSpec& h = ap.agg[hk]; memset(&h, 0, sizeof h);
+                h.kind = AG_COUNT_MERGE; h.hidden = 1; h.vclass = h.arg_vclass = VC_I64; h.nullable = 1; h.acc_owner = 1;
+                out.arg_cols_mask[(size_t)hk] = 1 << ci;
+                if (!lw.emit(OP_LOAD_COL, (uint8_t)ci, 2, 0)) return false;
+                h.arg_out = (uint8_t)reg;
+                if (!lw.out_reg(reg++)) return false;
+                int hl = new_lane(LN_ADD_I64); if (hl < 0) return false;
+                h.acc_lane = (uint8_t)hl;
+                a.cnt_lane = (uint8_t)hl; a.cnt_owner = 0;
+            } else if (f.name == "count" || f.name == "count_star") {
+                a.kind = AG_COUNT_MERGE; a.vclass = VC_I64; op = LN_ADD_I64;
+            } else {
+                if (f.name == "sum") a.kind = AG_SUM;
+                else {
+                    const bool mn = f.name == "min";
+                    a.kind = mn ? AG_MIN : AG_MAX;
+                    op = cls == VC_F64 ? (mn ? LN_MIN_F64 : LN_MAX_F64) : (cls == VC_U64 ? (mn ? LN_MIN_U64 : LN_MAX_U64) : (mn ? LN_MIN_I64 : LN_MAX_I64));
+                }
+                int cl = new_lane(LN_ADD_I64); if (cl < 0) return false;
+                a.cnt_lane = (uint8_t)cl; a.cnt_owner = 1;
+            }
+            int al = new_lane(op); if (al < 0) return false;
+            a.acc_lane = (uint8_t)al; a.acc_owner = 1;
+            continue;
+        }
         if (f.name == "count_star") { a.kind = AG_COUNT_STAR; continue; }
         if (f.ch.empty()) return in.fail(BKGPU_EINVAL, "%s() without an argument", f.name.c_str());
         if (f.ch.size() > 1) return in.fail(BKGPU_EUNSUPPORTED, "%s() with %zu arguments", f.name.c_str(), f.ch.size());
@@ -577,6 +643,8 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
         if (!acc_lane_of.count(akey)) { int l = new_lane(op); if (l < 0) return false; acc_lane_of[akey] = l; a.acc_owner = 1; }
         a.acc_lane = (uint8_t)acc_lane_of[akey];
     }
+    ap.n_agg = n_visible + n_hidden;
+    out.arg_cols_mask.resize((size_t)ap.n_agg); out.arg_can_null.resize((size_t)ap.n_agg);
     p.n_out = reg;
     if (reg > MAX_GROUP + MAX_AGG + 1) return in.fail(BKGPU_EUNSUPPORTED, "too many program outputs");
     // ---- output schema ----
@@ -585,7 +653,7 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
         bool sr = e.node_type == BK_SLOT_REF;
         out.out_cols.push_back({sr ? e.tuple_id : -1, sr ? e.slot_id : g, e.col_type, 0});
     }
-    for (int k = 0; k < ap.n_agg; k++) {
+    for (int k = 0; k < n_visible; k++) {
         const HExpr& f = agg.agg_fns[(size_t)k];
         int ft = in.slot_type(f.tuple_id, f.final_slot);
         if (ft == BK_INVALID_TYPE || ft == BK_STRING) ft = f.col_type;
@@ -598,7 +666,7 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
     DirectPlan& d = out.direct; memset(&d, 0, sizeof d); memset(d.agg_val, 0xFF, sizeof d.agg_val);
     do {
         std::vector<int> order;  // cols indices in [terms][key][values] order
-        if (!allow_direct) break;
+        if (!allow_direct || out.is_merge) break;
         if (!conjuncts.empty()) {
             if (conjuncts.size() > 2) break;
             bool ok = true;
