@@ -318,6 +318,32 @@ __global__ void __launch_bounds__(256) k_join_gather(DevCol pk, int from_prim, i
     }
     if (__any_sync(0xFFFFFFFFu, miss) && (threadIdx.x & 31) == 0) atomicExch(miss_flag, 1u);
 }
+// K4 fused probe (JoinProbe): compose the grouped-by build attribute onto the key index built by k_join_build_fast
+__global__ void k_join_compose(JoinFast jf, const uint32_t* attr_by_row, uint32_t* attr_of_key, uint64_t* packed_attr, uint32_t* bad_flag) {
+    const uint64_t n = jf.mode == 1 ? jf.dense_size : (uint64_t)jf.packed_mask + 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (jf.mode == 1) {
+            const uint32_t r = jf.dense[i];
+            attr_of_key[i] = r == 0xFFFFFFFFu ? 0u : __ldg(attr_by_row + r);
+        } else {
+            const uint64_t e = jf.packed[i];
+            uint64_t o = ~0ull;
+            if (e != ~0ull) {
+                o = (e & 0xFFFFFFFF00000000ull) | __ldg(attr_by_row + (uint32_t)e);
+                if (o == ~0ull) atomicExch(bad_flag, 1u);   // (key, attribute) = (0xFFFFFFFF, 0xFFFFFFFF) would read as a free slot
+            }
+            packed_attr[i] = o;
+        }
+    }
+}
+cudaError_t launch_join_compose(const JoinFast& jf, const uint32_t* attr_by_row, uint32_t* attr_of_key, uint64_t* packed_attr, uint32_t* bad_flag, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(bad_flag, 0, 4, s);
+    if (e != cudaSuccess) return e;
+    const uint64_t n = jf.mode == 1 ? jf.dense_size : (uint64_t)jf.packed_mask + 1;
+    int grid = (int)((n + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
+    k_join_compose<<<grid, 256, 0, s>>>(jf, attr_by_row, attr_of_key, packed_attr, bad_flag);
+    return cudaGetLastError();
+}
 cudaError_t launch_join_minmax(const DevCol& key, int from_prim, int cast_prim_, int64_t nrows, uint64_t bias, uint64_t* mm, cudaStream_t s) {
     const uint64_t init[2] = {~0ull, 0ull};
     cudaError_t e = cudaMemcpyAsync(mm, init, 16, cudaMemcpyHostToDevice, s);

@@ -15,6 +15,20 @@ struct JoinArgs {
     int32_t probe_prim, cast_prim;
 };
 
+// FK -> PK join fused into the lean aggregate: the GROUP BY key is a build-side (dimension) attribute reached through
+// the probe row's foreign key.  At build time the attribute is composed onto the key index (attr_of_key), so the probe
+// is ONE random 4-byte read per fact row (served from L2: a 10M-key dimension is 40 MB); rows without a partner drop
+// out (inner join), which the filter mask already expresses.
+struct JoinProbe {
+    int32_t mode;                // 0 = off, 1 = dense index, 2 = packed (key32 << 32 | attr32) open-addressed table
+    int32_t key_signed;          // probe key column is a signed 32-bit type (canonical image sign-extends)
+    const uint32_t* attr;        // mode 1: attribute by (key image ^ bias) - dense_min
+    const uint32_t* present;     // mode 1: build row per key, 0xFFFFFFFF = no such key; nullptr = every key of the range exists
+    uint64_t dense_min, dense_size, bias;
+    const uint64_t* packed;      // mode 2
+    uint32_t packed_mask;
+};
+
 struct AggArgs {
     DevCol cols[MAX_COLS];   // direct kernels: ordered [predicate][key][value] columns
     int32_t n_cols;
@@ -34,6 +48,7 @@ struct AggArgs {
     int32_t smem_paired;     // shared lanes are interleaved in 16-byte pairs {lane 2p, lane 2p+1} per slot (lean kernel: ATOMS.CAS.128)
     int32_t lean;            // batch qualifies for k_agg_group_lean (see agg_direct.cuh)
     int32_t smem_sentinel;   // shared table of one-word keys: the key word doubles as slot state (EMPTY_KEY = free)
+    JoinProbe jp;            // lean kernel only: the key column holds the probe-side foreign key (see JoinProbe)
 };
 
 size_t agg_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2);
@@ -54,6 +69,7 @@ struct GatherCols { int32_t n; const uint8_t* src[MAX_COLS]; uint8_t* dst[MAX_CO
 cudaError_t launch_join_minmax(const DevCol& key, int from_prim, int cast_prim, int64_t nrows, uint64_t bias, uint64_t* mm, cudaStream_t s);
 cudaError_t launch_join_build_fast(const DevCol& key, int from_prim, int cast_prim, int64_t nrows, const JoinFast& jf, uint32_t* dense_w, uint64_t* packed_w, uint32_t* dup_flag, cudaStream_t s);
 cudaError_t launch_join_gather(const DevCol& probe_key, int from_prim, int cast_prim, int64_t nrows, const JoinFast& jf, const GatherCols& gc, uint32_t* miss_flag, cudaStream_t s);
+cudaError_t launch_join_compose(const JoinFast& jf, const uint32_t* attr_by_row, uint32_t* attr_of_key, uint64_t* packed_attr, uint32_t* bad_flag, cudaStream_t s);
 cudaError_t launch_unpack_validity(const uint8_t* bitmap, int64_t n, uint8_t* null_bytes, cudaStream_t s);
 cudaError_t launch_pack_validity(const uint8_t* null_bytes, int64_t n, uint8_t* bitmap, cudaStream_t s);
 cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStream_t s);

@@ -192,7 +192,25 @@ static __device__ __noinline__ void smem_update_row_generic(const AggArgs& a, ui
 }
 
 // one of the <= 3 ragged rows at the end of a batch: element loads, straight to the global table
-template <int NP, int NA>
+// one foreign key -> dimension attribute (JoinProbe); false = no partner
+static __device__ __noinline__ bool join_probe_one(const JoinProbe& jp, uint32_t k, uint32_t& attr) {
+    if (jp.mode == 1) {
+        const uint64_t img = jp.key_signed ? (uint64_t)(int64_t)(int32_t)k : (uint64_t)k;
+        const uint64_t off = (img ^ jp.bias) - jp.dense_min;
+        if (off >= jp.dense_size || (jp.present && __ldg(jp.present + off) == 0xFFFFFFFFu)) return false;
+        attr = __ldg(jp.attr + off);
+        return true;
+    }
+    uint32_t slot = (k * 0x9E3779B1u) & jp.packed_mask;
+    for (;;) {
+        const uint64_t e = __ldg((const unsigned long long*)(jp.packed + slot));
+        if (e == ~0ull) return false;
+        if ((uint32_t)(e >> 32) == k) { attr = (uint32_t)e; return true; }
+        slot = (slot + 1) & jp.packed_mask;
+    }
+}
+
+template <int NP, int NA, bool JOIN = false>
 static __device__ __noinline__ uint32_t direct_tail_row(const AggArgs& a, int64_t row) {
     const AggPlan& ap = a.plan;
     for (int t = 0; t < NP; t++) {
@@ -203,7 +221,11 @@ static __device__ __noinline__ uint32_t direct_tail_row(const AggArgs& a, int64_
     int vbase = NP;
     if (ap.n_keyw > 0) {
         const uint64_t kmask = ap.key_bits[0] >= 64 ? ~0ull : ((1ull << ap.key_bits[0]) - 1ull);
-        if (elem_is_null(a.cols[NP], row)) key[ap.key_null_word[0] == 1 ? 1 : 0] |= 1ull << ap.key_null_shift[0];
+        if (JOIN) {   // (lean shape: no NULLs in the batch)
+            uint32_t attr = 0;
+            if (!join_probe_one(a.jp, (uint32_t)load_elem(a.cols[NP], row), attr)) return 0;
+            key[0] = (uint64_t)attr & kmask;
+        } else if (elem_is_null(a.cols[NP], row)) key[ap.key_null_word[0] == 1 ? 1 : 0] |= 1ull << ap.key_null_shift[0];
         else key[0] = load_elem(a.cols[NP], row) & kmask;
         vbase = NP + 1;
     }
@@ -490,7 +512,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 // fixed the hot loop has no descriptor interpretation left in it.  Everything else takes
 // k_agg_group_direct above (same results, more instructions per row).
 // ------------------------------------------------------------------------------------------
-template <int NP, int NA>
+template <int NP, int NA, bool JOIN>
 __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid_constant__ AggArgs a) {
     constexpr int NS = NP + 1 + NA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -562,6 +584,48 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
                 pass &= term_mask_i32(tcmp[t], tconst[t], r8);
             }
         }
+        if (JOIN) {
+            // K4 fused: the foreign keys of the surviving rows become the dimension attribute the query groups by; the
+            // four lookups of a lane fly together, rows without a partner leave the mask (inner join)
+            const JoinProbe& jp = a.jp;
+            uint32_t g[4]; uint32_t hit = 0;
+            if (jp.mode == 1) {
+                uint64_t off[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint64_t img = jp.key_signed ? (uint64_t)(int64_t)(int32_t)kr[j] : (uint64_t)kr[j];
+                    off[j] = (img ^ jp.bias) - jp.dense_min;
+                    g[j] = 0;
+                    if (((pass >> j) & 1u) && off[j] < jp.dense_size) { g[j] = __ldg(jp.attr + off[j]); hit |= 1u << j; }
+                }
+                if (jp.present) {
+                    uint32_t pr4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) pr4[j] = ((hit >> j) & 1u) ? __ldg(jp.present + off[j]) : 0xFFFFFFFFu;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (pr4[j] == 0xFFFFFFFFu) hit &= ~(1u << j);
+                }
+            } else {
+                uint32_t slot[4]; uint64_t e[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    slot[j] = (kr[j] * 0x9E3779B1u) & jp.packed_mask;
+                    e[j] = ((pass >> j) & 1u) ? __ldg((const unsigned long long*)(jp.packed + slot[j])) : ~0ull;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    g[j] = 0;
+                    while (e[j] != ~0ull) {
+                        if ((uint32_t)(e[j] >> 32) == kr[j]) { g[j] = (uint32_t)e[j]; hit |= 1u << j; break; }
+                        slot[j] = (slot[j] + 1) & jp.packed_mask;
+                        e[j] = __ldg((const unsigned long long*)(jp.packed + slot[j]));
+                    }
+                }
+            }
+            pass &= hit;
+#pragma unroll
+            for (int j = 0; j < 4; j++) kr[j] = g[j];
+        }
         // compact the surviving rows of this warp into its queue (straight from the load registers) ...
         uint32_t bal[4];
 #pragma unroll
@@ -626,15 +690,18 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
                         if (acc_f64[s]) smem32_add_f64(acc_addr[s] + slot * 16u, bits_f64(v[s])); else smem32_add_u64(acc_addr[s] + slot * 16u, v[s]);
                     }
                 }
-            } else {
+            } else {   // rare: re-read the entry from the queue so that v[] never needs an address (no local-memory copy per pass)
                 uint64_t key[2] = {k0, 0ull};
-                global_update_row<NA>(a, key, v, 0u);
+                uint64_t gv[NA > 0 ? NA : 1];
+#pragma unroll
+                for (int s = 0; s < NA; s++) gv[s] = lds64(qval + (s * QCAP + e) * 8u);
+                global_update_row<NA>(a, key, gv, 0u);
             }
         }
         __syncwarp();
     }
     smem_table_flush(st, a);
-    if (blockIdx.x == 0 && threadIdx.x < (a.nrows & 3)) passed += direct_tail_row<NP, NA>(a, (a.nrows & ~(int64_t)3) + threadIdx.x);
+    if (blockIdx.x == 0 && threadIdx.x < (a.nrows & 3)) passed += direct_tail_row<NP, NA, JOIN>(a, (a.nrows & ~(int64_t)3) + threadIdx.x);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) passed += __shfl_xor_sync(0xFFFFFFFFu, passed, d);
     if (lane == 0 && passed) atomicAdd((unsigned long long*)a.rows_passed, (unsigned long long)passed);
@@ -659,18 +726,43 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_scalar_direct(const _
     uint32_t sf[NS > 0 ? NS : 1];
 #pragma unroll
     for (int s = 0; s < NS; s++) sf[s] = slot_flags(a.cols[s]);
-    const int64_t nquads = a.nrows >> 2;
-#pragma unroll 1
-    for (int64_t q = (int64_t)blockIdx.x * DIRECT_THREADS + threadIdx.x; q < nquads; q += (int64_t)gridDim.x * DIRECT_THREADS) {
-        RawQuad raw[NS > 0 ? NS : 1];
+    // `int32 column <cmp> int32 constant` terms compare the loaded words directly (no 64-bit decode)
+    bool term32[NP > 0 ? NP : 1]; int32_t term_c32[NP > 0 ? NP : 1];
 #pragma unroll
-        for (int s = 0; s < NS; s++) raw_quad_load(a.cols[s], sf[s], q, raw[s]);
+    for (int t = 0; t < NP; t++) {
+        const DirectTerm tm = a.direct.term[t];
+        const int64_t c = (int64_t)tm.cbits;
+        term32[t] = a.cols[t].stype == ST_I32 && !(sf[t] & SF_SPECIAL) && tm.vclass == VC_I64 && c >= -2147483648ll && c <= 2147483647ll;
+        term_c32[t] = (int32_t)c;
+    }
+    const int64_t nquads = a.nrows >> 2;
+    // U independent row quads per thread and trip: with one or two narrow columns a single 16-byte load per thread
+    // leaves too few bytes in flight to cover HBM latency (148 SMs x 512 threads x 16 B = 1.2 MB)
+    constexpr int U = NS <= 1 ? 4 : (NS <= 3 ? 2 : 1);
+    const int64_t T = (int64_t)gridDim.x * DIRECT_THREADS;
+#pragma unroll 1
+    for (int64_t q0 = (int64_t)blockIdx.x * DIRECT_THREADS + threadIdx.x; q0 < nquads; q0 += T * U) {
+      RawQuad rawu[U][NS > 0 ? NS : 1];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (q0 + u * T < nquads) {
+#pragma unroll
+            for (int s = 0; s < NS; s++) raw_quad_load(a.cols[s], sf[s], q0 + u * T, rawu[u][s]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (q0 + u * T >= nquads) break;
+        RawQuad (&raw)[NS > 0 ? NS : 1] = rawu[u];
         uint32_t pass = 0xFu;
 #pragma unroll
         for (int t = 0; t < NP; t++) {
-            uint64_t pv[4];
-            raw_quad_decode(raw[t], sf[t], a.cols[t], pv);
-            pass &= term_mask(a.direct.term[t], pv) & ~raw[t].nm;
+            if (term32[t]) pass &= term_mask_i32(a.direct.term[t].cmp, term_c32[t], raw[t].r) & ~raw[t].nm;
+            else {
+                uint64_t pv[4];
+                raw_quad_decode(raw[t], sf[t], a.cols[t], pv);
+                pass &= term_mask(a.direct.term[t], pv) & ~raw[t].nm;
+            }
         }
         rows += __popc(pass);
 #pragma unroll
@@ -695,6 +787,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_scalar_direct(const _
                 } else acc[s][k] = combine4_generic(op, acc[s][k], v, ok, vo.arg_class, vo.lane_class[k]);
             }
         }
+      }
     }
     const GroupTable& gt = a.gt;
 #pragma unroll
@@ -746,10 +839,12 @@ static inline cudaError_t launch_direct(const AggArgs& a, int sm_count, size_t s
         }
         if (a.lean) {
             if (smem > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaError_t e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
             }
-            k_agg_group_lean<NP, NA><<<direct_grid(k_agg_group_lean<NP, NA>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
+            if (a.jp.mode) k_agg_group_lean<NP, NA, true><<<direct_grid(k_agg_group_lean<NP, NA, true>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
+            else k_agg_group_lean<NP, NA, false><<<direct_grid(k_agg_group_lean<NP, NA, false>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
         } else
         k_agg_group_direct<NP, NA><<<direct_grid(k_agg_group_direct<NP, NA>, smem, sm_count, a.nrows), DIRECT_THREADS, smem, s>>>(a);
     } else {

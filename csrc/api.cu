@@ -72,6 +72,10 @@ struct bkgpu_plan {
     int64_t jb_rows = 0, jb_cap = 0;
     uint64_t* jt_keys = nullptr; uint32_t* jt_rows = nullptr; uint32_t jt_mask = 0; bool jt_built = false, jt_generic = false;
     JoinFast jf{}; uint32_t* jf_dense = nullptr; uint64_t* jf_packed = nullptr;   // FK -> PK fast path (unique build keys)
+    JoinProbe jp{}; uint32_t* jp_attr = nullptr; uint64_t* jp_packed = nullptr; int jp_key_pos = 0;   // ... fused into the lean aggregate
+    size_t jf_dense_cap = 0, jf_packed_cap = 0, jp_attr_cap = 0, jp_packed_cap = 0, j_scratch_cap = 0;
+    uint64_t* j_scratch = nullptr;   // [0..1] key min / max, then u32 flags: [4] duplicate build key, [5] fused probe unusable
+    int no_fused_probe = 0;
     std::vector<uint8_t*> jg_buf; int64_t jg_rows = 0;                            // gathered build columns, one chunk
     std::vector<ColRef> probe_want; std::vector<int> probe_map;   // probe-side columns and their index in c.cols
     // sort / filter state
@@ -136,6 +140,15 @@ static void dev_free(bkgpu_plan* p, void* ptr) {
     if (it != p->dev_allocs.end()) p->dev_allocs.erase(it);
     cudaFree(ptr);
 }
+// grow-only device buffer: plans are re-armed with bkgpu_reset and run again; cudaMalloc / cudaFree per run would
+// serialise the device every time
+static int ensure_buf(bkgpu_plan* p, void** ptr, size_t* cap, size_t bytes) {
+    if (*ptr && *cap >= bytes) return BKGPU_OK;
+    dev_free(p, *ptr); *ptr = nullptr; *cap = 0;
+    const int rc = dev_alloc(p, ptr, bytes);
+    if (rc == BKGPU_OK) *cap = bytes;
+    return rc;
+}
 static EventPair* timer_begin(bkgpu_plan* p, std::vector<EventPair>& v, int64_t bytes) {
     EventPair ep{};
     if (cudaEventCreate(&ep.a) != cudaSuccess || cudaEventCreate(&ep.b) != cudaSuccess) return nullptr;
@@ -187,6 +200,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "partial_capacity") { if (v < 1) return p->fail(BKGPU_EINVAL, "partial_capacity must be positive"); p->partial_cap = v; }
     else if (k == "force_generic") p->force_generic = v != 0;
     else if (k == "no_lean") p->no_lean = v != 0;
+    else if (k == "no_fused_probe") p->no_fused_probe = v != 0;
     else if (k == "output_on_device") p->output_on_device = v != 0;
     else if (k == "region_base") p->region_base = v;
     else return p->fail(BKGPU_EINVAL, "unknown option '%s'", key);
@@ -248,7 +262,8 @@ static int pick_smem_log2(bkgpu_plan* p, int n_smem_lanes, bool direct, int na) 
     return log2;
 }
 
-static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols, int64_t nrows, bool vec_ok) {
+// `jp`: fused FK -> PK probe (lean kernel only); returns +1 without launching when this batch does not fit the lean kernel
+static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols, int64_t nrows, bool vec_ok, const JoinProbe* jp = nullptr) {
     AggArgs a; memset(&a, 0, sizeof a);
     a.plan = c.ap; a.prog = c.prog; a.direct = c.direct; a.gt = p->gt; a.rows_passed = p->d_rows_passed;
     if (c.kind == PK_JOIN_AGG) {
@@ -335,6 +350,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
             if (a.smem_cap_log2 <= 0) { a.lean = 0; a.smem_paired = 0; return p->fail(BKGPU_ENOMEM, "lean kernel: shared table does not fit"); }
         }
     }
+    if (jp) { if (!a.lean) return 1; a.jp = *jp; }
     const int64_t kMax = (int64_t)1 << 30;  // rows per launch (32-bit counters inside a CTA)
     int64_t algo_bytes_per_row = 0;
     for (int i = 0; i < a.n_cols; i++) algo_bytes_per_row += storage_bytes(a.cols[i].stype);
@@ -493,6 +509,45 @@ static int join_retain_build(bkgpu_plan* p, const bkgpu_column* cols, int ncols,
     return BKGPU_OK;
 }
 
+// Fused probe (JoinProbe in agg.h): usable when the only build-side column the aggregate reads is its 4-byte GROUP BY
+// key and the probe key is a 32-bit integer column whose cast to the comparison type keeps the canonical image.
+static int join_compose_probe(bkgpu_plan* p, uint32_t* flag) {
+    const Compiled& c = p->c;
+    p->jp = JoinProbe{};
+    if (!c.jfast || !c.jfast->has_direct || c.jfast->direct.n_keys != 1) return BKGPU_OK;
+    const Compiled& f = *c.jfast;
+    const size_t kpos = (size_t)f.direct.n_terms;
+    int attr_main = -1;
+    for (size_t i = 0; i < f.direct_cols.size(); i++) {
+        const int m = c.jfast_of_main[(size_t)f.direct_cols[i]];
+        if (c.col_side[(size_t)m] != 1) continue;
+        if (i != kpos) return BKGPU_OK;   // a predicate or an aggregate argument comes from the build side: gather path
+        attr_main = m;
+    }
+    if (attr_main < 0) return BKGPU_OK;
+    const int ast = prim_storage(c.cols[(size_t)attr_main].prim);
+    if ((ast != ST_I32 && ast != ST_U32) || (c.cols[(size_t)attr_main].prim != BK_INT32 && c.cols[(size_t)attr_main].prim != BK_UINT32)) return BKGPU_OK;
+    const int pp = c.cols[(size_t)c.probe_key_col].prim, ct = c.join_key_prim;
+    const bool ident = (pp == BK_INT32 && (ct == BK_INT32 || ct == BK_INT64)) || (pp == BK_UINT32 && (ct == BK_UINT32 || ct == BK_UINT64 || ct == BK_INT64));
+    if (!ident) return BKGPU_OK;
+    int rc;
+    JoinProbe jp{};
+    jp.mode = p->jf.mode; jp.key_signed = pp == BK_INT32 ? 1 : 0;
+    jp.dense_min = p->jf.dense_min; jp.dense_size = p->jf.dense_size; jp.bias = p->jf.bias; jp.packed_mask = p->jf.packed_mask;
+    if (jp.mode == 1) {
+        if ((rc = ensure_buf(p, (void**)&p->jp_attr, &p->jp_attr_cap, (size_t)jp.dense_size * 4))) return rc;
+        jp.attr = p->jp_attr;
+        jp.present = (uint64_t)p->jb_rows == jp.dense_size ? nullptr : p->jf.dense;   // unique, NULL-free keys filling the range: every key exists
+    } else {
+        if ((rc = ensure_buf(p, (void**)&p->jp_packed, &p->jp_packed_cap, ((size_t)jp.packed_mask + 1) * 8))) return rc;
+        jp.packed = p->jp_packed;
+    }
+    CK(p, launch_join_compose(p->jf, (const uint32_t*)p->jb_vals[(size_t)attr_main], p->jp_attr, p->jp_packed, flag, p->stream));
+    p->stats.kernel_launches++;
+    p->jp = jp; p->jp_key_pos = (int)kpos;   // (the caller drops it again when `flag` comes back set)
+    return BKGPU_OK;
+}
+
 static int join_build_table(bkgpu_plan* p) {
     const Compiled& c = p->c;
     const size_t nc = c.cols.size();
@@ -510,16 +565,15 @@ static int join_build_table(bkgpu_plan* p) {
     key.values = p->jb_vals[ki]; key.validity = p->jb_bitmap[ki]; key.stype = prim_storage(c.cols[ki].prim); key.prim = c.cols[ki].prim;
     p->jt_built = true; p->jt_generic = false;   // the multimap of the general probe is built on first use (join_generic_table)
     // ---- FK -> PK fast path: are the build keys unique, and is their range dense or their type <= 32 bits? ----
-    p->jf = JoinFast{};
+    p->jf = JoinFast{}; p->jp = JoinProbe{};
     if (p->jg_buf.empty()) p->jg_buf.assign(nc, nullptr);
     bool build_nulls = false;
     for (size_t i = 0; i < nc; i++) if (c.col_side[i] == 1 && p->jb_has_null[i]) build_nulls = true;   // gathered columns must be NULL-free
     if (c.jfast && !build_nulls && p->jb_rows > 0) {
         const int cls = host_prim_class(c.join_key_prim);
         const uint64_t bias = cls == VC_I64 ? 0x8000000000000000ull : 0ull;
-        uint64_t* mm = nullptr; uint32_t* dup = nullptr;
-        if ((rc = dev_alloc(p, (void**)&mm, 16))) return rc;
-        if ((rc = dev_alloc(p, (void**)&dup, 8))) return rc;
+        if ((rc = ensure_buf(p, (void**)&p->j_scratch, &p->j_scratch_cap, 64))) return rc;
+        uint64_t* mm = p->j_scratch; uint32_t* dup = (uint32_t*)(p->j_scratch + 2);
         CK(p, launch_join_minmax(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, bias, mm, p->stream));
         uint64_t h_mm[2];
         CK(p, cudaMemcpyAsync(h_mm, mm, 16, cudaMemcpyDeviceToHost, p->stream));
@@ -529,23 +583,25 @@ static int join_build_table(bkgpu_plan* p) {
         const int kb = storage_bytes(prim_storage(c.join_key_prim));
         if (range > 0 && range <= (uint64_t)4 * (uint64_t)p->jb_rows + 1024 && range <= (1ull << 30)) {
             jf.mode = 1; jf.dense_min = h_mm[0]; jf.dense_size = range;
-            dev_free(p, p->jf_dense); if ((rc = dev_alloc(p, (void**)&p->jf_dense, (size_t)range * 4))) return rc;
+            if ((rc = ensure_buf(p, (void**)&p->jf_dense, &p->jf_dense_cap, (size_t)range * 4))) return rc;
             jf.dense = p->jf_dense;
         } else if (kb <= 4) {
             uint32_t pc = 1024; while ((int64_t)pc < 2 * p->jb_rows) pc <<= 1;
             jf.mode = 2; jf.packed_mask = pc - 1;
-            dev_free(p, p->jf_packed); if ((rc = dev_alloc(p, (void**)&p->jf_packed, (size_t)pc * 8))) return rc;
+            if ((rc = ensure_buf(p, (void**)&p->jf_packed, &p->jf_packed_cap, (size_t)pc * 8))) return rc;
             jf.packed = p->jf_packed;
         }
         if (jf.mode) {
             CK(p, launch_join_build_fast(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, jf, p->jf_dense, p->jf_packed, dup, p->stream));
-            uint32_t h_dup = 0;
-            CK(p, cudaMemcpyAsync(&h_dup, dup, 4, cudaMemcpyDeviceToHost, p->stream));
-            CK(p, cudaStreamSynchronize(p->stream));
             p->stats.kernel_launches += 2;
-            if (!h_dup) p->jf = jf;   // unique keys: the gather path is valid
+            p->jf = jf;
+            if ((rc = join_compose_probe(p, dup + 1))) return rc;   // enqueued behind the build: both flags come back in one round trip
+            uint32_t h_flags[2] = {0, 0};
+            CK(p, cudaMemcpyAsync(h_flags, dup, 8, cudaMemcpyDeviceToHost, p->stream));
+            CK(p, cudaStreamSynchronize(p->stream));
+            if (h_flags[0]) { p->jf = JoinFast{}; p->jp = JoinProbe{}; }   // duplicate build keys: not a PK, the general probe runs
+            else if (h_flags[1]) p->jp = JoinProbe{};
         }
-        dev_free(p, mm); dev_free(p, dup);
     }
     return BKGPU_OK;
 }
@@ -578,6 +634,19 @@ static int join_probe_batch(bkgpu_plan* p, const DevCol* probe_cols, int64_t nro
     }
     for (size_t w = 0; w < p->probe_map.size(); w++) all[(size_t)p->probe_map[w]] = probe_cols[w];
     // ---- FK -> PK fast path: gather the build columns next to the probe rows, then the ordinary (lean) aggregate ----
+    if (p->jf.mode != 0 && p->jp.mode != 0 && c.jfast && !p->force_generic && !p->no_fused_probe) {
+        // ---- fused probe: the lean aggregate reads the foreign key and looks the group key up itself ----
+        const Compiled& f = *c.jfast;
+        std::vector<DevCol> fc(f.cols.size());
+        const int key_fcol = f.direct_cols[(size_t)p->jp_key_pos];
+        bool vec_ok = true;
+        for (size_t i = 0; i < f.cols.size(); i++) {
+            fc[i] = (int)i == key_fcol ? all[(size_t)c.probe_key_col] : all[(size_t)c.jfast_of_main[i]];
+            if (((uintptr_t)fc[i].values & 31) != 0) vec_ok = false;
+        }
+        const int rc = launch_agg_batch(p, f, fc.data(), nrows, vec_ok, &p->jp);
+        if (rc <= 0) return rc;   // launched (0) or failed (< 0); +1: this batch does not fit the lean kernel
+    }
     if (p->jf.mode != 0 && c.jfast && !p->force_generic) {
         const Compiled& f = *c.jfast;
         const int64_t chunk = 16 << 20;   // the gathered chunk is re-read immediately: keep it L2-sized

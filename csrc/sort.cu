@@ -265,6 +265,78 @@ __global__ void __launch_bounds__(1024) k_sort_small(const uint64_t* k1, const u
     }
 }
 
+// one CTA: the r-th smallest (0-based) of n <= SAMPLE_N composite keys by radix selection — most significant byte
+// first over the 16 bytes of (key, idx), a 256-bin shared histogram per byte, stopping as soon as the selected bin
+// holds one element (random 64-bit keys: 2 rounds).  Same threshold rules as k_sort_small's rank output; replaces
+// a full bitonic sort of the sample (~70 us) on the top-k chain (profiles/r01_topk_history.md).
+__global__ void __launch_bounds__(1024) k_select_rank(const uint64_t* key, const uint64_t* idx, const uint32_t* np, uint32_t nmax,
+                                                      uint32_t rank, uint64_t* rank_out,
+                                                      const uint32_t* pop_ptr, uint32_t k_want, uint32_t widen, uint32_t room, const uint64_t* cap_thr) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_bin, s_rank, s_cnt;
+    __shared__ uint64_t s_res[2];
+    constexpr int PER = SAMPLE_N / 1024;
+    uint32_t n = *np; if (n > nmax) n = nmax; if (n > (uint32_t)SAMPLE_N) n = SAMPLE_N;
+    uint32_t r = rank;
+    if (pop_ptr) {
+        const double pop = (double)*pop_ptr;
+        if (pop <= (double)room) r = 0xFFFFFFFFu;
+        else { double w = ((double)k_want * (double)SAMPLE_N / pop * 1.5 + 32.0) * (double)widen; r = w >= (double)(SAMPLE_N - 1) ? 0xFFFFFFFFu : (uint32_t)w; }
+    }
+    if (threadIdx.x == 0) { s_res[0] = ~0ull; s_res[1] = ~0ull; }
+    if (n > 0 && r < n) {   // (uniform across the CTA)
+        uint64_t k[PER], ix[PER]; uint32_t alive = 0;
+#pragma unroll
+        for (int e = 0; e < PER; e++) {
+            const uint32_t i = threadIdx.x + e * 1024;
+            k[e] = 0; ix[e] = 0;
+            if (i < n) { k[e] = key[i]; ix[e] = idx[i]; alive |= 1u << e; }
+        }
+        uint32_t rr = r;
+        for (int byte = 15; byte >= 0; byte--) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            uint32_t dig[PER];
+#pragma unroll
+            for (int e = 0; e < PER; e++) {
+                dig[e] = (uint32_t)((byte >= 8 ? k[e] >> ((byte - 8) * 8) : ix[e] >> (byte * 8)) & 255ull);
+                if ((alive >> e) & 1u) atomicAdd(&hist[dig[e]], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {   // warp 0: the bin that holds rank rr
+                uint32_t h[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { h[j] = hist[threadIdx.x * 8 + j]; sum += h[j]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)threadIdx.x >= d) incl += o; }
+                uint32_t cum = incl - sum;
+                if (rr >= cum && rr < incl) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (rr < cum + h[j]) { s_bin = threadIdx.x * 8 + j; s_rank = rr - cum; s_cnt = h[j]; break; }
+                        cum += h[j];
+                    }
+                }
+            }
+            __syncthreads();
+            const uint32_t bin = s_bin;
+#pragma unroll
+            for (int e = 0; e < PER; e++) if (dig[e] != bin) alive &= ~(1u << e);
+            rr = s_rank;
+            if (s_cnt == 1 || byte == 0) break;
+        }
+#pragma unroll
+        for (int e = 0; e < PER; e++) if ((alive >> e) & 1u) { s_res[0] = k[e]; s_res[1] = ix[e]; }   // one element (or identical ones)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t tk = s_res[0], ti = s_res[1];
+        if (cap_thr && comp_lt(cap_thr[0], cap_thr[1], tk, ti)) { tk = cap_thr[0]; ti = cap_thr[1]; }   // never looser than the k-th row kept so far
+        rank_out[0] = tk; rank_out[1] = ti; rank_out[2] = n;
+    }
+}
+
 // ---- payload: gather rows of the current batch / move rows kept from earlier batches ----
 struct GatherArgs {
     DevCol cols[MAX_COLS]; int32_t n_cols; uint64_t row_base; int64_t nrows;
@@ -565,8 +637,7 @@ int select_topk_class(SortState* s, const RowArgs& ra, int cls, cudaStream_t st,
             k_sample_rows<<<(SAMPLE_N + 255) / 256, 256, 0, st>>>(ra, cls, s->samp_key, s->samp_idx, cnt, 0x5bd1e995ull + attempt * 7919);
             double w = ((double)k * (double)SAMPLE_N / (double)ra.nrows * 1.5 + 32.0) * (double)widen;
             uint32_t rank = w >= (double)(SAMPLE_N - 1) ? 0xFFFFFFFFu : (uint32_t)w;
-            k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr,
-                                                        rank, thr, nullptr, 0, 0, 0, pool_thr);
+            k_select_rank<<<1, 1024, 0, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, rank, thr, nullptr, 0, 0, 0, pool_thr);
             stats->kernel_launches += 2;
         } else if (pool_thr) {
             SCK(cudaMemcpyAsync(thr, pool_thr, 16, cudaMemcpyDeviceToDevice, st));
@@ -588,8 +659,7 @@ int select_topk_class(SortState* s, const RowArgs& ra, int cls, cudaStream_t st,
             SCK(cudaMemsetAsync(cnt, 0, 4, st));
             k_sample_pairs<<<(SAMPLE_N + 255) / 256, 256, 0, st>>>(s->cand_key[from], s->cand_idx[from], cnt + src_cnt[lvl], s->cand_cap, s->samp_key, s->samp_idx, cnt,
                                                                    0x9e3779b9ull + attempt * 104729 + lvl);
-            k_sort_small<<<1, 1024, SMALL_N * 16, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr,
-                                                        0, thr + 3 * (lvl + 1), cnt + src_cnt[lvl], k, widen, room, nullptr);
+            k_select_rank<<<1, 1024, 0, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, 0, thr + 3 * (lvl + 1), cnt + src_cnt[lvl], k, widen, room, nullptr);
             k_collect_pairs<<<grid_for(lvl == 0 ? (int64_t)s->cand_cap / 4 : 65536, 256, s->sm_count), 256, 0, st>>>(
                 s->cand_key[from], s->cand_idx[from], cnt + src_cnt[lvl], thr + 3 * (lvl + 1), s->cand_key[to], s->cand_idx[to], cnt + dst_cnt[lvl], s->cand_cap);
             stats->kernel_launches += 3;

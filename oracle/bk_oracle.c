@@ -732,6 +732,8 @@ static int scan_open(Ctx* c, Node* n) {
         if (s->nrows >= 0 && s->nrows != c->cols[i].length) { snprintf(c->err, c->errlen, "ragged columns in tuple %d", n->tuple_id); return -1; }
         s->nrows = c->cols[i].length;
     }
+    /* a scalar merger's input rows carry only the aggregate tuple: the batch length is then any column's */
+    if (s->nrows < 0 && g_scan_nodes == 1 && c->n_cols > 0) s->nrows = c->cols[0].length;
     if (s->nrows < 0) s->nrows = 0;
     /* A store returns rows that carry the scan tuple AND the aggregate tuple (region.cpp:3166-3216);
      * with a single scan node every input tuple therefore shares the row index (MERGE_AGG input). */

@@ -14,15 +14,18 @@ def test_c3_join_groupby():
     fact, dim = datagen.c3_fact(0, 400_000, 20_000), datagen.c3_dim(0, 20_000, 20_000, n_groups=100)
     got, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact])
     assert len(got[0]) == 100
-    # unique build keys, every probe row matched: the FK -> PK gather path feeds the lean aggregate kernel
+    # unique build keys: the lean aggregate kernel looks the GROUP BY attribute up through the foreign key itself
+    assert stats.main_kernel_name.decode() == "k_agg_group_lean"
+    # ... or, with the fused probe switched off, reads build columns gathered to probe-row alignment
+    _, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact], options={"no_fused_probe": 1})
     assert stats.main_kernel_name.decode() == "k_agg_group_lean"
     _, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact], options={"force_generic": 1})
     assert stats.main_kernel_name.decode() == "k_agg_interp"
 
 
 def test_join_fast_path_sparse_keys_and_unmatched_rows():
-    """unique but sparse build keys (packed table instead of the dense array) and probe rows without a partner:
-    those chunks fall back to the general probe; results stay identical"""
+    """unique but sparse build keys (packed table instead of the dense array) and probe rows without a partner: the
+    fused probe drops them (inner join); the gather path hands such chunks to the general probe; results stay identical"""
     rng = np.random.default_rng(41)
     nd, nf = 5_000, 120_000
     pk = rng.permutation(1 << 24)[:nd].astype(np.int32) * 97          # sparse: range >> 4 * n
@@ -34,7 +37,24 @@ def test_join_fast_path_sparse_keys_and_unmatched_rows():
     fk2 = fk.copy(); fk2[::1000] = 5                                   # 5 is not a build key
     fact_miss = [make_column(0, 1, T.INT32, fk2), make_column(0, 2, T.DOUBLE, fact_all[1].values)]
     _, stats, _ = run_both(queries.c3_join_groupby(), fact_miss + dim, keys=["1_2"], batches=[dim, fact_miss])
+    assert stats.main_kernel_name.decode() == "k_agg_group_lean"
+    _, stats, _ = run_both(queries.c3_join_groupby(), fact_miss + dim, keys=["1_2"], batches=[dim, fact_miss], options={"no_fused_probe": 1})
     assert stats.main_kernel_name.decode() == "k_agg_interp"
+
+
+@pytest.mark.parametrize("nf", [100_003, 64_001, 2])
+def test_join_fused_probe_dense_with_gaps_negative_keys_and_ragged_tail(nf):
+    """dense key index with holes (present[] consulted), negative keys (bias), probe keys outside the range, a batch
+    length that is not a multiple of four (tail rows probe one by one), unsigned attribute values above 2^31"""
+    rng = np.random.default_rng(nf)
+    nd = 3_000
+    pk = (rng.permutation(4_000)[:nd] - 2_000).astype(np.int32)        # range 4000 > 3000 keys: gaps
+    dim = [make_column(1, 1, T.INT32, pk), make_column(1, 2, T.INT32, rng.integers(-7, 7, nd))]
+    fk = rng.integers(-2_500, 2_500, nf).astype(np.int32)              # some outside [min, max], some in gaps
+    fact = [make_column(0, 1, T.INT32, fk), make_column(0, 2, T.DOUBLE, rng.random(nf))]
+    _, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact])
+    if nf > 4:
+        assert stats.main_kernel_name.decode() == "k_agg_group_lean"
 
 
 def test_c3_streamed_in_several_batches_host_and_build_first_rule():

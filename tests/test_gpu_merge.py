@@ -35,7 +35,7 @@ def _regions_partial_rows(n, regions, n_groups):
 @pytest.mark.parametrize("n,regions,groups", [(60_000, 4, 1000), (5_000, 7, 37)])
 def test_merge_rows_matches_oracle_and_single_pass(n, regions, groups):
     rows = _regions_partial_rows(n, regions, groups)
-    got, _ = run_both(queries.c2_filter_groupby(merge=True), rows, ["0_1"])
+    got, _, _ = run_both(queries.c2_filter_groupby(merge=True), rows, ["0_1"])
     single = oracle.execute(queries.c2_filter_groupby().serialize(), datagen.c2_table(0, n, n_groups=groups))
     assert_same_rows(got, single.columns, ["0_1"], rel=1e-9, abs_tol=1e-9)
 
