@@ -230,6 +230,9 @@ def main():
     _lib.check(L.bkgpu_init(ctypes.byref(h), plan_bytes, len(plan_bytes), dev, comm if world > 1 else None))
     _lib.check(L.bkgpu_set_option(h, b"stream", stream.cuda_stream), h)
     _lib.check(L.bkgpu_set_option(h, b"group_capacity_log2", 14), h)
+    for kv in filter(None, os.environ.get("BKGPU_BENCH_OPTS", "").split(",")):   # A/B of kernel variants: "l2_lanes=1,no_lean=1"
+        k, v = kv.split("=")
+        _lib.check(L.bkgpu_set_option(h, k.encode(), int(v)), h)
     _lib.check(L.bkgpu_open(h), h)
     out = (BkgpuColumn * 16)()
 

@@ -843,8 +843,10 @@ static inline cudaError_t launch_direct(const AggArgs& a, int sm_count, size_t s
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
             }
-            if (a.jp.mode) k_agg_group_lean<NP, NA, true><<<direct_grid(k_agg_group_lean<NP, NA, true>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
-            else k_agg_group_lean<NP, NA, false><<<direct_grid(k_agg_group_lean<NP, NA, false>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
+            int grid = a.jp.mode ? direct_grid(k_agg_group_lean<NP, NA, true>, smem, sm_count, a.nrows, LEAN_THREADS)
+                                 : direct_grid(k_agg_group_lean<NP, NA, false>, smem, sm_count, a.nrows, LEAN_THREADS);
+            if (a.jp.mode) k_agg_group_lean<NP, NA, true><<<grid, LEAN_THREADS, smem, s>>>(a);
+            else k_agg_group_lean<NP, NA, false><<<grid, LEAN_THREADS, smem, s>>>(a);
         } else
         k_agg_group_direct<NP, NA><<<direct_grid(k_agg_group_direct<NP, NA>, smem, sm_count, a.nrows), DIRECT_THREADS, smem, s>>>(a);
     } else {

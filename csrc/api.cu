@@ -63,7 +63,8 @@ struct bkgpu_plan {
     uint64_t* d_partial = nullptr;  // export buffer (this rank)
     uint64_t* d_gather = nullptr;   // nranks export buffers
     uint64_t* d_outv = nullptr; uint8_t* d_outn = nullptr; size_t out_cap_alloc = 0;  // extraction buffers (kept across resets)
-    std::vector<uint64_t> hv; std::vector<uint8_t> hn;
+    std::vector<cudaEvent_t> event_pool;
+    uint64_t* h_outv = nullptr; uint8_t* h_outn = nullptr; size_t h_out_cap = 0;   // pinned landing area of the extracted rows
     uint32_t known_groups = 0;
     uint32_t* h_pinned = nullptr;   // [0] groups seen (async copy after every aggregate launch), pinned
     // hash join (K4): retained build side + multimap
@@ -151,7 +152,10 @@ static int ensure_buf(bkgpu_plan* p, void** ptr, size_t* cap, size_t bytes) {
 }
 static EventPair* timer_begin(bkgpu_plan* p, std::vector<EventPair>& v, int64_t bytes) {
     EventPair ep{};
-    if (cudaEventCreate(&ep.a) != cudaSuccess || cudaEventCreate(&ep.b) != cudaSuccess) return nullptr;
+    for (cudaEvent_t* e : {&ep.a, &ep.b}) {   // events are recycled: a re-armed plan launches the same kernels again and again
+        if (!p->event_pool.empty()) { *e = p->event_pool.back(); p->event_pool.pop_back(); }
+        else if (cudaEventCreate(e) != cudaSuccess) return nullptr;
+    }
     ep.bytes = bytes;
     cudaEventRecord(ep.a, p->stream);
     v.push_back(ep);
@@ -348,6 +352,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
             if (a.n_smem_lanes < 2) a.n_smem_lanes = 2;
             a.smem_cap_log2 = pick_smem_log2(p, a.n_smem_lanes, true, na);
             if (a.smem_cap_log2 <= 0) { a.lean = 0; a.smem_paired = 0; return p->fail(BKGPU_ENOMEM, "lean kernel: shared table does not fit"); }
+
         }
     }
     if (jp) { if (!a.lean) return 1; a.jp = *jp; }
@@ -769,7 +774,7 @@ static int agg_finish(bkgpu_plan* p) {
     for (int k = 0; k < ap.n_agg; k++) if (!ap.agg[k].hidden) n_img += ap.agg[k].kind == AG_AVG ? 3 : 1;
     int rc;
     uint32_t n_out = 0, out_cap = 0;
-    std::vector<uint64_t>& hv = p->hv; std::vector<uint8_t>& hn = p->hn;
+    uint64_t* hv = nullptr; uint8_t* hn = nullptr;
     for (int attempt = 0; attempt < 2; attempt++) {
         // speculative extraction into the buffers kept from earlier runs: counts, cursor and rows come back
         // in ONE synchronisation; only a result larger than the buffers costs a second round
@@ -785,13 +790,24 @@ static int agg_finish(bkgpu_plan* p) {
         out_cap = (uint32_t)p->out_cap_alloc;
         CK(p, launch_extract(gt, ap, p->d_outv, p->d_outn, out_cap, p->d_cursor, p->c.emit_default ? 1 : 0, p->stream));
         p->stats.kernel_launches++;
-        hv.resize((size_t)out_cap * (size_t)n_img); hn.resize((size_t)out_cap * (size_t)n_img);
-        CK(p, cudaMemcpyAsync(host_counts, gt.n_groups, 8, cudaMemcpyDeviceToHost, p->stream));
-        CK(p, cudaMemcpyAsync(&n_out, p->d_cursor, 4, cudaMemcpyDeviceToHost, p->stream));
-        CK(p, cudaMemcpyAsync(hv.data(), p->d_outv, hv.size() * 8, cudaMemcpyDeviceToHost, p->stream));
-        CK(p, cudaMemcpyAsync(hn.data(), p->d_outn, hn.size(), cudaMemcpyDeviceToHost, p->stream));
+        const size_t n_words = (size_t)out_cap * (size_t)n_img;
+        if (p->h_out_cap < n_words) {   // pinned: the four copies below are truly asynchronous and land in one synchronisation
+            if (p->h_outv) cudaFreeHost(p->h_outv);
+            if (p->h_outn) cudaFreeHost(p->h_outn);
+            p->h_outv = nullptr; p->h_outn = nullptr; p->h_out_cap = 0;
+            CK(p, cudaHostAlloc((void**)&p->h_outv, n_words * 8, cudaHostAllocDefault));
+            CK(p, cudaHostAlloc((void**)&p->h_outn, n_words, cudaHostAllocDefault));
+            p->h_out_cap = n_words;
+        }
+        hv = p->h_outv; hn = p->h_outn;
+        uint32_t* hc3 = p->h_pinned ? p->h_pinned + 8 : nullptr;   // [8] groups [9] overflow [10] rows extracted
+        CK(p, cudaMemcpyAsync(hc3 ? hc3 : host_counts, gt.n_groups, 8, cudaMemcpyDeviceToHost, p->stream));
+        CK(p, cudaMemcpyAsync(hc3 ? hc3 + 2 : &n_out, p->d_cursor, 4, cudaMemcpyDeviceToHost, p->stream));
+        CK(p, cudaMemcpyAsync(hv, p->d_outv, n_words * 8, cudaMemcpyDeviceToHost, p->stream));
+        CK(p, cudaMemcpyAsync(hn, p->d_outn, n_words, cudaMemcpyDeviceToHost, p->stream));
         CK(p, cudaStreamSynchronize(p->stream));
-        p->stats.d2h_bytes += (int64_t)(hv.size() * 8 + hn.size() + 12);
+        if (hc3) { host_counts[0] = hc3[0]; host_counts[1] = hc3[1]; n_out = hc3[2]; }
+        p->stats.d2h_bytes += (int64_t)(n_words * 9 + 12);
         if (host_counts[1]) return p->fail(BKGPU_ETOOBIG, "group table overflow (capacity 2^%d slots / partial_capacity %lld): raise group_capacity_log2",
                                            (int)gt.cap_log2, (long long)p->partial_cap);
         if (host_counts[0] > p->known_groups) p->known_groups = host_counts[0];
@@ -836,13 +852,13 @@ static void resolve_timers(bkgpu_plan* p) {
     for (auto& ep : p->timed) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) { p->stats.main_kernel_ms += ms; p->stats.main_kernel_launches++; p->stats.main_kernel_bytes += ep.bytes; }
-        cudaEventDestroy(ep.a); cudaEventDestroy(ep.b);
+        p->event_pool.push_back(ep.a); p->event_pool.push_back(ep.b);
     }
     p->timed.clear();
     for (auto& ep : p->timed_coll) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) p->stats.collective_ms += ms;
-        cudaEventDestroy(ep.a); cudaEventDestroy(ep.b);
+        p->event_pool.push_back(ep.a); p->event_pool.push_back(ep.b);
     }
     p->timed_coll.clear();
 }
@@ -941,9 +957,12 @@ extern "C" void bkgpu_close(bkgpu_plan* p) {
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
     resolve_timers(p);
     if (p->sort) sort_close(p->sort);
+    for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
     for (void* q : p->dev_allocs) cudaFree(q);
     for (int i = 0; i < 2; i++) { if (p->stage_free[i]) cudaEventDestroy(p->stage_free[i]); if (p->stage_ready[i]) cudaEventDestroy(p->stage_ready[i]); }
     if (p->h_pinned) cudaFreeHost(p->h_pinned);
+    if (p->h_outv) cudaFreeHost(p->h_outv);
+    if (p->h_outn) cudaFreeHost(p->h_outn);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;

@@ -567,6 +567,8 @@ struct SortState {
     uint64_t *samp_key = nullptr, *samp_idx = nullptr;
     uint32_t* d_counts = nullptr;   // [0] sample count, [1] candidate count A, [2] candidate count B, [3] class count, [4] pool out n
     uint64_t* d_rank = nullptr;     // {key, idx, n}
+    uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;   // pinned landing area of the top-k rows
+    uint32_t* h_counts = nullptr;                         // pinned copy of d_counts
     // full sort / filter-only: retained rows
     std::vector<uint8_t*> ret_vals, ret_null; int64_t ret_rows = 0, ret_cap = 0;
     std::vector<uint8_t*> key_img;  // per ORDER BY key: retained images (full sort)
@@ -618,6 +620,7 @@ int select_topk_class(SortState* s, const RowArgs& ra, int cls, cudaStream_t st,
     uint64_t* thr = s->d_rank;       // three {key, idx, n} triples: thresholds of the three levels
     const uint32_t old_n = std::min<uint32_t>(P.n, k);
     const uint32_t room = SMALL_N - old_n;
+    const uint32_t trim = std::min<uint32_t>(room, std::max<uint32_t>(2 * k, 2048) - std::min<uint32_t>(old_n, 1024));
     const int nxt = P.cur ^ 1;
     const uint64_t* pool_thr = nullptr;
     if (P.n >= k) {   // later rows must beat the k-th composite key kept so far
@@ -659,7 +662,8 @@ int select_topk_class(SortState* s, const RowArgs& ra, int cls, cudaStream_t st,
             SCK(cudaMemsetAsync(cnt, 0, 4, st));
             k_sample_pairs<<<(SAMPLE_N + 255) / 256, 256, 0, st>>>(s->cand_key[from], s->cand_idx[from], cnt + src_cnt[lvl], s->cand_cap, s->samp_key, s->samp_idx, cnt,
                                                                    0x9e3779b9ull + attempt * 104729 + lvl);
-            k_select_rank<<<1, 1024, 0, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, 0, thr + 3 * (lvl + 1), cnt + src_cnt[lvl], k, widen, room, nullptr);
+            // (levels keep trimming until about two k-fulls are left: the one-CTA sort below costs 35 us for <= 2048 keys, 150 us for 8192)
+            k_select_rank<<<1, 1024, 0, st>>>(s->samp_key, s->samp_idx, cnt, SAMPLE_N, 0, thr + 3 * (lvl + 1), cnt + src_cnt[lvl], k, widen, trim, nullptr);
             k_collect_pairs<<<grid_for(lvl == 0 ? (int64_t)s->cand_cap / 4 : 65536, 256, s->sm_count), 256, 0, st>>>(
                 s->cand_key[from], s->cand_idx[from], cnt + src_cnt[lvl], thr + 3 * (lvl + 1), s->cand_key[to], s->cand_idx[to], cnt + dst_cnt[lvl], s->cand_cap);
             stats->kernel_launches += 3;
@@ -672,8 +676,10 @@ int select_topk_class(SortState* s, const RowArgs& ra, int cls, cudaStream_t st,
         g.n_cols = s->ncols; g.row_base = ra.row_base; g.nrows = ra.nrows; g.old_idx = P.idx[P.cur]; g.old_n = old_n;
         k_gather_topk<<<std::max(1, (int)((k + 127) / 128)), 128, 0, st>>>(g, P.idx[nxt], cnt + 4);
         stats->kernel_launches += 3;
-        SCK(cudaMemcpyAsync(h, cnt, 32, cudaMemcpyDeviceToHost, st));
+        if (!s->h_counts) SCK(cudaHostAlloc((void**)&s->h_counts, 64, cudaHostAllocDefault));
+        SCK(cudaMemcpyAsync(s->h_counts, cnt, 32, cudaMemcpyDeviceToHost, st));
         SCK(cudaStreamSynchronize(st));
+        memcpy(h, s->h_counts, 32);
         const uint32_t c1 = h[1], c2 = h[2], cls_rows = h[3], c3 = h[5];
         const bool ok1 = c1 <= s->cand_cap && (c1 >= k || c1 >= cls_rows || pool_thr != nullptr);
         const bool ok2 = c2 <= s->cand_cap && (c2 >= std::min(k, c1));
@@ -858,50 +864,58 @@ size_t sort_partial_bytes(SortState* s) {
     return 8 * (1 + 2 * 2 * k) + (size_t)s->ncols * 2 * (k * 8 + ((k + 7) & ~(size_t)7));
 }
 
-static int pool_rows_to_host(SortState* s, int p, std::vector<uint64_t>& key, std::vector<uint64_t>& idx, std::vector<std::vector<uint8_t>>& vals,
-                             std::vector<std::vector<uint8_t>>& nulls, cudaStream_t st, std::string& err) {
-    Pool& P = s->pool[p];
-    const size_t n = P.n;
-    key.resize(n); idx.resize(n); vals.assign((size_t)s->ncols, {}); nulls.assign((size_t)s->ncols, {});
-    if (n) {
-        SCK(cudaMemcpyAsync(key.data(), P.key[P.cur], n * 8, cudaMemcpyDeviceToHost, st));
-        SCK(cudaMemcpyAsync(idx.data(), P.idx[P.cur], n * 8, cudaMemcpyDeviceToHost, st));
-    }
-    for (int c = 0; c < s->ncols; c++) {
-        const int eb = elem_bytes_of(s->c.cols[(size_t)c].prim);
-        vals[(size_t)c].resize(n * eb + 1); nulls[(size_t)c].resize(n + 1);
-        if (n) {
-            SCK(cudaMemcpyAsync(vals[(size_t)c].data(), P.vals[P.cur][c], n * eb, cudaMemcpyDeviceToHost, st));
-            SCK(cudaMemcpyAsync(nulls[(size_t)c].data(), P.nulls[P.cur][c], n, cudaMemcpyDeviceToHost, st));
-        }
-    }
-    SCK(cudaStreamSynchronize(st));
-    return 0;
-}
-
 // host image of the k best rows of this rank: class-tagged, ready to be merged with other ranks'
 struct HostRows {
     std::vector<uint8_t> cls; std::vector<uint64_t> key, idx;
     std::vector<std::vector<uint8_t>> vals, nulls;   // per column, row-major fixed width
 };
 
+// the k surviving rows of both pools (keys present / NULL keys) land in ONE pinned staging block: every copy is truly
+// asynchronous and the whole result costs a single synchronisation
 static int topk_host_rows(SortState* s, HostRows& h, cudaStream_t st, std::string& err) {
     h.vals.assign((size_t)s->ncols, {}); h.nulls.assign((size_t)s->ncols, {});
+    size_t row_bytes = 16;
+    for (int c = 0; c < s->ncols; c++) row_bytes += (size_t)elem_bytes_of(s->c.cols[(size_t)c].prim) + 1;
+    const size_t n_tot = (size_t)s->pool[0].n + (size_t)s->pool[1].n;
+    const size_t need = n_tot * row_bytes + 64 * (size_t)(s->ncols + 2) * 2;
+    if (s->h_stage_cap < need) {
+        if (s->h_stage) cudaFreeHost(s->h_stage);
+        s->h_stage = nullptr; s->h_stage_cap = 0;
+        SCK(cudaHostAlloc((void**)&s->h_stage, need * 2, cudaHostAllocDefault));
+        s->h_stage_cap = need * 2;
+    }
+    struct Seg { size_t key, idx; std::vector<size_t> val, nul; } seg[2];
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 63) & ~(size_t)63; return o; };
     for (int p = 0; p < 2; p++) {
-        std::vector<uint64_t> key, idx; std::vector<std::vector<uint8_t>> vals, nulls;
-        int rc = pool_rows_to_host(s, p, key, idx, vals, nulls, st, err);
-        if (rc) return rc;
-        for (size_t i = 0; i < key.size(); i++) { h.cls.push_back((uint8_t)(p + 1)); h.key.push_back(key[i]); h.idx.push_back(idx[i]); }
+        Pool& P = s->pool[p];
+        const size_t n = P.n;
+        if (!n) continue;
+        seg[p].key = take(n * 8); seg[p].idx = take(n * 8);
+        SCK(cudaMemcpyAsync(s->h_stage + seg[p].key, P.key[P.cur], n * 8, cudaMemcpyDeviceToHost, st));
+        SCK(cudaMemcpyAsync(s->h_stage + seg[p].idx, P.idx[P.cur], n * 8, cudaMemcpyDeviceToHost, st));
         for (int c = 0; c < s->ncols; c++) {
-            const int eb = elem_bytes_of(s->c.cols[(size_t)c].prim);
-            h.vals[(size_t)c].insert(h.vals[(size_t)c].end(), vals[(size_t)c].begin(), vals[(size_t)c].begin() + (ptrdiff_t)(key.size() * eb));
-            h.nulls[(size_t)c].insert(h.nulls[(size_t)c].end(), nulls[(size_t)c].begin(), nulls[(size_t)c].begin() + (ptrdiff_t)key.size());
+            const size_t eb = (size_t)elem_bytes_of(s->c.cols[(size_t)c].prim);
+            seg[p].val.push_back(take(n * eb)); seg[p].nul.push_back(take(n));
+            SCK(cudaMemcpyAsync(s->h_stage + seg[p].val.back(), P.vals[P.cur][c], n * eb, cudaMemcpyDeviceToHost, st));
+            SCK(cudaMemcpyAsync(s->h_stage + seg[p].nul.back(), P.nulls[P.cur][c], n, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    SCK(cudaStreamSynchronize(st));
+    for (int p = 0; p < 2; p++) {
+        const size_t n = s->pool[p].n;
+        if (!n) continue;
+        const uint64_t* key = (const uint64_t*)(s->h_stage + seg[p].key); const uint64_t* idx = (const uint64_t*)(s->h_stage + seg[p].idx);
+        for (size_t i = 0; i < n; i++) { h.cls.push_back((uint8_t)(p + 1)); h.key.push_back(key[i]); h.idx.push_back(idx[i]); }
+        for (int c = 0; c < s->ncols; c++) {
+            const size_t eb = (size_t)elem_bytes_of(s->c.cols[(size_t)c].prim);
+            const uint8_t* v = s->h_stage + seg[p].val[(size_t)c]; const uint8_t* nb = s->h_stage + seg[p].nul[(size_t)c];
+            h.vals[(size_t)c].insert(h.vals[(size_t)c].end(), v, v + n * eb);
+            h.nulls[(size_t)c].insert(h.nulls[(size_t)c].end(), nb, nb + n);
         }
     }
     return 0;
 }
-
-// order host rows by (class rank, key image, arrival index), apply offset / limit, build output columns
 static void finish_host_rows(SortState* s, const HostRows& h, std::vector<SortOutCol>& out, int64_t* nrows) {
     const bool null_first = s->c.sort_keys[0].null_first;
     std::vector<uint32_t> order(h.key.size());
@@ -1086,6 +1100,8 @@ int sort_finish(SortState* s, void* nccl_comm, int nranks, cudaStream_t st, bkgp
 void sort_close(SortState* s) {
     if (!s) return;
     for (void* p : s->allocs) cudaFree(p);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    if (s->h_counts) cudaFreeHost(s->h_counts);
     delete s;
 }
 
