@@ -148,6 +148,95 @@ struct RuntimeState {
     bool is_cancelled() const { return cancelled; }
 };
 
+// ---------------------------------------------------------------- rows <-> columns (f1: the MemRow / RowBatch bridge)
+// What `MemRow::get_value(tuple, slot)` hands an operator: a typed value or NULL (include/mem_row/mem_row.h:28-215,
+// ExprValue in include/common/expr_value.h).  64-bit payload in the slot's value class.
+struct Value {
+    bool is_null = true;
+    union { int64_t i64; uint64_t u64; double f64; };
+    Value() : i64(0) {}
+    static Value of_int(int64_t v) { Value x; x.is_null = false; x.i64 = v; return x; }
+    static Value of_uint(uint64_t v) { Value x; x.is_null = false; x.u64 = v; return x; }
+    static Value of_double(double v) { Value x; x.is_null = false; x.f64 = v; return x; }
+};
+using MemRowValues = std::vector<Value>;   // one Value per slot of the chunk's schema, in schema order
+
+// Chunk: row -> column builder with the reference's type map (src/runtime/chunk.cpp:33-92: INT8/16/32,TIME -> int32;
+// INT64 -> int64; UINT8/16/32,TIMESTAMP,DATE -> uint32; UINT64,DATETIME -> uint64; FLOAT -> f32; DOUBLE -> f64; BOOL -> u8)
+class Chunk {
+public:
+    struct Slot { int tuple_id, slot_id, prim_type; };
+    explicit Chunk(std::vector<Slot> schema) : _schema(std::move(schema)) { reset(); }
+    static int storage_bytes(int prim) {
+        switch (prim) {
+            case BK_BOOL: return 1;
+            case BK_INT8: case BK_INT16: case BK_INT32: case BK_TIME: case BK_UINT8: case BK_UINT16: case BK_UINT32: case BK_TIMESTAMP: case BK_DATE: case BK_FLOAT: return 4;
+            case BK_INT64: case BK_UINT64: case BK_DATETIME: case BK_DOUBLE: return 8;
+            default: return -1;
+        }
+    }
+    int add_row(const MemRowValues& row) {   // Chunk::add_row / decode_row (chunk.cpp:335-384)
+        if (row.size() != _schema.size()) return -1;
+        for (size_t c = 0; c < _schema.size(); c++) {
+            Column& col = _batch.columns[c];
+            const Value& v = row[c];
+            const int eb = col.elem_size;
+            const size_t off = col.values.size();
+            col.values.resize(off + (size_t)eb, 0);
+            if (v.is_null) {
+                if (col.validity.empty()) col.validity.assign((size_t)(_rows + 8) / 8, 0xFF);
+                if (col.validity.size() * 8 <= (size_t)_rows) col.validity.resize((size_t)_rows / 8 + 1, 0xFF);
+                col.validity[(size_t)_rows >> 3] &= (uint8_t)~(1u << (_rows & 7));
+            } else {
+                if (!col.validity.empty() && col.validity.size() * 8 <= (size_t)_rows) col.validity.resize((size_t)_rows / 8 + 1, 0xFF);
+                uint8_t* dst = col.values.data() + off;
+                switch (_schema[c].prim_type) {
+                    case BK_FLOAT: { float f = (float)v.f64; memcpy(dst, &f, 4); } break;
+                    case BK_DOUBLE: memcpy(dst, &v.f64, 8); break;
+                    case BK_BOOL: dst[0] = v.i64 ? 1 : 0; break;
+                    default: memcpy(dst, &v.i64, (size_t)eb); break;   // little-endian narrowing of the integer payload
+                }
+            }
+            col.length = _rows + 1;
+        }
+        _rows++;
+        return 0;
+    }
+    int64_t size() const { return _rows; }
+    RowBatch finish() {   // Chunk::finish_and_make_record_batch
+        for (auto& c : _batch.columns) if (!c.validity.empty()) c.validity.resize((size_t)(_rows + 7) / 8 + 1, 0xFF);
+        RowBatch out = std::move(_batch); reset(); return out;
+    }
+    // column batch -> rows (what a parent row-engine operator pulls out of a GPU subtree)
+    static std::vector<MemRowValues> to_rows(const RowBatch& b) {
+        std::vector<MemRowValues> rows((size_t)b.size(), MemRowValues(b.columns.size()));
+        for (size_t c = 0; c < b.columns.size(); c++) {
+            const Column& col = b.columns[c];
+            for (int64_t r = 0; r < col.length; r++) {
+                if (col.is_null(r)) continue;
+                Value& v = rows[(size_t)r][c]; v.is_null = false;
+                const uint8_t* src = col.values.data() + (size_t)r * (size_t)col.elem_size;
+                switch (col.prim_type) {
+                    case BK_FLOAT: { float f; memcpy(&f, src, 4); v.f64 = f; } break;
+                    case BK_DOUBLE: memcpy(&v.f64, src, 8); break;
+                    case BK_BOOL: v.i64 = src[0]; break;
+                    case BK_INT8: case BK_INT16: case BK_INT32: case BK_TIME: { int32_t x; memcpy(&x, src, 4); v.i64 = x; } break;
+                    case BK_UINT8: case BK_UINT16: case BK_UINT32: case BK_TIMESTAMP: case BK_DATE: { uint32_t x; memcpy(&x, src, 4); v.u64 = x; } break;
+                    case BK_STRING: memcpy(&v.f64, src, 8); break;   // AVG intermediate: the sum half (count: src + 8)
+                    default: memcpy(&v.i64, src, 8); break;
+                }
+            }
+        }
+        return rows;
+    }
+private:
+    void reset() {
+        _rows = 0; _batch.columns.clear();
+        for (auto& s : _schema) { Column c; c.tuple_id = s.tuple_id; c.slot_id = s.slot_id; c.prim_type = s.prim_type; c.elem_size = storage_bytes(s.prim_type); _batch.columns.push_back(std::move(c)); }
+    }
+    std::vector<Slot> _schema; RowBatch _batch; int64_t _rows = 0;
+};
+
 // ---------------------------------------------------------------- operators
 class ExecNode {
 public:
@@ -174,6 +263,23 @@ public:
     }
 private:
     std::vector<RowBatch> _batches; size_t _pos = 0;
+};
+
+// leaf of a ROW engine below a GPU subtree: rows arrive one by one (RocksdbScanNode::get_next fills a RowBatch of <= 1024
+// MemRows, include/runtime/row_batch.h:24-231); the Chunk turns every `capacity` of them into one column batch
+class RowScanNode : public ExecNode {
+public:
+    RowScanNode(std::vector<Chunk::Slot> schema, std::vector<MemRowValues> rows, int64_t capacity = 1024)
+        : _chunk(std::move(schema)), _rows(std::move(rows)), _capacity(capacity) {}
+    int get_next(RuntimeState*, RowBatch* batch, bool* eos) override {
+        batch->clear();
+        while (_pos < _rows.size() && _chunk.size() < _capacity) if (_chunk.add_row(_rows[_pos++]) < 0) return -1;
+        if (_chunk.size() > 0) *batch = _chunk.finish();
+        *eos = _pos >= _rows.size();
+        return 0;
+    }
+private:
+    Chunk _chunk; std::vector<MemRowValues> _rows; size_t _pos = 0; int64_t _capacity;
 };
 
 // the fused AGG -> [FILTER] -> SCAN / SORT / AGG -> JOIN / FILTER subtree on the GPU

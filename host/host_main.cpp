@@ -6,6 +6,8 @@
 //   bkgpu_host plan    <c1|c2|c3|c5>                       hex of the serialized plan (compared with plan.py's bytes)
 //   bkgpu_host explain <c1|c2|c3|c5>                       bkgpu_plan_explain of it (no GPU needed)
 //   bkgpu_host run     <c1|c2|c3|c5> <rows> [batch_rows]   executes on cuda:0 and prints one result row per line
+//   bkgpu_host rows    c2 <rows> [capacity]                 the same table fed ROW by row (MemRow-style values with NULLs every
+//                                                           17th key) through Chunk -> column batches -> GPU -> Chunk::to_rows
 #include <cinttypes>
 #include <cmath>
 #include <cstdio>
@@ -149,6 +151,38 @@ int main(int argc, char** argv) {
     RuntimeState state; state.row_batch_capacity = 4096;
     GpuExecNode root;
     if (root.init(plan) < 0) return 1;
+    if (mode == "rows") {   // f1: a row-engine child below the GPU subtree
+        std::vector<int32_t> k = gen_uniform_i32(2, 1, 0, rows, 0, 1000), f = gen_uniform_i32(2, 2, 0, rows, 0, 1 << 20);
+        std::vector<double> a = gen_u01(2, 3, 0, rows), b = gen_normal(2, 4, 0, rows, 1000.0 * 1.7320508075688772);
+        std::vector<MemRowValues> mem_rows((size_t)rows);
+        for (int64_t i = 0; i < rows; i++) {
+            MemRowValues& r = mem_rows[(size_t)i];
+            r = {k[(size_t)i] % 17 == 0 ? Value() : Value::of_int(k[(size_t)i]), Value::of_int(f[(size_t)i]), Value::of_double(a[(size_t)i]), Value::of_double(b[(size_t)i])};
+        }
+        root.add_child(std::unique_ptr<ExecNode>(new RowScanNode({{0, 1, BK_INT32}, {0, 2, BK_INT32}, {0, 3, BK_DOUBLE}, {0, 4, BK_DOUBLE}}, std::move(mem_rows), argc > 4 ? atoll(argv[4]) : 1024)));
+        if (root.open(&state) < 0) { fprintf(stderr, "open failed (%d): %s\n", state.error_code, state.error_msg.c_str()); return 1; }
+        bool eos = false; int64_t total = 0;
+        while (!eos) {
+            RowBatch batch;
+            if (root.get_next(&state, &batch, &eos) < 0) { fprintf(stderr, "get_next failed (%d): %s\n", state.error_code, state.error_msg.c_str()); return 1; }
+            std::vector<MemRowValues> out = Chunk::to_rows(batch);   // back to rows for a row-engine parent
+            for (auto& r : out) {
+                for (size_t c = 0; c < r.size(); c++) {
+                    const Column& col = batch.columns[c];
+                    printf("%s%d_%d=", c ? " " : "", col.tuple_id, col.slot_id);
+                    if (r[c].is_null) printf("NULL");
+                    else if (col.prim_type == BK_DOUBLE) printf("%.17g", r[c].f64);
+                    else if (col.prim_type == BK_STRING) printf("blob(%.17g,%" PRId64 ")", col.at<double>(2 * (int64_t)(&r - &out[0])), col.at<int64_t>(2 * (int64_t)(&r - &out[0]) + 1));
+                    else printf("%" PRId64, r[c].i64);
+                }
+                printf("\n");
+            }
+            total += batch.size();
+        }
+        root.close(&state);
+        fprintf(stderr, "rows_returned=%" PRId64 " scan_rows=%" PRId64 " filter_rows=%" PRId64 "\n", total, state.num_scan_rows, state.num_filter_rows);
+        return 0;
+    }
     if (cfg == "c3") { root.add_child(scan_of(cfg, 1, rows / 10, batch_rows)); root.add_child(scan_of(cfg, 0, rows, batch_rows)); }   // driver (dim) first
     else root.add_child(scan_of(cfg, 0, rows, batch_rows));
     if (root.open(&state) < 0) { fprintf(stderr, "open failed (%d): %s\n", state.error_code, state.error_msg.c_str()); return 1; }

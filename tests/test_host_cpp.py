@@ -98,3 +98,24 @@ def test_cpp_exec_node_tree_matches_oracle(host_bin, cfg, rows, batch, key):
             assert _same(g[nm], w[nm]), (nm, g, w)
     if cfg != "c3":
         assert "scan_rows=%d" % rows in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,capacity", [(50_001, 1024), (3_000, 7)])
+def test_cpp_row_engine_child_through_chunk_adapter(host_bin, rows, capacity):
+    """f1: MemRow-style rows (NULL keys included) -> Chunk column batches of `capacity` rows -> GPU -> rows again."""
+    r = subprocess.run([host_bin, "rows", "c2", str(rows), str(capacity)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = _parse(r.stdout)
+    cols = datagen.c2_table(0, rows)
+    from baikaldb_b200.column import make_column
+    k = cols[0]
+    cols[0] = make_column(k.tuple_id, k.slot_id, k.prim_type, k.values, k.values % 17 != 0)
+    want = _oracle_rows(PLANS["c2"](), cols)
+    assert len(got) == len(want)
+    keyf = lambda x: (x["0_1"] is None, x["0_1"] or 0)
+    for g, w in zip(sorted(got, key=keyf), sorted(want, key=keyf)):
+        assert set(g) == set(w)
+        for nm in g:
+            assert (g[nm] is None and w[nm] is None) or _same(g[nm], w[nm]), (nm, g, w)
+    assert "scan_rows=%d" % rows in r.stderr
