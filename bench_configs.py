@@ -51,6 +51,9 @@ def run(name, plan, pushes, rows, algo_bytes, steps, warmup, options=()):
     _lib.check(L.bkgpu_set_option(h, b"stream", stream.cuda_stream), h)
     for k, v in options:
         _lib.check(L.bkgpu_set_option(h, k, v), h)
+    for kv in filter(None, os.environ.get("BKGPU_BENCH_OPTS", "").split(",")):   # A/B of kernel variants
+        k, v = kv.split("=")
+        _lib.check(L.bkgpu_set_option(h, k.encode(), int(v)), h)
     _lib.check(L.bkgpu_open(h), h)
     out = (BkgpuColumn * 16)()
 
