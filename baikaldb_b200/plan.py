@@ -258,6 +258,20 @@ def left_shift(a, b): return fn(FuncType.LS, "left_shift", a, b)
 def right_shift(a, b): return fn(FuncType.RS, "right_shift", a, b)
 
 
+# named builtins (parser::FT_COMMON; registered in src/expr/fn_manager.cpp:104-125,250-253,303-309)
+def common(name: str, *children: Expr) -> Expr: return fn(FuncType.COMMON, name, *children)
+def if_(cond, a, b): return common("if", cond, a, b)
+def ifnull(a, b): return common("ifnull", a, b)
+def case_when(*when_then_else: Expr) -> Expr: return common("case_when", *when_then_else)
+def abs_(a): return common("abs", a)
+def floor_(a): return common("floor", a)
+def ceil_(a): return common("ceil", a)
+def round_(a, bits: Optional[Expr] = None): return common("round", a) if bits is None else common("round", a, bits)
+def cast_to_signed(a): return common("cast_to_signed", a)
+def cast_to_unsigned(a): return common("cast_to_unsigned", a)
+def cast_to_double(a): return common("cast_to_double", a)
+
+
 def _pred(node_type: int, fn_op: int, name: str, *children: Expr) -> Expr:
     return Expr(node_type, T.BOOL, list(children), fn_op=int(fn_op), name=name)
 

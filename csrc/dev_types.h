@@ -61,7 +61,11 @@ enum Op : uint8_t {
     OP_IS_TRUE,
     OP_IN,           // a = first const, b = count, c = (has_null << 4) | VClass   predicate.cpp:150-189
     OP_OUT,          // a = output register: pop top of stack into out[a]
+    OP_SELECT,       // pops [cond, a, b]: cond non-NULL true ? a : b      if_ / case_when (internal_functions.cpp:2351-2388)
+    OP_IFNULL,       // pops [a, b]: a NULL ? b : a                           ifnull (internal_functions.cpp:2390-2395)
+    OP_MATH,         // a = MathFn on a DOUBLE image, b = constant index (round: 10^bits)   internal_functions.cpp:52-99
 };
+enum MathFn : uint8_t { MF_ABS = 0, MF_FLOOR = 1, MF_CEIL = 2, MF_ROUND = 3 };
 struct Instr { uint8_t op, a, b, c; };
 
 struct Program {

@@ -126,6 +126,36 @@ static __device__ __noinline__ void run_program(const Program& p, const DevCol* 
                     if (!found && (in.c >> 4)) nul |= 1u << (sp - 1);  // not found and the list holds a NULL
                 }
             } break;
+            case OP_SELECT: {   // get_numberic<bool>() of a NULL condition is false
+                sp -= 2;
+                const bool take_a = !((nul >> (sp - 1)) & 1u) && st[sp - 1] != 0;
+                const int src = take_a ? sp : sp + 1;
+                st[sp - 1] = st[src];
+                nul = ((nul >> src) & 1u) ? (nul | (1u << (sp - 1))) : (nul & ~(1u << (sp - 1)));
+            } break;
+            case OP_IFNULL:
+                sp--;
+                if ((nul >> (sp - 1)) & 1u) {
+                    st[sp - 1] = st[sp];
+                    nul = ((nul >> sp) & 1u) ? (nul | (1u << (sp - 1))) : (nul & ~(1u << (sp - 1)));
+                }
+                break;
+            case OP_MATH:
+                if (!((nul >> (sp - 1)) & 1u)) {
+                    const double x = bits_f64(st[sp - 1]);
+                    double r;
+                    switch (in.a) {
+                        case MF_ABS: r = x < 0 ? -x : x; break;
+                        case MF_FLOOR: r = floor(x); break;
+                        case MF_CEIL: r = ceil(x); break;
+                        default: {   // round half away from zero at `bits` decimals: -::round(-x * base) / base for x < 0
+                            const double base = bits_f64(p.cbits[in.b]);
+                            r = base > 0 ? (x < 0 ? -__ddiv_rn(round(__dmul_rn(-x, base)), base) : __ddiv_rn(round(__dmul_rn(x, base)), base)) : 0.0;
+                        } break;
+                    }
+                    st[sp - 1] = f64_bits(r);
+                }
+                break;
             case OP_OUT:
                 sp--;
                 out[in.a] = st[sp];

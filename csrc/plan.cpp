@@ -296,6 +296,45 @@ static bool infer_expr(Infer& in, HExpr& e) {
                 else complete(e, 1, BK_INT64, BK_INT64);
                 break;
             case BK_FT_LOGIC_NOT: complete(e, 1, BK_BOOL, BK_BOOL); break;
+            case BK_FT_COMMON: {   // return_type_map + complete_common_fn (fn_manager.cpp:398-401,466-514); no argument casts
+                std::vector<int> merge;
+                const size_t n = types.size();
+                if (e.name == "if") { if (n != 3) return in.fail(BKGPU_EINVAL, "if() needs three arguments"); merge = {types[1], types[2]}; }
+                else if (e.name == "ifnull") { if (n != 2) return in.fail(BKGPU_EINVAL, "ifnull() needs two arguments"); merge = {types[0], types[1]}; }
+                else if (e.name == "case_when") {
+                    if (n < 2) return in.fail(BKGPU_EINVAL, "case_when needs a WHEN/THEN pair");
+                    for (size_t i = 1; i < n; i++) if (i % 2 == 1 || i + 1 == n) merge.push_back(types[i]);
+                }
+                else if (e.name == "abs" || e.name == "round" || e.name == "cast_to_double") e.return_type = BK_DOUBLE;
+                else if (e.name == "floor" || e.name == "ceil" || e.name == "cast_to_signed") e.return_type = BK_INT64;
+                else if (e.name == "cast_to_unsigned") e.return_type = BK_UINT64;
+                else return in.fail(BKGPU_EUNSUPPORTED, "function '%s' is outside the GPU path", e.name.c_str());
+                if (!merge.empty()) {   // has_merged_type (include/common/type_utils.h:502-560)
+                    bool all_null = true, all_equal = true, all_num = true, has_dbl = false, has_u64 = false, has_signed = false;
+                    int first = BK_NULL_TYPE;
+                    for (int t : merge) {
+                        if (t == BK_NULL_TYPE) continue;
+                        if (all_null) { first = t; all_null = false; }
+                        if (t != first) all_equal = false;
+                        if (!(is_double_t(t) || is_int_t(t) || t == BK_BOOL)) all_num = false;
+                        if (is_double_t(t)) has_dbl = true;
+                        if (t == BK_UINT64) has_u64 = true;
+                        if (t == BK_INT8 || t == BK_INT16 || t == BK_INT32 || t == BK_INT64) has_signed = true;
+                    }
+                    if (all_null) return in.fail(BKGPU_EUNSUPPORTED, "%s: every branch is NULL", e.name.c_str());
+                    if (all_equal) e.return_type = first;
+                    else if (all_num) e.return_type = has_dbl ? BK_DOUBLE : (has_u64 ? (has_signed ? BK_DOUBLE : BK_UINT64) : BK_INT64);
+                    else return in.fail(BKGPU_EUNSUPPORTED, "%s over date/time or STRING branches is outside the GPU path", e.name.c_str());
+                    if (e.return_type == BK_STRING || is_datetime_family(e.return_type))
+                        return in.fail(BKGPU_EUNSUPPORTED, "%s returning type %d is outside the GPU path", e.name.c_str(), e.return_type);
+                }
+                if ((e.name == "abs" || e.name == "floor" || e.name == "ceil" || e.name.rfind("cast_to_", 0) == 0) && n != 1)
+                    return in.fail(BKGPU_EINVAL, "%s() needs one argument", e.name.c_str());
+                if (e.name == "round" && (n < 1 || n > 2 || (n == 2 && (!is_literal_node(e.ch[1].node_type) || e.ch[1].lit_null))))
+                    return in.fail(BKGPU_EUNSUPPORTED, "round() needs a literal number of decimals");
+                for (auto& c : e.ch)
+                    if (c.col_type == BK_STRING || is_datetime_family(c.col_type)) return in.fail(BKGPU_EUNSUPPORTED, "%s over STRING / date-time arguments", e.name.c_str());
+            } break;
             default: return in.fail(BKGPU_EUNSUPPORTED, "function fn_op=%d name='%s' is outside the GPU path", e.fn_op, e.name.c_str());
         }
         if (!e.col_type) e.col_type = e.return_type;
@@ -415,6 +454,7 @@ struct Lower {
                 return emit(OP_IN, (uint8_t)first, (uint8_t)cnt, (uint8_t)((has_null ? 16 : 0) | host_prim_class(map_type)));
             }
             case BK_FUNCTION_CALL: {
+                if (e.fn_op == BK_FT_COMMON) return common_fn(e, depth);
                 int d0 = depth;
                 for (size_t i = 0; i < e.ch.size(); i++) {
                     if (!expr(e.ch[i], depth)) return false;
@@ -444,6 +484,55 @@ struct Lower {
             default: return in->fail(BKGPU_EUNSUPPORTED, "expr node type %d cannot be lowered", e.node_type);
         }
     }
+    // named builtins (FT_COMMON): arguments are NOT cast (arg_types stay empty), the result is cast to the node's col_type
+    bool branch(const HExpr& c, int to, int& depth) { return expr(c, depth) && cast(c.col_type, to); }
+    bool common_fn(const HExpr& e, int& depth) {
+        const int d0 = depth;
+        const int ct = e.col_type;
+        if (e.name == "if") {
+            if (!expr(e.ch[0], depth) || !to_bool(e.ch[0]) || !branch(e.ch[1], ct, depth) || !branch(e.ch[2], ct, depth)) return false;
+            depth = d0 + 1;
+            return emit(OP_SELECT);
+        }
+        if (e.name == "ifnull") {
+            if (!branch(e.ch[0], ct, depth) || !branch(e.ch[1], ct, depth)) return false;
+            depth = d0 + 1;
+            return emit(OP_IFNULL);
+        }
+        if (e.name == "case_when") {   // WHEN c1 THEN t1 ... [ELSE e]  ==  if(c1, t1, if(c2, t2, ... e | NULL))
+            const size_t n = e.ch.size(), pairs = n / 2;
+            for (size_t i = 0; i < pairs; i++)
+                if (!expr(e.ch[2 * i], depth) || !to_bool(e.ch[2 * i]) || !branch(e.ch[2 * i + 1], ct, depth)) return false;
+            if (n % 2 == 1) { if (!branch(e.ch[n - 1], ct, depth)) return false; }
+            else { int k = add_const(0, true); if (k < 0 || !emit(OP_CONST, (uint8_t)k)) return false; depth++; }
+            if (depth > STACK_DEPTH - 1) return in->fail(BKGPU_EUNSUPPORTED, "CASE with %zu branches exceeds the device stack", pairs);
+            for (size_t i = 0; i < pairs; i++) if (!emit(OP_SELECT)) return false;
+            depth = d0 + 1;
+            return true;
+        }
+        if (!expr(e.ch[0], depth)) return false;
+        const int at = e.ch[0].col_type;
+        if (e.name == "cast_to_signed") return cast(at, BK_INT64) && cast(BK_INT64, ct);
+        if (e.name == "cast_to_unsigned") return cast(at, BK_UINT64) && cast(BK_UINT64, ct);
+        if (e.name == "cast_to_double") return cast(at, BK_DOUBLE) && cast(BK_DOUBLE, ct);
+        if (!cast(at, BK_DOUBLE)) return false;   // get_numberic<double>()
+        if (e.name == "abs") return emit(OP_MATH, MF_ABS) && cast(BK_DOUBLE, ct);
+        if (e.name == "floor") return emit(OP_MATH, MF_FLOOR) && emit(OP_CAST, (uint8_t)BK_DOUBLE, (uint8_t)BK_INT64) && cast(BK_INT64, ct);
+        if (e.name == "ceil") return emit(OP_MATH, MF_CEIL) && emit(OP_CAST, (uint8_t)BK_DOUBLE, (uint8_t)BK_INT64) && cast(BK_INT64, ct);
+        if (e.name == "round") {
+            int bits = 0;
+            if (e.ch.size() == 2) {   // input[1].get_numberic<int>() of the literal (cast to its col_type first, literal.h:204-206)
+                const HExpr& l = e.ch[1];
+                uint64_t img = l.col_type ? host_cast_prim(l.lit_bits, l.lit_prim, l.col_type) : l.lit_bits;
+                bits = (int)(int64_t)host_cast_prim(img, l.col_type ? l.col_type : l.lit_prim, BK_INT32);
+            }
+            const double base = std::pow(10.0, bits);
+            uint64_t bb; memcpy(&bb, &base, 8);
+            int k = add_const(bb, false); if (k < 0) return false;
+            return emit(OP_MATH, MF_ROUND, (uint8_t)k) && cast(BK_DOUBLE, ct);
+        }
+        return in->fail(BKGPU_EUNSUPPORTED, "function '%s'", e.name.c_str());
+    }
     // children of logical predicates are read with get_numberic<bool>() (predicate.h:31)
     bool to_bool(const HExpr& c) { return c.col_type == BK_BOOL ? true : emit(OP_CAST, (uint8_t)c.col_type, (uint8_t)BK_BOOL); }
     bool out_reg(int r) { return emit(OP_OUT, (uint8_t)r); }
@@ -466,6 +555,7 @@ static bool expr_makes_null(const HExpr& e) {
     if (e.node_type == BK_NULL_LITERAL) return true;
     if (e.node_type == BK_IS_NULL_PREDICATE || e.node_type == BK_IS_TRUE_PREDICATE) return false;
     if (e.node_type == BK_FUNCTION_CALL && (e.fn_op == BK_FT_DIVIDES || e.fn_op == BK_FT_MOD)) return true;
+    if (e.node_type == BK_FUNCTION_CALL && e.fn_op == BK_FT_COMMON && e.name == "case_when" && e.ch.size() % 2 == 0) return true;
     if (e.node_type == BK_IN_PREDICATE) for (size_t i = 1; i < e.ch.size(); i++) if (e.ch[i].lit_null) return true;
     for (auto& c : e.ch) if (expr_makes_null(c)) return true;
     return false;
@@ -735,8 +825,8 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
 // ---------------------------------------------------------------- explain
 static const char* op_name(int op) {
     static const char* n[] = {"END", "LOAD_COL", "CONST", "CAST", "CMP", "ARITH", "DIV_F64", "MOD", "BIT", "BIT_NOT", "NEG",
-                              "LOGIC_NOT", "AND", "OR", "XOR", "NOT3", "IS_NULL", "IS_TRUE", "IN", "OUT"};
-    return op >= 0 && op <= OP_OUT ? n[op] : "?";
+                              "LOGIC_NOT", "AND", "OR", "XOR", "NOT3", "IS_NULL", "IS_TRUE", "IN", "OUT", "SELECT", "IFNULL", "MATH"};
+    return op >= 0 && op <= OP_MATH ? n[op] : "?";
 }
 static void explain(Compiled& c) {
     char buf[256];

@@ -243,6 +243,7 @@ int bko_key_encode(int type, uint64_t bits, uint8_t out[8]) {
 /* =========================== plan description =========================== */
 typedef struct { int tuple_id, n_slots; int* slot_ids; int* types; } TupleDesc;
 
+#define MAX_FN_ARGS 16
 typedef struct Expr {
     int node_type, col_type, nchildren;
     struct Expr** children;
@@ -577,6 +578,36 @@ static int type_infer(Ctx* c, Expr* e) {
             else complete(e, 1, T_INT64, T_INT64);
             break;
         case FT_LOGIC_NOT: complete(e, 1, T_BOOL, T_BOOL); break;
+        case FT_COMMON: { /* return_type_map[fn.name()] + complete_common_fn, fn_manager.cpp:398-401,466-514; arg_types stay empty */
+            int merge[MAX_FN_ARGS], nm = 0, nn = e->nchildren;
+            if (nn > MAX_FN_ARGS) { snprintf(c->err, c->errlen, "%s: too many arguments", e->name); return -1; }
+            if (!strcmp(e->name, "if")) { if (nn != 3) { snprintf(c->err, c->errlen, "if() needs 3 arguments"); return -1; } merge[nm++] = e->children[1]->col_type; merge[nm++] = e->children[2]->col_type; }
+            else if (!strcmp(e->name, "ifnull")) { if (nn != 2) { snprintf(c->err, c->errlen, "ifnull() needs 2 arguments"); return -1; } merge[nm++] = e->children[0]->col_type; merge[nm++] = e->children[1]->col_type; }
+            else if (!strcmp(e->name, "case_when")) { for (int i = 1; i < nn; i++) if (i % 2 == 1 || i + 1 == nn) merge[nm++] = e->children[i]->col_type; }
+            else if (!strcmp(e->name, "abs") || !strcmp(e->name, "round") || !strcmp(e->name, "cast_to_double")) e->return_type = T_DOUBLE;
+            else if (!strcmp(e->name, "floor") || !strcmp(e->name, "ceil") || !strcmp(e->name, "cast_to_signed")) e->return_type = T_INT64;
+            else if (!strcmp(e->name, "cast_to_unsigned")) e->return_type = T_UINT64;
+            else { snprintf(c->err, c->errlen, "unsupported function %s", e->name); return -1; }
+            if (nm) { /* has_merged_type, include/common/type_utils.h:502-560 */
+                int all_null = 1, all_equal = 1, all_num = 1, has_dbl = 0, has_u64 = 0, has_sgn = 0, first = T_NULL;
+                for (int i = 0; i < nm; i++) {
+                    int t = merge[i];
+                    if (t == T_NULL) continue;
+                    if (all_null) { first = t; all_null = 0; }
+                    if (t != first) all_equal = 0;
+                    if (!(is_double(t) || is_int(t) || t == T_BOOL)) all_num = 0;
+                    if (is_double(t)) has_dbl = 1;
+                    if (t == T_UINT64) has_u64 = 1;
+                    if (is_signed(t)) has_sgn = 1;
+                }
+                if (all_null) e->return_type = T_NULL;
+                else if (all_equal) e->return_type = first;
+                else if (all_num) e->return_type = has_dbl ? T_DOUBLE : (has_u64 ? (has_sgn ? T_DOUBLE : T_UINT64) : T_INT64);
+                else { snprintf(c->err, c->errlen, "%s: date/time or string branches are outside the path", e->name); return -1; }
+            }
+            if (e->col_type == T_INVALID) e->col_type = e->return_type;
+            return 0;
+        }
         default: snprintf(c->err, c->errlen, "unsupported fn_op %d", e->fn_op); return -1;
     }
     if (e->col_type == T_INVALID) e->col_type = e->return_type;
@@ -588,6 +619,34 @@ static int type_infer(Ctx* c, Expr* e) {
 
 static int in_int(const Expr* e, int64_t v) { for (int i = 0; i < e->set_n; i++) if (e->int_set[i] == v) return 1; return 0; }
 static int in_dbl(const Expr* e, double v) { for (int i = 0; i < e->set_n; i++) if (e->dbl_set[i] == v) return 1; return 0; }
+
+/* named builtins, src/expr/internal_functions.cpp: round :52-68, floor :70-77, ceil :79-86, abs :88-99, case_when :2351-2366,
+ * if_ :2383-2388, ifnull :2390-2395, cast_to_signed/unsigned/double :2941-2963 */
+static ExprValue call_common(const Expr* e, ExprValue* a, int n) {
+    ExprValue r;
+    if (!strcmp(e->name, "if")) return (!ev_is_null(&a[0]) && num_bool(&a[0])) ? a[1] : a[2]; /* get_numberic<bool>() of NULL is false */
+    if (!strcmp(e->name, "ifnull")) return ev_is_null(&a[0]) ? a[1] : a[0];
+    if (!strcmp(e->name, "case_when")) {
+        for (int i = 0; i < n / 2; i++) if (!ev_is_null(&a[2 * i]) && num_bool(&a[2 * i])) return a[2 * i + 1];
+        return n % 2 == 0 ? ev_null() : a[n - 1];
+    }
+    if (n < 1 || ev_is_null(&a[0])) return ev_null();
+    if (!strcmp(e->name, "cast_to_signed")) { r = a[0]; ev_cast_to(&r, T_INT64); return r; }
+    if (!strcmp(e->name, "cast_to_unsigned")) { r = a[0]; ev_cast_to(&r, T_UINT64); return r; }
+    if (!strcmp(e->name, "cast_to_double")) { r = a[0]; ev_cast_to(&r, T_DOUBLE); return r; }
+    double x = num_f64(&a[0]);
+    if (!strcmp(e->name, "abs")) { r = ev_typed(T_DOUBLE); r.u.double_val = x < 0 ? -x : x; return r; }
+    if (!strcmp(e->name, "floor")) { r = ev_typed(T_INT64); r.u.int64_val = (int64_t)floor(x); return r; }
+    if (!strcmp(e->name, "ceil")) { r = ev_typed(T_INT64); r.u.int64_val = (int64_t)ceil(x); return r; }
+    if (!strcmp(e->name, "round")) {
+        int bits = n == 2 ? num_i32(&a[1]) : 0;
+        double base = pow(10, bits);
+        r = ev_typed(T_DOUBLE);
+        if (base > 0) r.u.double_val = x < 0 ? -round(-x * base) / base : round(x * base) / base;
+        return r;
+    }
+    return ev_null();
+}
 
 static ExprValue call_fn(const Expr* e, ExprValue* a) { /* operators.cpp:18-103 */
     int at = e->arg_types[0];
@@ -700,11 +759,11 @@ static ExprValue expr_value(const Ctx* c, Expr* e, const MemRow* row) {
             return e->has_null ? ev_null() : ev_bool(0);
         }
         case E_FUNCTION_CALL: { /* scalar_fn_call.cpp:194-225 */
-            ExprValue args[4];
-            int n = e->nchildren < 4 ? e->nchildren : 4;
+            ExprValue args[MAX_FN_ARGS];
+            int n = e->nchildren < MAX_FN_ARGS ? e->nchildren : MAX_FN_ARGS;
             for (int i = 0; i < n; i++) args[i] = expr_value(c, e->children[i], row);
             for (int i = 0; i < e->n_arg_types && i < n; i++) ev_cast_to(&args[i], e->arg_types[i]);
-            ExprValue r = call_fn(e, args);
+            ExprValue r = e->fn_op == FT_COMMON ? call_common(e, args, n) : call_fn(e, args);
             ev_cast_to(&r, e->col_type);
             return r;
         }
