@@ -171,15 +171,34 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries also write there (NCCL prints "NCCL version ..." to stdout when
+    NCCL_DEBUG is set on the box): keep the real stdout aside and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     import numpy as np
@@ -401,7 +420,7 @@ def main():
             "hbm_gbs_whole_step": total_rows * BYTES_PER_ROW * args.steps / (r["ms"] / 1e3) / 1e9 / world,
             "result_groups": ngroups_out, "verified_vs_torch": verified,
         }
-        print(json.dumps(line))
+        emit(line)
     L.bkgpu_close(h)
     if world > 1:
         L.bkgpu_nccl_comm_destroy(comm)

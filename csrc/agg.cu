@@ -133,6 +133,33 @@ __global__ void k_partial_export(GroupTable gt, AggPlan ap, uint64_t* dst, uint3
 }
 __global__ void k_partial_count(uint64_t* dst, const uint32_t* cursor) { dst[0] = *cursor; }
 
+// hash repartition (the reference's exchange between fragments, src/exec/exchange_sender_node.cpp:867-957): every group of this
+// rank's table goes to the segment of the rank that OWNS its key; segment layout = the partial state layout above
+__device__ __forceinline__ uint32_t owner_of(const uint64_t* key, int kw, int nranks) {
+    uint64_t h = 0xC2B2AE3D27D4EB4Full;
+    for (int i = 0; i < kw; i++) { h ^= key[i]; h *= 0x9FB21C651E98DF25ull; h ^= h >> 29; }
+    return (uint32_t)((h >> 17) % (uint64_t)nranks);
+}
+__global__ void k_partial_export_parts(GroupTable gt, AggPlan ap, uint64_t* dst, size_t words_per_seg, uint32_t pcap, uint32_t* cursors, int nranks) {
+    const uint32_t cap = gt.cap_mask + 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        if (gt.state[i] != 2u) continue;
+        uint64_t key[MAX_KEYW];
+        for (int w = 0; w < ap.n_keyw; w++) key[w] = gt.keys[(size_t)w * cap + i];
+        const uint32_t o = owner_of(key, ap.n_keyw, nranks);
+        const uint32_t pos = atomicAdd(cursors + o, 1u);
+        if (pos >= pcap) { atomicExch(gt.overflow, 1u); continue; }
+        uint64_t* dkeys = dst + (size_t)o * words_per_seg + 1;
+        uint64_t* dlanes = dkeys + (size_t)ap.n_keyw * pcap;
+        for (int w = 0; w < ap.n_keyw; w++) dkeys[(size_t)w * pcap + pos] = key[w];
+        for (int l = 0; l < ap.n_lanes; l++) dlanes[(size_t)l * pcap + pos] = gt.lanes[(size_t)l * cap + i];
+    }
+}
+__global__ void k_partial_counts(uint64_t* dst, size_t words_per_seg, const uint32_t* cursors, uint32_t pcap, int nranks) {
+    const int r = threadIdx.x;
+    if (r < nranks) dst[(size_t)r * words_per_seg] = cursors[r] < pcap ? cursors[r] : pcap;
+}
+
 // K3: fold `nranks` exported partials into the (re-initialised) global table
 __global__ void k_partial_merge(GroupTable gt, AggPlan ap, const uint64_t* src, size_t words_per_rank, uint32_t pcap, int nranks) {
     for (int r = 0; r < nranks; r++) {
@@ -412,6 +439,16 @@ cudaError_t launch_partial_export(const GroupTable& gt, const AggPlan& ap, uint6
     if (e != cudaSuccess) return e;
     k_partial_export<<<grid, 256, 0, s>>>(gt, ap, dst, pcap, cursor);
     k_partial_count<<<1, 1, 0, s>>>(dst, cursor);
+    return cudaGetLastError();
+}
+cudaError_t launch_partial_export_parts(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, size_t words_per_seg, uint32_t pcap, uint32_t* cursors, int nranks, cudaStream_t s) {
+    if (nranks > 1024) return cudaErrorInvalidValue;
+    const uint32_t cap = gt.cap_mask + 1;
+    int grid = (int)((cap + 255) / 256); if (grid > 1184) grid = 1184;
+    cudaError_t e = cudaMemsetAsync(cursors, 0, sizeof(uint32_t) * (size_t)nranks, s);
+    if (e != cudaSuccess) return e;
+    k_partial_export_parts<<<grid, 256, 0, s>>>(gt, ap, dst, words_per_seg, pcap, cursors, nranks);
+    k_partial_counts<<<1, 1024, 0, s>>>(dst, words_per_seg, cursors, pcap, nranks);
     return cudaGetLastError();
 }
 cudaError_t launch_partial_merge(const GroupTable& gt, const AggPlan& ap, const uint64_t* src, size_t words_per_rank, uint32_t pcap, int nranks, cudaStream_t s) {

@@ -62,6 +62,7 @@ struct bkgpu_plan {
     uint32_t* d_cursor = nullptr;
     uint64_t* d_partial = nullptr;  // export buffer (this rank)
     uint64_t* d_gather = nullptr;   // nranks export buffers
+    uint32_t* d_part_cursors = nullptr; int repartition = 0;   // hash repartition of the groups across ranks (option "repartition")
     uint64_t* d_outv = nullptr; uint8_t* d_outn = nullptr; size_t out_cap_alloc = 0;  // extraction buffers (kept across resets)
     std::vector<cudaEvent_t> event_pool;
     uint64_t* h_outv = nullptr; uint8_t* h_outn = nullptr; size_t h_out_cap = 0;   // pinned landing area of the extracted rows
@@ -205,6 +206,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "force_generic") p->force_generic = v != 0;
     else if (k == "no_lean") p->no_lean = v != 0;
     else if (k == "no_fused_probe") p->no_fused_probe = v != 0;
+    else if (k == "repartition") p->repartition = v != 0;
     else if (k == "output_on_device") p->output_on_device = v != 0;
     else if (k == "region_base") p->region_base = v;
     else return p->fail(BKGPU_EINVAL, "unknown option '%s'", key);
@@ -759,11 +761,20 @@ static int agg_finish(bkgpu_plan* p) {
         const uint32_t pcap = (uint32_t)p->partial_cap;
         const size_t words = 1 + (size_t)(ap.n_keyw + ap.n_lanes) * pcap;
         int rc;
-        if (!p->d_partial && (rc = dev_alloc(p, (void**)&p->d_partial, words * 8))) return rc;
+        const bool repart = p->repartition && ap.n_keyw > 0;   // (a scalar aggregate has one group: nothing to partition)
+        if (!p->d_partial && (rc = dev_alloc(p, (void**)&p->d_partial, words * 8 * (repart ? (size_t)p->nranks : 1)))) return rc;
         if (!p->d_gather && (rc = dev_alloc(p, (void**)&p->d_gather, words * 8 * (size_t)p->nranks))) return rc;
         EventPair* ep = timer_begin(p, p->timed_coll, 0);
+        if (repart) {
+            // hash repartition: every rank keeps only the groups it owns — an all-to-all of per-owner segments instead of the
+            // all-gather; the merged table (and the result) of a rank is its partition, the union over ranks is the answer
+            if (!p->d_part_cursors && (rc = dev_alloc(p, (void**)&p->d_part_cursors, 4 * (size_t)p->nranks))) return rc;
+            CK(p, launch_partial_export_parts(gt, ap, p->d_partial, words, pcap, p->d_part_cursors, p->nranks, p->stream));
+            if (nccl_all_to_all(p->nccl_comm, p->d_partial, p->d_gather, words, p->nranks, p->stream) != 0) return p->fail(BKGPU_ENCCL, "all-to-all: %s", nccl_last_error());
+        } else {
         CK(p, launch_partial_export(gt, ap, p->d_partial, pcap, p->d_cursor, p->stream));
         if (nccl_all_gather(p->nccl_comm, p->d_partial, p->d_gather, words, p->stream) != 0) return p->fail(BKGPU_ENCCL, "ncclAllGather: %s", nccl_last_error());
+        }
         CK(p, launch_table_init(gt, ap, p->stream));
         CK(p, launch_partial_merge(gt, ap, p->d_gather, words, pcap, p->nranks, p->stream));
         timer_end(p, ep);

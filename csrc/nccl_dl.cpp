@@ -17,6 +17,10 @@ ncclResult_t (*p_CommUserRank)(const ncclComm_t, int*) = nullptr;
 ncclResult_t (*p_CommDestroy)(ncclComm_t) = nullptr;
 ncclResult_t (*p_AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 const char* (*p_GetErrorString)(ncclResult_t) = nullptr;
+ncclResult_t (*p_Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+ncclResult_t (*p_Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+ncclResult_t (*p_GroupStart)() = nullptr;
+ncclResult_t (*p_GroupEnd)() = nullptr;
 
 bool load() {
     std::call_once(g_once, [] {
@@ -25,6 +29,7 @@ bool load() {
         if (!g_lib) { g_err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return; }
 #define BIND(sym) *(void**)(&p_##sym) = dlsym(g_lib, "nccl" #sym)
         BIND(GetUniqueId); BIND(CommInitRank); BIND(CommCount); BIND(CommUserRank); BIND(CommDestroy); BIND(AllGather); BIND(GetErrorString);
+        BIND(Send); BIND(Recv); BIND(GroupStart); BIND(GroupEnd);
 #undef BIND
         if (!p_GetUniqueId || !p_CommInitRank || !p_CommCount || !p_CommDestroy || !p_AllGather) { g_err = "libnccl lacks a required symbol"; g_lib = nullptr; }
     });
@@ -60,5 +65,15 @@ void nccl_comm_destroy(void* comm) { if (load() && comm) p_CommDestroy((ncclComm
 int nccl_all_gather(void* comm, const void* send, void* recv, size_t words, cudaStream_t stream) {
     if (!load()) return -1;
     return check(p_AllGather(send, recv, words, ncclUint64, (ncclComm_t)comm, stream), "ncclAllGather");
+}
+int nccl_all_to_all(void* comm, const void* send, void* recv, size_t words, int nranks, cudaStream_t stream) {
+    if (!load()) return -1;
+    if (!p_Send || !p_Recv || !p_GroupStart || !p_GroupEnd) { g_err = "libnccl lacks ncclSend/ncclRecv"; return -1; }
+    if (check(p_GroupStart(), "ncclGroupStart")) return -1;
+    for (int r = 0; r < nranks; r++) {
+        if (check(p_Send((const uint64_t*)send + (size_t)r * words, words, ncclUint64, r, (ncclComm_t)comm, stream), "ncclSend")) { p_GroupEnd(); return -1; }
+        if (check(p_Recv((uint64_t*)recv + (size_t)r * words, words, ncclUint64, r, (ncclComm_t)comm, stream), "ncclRecv")) { p_GroupEnd(); return -1; }
+    }
+    return check(p_GroupEnd(), "ncclGroupEnd");
 }
 }  // namespace bk

@@ -14,4 +14,7 @@ int nccl_comm_rank(void* comm, int* rank);
 void nccl_comm_destroy(void* comm);
 // all-gather `words` 64-bit words per rank
 int nccl_all_gather(void* comm, const void* send, void* recv, size_t words, cudaStream_t stream);
+// all-to-all: segment r of `send` (words 64-bit words each) goes to rank r; segment r of `recv` arrives from rank r
+// (grouped ncclSend / ncclRecv pairs)
+int nccl_all_to_all(void* comm, const void* send, void* recv, size_t words, int nranks, cudaStream_t stream);
 }  // namespace bk

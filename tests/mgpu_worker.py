@@ -63,6 +63,30 @@ def main():
     whole = datagen.c2_table(0, n_region * world, n_groups=500)
     want = oracle.execute(queries.c2_filter_groupby().serialize(), whole)
     assert_same_rows(got, want.columns, ["0_1"])      # every rank holds the merged result
+    # ---- f3: hash repartition (all-to-all): every rank returns only the groups it owns; their union is the answer ----
+    hi = datagen.c2_table(rank * n_region, n_region, n_groups=40_000)            # more groups than one 65536-slot partial would
+    part, stats = run_plan(queries.c2_filter_groupby(), hi, comm, dev, {"repartition": 1, "group_capacity_log2": 18})   # comfortably merge N times
+    assert stats.collective_ms > 0
+    mine_keys = torch.tensor(np.asarray(part[0].values, dtype=np.int64), device="cuda")
+    sizes = torch.zeros(world, dtype=torch.int64, device="cuda"); sizes[rank] = mine_keys.numel()
+    dist.all_reduce(sizes)
+    pad = int(sizes.max().item())
+    def gather_col(c):
+        isblob = np.asarray(c.values).ndim == 2
+        v = np.asarray(c.values)
+        raw = v.view(np.int64).reshape(len(v), -1) if (isblob or v.dtype.itemsize == 8) else v.astype(np.int64).reshape(len(v), 1)
+        t = torch.zeros((pad, raw.shape[1]), dtype=torch.int64, device="cuda"); t[:len(v)] = torch.from_numpy(np.ascontiguousarray(raw)).cuda()
+        outs = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        full = np.concatenate([o.cpu().numpy()[:int(sizes[r].item())] for r, o in enumerate(outs)])
+        if isblob: return full.view(np.uint8).reshape(len(full), 16)
+        return full[:, 0].view(v.dtype) if v.dtype.itemsize == 8 else full[:, 0].astype(v.dtype)
+    assert all(c.valid is None for c in part)
+    union = [make_column(c.tuple_id, c.slot_id, c.prim_type, gather_col(c)) for c in part]
+    assert len(set(union[0].values.tolist())) == len(union[0]), "a group came back from two ranks"
+    assert 0 < len(part[0]) < len(union[0])
+    whole_hi = datagen.c2_table(0, n_region * world, n_groups=40_000)
+    assert_same_rows(union, oracle.execute(queries.c2_filter_groupby().serialize(), whole_hi).columns, ["0_1"])
     # ---- C5: ORDER BY ... LIMIT over regions; duplicates across regions break ties by (region, row) ----
     rng = np.random.default_rng(77)
     keys = rng.integers(0, 5000, n_region * world)

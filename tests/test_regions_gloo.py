@@ -1,7 +1,9 @@
 """CPU, world_size 2 over gloo: the host-side decomposition the multi-GPU path relies on — regions -> per-rank
 partial aggregates -> all_gather -> MERGE_AGG (AggFnCall::merge, src/expr/agg_fn_call.cpp:719-822) equals the
 single-region result; per-rank top-k -> all_gather -> final top-k with (region, row) tie order equals the global
-top-k (SelectManagerNode merge of sorted runs, select_manager_node.cpp:50-51).  Uses the oracle on each rank."""
+top-k (SelectManagerNode merge of sorted runs, select_manager_node.cpp:50-51); hash repartition of the partial rows (each
+rank merges the groups it owns, exchange_sender_node.cpp:867-957) yields disjoint partitions whose union is the same
+result.  Uses the oracle on each rank."""
 import os
 import subprocess
 import sys
@@ -40,6 +42,22 @@ for k in m:
     assert m[k][mn.index("1_1")] == w[k][wn.index("1_1")]
     assert abs(m[k][mn.index("1_2")] - w[k][wn.index("1_2")]) <= 1e-9 * abs(w[k][wn.index("1_2")])
     assert abs(m[k][mn.index("1_3")] - w[k][wn.index("1_3")]) <= 1e-9 * abs(w[k][wn.index("1_3")]) + 1e-12
+# f3 hash repartition: rank r merges only the partial rows of the groups it owns; the union over ranks is the answer
+keycol = [i for i in range(len(payload)) if (payload[i][0], payload[i][1]) == (0, 1)][0]
+own = (cols[keycol].values.astype(np.int64) % world) == rank
+mine_rows = [make_column(c.tuple_id, c.slot_id, c.prim_type, c.values[own], None if c.valid is None else c.valid[own]) for c in cols]
+part = oracle.execute(queries.c2_filter_groupby(merge=True).serialize(), mine_rows)
+parts = [None] * world
+dist.all_gather_object(parts, [(c.name, c.to_list()) for c in part.columns])
+union = {}
+for pr in parts:
+    d = dict(pr)
+    for i, k in enumerate(d["0_1"]):
+        assert k not in union, "a group came back from two ranks"
+        union[k] = (d["1_1"][i], d["1_2"][i], d["1_3"][i])
+assert set(union) == {k[0] for k in w}
+for k in w:
+    assert union[k[0]][0] == w[k][wn.index("1_1")] and abs(union[k[0]][1] - w[k][wn.index("1_2")]) <= 1e-9 * abs(w[k][wn.index("1_2")])
 # top-k
 rng = np.random.default_rng(3)
 keys = rng.integers(0, 300, n * world)
