@@ -103,6 +103,16 @@ def main():
         ts = [gen(n, s, 1) for s in specs]
         run("C1 COUNT(*) WHERE int32 < k", queries.c1_count_where(), [(cols_array(specs, ts), 1, n)], n, 4 * n, a.steps, a.warmup)
         del ts
+    if "c2n" in a.configs:   # C2 with NULLs: validity bitmaps on both value columns (~30 % NULL), device-resident
+        n = int(100_000_000 * a.scale)
+        specs = [(0, 1, T.INT32, 0, 1, 0, 1000, 1.0), (0, 2, T.INT32, 0, 2, 0, 1 << 20, 1.0), (0, 3, T.DOUBLE, 1, 3, 0, 0, 1.0), (0, 4, T.DOUBLE, 2, 4, 0, 0, 1732.05)]
+        ts = [gen(n, s, 2) for s in specs]
+        arr = cols_array(specs, ts)
+        bm = [torch.randint(0, 256, ((n + 7) // 8 + 64,), dtype=torch.uint8, device="cuda") | torch.randint(0, 256, ((n + 7) // 8 + 64,), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        for i, b in zip((2, 3), bm):
+            arr[i].validity = b.data_ptr()
+        run("C2 with ~25 % NULLs in both value columns", queries.c2_filter_groupby(), [(arr, 4, n)], n, 24 * n + n // 4, a.steps, a.warmup, options=[(b"group_capacity_log2", 14)])
+        del ts, bm
     if "c5" in a.configs:
         n = int(125_000_000 * a.scale)
         specs = [(0, 1, T.INT64, 3, 1, 0, 0, 1.0), (0, 2, T.INT32, 0, 2, 0, 1 << 30, 1.0)]

@@ -512,7 +512,9 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 // fixed the hot loop has no descriptor interpretation left in it.  Everything else takes
 // k_agg_group_direct above (same results, more instructions per row).
 // ------------------------------------------------------------------------------------------
-template <int NP, int NA, bool JOIN>
+// NULLS: predicate / value columns may carry validity bitmaps (a NULL predicate operand drops the row, a NULL value skips that
+// aggregate: its sum gets +0 and its non-NULL counter no increment); the key column stays NULL-free in this kernel.
+template <int NP, int NA, bool JOIN, bool NULLS = false>
 __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid_constant__ AggArgs a) {
     constexpr int NS = NP + 1 + NA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -525,6 +527,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
     uint64_t* qbase = (uint64_t*)(smem_raw + ((table_bytes + 15) & ~(size_t)15)) + (size_t)warp * (qwords + QCAP / 8);
     const uint32_t qkey = smem_addr(qbase);
     const uint32_t qval = qkey + QCAP * 8u;
+    const uint32_t qnull = qkey + (uint32_t)qwords * 8u;   // NULLS: one byte of per-value NULL bits per queue entry
     const uint64_t kmask = ap.key_bits[0] >= 64 ? ~0ull : ((1ull << ap.key_bits[0]) - 1ull);
     const bool key8 = a.cols[NP].stype == ST_I64 || a.cols[NP].stype == ST_U64;
     const uint32_t cap_mask = st.cap_mask, tcap = st.cap_mask + 1;
@@ -543,6 +546,19 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
         acc_addr[s] = lanes_addr + ((sl >> 1) * tcap * 2u + (sl & 1u)) * 8u;
         acc_f64[s] = a.vops[s].op[0] == LN_ADD_F64;
     }
+    const uint8_t* valid[NS]; uint32_t cnt_addr[NA > 0 ? NA : 1];
+    if (NULLS) {
+#pragma unroll
+        for (int t = 0; t < NP; t++) valid[t] = a.cols[t].validity;
+        valid[NP] = nullptr;
+#pragma unroll
+        for (int s = 0; s < NA; s++) {
+            valid[NP + 1 + s] = a.cols[NP + 1 + s].validity;
+            const uint32_t cl = a.vops[s].cnt_smem;   // shared lane of the non-NULL counter (0xFF: the column has no NULLs in this batch)
+            cnt_addr[s] = cl == 0xFF ? 0u : lanes_addr + ((cl >> 1) * tcap * 2u + (cl & 1u)) * 8u;
+        }
+    }
+    uint32_t nmask = 0;   // NULLS: 4 NULL bits per column for the quad held in the load registers
     // 128-bit shared CAS shapes: {row count, sum} (one double sum) or {sumA, sumB} (value columns 0 and 1 both double)
     // (fusing {row count, sum} into one CAS.128 measured SLOWER than RED.u32 + CAS.64 — the native 32-bit reduction is
     //  cheaper than widening the compare-and-swap — so it stays off; the code is kept for the record)
@@ -568,6 +584,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
         for (int s = 0; s < NA; s++) { const U64x4 r = ldg256_u64(vptr[s] + q * 32);
 #pragma unroll
             for (int j = 0; j < 4; j++) vr[s][j] = r.v[j]; }
+        if (NULLS) {
+            nmask = 0;
+#pragma unroll
+            for (int c = 0; c < NS; c++)
+                if (c != NP && valid[c]) nmask |= ((~((uint32_t)__ldg(valid[c] + (q >> 1)) >> ((q & 1) * 4))) & 0xFu) << (4 * c);
+        }
     };
     if (q0 + lane < nquads) issue_loads(q0 + lane);
 #pragma unroll 1
@@ -582,8 +604,10 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
 #pragma unroll
                 for (int j = 0; j < 4; j++) r8[j] = pr[t][j];
                 pass &= term_mask_i32(tcmp[t], tconst[t], r8);
+                if (NULLS) pass &= ~(nmask >> (4 * t));
             }
         }
+        const uint32_t vnull = NULLS ? nmask >> (4 * (NP + 1)) : 0u;   // per value column s: bits [4s, 4s+4) = rows j
         if (JOIN) {
             // K4 fused: the foreign keys of the surviving rows become the dimension attribute the query groups by; the
             // four lookups of a lane fly together, rows without a partner leave the mask (inner join)
@@ -638,6 +662,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
                 sts64(qkey + pos * 8u, key8 ? ((uint64_t)kr[2 * j] | ((uint64_t)kr[2 * j + 1] << 32)) : ((uint64_t)kr[j] & kmask));
 #pragma unroll
                 for (int s = 0; s < NA; s++) sts64(qval + (s * QCAP + pos) * 8u, vr[s][j]);
+                if (NULLS) {
+                    uint32_t nb = 0;
+#pragma unroll
+                    for (int s = 0; s < NA; s++) nb |= ((vnull >> (4 * s + j)) & 1u) << s;
+                    sts8(qnull + pos, nb);
+                }
             }
             total += __popc(bal[j]);
         }
@@ -655,6 +685,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
             uint64_t v[NA > 0 ? NA : 1];
 #pragma unroll
             for (int s = 0; s < NA; s++) v[s] = lds64(qval + (s * QCAP + e) * 8u);
+            uint32_t nb = 0;
+            if (NULLS) {
+                nb = lds8(qnull + e);
+#pragma unroll
+                for (int s = 0; s < NA; s++) if ((nb >> s) & 1u) v[s] = 0ull;   // +0 / +0.0 leaves the sum unchanged
+            }
             const uint32_t h = ((uint32_t)k0 ^ (uint32_t)(k0 >> 32)) * 0x9E3779B1u;
             int slot = -1;
             if (k0 != EMPTY_KEY) slot = smem32_upsert1(keys_addr, cap_mask, k0, h >> hash_shift);
@@ -671,6 +707,10 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
                     }
                 } else {
                     reds_inc32(lanes_addr + slot * 16u);   // pair 0, half 0 = row count
+                    if (NULLS) {
+#pragma unroll
+                        for (int s = 0; s < NA; s++) if (cnt_addr[s] && !((nb >> s) & 1u)) reds_inc32(cnt_addr[s] + slot * 16u);
+                    }
                     int first = 0;
                     if (pair2) {   // {sumA, sumB}: both double sums of the group move in one ATOMS.CAS.128
                         const uint32_t addr = acc_addr[0] + slot * 16u;
@@ -695,7 +735,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
                 uint64_t gv[NA > 0 ? NA : 1];
 #pragma unroll
                 for (int s = 0; s < NA; s++) gv[s] = lds64(qval + (s * QCAP + e) * 8u);
-                global_update_row<NA>(a, key, gv, 0u);
+                global_update_row<NA>(a, key, gv, nb);
             }
         }
         __syncwarp();
@@ -845,7 +885,12 @@ static inline cudaError_t launch_direct(const AggArgs& a, int sm_count, size_t s
             }
             int grid = a.jp.mode ? direct_grid(k_agg_group_lean<NP, NA, true>, smem, sm_count, a.nrows, LEAN_THREADS)
                                  : direct_grid(k_agg_group_lean<NP, NA, false>, smem, sm_count, a.nrows, LEAN_THREADS);
-            if (a.jp.mode) k_agg_group_lean<NP, NA, true><<<grid, LEAN_THREADS, smem, s>>>(a);
+            if (a.lean_nulls) {
+                cudaError_t e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                k_agg_group_lean<NP, NA, false, true><<<direct_grid(k_agg_group_lean<NP, NA, false, true>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
+            }
+            else if (a.jp.mode) k_agg_group_lean<NP, NA, true><<<grid, LEAN_THREADS, smem, s>>>(a);
             else k_agg_group_lean<NP, NA, false><<<grid, LEAN_THREADS, smem, s>>>(a);
         } else
         k_agg_group_direct<NP, NA><<<direct_grid(k_agg_group_direct<NP, NA>, smem, sm_count, a.nrows), DIRECT_THREADS, smem, s>>>(a);

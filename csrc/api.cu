@@ -77,7 +77,7 @@ struct bkgpu_plan {
     JoinProbe jp{}; uint32_t* jp_attr = nullptr; uint64_t* jp_packed = nullptr; int jp_key_pos = 0;   // ... fused into the lean aggregate
     size_t jf_dense_cap = 0, jf_packed_cap = 0, jp_attr_cap = 0, jp_packed_cap = 0, j_scratch_cap = 0;
     uint64_t* j_scratch = nullptr;   // [0..1] key min / max, then u32 flags: [4] duplicate build key, [5] fused probe unusable
-    int no_fused_probe = 0;
+    int no_fused_probe = 0, no_lean_nulls = 0;
     std::vector<uint8_t*> jg_buf; int64_t jg_rows = 0;                            // gathered build columns, one chunk
     std::vector<ColRef> probe_want; std::vector<int> probe_map;   // probe-side columns and their index in c.cols
     // sort / filter state
@@ -207,6 +207,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "no_lean") p->no_lean = v != 0;
     else if (k == "no_fused_probe") p->no_fused_probe = v != 0;
     else if (k == "repartition") p->repartition = v != 0;
+    else if (k == "no_lean_nulls") p->no_lean_nulls = v != 0;
     else if (k == "output_on_device") p->output_on_device = v != 0;
     else if (k == "region_base") p->region_base = v;
     else return p->fail(BKGPU_EINVAL, "unknown option '%s'", key);
@@ -321,7 +322,9 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
     if (direct && lean_keyw && a.smem_cap_log2 > 0 && !p->no_lean) {  // does this batch fit the lean kernel?
         bool ok = true;
         const int np = c.direct.n_terms, na = c.direct.n_vals;
-        for (int i = 0; i < a.n_cols; i++) if (a.cols[i].validity) ok = false;
+        bool any_valid = false;
+        for (int i = 0; i < a.n_cols; i++) if (a.cols[i].validity) any_valid = true;
+        if (a.cols[np].validity || (any_valid && (jp || p->no_lean_nulls))) ok = false;   // NULL keys (and NULLs under the fused probe) take the general kernel
         for (int t = 0; t < np && ok; t++) {
             const DirectTerm& tm = c.direct.term[t];
             const int64_t cv = (int64_t)tm.cbits;
@@ -332,7 +335,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
         for (int v = 0; v < na && ok; v++) {
             const DevCol& vc = a.cols[np + 1 + v];
             const ValOps& vo = a.vops[v];
-            ok = (vc.stype == ST_F64 || vc.stype == ST_I64 || vc.stype == ST_U64) && vo.n_ops == 1 && vo.cnt_smem == 0xFF &&
+            ok = (vc.stype == ST_F64 || vc.stype == ST_I64 || vc.stype == ST_U64) && vo.n_ops == 1 && (vo.cnt_smem == 0xFF || vo.cnt_glob != 0) &&
                  ((vo.op[0] == LN_ADD_F64 && vc.stype == ST_F64 && vo.lane_class[0] == VC_F64) || (vo.op[0] == LN_ADD_I64 && vc.stype != ST_F64));
         }
         a.lean = ok ? 1 : 0;
@@ -350,7 +353,14 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
                 const int sl = vo.op[0] == LN_ADD_F64 ? next_f++ : next_i++;
                 vo.smem_lane[0] = (uint8_t)sl; a.smem_lane[vo.glob_lane[0]] = (uint8_t)sl;
             }
-            a.n_smem_lanes = (std::max(next_f, next_i) + 1) & ~1;
+            int next = std::max(next_f, next_i);
+            for (int v = 0; v < na; v++) {   // non-NULL counters of the value columns that carry NULLs in this batch
+                ValOps& vo = a.vops[v];
+                if (vo.cnt_smem == 0xFF) continue;
+                vo.cnt_smem = (uint8_t)next; a.smem_lane[vo.cnt_glob] = (uint8_t)next; next++;
+            }
+            a.lean_nulls = any_valid ? 1 : 0;
+            a.n_smem_lanes = (next + 1) & ~1;
             if (a.n_smem_lanes < 2) a.n_smem_lanes = 2;
             a.smem_cap_log2 = pick_smem_log2(p, a.n_smem_lanes, true, na);
             if (a.smem_cap_log2 <= 0) { a.lean = 0; a.smem_paired = 0; return p->fail(BKGPU_ENOMEM, "lean kernel: shared table does not fit"); }

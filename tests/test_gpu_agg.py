@@ -41,6 +41,29 @@ def test_lean_int64_key_and_integer_sums():
     assert stats.main_kernel_name.decode() == "k_agg_group_lean"
 
 
+@pytest.mark.parametrize("n", [3, 130, 70_001, 400_000])
+@pytest.mark.parametrize("which", ["values", "predicate", "all", "one_value_all_null"])
+def test_lean_kernel_with_null_predicate_and_value_columns(n, which):
+    """C2's shape with validity bitmaps on the filter and/or value columns (the key stays NULL-free): still the lean kernel —
+    a NULL filter operand drops the row, a NULL value adds +0 and skips that aggregate's non-NULL counter; SUM / AVG of a
+    group whose inputs are all NULL come back NULL"""
+    rng = np.random.default_rng(n)
+    cols = datagen.c2_table(0, n, n_groups=40)
+    mk = lambda c, valid: make_column(c.tuple_id, c.slot_id, c.prim_type, c.values, valid)
+    if which in ("values", "all"):
+        cols[2] = mk(cols[2], rng.random(n) > 0.3); cols[3] = mk(cols[3], rng.random(n) > 0.5)
+    if which in ("predicate", "all"):
+        cols[1] = mk(cols[1], rng.random(n) > 0.2)
+    if which == "one_value_all_null":
+        cols[3] = mk(cols[3], np.zeros(n, bool)); cols[2] = mk(cols[2], cols[0].values % 7 != 0)   # whole groups without a non-NULL input
+    got, stats, _ = run_both(queries.c2_filter_groupby(), cols, keys=["0_1"])
+    if n > 4:
+        assert stats.main_kernel_name.decode() == "k_agg_group_lean"
+    _, stats, _ = run_both(queries.c2_filter_groupby(), cols, keys=["0_1"], options={"no_lean_nulls": 1})
+    if n > 4:
+        assert stats.main_kernel_name.decode() == "k_agg_group_direct"
+
+
 @pytest.mark.parametrize("k", [0, 1, 10486, 1 << 19, 1038090, 1 << 20])
 def test_c2_selectivity(k):  # 0%, ~0%, 1%, 50%, 99%, 100%
     cols = datagen.c2_table(0, 200_000)
