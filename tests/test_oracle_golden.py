@@ -224,3 +224,41 @@ def test_three_valued_logic_and_null_arithmetic():
     root2 = P.agg(P.where(P.scan(0), *conj2), 1, [], aggs)
     pl2 = P.Plan(P.packet(root2), pl.tuples)
     assert oracle.execute(pl2.serialize(), [a, b, c, d]).columns[0].to_list() == [3]
+
+
+# ---- test/test_expr_value.cpp TEST(type_merge, type_merge) :655-840: return types of case_when / if (complete_common_fn +
+#      has_merged_type).  The numeric vectors are on the GPU path; both the oracle's inference and the device lowering
+#      (bkgpu_plan_explain, host-only) must give the reference's answer.  (STRING / date-time merges stay outside the path.) ----
+TYPE_MERGE_VECTORS = [
+    ("case_when", [T.INT8, T.INT64], T.INT64),                       # {STRING, INT8, INT64}        -> INT64   (:667-673)
+    ("case_when2", [T.INT8, T.DOUBLE], T.DOUBLE),                    # {STRING, INT8, INT64, DOUBLE} -> DOUBLE  (:676-682; index 2 is a condition)
+    ("case_when", [T.INT64, T.UINT64], T.DOUBLE),                    # {STRING, INT64, UINT64}       -> DOUBLE  (:685-691)
+    ("if", [T.INT8, T.INT64], T.INT64),                              # if {STRING, INT8, INT64}      -> INT64
+    ("if", [T.INT64, T.UINT64], T.DOUBLE),                           # if {STRING, INT64, UINT64}    -> DOUBLE
+    ("if", [T.NULL_TYPE, T.INT8], T.INT8),                           # if {STRING, NULL_TYPE, INT8}  -> INT8
+]
+
+
+@pytest.mark.parametrize("fn_name,branch_types,expected", TYPE_MERGE_VECTORS)
+def test_type_merge_known_answers(fn_name, branch_types, expected):
+    import re
+    from baikaldb_b200 import _lib
+    slots = {T.INT8: 1, T.INT64: 2, T.UINT64: 3, T.DOUBLE: 4}
+    tuple0 = [(s, t) for t, s in slots.items()] + [(9, T.INT32)]
+    branch = lambda t: P.null_lit() if t == T.NULL_TYPE else P.slot_ref(0, slots[t], t)
+    cond = P.gt(P.slot_ref(0, 9, T.INT32), P.int_lit(0))
+    a, b = branch(branch_types[0]), branch(branch_types[1])
+    if fn_name == "if":
+        e = P.if_(cond, a, b)
+    elif fn_name == "case_when2":
+        e = P.case_when(cond, a, P.lt(P.slot_ref(0, 2, T.INT64), P.int_lit(5)), b)     # WHEN c THEN a WHEN c2(INT64-typed slot in it) ... ELSE b
+    else:
+        e = P.case_when(cond, a, b)                                                     # WHEN c THEN a ELSE b
+    aggs = [P.agg_expr("min", 1, 1, None, e)]
+    pl = P.Plan(P.agg(P.scan(0), 1, [], aggs), {0: sorted(tuple0), 1: []})     # the aggregate slot is left undeclared: its type is the inferred one
+    cols = [make_column(0, 1, T.INT8, [1, -2]), make_column(0, 2, T.INT64, [10, 3]), make_column(0, 3, T.UINT64, [7, 8]),
+            make_column(0, 4, T.DOUBLE, [0.5, 1.5]), make_column(0, 9, T.INT32, [1, 0])]
+    res = oracle.execute(pl.serialize(), cols)
+    assert res.columns[0].prim_type == expected                                         # MIN(x) carries x's inferred type
+    out_prims = re.findall(r"agg\[0\].*out_prim=(\d+)", _lib.explain(pl.serialize()))
+    assert out_prims and int(out_prims[0]) == int(expected)
