@@ -762,13 +762,20 @@ static void put_value(HostCol& hc, int64_t row, uint64_t bits, bool isnull, int 
     }
 }
 
+// groups per rank in the exchanged partial state: never more than the group table can hold (every rank runs the same plan with
+// the same options, so all ranks agree on it) — a 2^14-slot table ships 0.8 MB per rank instead of the 3 MB of the default cap
+static uint32_t eff_pcap(const bkgpu_plan* p) {
+    const int64_t table = p->c.ap.n_keyw == 0 ? 1 : (int64_t)1 << p->group_cap_log2;
+    return (uint32_t)std::min<int64_t>(p->partial_cap, table);
+}
+
 static int agg_finish(bkgpu_plan* p) {
     const AggPlan& ap = p->c.ap;
     GroupTable& gt = p->gt;
     uint32_t host_counts[2] = {0, 0};
     if (p->nccl_comm && p->nranks > 1) {
         // regions -> one set per GPU; partial tables meet in ONE all-gather and are folded by K3
-        const uint32_t pcap = (uint32_t)p->partial_cap;
+        const uint32_t pcap = eff_pcap(p);
         const size_t words = 1 + (size_t)(ap.n_keyw + ap.n_lanes) * pcap;
         int rc;
         const bool repart = p->repartition && ap.n_keyw > 0;   // (a scalar aggregate has one group: nothing to partition)
@@ -998,7 +1005,7 @@ extern "C" int bkgpu_get_stats(bkgpu_plan* p, bkgpu_stats* out) {
 // ------------------------------------------------------------------ partial state
 extern "C" int bkgpu_partial_capacity(bkgpu_plan* p, size_t* bytes) {
     if (!p || !bytes) return thread_fail(BKGPU_EINVAL, "bkgpu_partial_capacity: NULL argument");
-    if (p->c.kind == PK_AGG || p->c.kind == PK_JOIN_AGG) { *bytes = 8 * (1 + (size_t)(p->c.ap.n_keyw + p->c.ap.n_lanes) * (size_t)p->partial_cap); return BKGPU_OK; }
+    if (p->c.kind == PK_AGG || p->c.kind == PK_JOIN_AGG) { *bytes = 8 * (1 + (size_t)(p->c.ap.n_keyw + p->c.ap.n_lanes) * (size_t)eff_pcap(p)); return BKGPU_OK; }
     if (p->c.kind == PK_SORT && p->sort) { *bytes = sort_partial_bytes(p->sort); return BKGPU_OK; }
     return p->fail(BKGPU_EUNSUPPORTED, "plan kind %d has no partial state", p->c.kind);
 }
@@ -1010,7 +1017,7 @@ extern "C" int bkgpu_partial_export(bkgpu_plan* p, void* dev_dst, size_t bytes) 
     if (bytes < need) return p->fail(BKGPU_EINVAL, "partial buffer too small: %zu < %zu", bytes, need);
     CK(p, cudaSetDevice(p->device));
     if (p->c.kind == PK_SORT) { rc = sort_partial_export(p->sort, dev_dst, p->stream, p->last_error); if (rc) g_thread_error = p->last_error; return rc; }
-    CK(p, launch_partial_export(p->gt, p->c.ap, (uint64_t*)dev_dst, (uint32_t)p->partial_cap, p->d_cursor, p->stream));
+    CK(p, launch_partial_export(p->gt, p->c.ap, (uint64_t*)dev_dst, eff_pcap(p), p->d_cursor, p->stream));
     p->stats.kernel_launches += 2;
     CK(p, cudaStreamSynchronize(p->stream));
     uint32_t ov = 0; CK(p, cudaMemcpy(&ov, p->gt.overflow, 4, cudaMemcpyDeviceToHost));
@@ -1034,7 +1041,7 @@ extern "C" int bkgpu_partial_merge(bkgpu_plan* p, const void* dev_src, size_t by
         return BKGPU_OK;
     }
     CK(p, launch_table_init(p->gt, p->c.ap, p->stream));
-    CK(p, launch_partial_merge(p->gt, p->c.ap, (const uint64_t*)dev_src, need / 8, (uint32_t)p->partial_cap, nranks, p->stream));
+    CK(p, launch_partial_merge(p->gt, p->c.ap, (const uint64_t*)dev_src, need / 8, eff_pcap(p), nranks, p->stream));
     p->stats.kernel_launches += 2;
     void* comm = p->nccl_comm; int nr = p->nranks; p->nccl_comm = nullptr; p->nranks = 1;  // already merged: finalize locally
     rc = agg_finish(p);
