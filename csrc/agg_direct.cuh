@@ -24,6 +24,7 @@ namespace bk {
 
 constexpr int ROWS_PER_LANE = 4;
 constexpr int QCAP = 32 * ROWS_PER_LANE;  // queue entries per warp
+constexpr int LEAN_QCAP = QCAP + 32;      // the lean kernel's ring: one iteration's survivors + the < 32 carried over
 
 // per-column decode flags, computed once per kernel
 enum : uint32_t { SF_IS8 = 1u, SF_SIGNED = 2u, SF_SPECIAL = 4u, SF_HASV = 8u };
@@ -523,10 +524,14 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
     const uint32_t lane_lt = (1u << lane) - 1u;
     SmemTable st = smem_table_init(smem_raw, a);
     const size_t table_bytes = (((size_t)(1 + a.n_smem_lanes) * 8 + 4) << a.smem_cap_log2);
-    const size_t qwords = (size_t)(1 + NA) * QCAP;
-    uint64_t* qbase = (uint64_t*)(smem_raw + ((table_bytes + 15) & ~(size_t)15)) + (size_t)warp * (qwords + QCAP / 8);
+    // per-warp queue: a ring of LEAN_QCAP entries [key][values NA][null bytes].  Only FULL passes of 32 entries are drained;
+    // the < 32 left over wait for the next iteration's survivors (at 50 % selectivity 64 +- 6 rows survive per iteration:
+    // draining whatever arrived costs 2.5 passes on average, the last one nearly empty; carrying the remainder costs 2.0)
+    constexpr uint32_t LQ = LEAN_QCAP;
+    const size_t qwords = (size_t)(1 + NA) * LQ;
+    uint64_t* qbase = (uint64_t*)(smem_raw + ((table_bytes + 15) & ~(size_t)15)) + (size_t)warp * (qwords + LQ / 8);
     const uint32_t qkey = smem_addr(qbase);
-    const uint32_t qval = qkey + QCAP * 8u;
+    const uint32_t qval = qkey + LQ * 8u;
     const uint32_t qnull = qkey + (uint32_t)qwords * 8u;   // NULLS: one byte of per-value NULL bits per queue entry
     const uint64_t kmask = ap.key_bits[0] >= 64 ? ~0ull : ((1ull << ap.key_bits[0]) - 1ull);
     const bool key8 = a.cols[NP].stype == ST_I64 || a.cols[NP].stype == ST_U64;
@@ -592,8 +597,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
         }
     };
     if (q0 + lane < nquads) issue_loads(q0 + lane);
+    uint32_t qhead = 0, qcount = 0;   // warp-uniform: ring start (a multiple of 32) and entries waiting in it
 #pragma unroll 1
-    for (; q0 < nquads; q0 += stride) {
+    for (;;) {
+        const bool last = q0 >= nquads;   // (warp-uniform) one extra trip drains what is left in the ring
+        uint32_t total = qcount;
+        if (!last) {
         const int64_t q = q0 + lane;
         uint32_t pass = 0;
         if (q < nquads) {
@@ -654,14 +663,16 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
         uint32_t bal[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) bal[j] = __ballot_sync(0xFFFFFFFFu, (pass >> j) & 1u);
-        int total = 0;
+        uint32_t fresh = 0;
+        const uint32_t tail = qhead + qcount;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if ((pass >> j) & 1u) {
-                const uint32_t pos = (uint32_t)(total + __popc(bal[j] & lane_lt));
+                uint32_t pos = tail + fresh + (uint32_t)__popc(bal[j] & lane_lt);
+                pos -= pos >= LQ ? LQ : 0u;
                 sts64(qkey + pos * 8u, key8 ? ((uint64_t)kr[2 * j] | ((uint64_t)kr[2 * j + 1] << 32)) : ((uint64_t)kr[j] & kmask));
 #pragma unroll
-                for (int s = 0; s < NA; s++) sts64(qval + (s * QCAP + pos) * 8u, vr[s][j]);
+                for (int s = 0; s < NA; s++) sts64(qval + (s * LQ + pos) * 8u, vr[s][j]);
                 if (NULLS) {
                     uint32_t nb = 0;
 #pragma unroll
@@ -669,22 +680,27 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
                     sts8(qnull + pos, nb);
                 }
             }
-            total += __popc(bal[j]);
+            fresh += __popc(bal[j]);
         }
+        total += fresh;
         // ... then reuse those registers for the next iteration's columns: they fly while the queue drains
         if (q + stride < nquads) issue_loads(q + stride);
         passed += __popc(pass);
+        }
         __syncwarp();
+        // (without a filter every iteration brings exactly four full passes: nothing to carry, the ring stays at 0)
+        const uint32_t limit = (last || NP == 0) ? total : (total & ~31u);
         // (a two-entries-per-lane variant of this loop measured 17% slower: more registers, more idle
         //  lanes in the last pass — profiles/r01_agg_kernel_history.md)
 #pragma unroll 1
-        for (int e0 = 0; e0 < total; e0 += 32) {
-            const int e = e0 + lane;
-            if (e >= total) continue;
+        for (uint32_t e0 = 0; e0 < limit; e0 += 32) {
+            if (e0 + lane >= limit) continue;   // (only the final trip has a ragged pass)
+            uint32_t e = qhead + e0 + lane;
+            e -= e >= LQ ? LQ : 0u;
             const uint64_t k0 = lds64(qkey + e * 8u);
             uint64_t v[NA > 0 ? NA : 1];
 #pragma unroll
-            for (int s = 0; s < NA; s++) v[s] = lds64(qval + (s * QCAP + e) * 8u);
+            for (int s = 0; s < NA; s++) v[s] = lds64(qval + (s * LQ + e) * 8u);
             uint32_t nb = 0;
             if (NULLS) {
                 nb = lds8(qnull + e);
@@ -734,11 +750,14 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
                 uint64_t key[2] = {k0, 0ull};
                 uint64_t gv[NA > 0 ? NA : 1];
 #pragma unroll
-                for (int s = 0; s < NA; s++) gv[s] = lds64(qval + (s * QCAP + e) * 8u);
+                for (int s = 0; s < NA; s++) gv[s] = lds64(qval + (s * LQ + e) * 8u);
                 global_update_row<NA>(a, key, gv, nb);
             }
         }
+        if (NP > 0) { qhead = (qhead + limit) % LQ; qcount = total - limit; }
         __syncwarp();
+        if (last) break;
+        q0 += stride;
     }
     smem_table_flush(st, a);
     if (blockIdx.x == 0 && threadIdx.x < (a.nrows & 3)) passed += direct_tail_row<NP, NA, JOIN>(a, (a.nrows & ~(int64_t)3) + threadIdx.x);
