@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
         for (int j = 0; j < 4; j++) {
             if ((pass >> j) & 1u) {
                 uint32_t pos = tail + fresh + (uint32_t)__popc(bal[j] & lane_lt);
-                pos -= pos >= LQ ? LQ : 0u;
+                if (NP > 0) pos -= pos >= LQ ? LQ : 0u;   // (no filter: nothing is ever carried, positions stay below 128)
                 sts64(qkey + pos * 8u, key8 ? ((uint64_t)kr[2 * j] | ((uint64_t)kr[2 * j + 1] << 32)) : ((uint64_t)kr[j] & kmask));
 #pragma unroll
                 for (int s = 0; s < NA; s++) sts64(qval + (s * LQ + pos) * 8u, vr[s][j]);
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
         for (uint32_t e0 = 0; e0 < limit; e0 += 32) {
             if (e0 + lane >= limit) continue;   // (only the final trip has a ragged pass)
             uint32_t e = qhead + e0 + lane;
-            e -= e >= LQ ? LQ : 0u;
+            if (NP > 0) e -= e >= LQ ? LQ : 0u;
             const uint64_t k0 = lds64(qkey + e * 8u);
             uint64_t v[NA > 0 ? NA : 1];
 #pragma unroll

@@ -101,3 +101,21 @@ def test_join_without_group_by_and_empty_sides():
     empty_dim = [make_column(c.tuple_id, c.slot_id, c.prim_type, c.values[:0]) for c in dim]
     got, _, _ = run_both(pl, fact + empty_dim, keys=[], batches=[empty_dim, fact])
     assert got[0].to_list() == [0] and got[1].to_list() == [None]
+
+
+@pytest.mark.parametrize("nf", [90_001, 400_000])
+def test_fused_probe_with_a_fact_side_filter(nf):
+    """WHERE on the probe (fact) side below an FK -> PK join: the filter term, the key lookup and the aggregation all run in the
+    lean kernel (predicate columns + fused probe + ring queue); some foreign keys have no partner"""
+    rng = np.random.default_rng(nf)
+    nd = 7_000
+    dim = [make_column(1, 1, T.INT32, rng.permutation(9_000)[:nd].astype(np.int32)), make_column(1, 2, T.INT32, rng.integers(0, 60, nd))]
+    fact = [make_column(0, 1, T.INT32, rng.integers(0, 9_000, nf)), make_column(0, 2, T.DOUBLE, rng.random(nf)), make_column(0, 3, T.INT32, rng.integers(0, 100, nf))]
+    aggs = [P.agg_expr("count_star", 2, 1), P.agg_expr("sum", 2, 2, None, P.slot_ref(0, 2, T.DOUBLE))]
+    inner = P.where(P.scan(0), P.lt(P.slot_ref(0, 3, T.INT32), P.int_lit(37)))
+    j = P.join(P.scan(1), inner, [P.eq(P.slot_ref(1, 1, T.INT32), P.slot_ref(0, 1, T.INT32))])
+    pl = P.Plan(P.agg(j, 2, [P.slot_ref(1, 2, T.INT32)], aggs), {0: [(1, T.INT32), (2, T.DOUBLE), (3, T.INT32)], 1: [(1, T.INT32), (2, T.INT32)],
+                                                                    2: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE])})
+    _, stats, _ = run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact])
+    assert stats.main_kernel_name.decode() == "k_agg_group_lean"
+    run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact], options={"no_fused_probe": 1})
