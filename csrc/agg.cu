@@ -232,9 +232,9 @@ size_t agg_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2) {
 
 // shared memory of the direct GROUP BY kernel: the table plus one compaction queue per warp
 size_t direct_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2, int na) {
-    const size_t table = (agg_smem_bytes(smem_keyw, n_smem_lanes, cap_log2) + 15) & ~(size_t)15;
+    const size_t table = (agg_smem_bytes(smem_keyw, n_smem_lanes, cap_log2) + 127) & ~(size_t)127;
     const size_t q_direct = ((size_t)(2 + na) * 128 + 16) * 8;  // QCAP = 128 entries per warp, up to 2 key words
-    const size_t q_lean = ((size_t)(1 + na) * 160 + 20) * 8;     // LEAN_QCAP = 160-entry ring, one key word
+    const size_t q_lean = ((((size_t)(1 + na) * 160 + 20) + 15) & ~(size_t)15) * 8 + 8;   // LEAN_QCAP = 160-entry ring, one key word, 128-byte aligned (+ slack for the base)
     const size_t queue = q_direct > q_lean ? q_direct : q_lean;
     const int warps = (DIRECT_THREADS > LEAN_THREADS ? DIRECT_THREADS : LEAN_THREADS) / 32;   // sized for the larger of the two CTA shapes
     return table + queue * warps;

@@ -529,7 +529,8 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
     // draining whatever arrived costs 2.5 passes on average, the last one nearly empty; carrying the remainder costs 2.0)
     constexpr uint32_t LQ = LEAN_QCAP;
     const size_t qwords = (size_t)(1 + NA) * LQ;
-    uint64_t* qbase = (uint64_t*)(smem_raw + ((table_bytes + 15) & ~(size_t)15)) + (size_t)warp * (qwords + LQ / 8);
+    // (each warp's ring starts on a 128-byte boundary: a pass of 32 consecutive 8-byte entries is then exactly two wavefronts)
+    uint64_t* qbase = (uint64_t*)(smem_raw + ((table_bytes + 127) & ~(size_t)127)) + (size_t)warp * ((qwords + LQ / 8 + 15) & ~(size_t)15);
     const uint32_t qkey = smem_addr(qbase);
     const uint32_t qval = qkey + LQ * 8u;
     const uint32_t qnull = qkey + (uint32_t)qwords * 8u;   // NULLS: one byte of per-value NULL bits per queue entry
@@ -771,7 +772,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
 // reduction, one set of global atomics per warp
 // ------------------------------------------------------------------------------------------
 template <int NP, int NA>
-__global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_scalar_direct(const __grid_constant__ AggArgs a) {
+__global__ void __launch_bounds__(DIRECT_THREADS, NA == 0 ? 2 : 1) k_agg_scalar_direct(const __grid_constant__ AggArgs a) {   // COUNT(*) only: two CTAs per SM
     constexpr int NS = NP + NA;
     const int lane = threadIdx.x & 31;
     uint64_t rows = 0;
