@@ -275,10 +275,21 @@ cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t
 // ---- FK -> PK fast path (see JoinFast in agg.h) ----
 __global__ void k_join_minmax(DevCol key, int from_prim, int cast_to, int64_t nrows, uint64_t bias, uint64_t* mm) {
     uint64_t lo = ~0ull, hi = 0;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
-        if (elem_is_null(key, r)) continue;
-        const uint64_t v = cast_prim(load_elem(key, r), from_prim, cast_to) ^ bias;
-        lo = v < lo ? v : lo; hi = v > hi ? v : hi;
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r0 < nrows; r0 += 4 * T) {   // four independent loads in flight per thread
+        uint64_t v[4]; bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t r = r0 + u * T;
+            ok[u] = r < nrows && !elem_is_null(key, r);
+            v[u] = ok[u] ? load_elem(key, r) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (!ok[u]) continue;
+            const uint64_t x = cast_prim(v[u], from_prim, cast_to) ^ bias;
+            lo = x < lo ? x : lo; hi = x > hi ? x : hi;
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
