@@ -113,6 +113,17 @@ def main():
             arr[i].validity = b.data_ptr()
         run("C2 with ~25 % NULLs in both value columns", queries.c2_filter_groupby(), [(arr, 4, n)], n, 24 * n + n // 4, a.steps, a.warmup, options=[(b"group_capacity_log2", 14)])
         del ts, bm
+    if "c2m" in a.configs:   # C2's table, MIN / MAX / SUM aggregates: the lean kernel's MM instantiation vs the general kernel
+        from baikaldb_b200 import plan as P
+        n = int(100_000_000 * a.scale)
+        specs = [(0, 1, T.INT32, 0, 1, 0, 1000, 1.0), (0, 2, T.INT32, 0, 2, 0, 1 << 20, 1.0), (0, 3, T.DOUBLE, 1, 3, 0, 0, 1.0), (0, 4, T.DOUBLE, 2, 4, 0, 0, 1732.05)]
+        ts = [gen(n, s, 2) for s in specs]
+        aggs = [P.agg_expr("count_star", 1, 1), P.agg_expr("min", 1, 2, None, P.slot_ref(0, 3, T.DOUBLE)), P.agg_expr("max", 1, 3, None, P.slot_ref(0, 3, T.DOUBLE)),
+                P.agg_expr("sum", 1, 4, None, P.slot_ref(0, 4, T.DOUBLE))]
+        root = P.agg(P.where(P.scan(0), P.lt(P.slot_ref(0, 2, T.INT32), P.int_lit(1 << 19))), 1, [P.slot_ref(0, 1, T.INT32)], aggs)
+        plan = P.Plan(root, {0: [(1, T.INT32), (2, T.INT32), (3, T.DOUBLE), (4, T.DOUBLE)], 1: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE, T.DOUBLE, T.DOUBLE])})
+        run("C2 table, COUNT(*), MIN(a), MAX(a), SUM(b)", plan, [(cols_array(specs, ts), 4, n)], n, 24 * n, a.steps, a.warmup, options=[(b"group_capacity_log2", 14)])
+        del ts
     if "c5" in a.configs:
         n = int(125_000_000 * a.scale)
         specs = [(0, 1, T.INT64, 3, 1, 0, 0, 1.0), (0, 2, T.INT32, 0, 2, 0, 1 << 30, 1.0)]

@@ -50,6 +50,7 @@ struct AggArgs {
     int32_t smem_sentinel;   // shared table of one-word keys: the key word doubles as slot state (EMPTY_KEY = free)
     JoinProbe jp;            // lean kernel only: the key column holds the probe-side foreign key (see JoinProbe)
     int32_t lean_nulls;      // lean kernel: some predicate / value column of this batch carries a validity bitmap
+    int32_t lean_mm;         // lean kernel: some value column feeds MIN / MAX lanes or more than one lane
 };
 
 size_t agg_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2);

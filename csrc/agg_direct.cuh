@@ -273,6 +273,18 @@ __device__ __forceinline__ void smem32_add_u64(uint32_t a, uint64_t v) {
     const uint32_t carry = (old + lo) < old ? 1u : 0u;
     if (hi + carry) atoms_add32(a + 4, hi + carry);
 }
+// MIN / MAX in shared memory: compare first, swap only when this value improves the extreme (64-bit min/max atomics are CAS
+// loops on sm_100a anyway: ATOMS.CAST.SPIN.64); lane_combine carries the reference's compare semantics (NaN never wins)
+__device__ __forceinline__ void smem32_minmax(uint32_t a, int op, uint64_t v) {
+    uint64_t cur = lds64(a);
+    for (;;) {
+        const uint64_t nw = lane_combine(op, cur, v);
+        if (nw == cur) break;
+        const uint64_t prev = atoms_cas64(a, cur, nw);
+        if (prev == cur) break;
+        cur = prev;
+    }
+}
 // probe of a sentinel-mode shared table (one-word keys: EMPTY_KEY = free slot): a hit costs one
 // LDS.64 and one compare.  Returns the slot's byte offset * 1 (slot index) or -1 after 16 probes.
 __device__ __forceinline__ int smem32_upsert1(uint32_t keys_addr, uint32_t cap_mask, uint64_t key, uint32_t slot) {
@@ -515,7 +527,9 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 // ------------------------------------------------------------------------------------------
 // NULLS: predicate / value columns may carry validity bitmaps (a NULL predicate operand drops the row, a NULL value skips that
 // aggregate: its sum gets +0 and its non-NULL counter no increment); the key column stays NULL-free in this kernel.
-template <int NP, int NA, bool JOIN, bool NULLS = false>
+// MM: value columns may feed MIN / MAX lanes (LDS -> compare -> ATOMS.CAS.64 only when the row improves the extreme: after the
+// first rows of a group that is one LDS per row) and up to three lanes each (SUM + MIN + MAX over one column).
+template <int NP, int NA, bool JOIN, bool NULLS = false, bool MM = false>
 __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid_constant__ AggArgs a) {
     constexpr int NS = NP + 1 + NA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -569,7 +583,8 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
     // (fusing {row count, sum} into one CAS.128 measured SLOWER than RED.u32 + CAS.64 — the native 32-bit reduction is
     //  cheaper than widening the compare-and-swap — so it stays off; the code is kept for the record)
     const bool fuse1 = false && NA == 1 && acc_f64[0] && a.vops[0].smem_lane[0] == 1;
-    const bool pair2 = NA >= 2 && acc_f64[0] && acc_f64[NA > 1 ? 1 : 0] && a.vops[0].smem_lane[0] == 2 && a.vops[NA > 1 ? 1 : 0].smem_lane[0] == 3;
+    const bool pair2 = NA >= 2 && acc_f64[0] && acc_f64[NA > 1 ? 1 : 0] && a.vops[0].smem_lane[0] == 2 && a.vops[NA > 1 ? 1 : 0].smem_lane[0] == 3 &&
+                       (!MM || (a.vops[0].n_ops == 1 && a.vops[NA > 1 ? 1 : 0].n_ops == 1));
     uint32_t passed = 0;
     const int64_t nquads = a.nrows >> 2;
     const int64_t stride = (int64_t)gridDim.x * LEAN_THREADS;
@@ -744,7 +759,20 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
 #pragma unroll
                     for (int s = 0; s < NA; s++) {
                         if (s < first) continue;
-                        if (acc_f64[s]) smem32_add_f64(acc_addr[s] + slot * 16u, bits_f64(v[s])); else smem32_add_u64(acc_addr[s] + slot * 16u, v[s]);
+                        if (MM) {
+                            if (NULLS && ((nb >> s) & 1u)) continue;   // a NULL input touches no lane
+                            const int nops = a.vops[s].n_ops;
+#pragma unroll 1
+                            for (int k = 0; k < nops; k++) {
+                                const int op = a.vops[s].op[k];
+                                const uint32_t sl = a.vops[s].smem_lane[k];
+                                const uint32_t addr = lanes_addr + ((sl >> 1) * tcap * 2u + (sl & 1u)) * 8u + slot * 16u;
+                                if (op == LN_ADD_F64) smem32_add_f64(addr, bits_f64(v[s]));
+                                else if (op == LN_ADD_I64) smem32_add_u64(addr, v[s]);
+                                else smem32_minmax(addr, op, v[s]);
+                            }
+                        }
+                        else if (acc_f64[s]) smem32_add_f64(acc_addr[s] + slot * 16u, bits_f64(v[s])); else smem32_add_u64(acc_addr[s] + slot * 16u, v[s]);
                     }
                 }
             } else {   // rare: re-read the entry from the queue so that v[] never needs an address (no local-memory copy per pass)
@@ -905,7 +933,13 @@ static inline cudaError_t launch_direct(const AggArgs& a, int sm_count, size_t s
             }
             int grid = a.jp.mode ? direct_grid(k_agg_group_lean<NP, NA, true>, smem, sm_count, a.nrows, LEAN_THREADS)
                                  : direct_grid(k_agg_group_lean<NP, NA, false>, smem, sm_count, a.nrows, LEAN_THREADS);
-            if (a.lean_nulls) {
+            if (a.lean_mm) {
+                cudaError_t e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                // (one instantiation serves batches with and without NULLs: without bitmaps the NULL masks are simply zero)
+                k_agg_group_lean<NP, NA, false, true, true><<<direct_grid(k_agg_group_lean<NP, NA, false, true, true>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
+            }
+            else if (a.lean_nulls) {
                 cudaError_t e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
                 k_agg_group_lean<NP, NA, false, true><<<direct_grid(k_agg_group_lean<NP, NA, false, true>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);

@@ -77,7 +77,7 @@ struct bkgpu_plan {
     JoinProbe jp{}; uint32_t* jp_attr = nullptr; uint64_t* jp_packed = nullptr; int jp_key_pos = 0;   // ... fused into the lean aggregate
     size_t jf_dense_cap = 0, jf_packed_cap = 0, jp_attr_cap = 0, jp_packed_cap = 0, j_scratch_cap = 0;
     uint64_t* j_scratch = nullptr;   // [0..1] key min / max, then u32 flags: [4] duplicate build key, [5] fused probe unusable
-    int no_fused_probe = 0, no_lean_nulls = 0;
+    int no_fused_probe = 0, no_lean_nulls = 0, no_lean_mm = 0;
     std::vector<uint8_t*> jg_buf; int64_t jg_rows = 0;                            // gathered build columns, one chunk
     std::vector<ColRef> probe_want; std::vector<int> probe_map;   // probe-side columns and their index in c.cols
     // sort / filter state
@@ -208,6 +208,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "no_fused_probe") p->no_fused_probe = v != 0;
     else if (k == "repartition") p->repartition = v != 0;
     else if (k == "no_lean_nulls") p->no_lean_nulls = v != 0;
+    else if (k == "no_lean_mm") p->no_lean_mm = v != 0;
     else if (k == "output_on_device") p->output_on_device = v != 0;
     else if (k == "region_base") p->region_base = v;
     else return p->fail(BKGPU_EINVAL, "unknown option '%s'", key);
@@ -332,12 +333,21 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
         }
         const DevCol& kc = a.cols[np];
         ok = ok && ((kc.stype == ST_I32 && kc.prim == BK_INT32) || (kc.stype == ST_U32 && kc.prim == BK_UINT32) || kc.stype == ST_I64 || kc.stype == ST_U64);
+        bool mm = false;   // some column feeds MIN / MAX or several lanes: the MM instantiation of the lean kernel
         for (int v = 0; v < na && ok; v++) {
             const DevCol& vc = a.cols[np + 1 + v];
             const ValOps& vo = a.vops[v];
-            ok = (vc.stype == ST_F64 || vc.stype == ST_I64 || vc.stype == ST_U64) && vo.n_ops == 1 && (vo.cnt_smem == 0xFF || vo.cnt_glob != 0) &&
-                 ((vo.op[0] == LN_ADD_F64 && vc.stype == ST_F64 && vo.lane_class[0] == VC_F64) || (vo.op[0] == LN_ADD_I64 && vc.stype != ST_F64));
+            ok = (vc.stype == ST_F64 || vc.stype == ST_I64 || vc.stype == ST_U64) && vo.n_ops <= 3 && (vo.cnt_smem == 0xFF || vo.cnt_glob != 0);
+            const int col_class = vc.stype == ST_F64 ? VC_F64 : (vc.stype == ST_U64 ? VC_U64 : VC_I64);
+            for (int k = 0; k < vo.n_ops && ok; k++) {
+                const int op = vo.op[k];
+                if (op == LN_ADD_F64) ok = vc.stype == ST_F64 && vo.lane_class[k] == VC_F64;
+                else if (op == LN_ADD_I64) ok = vc.stype != ST_F64;
+                else { ok = vo.lane_class[k] == col_class && vo.arg_class == col_class; mm = true; }   // MIN / MAX in the column's own class
+            }
+            if (vo.n_ops != 1) mm = true;
         }
+        if (mm && (jp || p->no_lean_mm)) ok = false;
         a.lean = ok ? 1 : 0;
         if (a.lean) {
             a.smem_sentinel = 1; a.smem_keyw = 1; a.smem_paired = 1;
@@ -345,14 +355,17 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
             // ({rows, sum}: a single atomic per row); otherwise double sums sit in pairs {sumA, sumB}
             memset(a.smem_lane, 0xFF, sizeof a.smem_lane);
             a.smem_lane[0] = 0;
-            int nf64 = 0;
-            for (int v = 0; v < na; v++) if (a.vops[v].op[0] == LN_ADD_F64) nf64++;
+            int nf64 = 0;   // columns that feed exactly one double sum (they sit in {sumA, sumB} pairs)
+            for (int v = 0; v < na; v++) if (a.vops[v].n_ops == 1 && a.vops[v].op[0] == LN_ADD_F64) nf64++;
             int next_f = nf64 == 1 ? 1 : 2, next_i = nf64 == 1 ? 2 : 2 + ((nf64 + 1) & ~1);
             for (int v = 0; v < na; v++) {
                 ValOps& vo = a.vops[v];
-                const int sl = vo.op[0] == LN_ADD_F64 ? next_f++ : next_i++;
-                vo.smem_lane[0] = (uint8_t)sl; a.smem_lane[vo.glob_lane[0]] = (uint8_t)sl;
+                for (int k = 0; k < vo.n_ops; k++) {
+                    const int sl = (vo.n_ops == 1 && vo.op[0] == LN_ADD_F64) ? next_f++ : next_i++;
+                    vo.smem_lane[k] = (uint8_t)sl; a.smem_lane[vo.glob_lane[k]] = (uint8_t)sl;
+                }
             }
+            a.lean_mm = mm ? 1 : 0;
             int next = std::max(next_f, next_i);
             for (int v = 0; v < na; v++) {   // non-NULL counters of the value columns that carry NULLs in this batch
                 ValOps& vo = a.vops[v];

@@ -64,6 +64,31 @@ def test_lean_kernel_with_null_predicate_and_value_columns(n, which):
         assert stats.main_kernel_name.decode() == "k_agg_group_direct"
 
 
+@pytest.mark.parametrize("nulls", [False, True])
+@pytest.mark.parametrize("n", [5, 4_099, 250_000])
+def test_lean_kernel_min_max_and_several_aggregates_per_column(n, nulls):
+    """MIN / MAX (double, int64, uint64), SUM + MIN + MAX over one column, COUNT(x) alone: the lean kernel's MM instantiation
+    (compare-then-CAS extremes), with and without NULLs; the general kernel gives the same rows"""
+    rng = np.random.default_rng(n + nulls)
+    valid = (lambda: rng.random(n) > 0.3) if nulls else (lambda: None)
+    cols = [make_column(0, 1, T.INT32, rng.integers(0, 23, n)), make_column(0, 2, T.INT32, rng.integers(0, 100, n)),
+            make_column(0, 3, T.DOUBLE, rng.normal(size=n) * 1e3, valid()), make_column(0, 4, T.INT64, rng.integers(-(1 << 40), 1 << 40, n), valid()),
+            make_column(0, 5, T.UINT64, rng.integers(0, 1 << 63, n, dtype=np.uint64) * 2, valid()), make_column(0, 6, T.DOUBLE, rng.random(n), valid())]
+    d, i64, u64, e = P.slot_ref(0, 3, T.DOUBLE), P.slot_ref(0, 4, T.INT64), P.slot_ref(0, 5, T.UINT64), P.slot_ref(0, 6, T.DOUBLE)
+    aggs = [P.agg_expr("count_star", 1, 1), P.agg_expr("min", 1, 2, None, d), P.agg_expr("max", 1, 3, None, d), P.agg_expr("sum", 1, 4, None, d),
+            P.agg_expr("max", 1, 5, None, i64), P.agg_expr("sum", 1, 6, None, i64), P.agg_expr("min", 1, 7, None, u64), P.agg_expr("count", 1, 8, None, e),
+            P.agg_expr("avg", 1, 9, 10, d)]
+    root = P.agg(P.where(P.scan(0), P.lt(P.slot_ref(0, 2, T.INT32), P.int_lit(70))), 1, [P.slot_ref(0, 1, T.INT32)], aggs)
+    pl = P.Plan(root, {0: [(1, T.INT32), (2, T.INT32), (3, T.DOUBLE), (4, T.INT64), (5, T.UINT64), (6, T.DOUBLE)],
+                       1: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE, T.DOUBLE, T.DOUBLE, T.INT64, T.INT64, T.UINT64, T.DOUBLE, T.DOUBLE])})
+    _, stats, _ = run_both(pl, cols, keys=["0_1"])
+    if n > 4:
+        assert stats.main_kernel_name.decode() == "k_agg_group_lean"
+    _, stats, _ = run_both(pl, cols, keys=["0_1"], options={"no_lean_mm": 1})
+    if n > 4:
+        assert stats.main_kernel_name.decode() == "k_agg_group_direct"
+
+
 @pytest.mark.parametrize("k", [0, 1, 10486, 1 << 19, 1038090, 1 << 20])
 def test_c2_selectivity(k):  # 0%, ~0%, 1%, 50%, 99%, 100%
     cols = datagen.c2_table(0, 200_000)
