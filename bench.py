@@ -58,16 +58,54 @@ def workload_name(n_gpus, rows):
 # clocks: sampled DURING the timed region (B200_PROFILING.md)
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region.  NVML in a background thread (one sample every ~2 ms: even a
+    10 ms region gets several); `nvidia-smi -lms` as a subprocess when pynvml is not importable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.f = None
+        self.nvml = None
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        try:
+            reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        except Exception:
+            reasons = 0
+        self.samples.append((float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)), int(reasons)))
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml:
+            import threading
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                        "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
@@ -75,6 +113,21 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.nvml:
+            try:
+                self._sample()   # the region has just ended (the caller synchronised): still the loaded state
+            except Exception:
+                pass
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=2)
+            if self.samples:
+                bits = 0
+                for _, r in self.samples:
+                    bits |= r
+                out.update(sm_mhz=statistics.median([c for c, _ in self.samples]), sm_max_mhz=self.max_sm,
+                           reasons=sorted(name for bit, name in self.REASONS if bits & bit), samples=len(self.samples), source="nvml")
+            return out
         if not self.p:
             return out
         time.sleep(0.15)
@@ -99,7 +152,7 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.f.name)
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
         return out
 
 
