@@ -63,6 +63,10 @@ struct bkgpu_plan {
     uint64_t* d_partial = nullptr;  // export buffer (this rank)
     uint64_t* d_gather = nullptr;   // nranks export buffers
     uint32_t* d_part_cursors = nullptr; int repartition = 0;   // hash repartition of the groups across ranks (option "repartition")
+    // merge over NVLink peer memory (option "peer_merge"): this rank's buffer, the peers' mappings of theirs, step counter
+    int peer_merge = 0, peer_rank = -1; bool peer_ready = false;
+    uint64_t* peer_local = nullptr; std::vector<uint64_t*> peer_ptr; uint64_t** d_peer_ptrs = nullptr; uint64_t peer_seq = 0; size_t peer_seg_words = 0;
+    uint32_t* d_peer_timeout = nullptr;
     uint64_t* d_outv = nullptr; uint8_t* d_outn = nullptr; size_t out_cap_alloc = 0;  // extraction buffers (kept across resets)
     std::vector<cudaEvent_t> event_pool;
     uint64_t* h_outv = nullptr; uint8_t* h_outn = nullptr; size_t h_out_cap = 0;   // pinned landing area of the extracted rows
@@ -207,6 +211,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "no_lean") p->no_lean = v != 0;
     else if (k == "no_fused_probe") p->no_fused_probe = v != 0;
     else if (k == "repartition") p->repartition = v != 0;
+    else if (k == "peer_merge") p->peer_merge = v != 0;
     else if (k == "no_lean_nulls") p->no_lean_nulls = v != 0;
     else if (k == "no_lean_mm") p->no_lean_mm = v != 0;
     else if (k == "output_on_device") p->output_on_device = v != 0;
@@ -241,7 +246,7 @@ extern "C" int bkgpu_open(bkgpu_plan* p) {
     CK(p, cudaSetDevice(p->device));
     if (!p->stream) { CK(p, cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)); p->own_stream = true; }
     CK(p, cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-    if (cudaHostAlloc((void**)&p->h_pinned, 64, cudaHostAllocDefault) == cudaSuccess) p->h_pinned[0] = 0; else p->h_pinned = nullptr;
+    if (cudaHostAlloc((void**)&p->h_pinned, 64, cudaHostAllocDefault) == cudaSuccess) memset(p->h_pinned, 0, 64); else p->h_pinned = nullptr;
     for (int i = 0; i < 2; i++) {
         CK(p, cudaEventCreateWithFlags(&p->stage_free[i], cudaEventDisableTiming));
         CK(p, cudaEventCreateWithFlags(&p->stage_ready[i], cudaEventDisableTiming));
@@ -775,6 +780,45 @@ static void put_value(HostCol& hc, int64_t row, uint64_t bits, bool isnull, int 
     }
 }
 
+// One-time setup of the peer-memory merge: allocate this rank's buffer, trade CUDA IPC handles through the communicator, map the peers'.
+static int peer_setup(bkgpu_plan* p, size_t seg_words) {
+    if (p->peer_ready) return p->peer_seg_words == seg_words ? BKGPU_OK : p->fail(BKGPU_ESTATE, "peer merge: the partial-state size changed after setup");
+    const int n = p->nranks;
+    if (nccl_comm_rank(p->nccl_comm, &p->peer_rank) != 0) return p->fail(BKGPU_ENCCL, "ncclCommUserRank: %s", nccl_last_error());
+    const size_t words = 2 * (size_t)n * seg_words + 2 * (size_t)n;
+    int rc;
+    if ((rc = dev_alloc(p, (void**)&p->peer_local, words * 8))) return rc;
+    CK(p, cudaMemsetAsync(p->peer_local, 0, words * 8, p->stream));
+    cudaIpcMemHandle_t mine;
+    CK(p, cudaIpcGetMemHandle(&mine, p->peer_local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    uint64_t *d_mine = nullptr, *d_all = nullptr;
+    if ((rc = dev_alloc(p, (void**)&d_mine, 64))) return rc;
+    if ((rc = dev_alloc(p, (void**)&d_all, 64 * (size_t)n))) return rc;
+    CK(p, cudaMemcpyAsync(d_mine, &mine, 64, cudaMemcpyHostToDevice, p->stream));
+    if (nccl_all_gather(p->nccl_comm, d_mine, d_all, 8, p->stream) != 0) return p->fail(BKGPU_ENCCL, "ncclAllGather (IPC handles): %s", nccl_last_error());
+    std::vector<cudaIpcMemHandle_t> all((size_t)n);
+    CK(p, cudaMemcpyAsync(all.data(), d_all, 64 * (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+    CK(p, cudaStreamSynchronize(p->stream));
+    p->peer_ptr.assign((size_t)n, nullptr);
+    for (int r = 0; r < n; r++) {
+        if (r == p->peer_rank) { p->peer_ptr[(size_t)r] = p->peer_local; continue; }
+        void* q = nullptr;
+        CK(p, cudaIpcOpenMemHandle(&q, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess));
+        p->peer_ptr[(size_t)r] = (uint64_t*)q;
+    }
+    if ((rc = dev_alloc(p, (void**)&p->d_peer_ptrs, 8 * (size_t)n))) return rc;
+    if ((rc = dev_alloc(p, (void**)&p->d_peer_timeout, 8))) return rc;
+    CK(p, cudaMemcpyAsync(p->d_peer_ptrs, p->peer_ptr.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, p->stream));
+    CK(p, cudaMemsetAsync(p->d_peer_timeout, 0, 8, p->stream));
+    // nobody may write into a buffer before its owner has zeroed it: one more trip through the communicator is the barrier
+    if (nccl_all_gather(p->nccl_comm, d_mine, d_all, 8, p->stream) != 0) return p->fail(BKGPU_ENCCL, "ncclAllGather (barrier): %s", nccl_last_error());
+    CK(p, cudaStreamSynchronize(p->stream));
+    dev_free(p, d_mine); dev_free(p, d_all);
+    p->peer_seg_words = seg_words; p->peer_ready = true;
+    return BKGPU_OK;
+}
+
 // groups per rank in the exchanged partial state: never more than the group table can hold (every rank runs the same plan with
 // the same options, so all ranks agree on it) — a 2^14-slot table ships 0.8 MB per rank instead of the 3 MB of the default cap
 static uint32_t eff_pcap(const bkgpu_plan* p) {
@@ -794,7 +838,17 @@ static int agg_finish(bkgpu_plan* p) {
         const bool repart = p->repartition && ap.n_keyw > 0;   // (a scalar aggregate has one group: nothing to partition)
         if (!p->d_partial && (rc = dev_alloc(p, (void**)&p->d_partial, words * 8 * (repart ? (size_t)p->nranks : 1)))) return rc;
         if (!p->d_gather && (rc = dev_alloc(p, (void**)&p->d_gather, words * 8 * (size_t)p->nranks))) return rc;
+        if (p->peer_merge && !repart && (rc = peer_setup(p, words))) return rc;
         EventPair* ep = timer_begin(p, p->timed_coll, 0);
+        if (p->peer_merge && !repart) {
+            const uint64_t seq = ++p->peer_seq;
+            CK(p, launch_peer_exchange(gt, ap, p->d_peer_ptrs, p->peer_local, p->nranks, p->peer_rank, words, pcap, seq, p->d_cursor, p->d_peer_timeout, p->stream));
+            CK(p, launch_table_init(gt, ap, p->stream));
+            CK(p, launch_partial_merge(gt, ap, p->peer_local + (size_t)(seq & 1) * (size_t)p->nranks * words, words, pcap, p->nranks, p->stream));
+            timer_end(p, ep);
+            p->stats.kernel_launches += 5;
+            if (p->h_pinned) CK(p, cudaMemcpyAsync(p->h_pinned + 12, p->d_peer_timeout, 4, cudaMemcpyDeviceToHost, p->stream));   // checked after the result's synchronisation
+        } else {
         if (repart) {
             // hash repartition: every rank keeps only the groups it owns — an all-to-all of per-owner segments instead of the
             // all-gather; the merged table (and the result) of a rank is its partition, the union over ranks is the answer
@@ -809,6 +863,7 @@ static int agg_finish(bkgpu_plan* p) {
         CK(p, launch_partial_merge(gt, ap, p->d_gather, words, pcap, p->nranks, p->stream));
         timer_end(p, ep);
         p->stats.kernel_launches += 4;
+        }
     }
     // device images: one per group expr, per aggregate its final (+2 for an AVG blob)
     int n_img = ap.n_group;
@@ -848,6 +903,7 @@ static int agg_finish(bkgpu_plan* p) {
         CK(p, cudaMemcpyAsync(hn, p->d_outn, n_words, cudaMemcpyDeviceToHost, p->stream));
         CK(p, cudaStreamSynchronize(p->stream));
         if (hc3) { host_counts[0] = hc3[0]; host_counts[1] = hc3[1]; n_out = hc3[2]; }
+        if (p->peer_ready && p->h_pinned && p->h_pinned[12]) return p->fail(BKGPU_ENCCL, "peer merge: a rank did not publish its partial state within the time limit");
         p->stats.d2h_bytes += (int64_t)(n_words * 9 + 12);
         if (host_counts[1]) return p->fail(BKGPU_ETOOBIG, "group table overflow (capacity 2^%d slots / partial_capacity %lld): raise group_capacity_log2",
                                            (int)gt.cap_log2, (long long)p->partial_cap);
@@ -998,6 +1054,7 @@ extern "C" void bkgpu_close(bkgpu_plan* p) {
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
     resolve_timers(p);
     if (p->sort) sort_close(p->sort);
+    for (size_t r = 0; r < p->peer_ptr.size(); r++) if ((int)r != p->peer_rank && p->peer_ptr[r]) cudaIpcCloseMemHandle(p->peer_ptr[r]);
     for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
     for (void* q : p->dev_allocs) cudaFree(q);
     for (int i = 0; i < 2; i++) { if (p->stage_free[i]) cudaEventDestroy(p->stage_free[i]); if (p->stage_ready[i]) cudaEventDestroy(p->stage_ready[i]); }

@@ -107,6 +107,8 @@ int   bkgpu_init(bkgpu_plan** out, const uint8_t* plan_desc, size_t len,
  *   "chunk_rows"           rows per host->device staging chunk of a host push
  *   "partial_capacity"     groups per rank in the exported partial state
  *   "region_base"          arrival index of this plan's first row: ORDER BY ties across GPUs break by (region, row)
+ *   "peer_merge"           with a communicator: partial states are written straight into the peers' buffers over NVLink (CUDA IPC)
+ *                          instead of gathered by NCCL (opt-in)
  *   "repartition"          with a communicator: groups are hash-partitioned across the ranks by one all-to-all (ncclSend/ncclRecv)
  *                          instead of gathered everywhere; each rank then returns only the groups it owns (high-cardinality GROUP BY)
  *   "force_generic" / "no_lean" / "no_fused_probe"   pin the kernel variant (tests, A/B measurements) */

@@ -63,6 +63,10 @@ def main():
     whole = datagen.c2_table(0, n_region * world, n_groups=500)
     want = oracle.execute(queries.c2_filter_groupby().serialize(), whole)
     assert_same_rows(got, want.columns, ["0_1"])      # every rank holds the merged result
+    # ---- the same merge over NVLink peer memory (CUDA IPC buffers, no collective call on the data path) ----
+    got_p, stats_p = run_plan(queries.c2_filter_groupby(), region, comm, dev, {"peer_merge": 1})
+    assert stats_p.collective_ms > 0
+    assert_same_rows(got_p, want.columns, ["0_1"])
     # ---- f3: hash repartition (all-to-all): every rank returns only the groups it owns; their union is the answer ----
     hi = datagen.c2_table(rank * n_region, n_region, n_groups=40_000)            # more groups than one 65536-slot partial would
     part, stats = run_plan(queries.c2_filter_groupby(), hi, comm, dev, {"repartition": 1, "group_capacity_log2": 18})   # comfortably merge N times
