@@ -87,6 +87,17 @@ def fragment(seed):
             P.agg_expr("avg", 1, 5, 6, e1), P.agg_expr("count", 1, 7, None, e2)]
     child = P.where(P.scan(0), g.pred(2)) if seed % 4 else P.scan(0)
     root = P.agg(child, 1, keys, aggs)
-    plan = P.Plan(root, {0: TUPLE0, 1: []})   # aggregate slots undeclared: their types are the inferred ones
+    # the aggregate tuple is declared with the types the (host-only) lowering infers for each aggregate: the planner would do the same
+    import re
+    from baikaldb_b200 import _lib
+    text = _lib.explain(P.Plan(root, {0: TUPLE0, 1: []}).serialize())
+    prims = [int(m) for m in re.findall(r"agg\[\d+\] .*out_prim=(\d+)", text)]
+    assert len(prims) == len(aggs)
+    slots = {}
+    for f, pt in zip(aggs, prims):
+        slots[f.final_slot_id] = pt
+        if f.intermediate_slot_id != f.final_slot_id:
+            slots[f.intermediate_slot_id] = int(T.STRING)
+    plan = P.Plan(root, {0: TUPLE0, 1: sorted(slots.items())})
     names = [f"0_{k.slot_id}" if k.node_type == P.ExprNodeType.SLOT_REF else f"-1_{i}" for i, k in enumerate(keys)]
     return plan, names
