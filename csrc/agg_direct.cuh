@@ -579,10 +579,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
         }
     }
     uint32_t nmask = 0;   // NULLS: 4 NULL bits per column for the quad held in the load registers
-    // 128-bit shared CAS shapes: {row count, sum} (one double sum) or {sumA, sumB} (value columns 0 and 1 both double)
-    // (fusing {row count, sum} into one CAS.128 measured SLOWER than RED.u32 + CAS.64 — the native 32-bit reduction is
-    //  cheaper than widening the compare-and-swap — so it stays off; the code is kept for the record)
-    const bool fuse1 = false && NA == 1 && acc_f64[0] && a.vops[0].smem_lane[0] == 1;
+    // 128-bit shared CAS shape: {sumA, sumB} — value columns 0 and 1 both feed one double sum and share a 16-byte word.
+    // (Fusing {row count, sum} into one CAS.128 for a single double sum measured SLOWER than RED.u32 + CAS.64: the native 32-bit
+    //  reduction is cheaper than widening the compare-and-swap — profiles/r01_agg_kernel_history.md.)
     const bool pair2 = NA >= 2 && acc_f64[0] && acc_f64[NA > 1 ? 1 : 0] && a.vops[0].smem_lane[0] == 2 && a.vops[NA > 1 ? 1 : 0].smem_lane[0] == 3 &&
                        (!MM || (a.vops[0].n_ops == 1 && a.vops[NA > 1 ? 1 : 0].n_ops == 1));
     uint32_t passed = 0;
@@ -727,17 +726,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
             int slot = -1;
             if (k0 != EMPTY_KEY) slot = smem32_upsert1(keys_addr, cap_mask, k0, h >> hash_shift);
             if (slot >= 0) {
-                if (fuse1) {   // {rows, sum} in one 16-byte word: LDS.128 -> (+1, +v) -> ATOMS.CAS.128: one atomic per row
-                    const uint32_t addr = lanes_addr + slot * 16u;
-                    uint64_t c0, c1;
-                    lds128(addr, c0, c1);
-                    for (;;) {
-                        uint64_t p0, p1;
-                        atoms_cas128(addr, c0, c1, c0 + 1ull, f64_bits(bits_f64(c1) + bits_f64(v[0])), p0, p1);
-                        if (p0 == c0 && p1 == c1) break;
-                        c0 = p0; c1 = p1;
-                    }
-                } else {
+                {
                     reds_inc32(lanes_addr + slot * 16u);   // pair 0, half 0 = row count
                     if (NULLS) {
 #pragma unroll

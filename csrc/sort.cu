@@ -521,28 +521,6 @@ __global__ void __launch_bounds__(256) k_radix_scatter(const uint64_t* key, cons
         __syncwarp();
     }
 }
-__global__ void k_compact_perm(const uint32_t* perm, const uint8_t* keep, uint32_t n, uint32_t* out, uint32_t* count, int null_first, int want_nulls_sep) {
-    // ordered compaction of the sorted permutation by `keep` (1 = row, 2 = NULL key row); single CTA (results are being copied to the host anyway)
-    __shared__ uint32_t run;
-    if (threadIdx.x == 0) run = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n; base += blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const bool take = i < n && keep[perm[i]] != 0;
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, take);
-        __shared__ uint32_t wc[32];
-        if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(b);
-        __syncthreads();
-        uint32_t before = run;
-        for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) before += wc[w];
-        if (take) out[before + __popc(b & ((1u << (threadIdx.x & 31)) - 1u))] = perm[i];
-        __syncthreads();
-        if (threadIdx.x == 0) { uint32_t t = 0; for (uint32_t w = 0; w < (blockDim.x >> 5); w++) t += wc[w]; run += t; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *count = run;
-    (void)null_first; (void)want_nulls_sep;
-}
 
 }  // namespace
 
