@@ -262,3 +262,41 @@ def test_type_merge_known_answers(fn_name, branch_types, expected):
     assert res.columns[0].prim_type == expected                                         # MIN(x) carries x's inferred type
     out_prims = re.findall(r"agg\[0\].*out_prim=(\d+)", _lib.explain(pl.serialize()))
     assert out_prims and int(out_prims[0]) == int(expected)
+
+
+def test_nullable_min_max_sum_count_row_oracle_equals_acero():
+    """NULL keys form their own group, NULL filter operands drop the row, aggregates skip NULL inputs, all-NULL groups give NULL
+    (COUNT 0): the row-engine restatement against Acero's hash_min / hash_max / hash_sum / hash_count / hash_mean on the same table
+    (the Acero functions the vectorized engine maps them to, src/expr/agg_fn_call.cpp:1365-1392)."""
+    import pyarrow.compute as pc
+    rng = np.random.default_rng(5)
+    n = 20_000
+    cols = [make_column(0, 1, T.INT32, rng.integers(0, 15, n), rng.random(n) > 0.1), make_column(0, 2, T.INT32, rng.integers(0, 100, n), rng.random(n) > 0.15),
+            make_column(0, 3, T.DOUBLE, rng.normal(size=n) * 100, (rng.random(n) > 0.4) & (rng.integers(0, 15, n) != 3)),
+            make_column(0, 4, T.INT64, rng.integers(-1 << 40, 1 << 40, n), rng.random(n) > 0.3)]
+    d, i64 = P.slot_ref(0, 3, T.DOUBLE), P.slot_ref(0, 4, T.INT64)
+    aggs = [P.agg_expr("count_star", 1, 1), P.agg_expr("min", 1, 2, None, d), P.agg_expr("max", 1, 3, None, d), P.agg_expr("sum", 1, 4, None, d),
+            P.agg_expr("count", 1, 5, None, d), P.agg_expr("max", 1, 6, None, i64), P.agg_expr("sum", 1, 7, None, i64), P.agg_expr("avg", 1, 8, 9, i64)]
+    root = P.agg(P.where(P.scan(0), P.lt(P.slot_ref(0, 2, T.INT32), P.int_lit(70))), 1, [P.slot_ref(0, 1, T.INT32)], aggs)
+    pl = P.Plan(root, {0: [(1, T.INT32), (2, T.INT32), (3, T.DOUBLE), (4, T.INT64)],
+                       1: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE, T.DOUBLE, T.DOUBLE, T.DOUBLE, T.INT64, T.INT64, T.INT64])})
+    row = oracle.execute(pl.serialize(), cols)
+    t = A.filter_groupby(A.to_table(cols), pc.field("0_2") < pc.scalar(pa_scalar(70)), ["0_1"],
+                         [("hash_count_all", None, "1_1"), ("hash_min", "0_3", "1_2"), ("hash_max", "0_3", "1_3"), ("hash_sum", "0_3", "1_4"),
+                          ("hash_count", "0_3", "1_5"), ("hash_max", "0_4", "1_6"), ("hash_sum", "0_4", "1_7"), ("hash_mean", "0_4", "1_8")])
+    want = A.table_rows(t, ["0_1"])
+    got = rows_as_set(row.columns, ["0_1"])
+    names = [c.name for c in row.columns]
+    assert set(got) == set(want) and (None,) in got
+    tn = t.column_names
+    for k in got:
+        for nm in ("1_1", "1_2", "1_3", "1_5", "1_6", "1_7"):          # exact: counts, extremes, integer sums
+            assert got[k][names.index(nm)] == want[k][tn.index(nm)], (k, nm)
+        for nm in ("1_4", "1_8"):                                       # double sum / mean: same adds, different order
+            a, b = got[k][names.index(nm)], want[k][tn.index(nm)]
+            assert (a is None and b is None) or abs(a - b) <= 1e-9 * max(1.0, abs(b)), (k, nm, a, b)
+
+
+def pa_scalar(v):
+    import pyarrow as pa
+    return pa.scalar(v, pa.int32())
