@@ -1,7 +1,5 @@
 """Randomised fragments (tests/fuzz_plans.py): every generated plan must lower (host-only check) and run on the oracle; on the GPU the
 device bytecode / kernels must return the oracle's rows — integers, keys, NULLs exact, doubles within 1e-6."""
-import os
-
 import pytest
 
 from baikaldb_b200 import _lib
@@ -23,7 +21,6 @@ def test_fuzz_plan_lowers_and_oracle_runs(seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("BKGPU_FUZZ") != "1", reason="opt-in: BKGPU_FUZZ=1")
 @pytest.mark.parametrize("seed", SEEDS)
 def test_fuzz_gpu_matches_oracle(seed):
     from tests.util import run_both
