@@ -111,7 +111,7 @@ int   bkgpu_init(bkgpu_plan** out, const uint8_t* plan_desc, size_t len,
  *                          instead of gathered by NCCL (opt-in)
  *   "repartition"          with a communicator: groups are hash-partitioned across the ranks by one all-to-all (ncclSend/ncclRecv)
  *                          instead of gathered everywhere; each rank then returns only the groups it owns (high-cardinality GROUP BY)
- *   "force_generic" / "no_lean" / "no_fused_probe"   pin the kernel variant (tests, A/B measurements) */
+ *   "force_generic" / "no_lean" / "no_lean_nulls" / "no_lean_mm" / "no_fused_probe"   pin the kernel variant (tests, A/B measurements) */
 int   bkgpu_set_option(bkgpu_plan*, const char* key, int64_t value);
 /* ExecNode::open(RuntimeState*) (exec_node.h:140): allocate tables. */
 int   bkgpu_open(bkgpu_plan*);
@@ -161,7 +161,7 @@ int   bkgpu_memcpy_d2h(int device, void* dst, const void* src, size_t bytes);
 
 /* Synthetic column generator on the device: counter-based, keyed by
  * (seed, column_id, absolute row index) so any shard of any table is reproducible
- * and bit-identical to oracle/datagen.py.  dist: 0 = uniform int in [lo,hi) (int32/
+ * and bit-identical to baikaldb_b200/datagen.py.  dist: 0 = uniform int in [lo,hi) (int32/
  * int64 by prim_type), 1 = uniform double in [0,1), 2 = approx-normal double
  * (Irwin-Hall 4) * scale, 3 = full-range int64, 4 = permutation of [0,n) (int32). */
 int   bkgpu_gen_column(int device, void* dev_dst, int32_t prim_type, int32_t dist,
