@@ -878,7 +878,7 @@ static bool infer_node(Infer& in, HNode& n) {
 
 int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& err) {
     if (!desc || len < 16 || (len & 3)) { err = "plan descriptor is empty or not a multiple of 4 bytes"; return BKGPU_EINVAL; }
-    Reader r{(const int32_t*)desc, len / 4};
+    Reader r{}; r.w = (const int32_t*)desc; r.n = len / 4;
     if ((uint32_t)r.rd() != BKGPU_PLAN_MAGIC) { err = "bad plan magic"; return BKGPU_EINVAL; }
     if (r.rd() != BKGPU_PLAN_VERSION) { err = "unsupported plan version"; return BKGPU_EINVAL; }
     int nt = r.rd(), nn = r.rd();
@@ -894,7 +894,7 @@ int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& er
     if (!r.fail && nn != 0) r.bad("plan node count mismatch");
     if (!r.fail && r.pos != r.n) r.bad("trailing words after the plan");
     if (r.fail) { err = r.err; return r.err.find("outside the GPU path") != std::string::npos ? BKGPU_EUNSUPPORTED : BKGPU_EINVAL; }
-    Infer in{&out.tuples};
+    Infer in{}; in.tuples = &out.tuples;
     if (!infer_node(in, root)) { err = in.err; return in.code; }
 
     bool under_packet = false;
@@ -1067,7 +1067,7 @@ bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& joi
     {
         auto jf = std::make_shared<Compiled>();
         jf->tuples = out.tuples; jf->build_tuple = -1;
-        Infer in2{&jf->tuples};
+        Infer in2{}; in2.tuples = &jf->tuples;
         if (lower_agg(in2, *jf, agg, conj, probe_tuple, under_packet, true) && memcmp(&jf->ap.n_keyw, &out.ap.n_keyw, sizeof(int32_t) * 4) == 0 &&
             jf->ap.n_lanes == out.ap.n_lanes) {
             bool ok = true;
