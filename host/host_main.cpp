@@ -6,6 +6,7 @@
 //   bkgpu_host plan    <c1|c2|c3|c5>                       hex of the serialized plan (compared with plan.py's bytes)
 //   bkgpu_host explain <c1|c2|c3|c5>                       bkgpu_plan_explain of it (no GPU needed)
 //   bkgpu_host run     <c1|c2|c3|c5> <rows> [batch_rows]   executes on cuda:0 and prints one result row per line
+//   bkgpu_host chunk   - <rows> [capacity]                   CPU only: rows -> Chunk -> column batches -> rows, checked value by value
 //   bkgpu_host rows    c2 <rows> [capacity]                 the same table fed ROW by row (MemRow-style values with NULLs every
 //                                                           17th key) through Chunk -> column batches -> GPU -> Chunk::to_rows
 #include <cinttypes>
@@ -140,6 +141,34 @@ int main(int argc, char** argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s plan|explain|run c1|c2|c3|c5 [rows] [batch_rows]\n", argv[0]); return 2; }
     std::string mode = argv[1], cfg = argv[2];
     Plan plan = cfg == "c1" ? plan_c1() : cfg == "c2" ? plan_c2() : cfg == "c3" ? plan_c3() : plan_c5();
+    if (mode == "chunk") {   // CPU-only: rows -> Chunk -> column batches of `capacity` rows -> rows again (f1 adapter round trip)
+        const int64_t rows = argc > 3 ? atoll(argv[3]) : 1000, capacity = argc > 4 ? atoll(argv[4]) : 64;
+        std::vector<int32_t> k = gen_uniform_i32(2, 1, 0, rows, 0, 1000); std::vector<double> a = gen_u01(2, 3, 0, rows); std::vector<int64_t> w = gen_i64_full(5, 1, 0, rows);
+        std::vector<MemRowValues> mem_rows((size_t)rows);
+        for (int64_t i = 0; i < rows; i++)
+            mem_rows[(size_t)i] = {k[(size_t)i] % 7 == 0 ? Value() : Value::of_int(k[(size_t)i]), i % 5 == 0 ? Value() : Value::of_double(a[(size_t)i]), Value::of_int(w[(size_t)i]),
+                                   Value::of_uint((uint64_t)w[(size_t)i] >> 40), Value::of_double((double)(float)a[(size_t)i]), Value::of_int(i & 1)};
+        RowScanNode scan({{0, 1, BK_INT32}, {0, 2, BK_DOUBLE}, {0, 3, BK_INT64}, {0, 4, BK_UINT32}, {0, 5, BK_FLOAT}, {0, 6, BK_BOOL}}, mem_rows, capacity);
+        RuntimeState st; bool eos = false; int64_t seen = 0, batches = 0, mismatches = 0;
+        while (!eos) {
+            RowBatch b;
+            if (scan.get_next(&st, &b, &eos) < 0) return 1;
+            if (b.columns.empty()) continue;
+            batches++;
+            if (b.size() > capacity) mismatches++;
+            std::vector<MemRowValues> back = Chunk::to_rows(b);
+            for (auto& r : back) {
+                const MemRowValues& o = mem_rows[(size_t)seen++];
+                for (size_t c = 0; c < r.size(); c++) {
+                    bool same = r[c].is_null == o[c].is_null;
+                    if (same && !o[c].is_null) same = (c == 1 || c == 4) ? r[c].f64 == o[c].f64 : (c == 3 ? r[c].u64 == o[c].u64 : r[c].i64 == o[c].i64);
+                    if (!same) mismatches++;
+                }
+            }
+        }
+        printf("rows=%" PRId64 " batches=%" PRId64 " mismatches=%" PRId64 "\n", seen, batches, mismatches);
+        return mismatches == 0 && seen == rows ? 0 : 1;
+    }
     if (mode == "plan") { for (uint8_t b : plan.serialize()) printf("%02x", b); printf("\n"); return 0; }
     if (mode == "explain") {
         std::vector<uint8_t> d = plan.serialize(); std::vector<char> text(1 << 16);

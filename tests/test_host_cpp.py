@@ -36,6 +36,14 @@ def test_cpp_explain(host_bin, cfg):
     assert out.startswith("kind=")
 
 
+@pytest.mark.parametrize("rows,capacity", [(1, 1), (1000, 64), (5003, 1024), (77, 1000)])
+def test_cpp_chunk_row_column_round_trip(host_bin, rows, capacity):
+    """f1 adapter on the CPU: MemRow-style values (NULLs, narrow ints, float, bool) -> Chunk column batches of <= capacity rows -> rows"""
+    r = subprocess.run([host_bin, "chunk", "-", str(rows), str(capacity)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"rows={rows} batches={(rows + capacity - 1) // capacity} mismatches=0" in r.stdout
+
+
 def _parse(text):
     rows = []
     for line in text.splitlines():
