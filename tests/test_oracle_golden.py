@@ -300,3 +300,64 @@ def test_nullable_min_max_sum_count_row_oracle_equals_acero():
 def pa_scalar(v):
     import pyarrow as pa
     return pa.scalar(v, pa.int32())
+
+
+def test_multi_key_group_by_with_null_keys_row_oracle_equals_acero():
+    """two GROUP BY expressions, NULLs in both: (NULL, x), (x, NULL) and (NULL, NULL) are groups of their own
+    (encode_exprs_key's null-flag byte, exec_node.cpp:555-571; Acero groups NULL keys the same way)"""
+    rng = np.random.default_rng(21)
+    n = 30_000
+    cols = [make_column(0, 1, T.INT32, rng.integers(0, 6, n), rng.random(n) > 0.15), make_column(0, 2, T.INT64, rng.integers(-2, 3, n), rng.random(n) > 0.15),
+            make_column(0, 3, T.DOUBLE, rng.random(n))]
+    aggs = [P.agg_expr("count_star", 1, 1), P.agg_expr("sum", 1, 2, None, P.slot_ref(0, 3, T.DOUBLE))]
+    pl = P.Plan(P.agg(P.scan(0), 1, [P.slot_ref(0, 1, T.INT32), P.slot_ref(0, 2, T.INT64)], aggs),
+                {0: [(1, T.INT32), (2, T.INT64), (3, T.DOUBLE)], 1: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE])})
+    row = oracle.execute(pl.serialize(), cols)
+    got = rows_as_set(row.columns, ["0_1", "0_2"])
+    t = A.filter_groupby(A.to_table(cols), None, ["0_1", "0_2"], [("hash_count_all", None, "1_1"), ("hash_sum", "0_3", "1_2")])
+    want = A.table_rows(t, ["0_1", "0_2"])
+    assert set(got) == set(want) and (None, None) in got and any(k[0] is None and k[1] is not None for k in got)
+    names, tn = [c.name for c in row.columns], t.column_names
+    for k in got:
+        assert got[k][names.index("1_1")] == want[k][tn.index("1_1")]
+        assert got[k][names.index("1_2")] == pytest.approx(want[k][tn.index("1_2")], rel=1e-9)
+
+
+def test_join_with_duplicate_and_null_keys_row_oracle_equals_acero():
+    """inner equi-join with several build rows per key and NULL keys on both sides: every (probe, build) pair counts once, NULL never
+    matches (Joiner multimap, joiner.cpp:608-685; Acero hashjoin 'inner')"""
+    rng = np.random.default_rng(23)
+    nd, nf = 2_000, 40_000
+    dim = [make_column(1, 1, T.INT32, rng.integers(0, 500, nd), rng.random(nd) > 0.1), make_column(1, 2, T.INT32, rng.integers(0, 12, nd))]
+    fact = [make_column(0, 1, T.INT32, rng.integers(-20, 520, nf), rng.random(nf) > 0.1), make_column(0, 2, T.DOUBLE, rng.random(nf))]
+    res = oracle.execute(queries.c3_join_groupby().serialize(), fact + dim)
+    got = rows_as_set(res.columns, ["1_2"])
+    names = [c.name for c in res.columns]
+    ac = A.c3_join_groupby(A.to_table(fact), A.to_table(dim))
+    want = A.table_rows(ac, ["1_2"])
+    an = ac.column_names
+    assert set(got) == set(want)
+    pairs = 0
+    for key, row in got.items():
+        assert row[names.index("2_1")] == want[key][an.index("2_1")]
+        assert row[names.index("2_2")] == pytest.approx(want[key][an.index("2_2")], rel=1e-9)
+        pairs += row[names.index("2_1")]
+    # independent count of matching pairs
+    dk = dim[0].values[dim[0].valid]
+    fk = fact[0].values[fact[0].valid]
+    assert pairs == int(np.bincount(dk, minlength=600)[np.clip(fk, 0, 599)][(fk >= 0) & (fk < 600)].sum())
+
+
+@pytest.mark.parametrize("asc", [True, False])
+def test_order_by_null_placement_row_oracle_equals_acero(asc):
+    """ORDER BY with NULL keys: the planner sets is_null_first = is_asc (logical_planner.cpp:4071) — NULLs first ascending, last
+    descending (MemRowCompare, mem_row_compare.cpp:18-38); Acero's order_by with the matching null_placement agrees on the keys"""
+    rng = np.random.default_rng(29)
+    n = 5_000
+    cols = [make_column(0, 1, T.INT64, rng.integers(-300, 300, n), rng.random(n) > 0.2), make_column(0, 2, T.INT32, np.arange(n))]
+    res = oracle.execute(queries.c5_topk(n, asc=asc).serialize(), cols)
+    keys = res.columns[0].to_list()
+    ac = A.c5_topk(A.to_table(cols), n, ascending=asc)
+    assert keys == ac.column("0_1").to_pylist()
+    nn = int((~cols[0].valid).sum())
+    assert (keys[:nn] == [None] * nn) if asc else (keys[-nn:] == [None] * nn)
