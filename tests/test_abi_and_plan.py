@@ -109,3 +109,20 @@ def test_datagen_permutation_and_reproducibility():
     y = datagen.c2_table(0, 1500)
     for cx, cy in zip(x, y):
         assert np.array_equal(cx.values, cy.values[1000:])
+
+
+def test_product_code_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under baikaldb_b200/, csrc/, host/ or include/ may import, link or execute it
+    (bench.py may, for its cpu_baseline / --impl reference legs only)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bad = []
+    for sub in ("baikaldb_b200", "csrc", "host", "include"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if not f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".hpp", "Makefile")):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|libbk_oracle|bko_execute|oracle/bk_oracle|acero_oracle", text, re.M):
+                    bad.append(os.path.join(sub, f))
+    assert not bad, bad
