@@ -192,6 +192,15 @@ class GpuExecNode:
         _lib.check(_lib.lib().bkgpu_push(self._handle, arr, n, nrows, 1 if on_device else 0), self._handle)
         del keep
 
+    # prepared-statement reuse: run the opened fragment again over new batches (bkgpu_reset keeps the compiled plan, the device
+    # tables and what earlier runs taught the plan about its group cardinality)
+    def reset(self) -> None:
+        _lib.check(_lib.lib().bkgpu_reset(self._handle), self._handle)
+        self._eos = False
+
+    def finish(self) -> None:
+        _lib.check(_lib.lib().bkgpu_finish(self._handle), self._handle)
+
     # -- ExecNode::get_next(RuntimeState*, RowBatch*, bool* eos): returns (rc, eos)
     def get_next(self, state: RuntimeState, batch: RowBatch) -> Tuple[int, bool]:
         L = _lib.lib()

@@ -51,7 +51,18 @@ struct AggArgs {
     JoinProbe jp;            // lean kernel only: the key column holds the probe-side foreign key (see JoinProbe)
     int32_t lean_nulls;      // lean kernel: some predicate / value column of this batch carries a validity bitmap
     int32_t lean_mm;         // lean kernel: some value column feeds MIN / MAX lanes or more than one lane
+    // warp-private kernel (agg_wp.cuh): chosen by the host for the plainest lean batches
+    int32_t wp;              // 1 = launch k_agg_group_wp
+    int32_t wp_gcap;         // dense group ids per warp table (multiple of 32)
+    int32_t wp_kt_log2;      // log2 words of the CTA's key -> id table
+    int32_t wp_warps;        // warps per CTA (one accumulator table each): 8, 12 or 16
+    int32_t wp_dense;        // 1 = no key table: id = key - wp_dense_sub (keys known to lie in a range of wp_gcap values)
+    uint32_t wp_dense_sub;
 };
+
+// shared memory of k_agg_group_wp: key table + id counter + one accumulator set {sums 8 B x na, cnt 4 B} x gcap per warp
+inline size_t wp_warp_bytes(int na, uint32_t gcap) { return ((size_t)gcap * (8u * (uint32_t)na + 4u) + 15) & ~(size_t)15; }
+inline size_t wp_smem_bytes(int na, uint32_t gcap, int kt_log2, int warps) { return (kt_log2 < 0 ? 0 : ((size_t)8 << kt_log2)) + 16 + wp_warp_bytes(na, gcap) * (size_t)warps; }
 
 size_t agg_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2);
 cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t s, const char** kernel_name);

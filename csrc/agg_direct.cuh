@@ -908,7 +908,11 @@ static inline int direct_grid(K kernel, size_t smem, int sm_count, int64_t nrows
 }
 
 template <int NP, int NA>
+static inline cudaError_t launch_wp(const AggArgs& a, int sm_count, cudaStream_t s);   // agg_wp.cuh
+
+template <int NP, int NA>
 static inline cudaError_t launch_direct(const AggArgs& a, int sm_count, size_t smem, cudaStream_t s, bool grouped) {
+    if (grouped && a.wp) return launch_wp<NP, NA>(a, sm_count, s);
     if (grouped) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k_agg_group_direct<NP, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -82,6 +82,9 @@ struct bkgpu_plan {
     size_t jf_dense_cap = 0, jf_packed_cap = 0, jp_attr_cap = 0, jp_packed_cap = 0, j_scratch_cap = 0;
     uint64_t* j_scratch = nullptr;   // [0..1] key min / max, then u32 flags: [4] duplicate build key, [5] fused probe unusable
     int no_fused_probe = 0, no_lean_nulls = 0, no_lean_mm = 0;
+    int use_wp = 0;               // 1 = launch the warp-private aggregate kernel where the batch fits it (opt-in: measured at par with k_agg_group_lean, profiles/r02_agg_wp_history.md)
+    int wp_kt_log2 = 0;           // log2 words of the warp-private kernel's key table (0 = sized from the cardinality)
+    int wp_warps = 0;             // warps per CTA of the warp-private kernel (0 = chosen from the table size; 8, 12 or 16)
     std::vector<uint8_t*> jg_buf; int64_t jg_rows = 0;                            // gathered build columns, one chunk
     std::vector<ColRef> probe_want; std::vector<int> probe_map;   // probe-side columns and their index in c.cols
     // sort / filter state
@@ -214,6 +217,9 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "peer_merge") p->peer_merge = v != 0;
     else if (k == "no_lean_nulls") p->no_lean_nulls = v != 0;
     else if (k == "no_lean_mm") p->no_lean_mm = v != 0;
+    else if (k == "use_wp") p->use_wp = v != 0;
+    else if (k == "wp_warps") { if (v != 0 && v != 8 && v != 12 && v != 16) return p->fail(BKGPU_EINVAL, "wp_warps: 0, 8, 12 or 16"); p->wp_warps = (int)v; }
+    else if (k == "wp_kt_log2") { if (v < 0 || v > 14) return p->fail(BKGPU_EINVAL, "wp_kt_log2 out of range"); p->wp_kt_log2 = (int)v; }
     else if (k == "output_on_device") p->output_on_device = v != 0;
     else if (k == "region_base") p->region_base = v;
     else return p->fail(BKGPU_EINVAL, "unknown option '%s'", key);
@@ -386,6 +392,35 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
         }
     }
     if (jp) { if (!a.lean) return 1; a.jp = *jp; }
+    // warp-private tables (agg_wp.cuh): the plainest lean batches whose groups fit one table per warp.  The capacity follows the
+    // cardinality learned from earlier batches / runs of this plan; an unknown cardinality starts with the largest table.
+    a.wp = 0;
+    if (a.lean && !a.lean_nulls && !a.lean_mm && p->use_wp && c.direct.n_vals <= 2) {
+        const int np = c.direct.n_terms, na = c.direct.n_vals;
+        const DevCol& kc = a.cols[np];
+        bool ok = kc.stype == ST_I32 || kc.stype == ST_U32;
+        for (int v = 0; v < na && ok; v++) ok = a.vops[v].n_ops == 1 && (a.vops[v].op[0] == LN_ADD_F64 || a.vops[v].op[0] == LN_ADD_I64);
+        if (p->h_pinned && p->h_pinned[0] > p->known_groups) p->known_groups = p->h_pinned[0];
+        if (ok) {
+            const size_t budget = 226 * 1024;
+            const uint32_t g = p->known_groups;
+            int warps = 8;
+            if (na <= 1 && g) {   // one value column: the tables are small enough for 12 or 16 warps (three / four per scheduler)
+                const uint32_t gc = (g + 31) & ~31u;
+                int kl4 = 8; while ((1u << kl4) < 4 * gc) kl4++;
+                if (wp_smem_bytes(na, gc, kl4, 16) <= budget) warps = 16;
+                else if (wp_smem_bytes(na, gc, kl4, 12) <= budget) warps = 12;
+            }
+            if (p->wp_warps && (na <= 1 || p->wp_warps == 8)) warps = p->wp_warps;
+            uint32_t gcap = g ? ((g + 31) & ~31u) : 0;
+            auto fits = [&](uint32_t gc, int kl) { return wp_smem_bytes(na, gc, kl, warps) <= budget; };
+            auto kt_for = [&](uint32_t gc, int factor) { int kl = 8; while ((1u << kl) < (uint32_t)factor * gc) kl++; return kl; };
+            if (gcap == 0) { gcap = 32; while (fits(gcap + 32, kt_for(gcap + 32, 2))) gcap += 32; }   // unknown: the largest table that fits
+            int kl = p->wp_kt_log2 > 0 ? p->wp_kt_log2 : kt_for(gcap, 4);          // key table at <= 25 % load when it fits ...
+            if (!fits(gcap, kl)) kl = kt_for(gcap, 2);                              // ... else <= 50 %
+            if (fits(gcap, kl)) { a.wp = 1; a.wp_gcap = (int)gcap; a.wp_kt_log2 = kl; a.wp_warps = warps; a.wp_dense = 0; a.wp_dense_sub = 0; }
+        }
+    }
     const int64_t kMax = (int64_t)1 << 30;  // rows per launch (32-bit counters inside a CTA)
     int64_t algo_bytes_per_row = 0;
     for (int i = 0; i < a.n_cols; i++) algo_bytes_per_row += storage_bytes(a.cols[i].stype);
@@ -401,7 +436,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
         cudaError_t e = launch_agg(b, direct, p->sm_count, p->stream, &name);
         timer_end(p, ep);
         if (e != cudaSuccess) return p->cuda_fail(e, "launch_agg");
-        snprintf(p->stats.main_kernel_name, sizeof p->stats.main_kernel_name, "%s", b.lean && direct ? "k_agg_group_lean" : name);
+        snprintf(p->stats.main_kernel_name, sizeof p->stats.main_kernel_name, "%s", b.wp && direct ? "k_agg_group_wp" : (b.lean && direct ? "k_agg_group_lean" : name));
         p->stats.kernel_launches++;
     }
     return BKGPU_OK;
