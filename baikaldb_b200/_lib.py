@@ -45,6 +45,10 @@ SYMBOLS = [
     ("bkgpu_cancel", None, [c_void_p]),
     ("bkgpu_close", None, [c_void_p]),
     ("bkgpu_get_stats", c_int, [c_void_p, POINTER(BkgpuStats)]),
+    ("bkgpu_region_register", c_int, [c_int, c_int64, POINTER(BkgpuColumn), c_int, c_int64, c_int]),
+    ("bkgpu_region_evict", c_int, [c_int, c_int64]),
+    ("bkgpu_region_info", c_int, [c_int, c_int64, POINTER(c_int64), POINTER(c_size_t)]),
+    ("bkgpu_push_region", c_int, [c_void_p, c_int64]),
     ("bkgpu_partial_capacity", c_int, [c_void_p, POINTER(c_size_t)]),
     ("bkgpu_partial_export", c_int, [c_void_p, c_void_p, c_size_t]),
     ("bkgpu_partial_merge", c_int, [c_void_p, c_void_p, c_size_t, c_int]),

@@ -108,13 +108,15 @@ __global__ void k_join_build(DevCol key, int from_prim, int cast_to, int64_t nro
 // ------------------------------------------------------------------------------------------
 // table maintenance: init, partial export / import (K3), result extraction + finalize
 // ------------------------------------------------------------------------------------------
-__global__ void k_table_init(GroupTable gt, AggPlan ap) {
+__global__ void k_table_init(GroupTable gt, AggPlan ap, int keep_overflow) {
     const uint32_t cap = gt.cap_mask + 1;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
         gt.state[i] = ap.n_keyw == 0 ? 2u : 0u;
         for (int l = 0; l < ap.n_lanes; l++) gt.lanes[(size_t)l * cap + i] = lane_identity(ap.lane_op[l]);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *gt.n_groups = 0; *gt.overflow = 0; }
+    // (re-initialisation between the export of a partial state and the merge keeps the overflow flag: a table that overflowed
+    //  while rows were pushed, or an export that met more groups than the exchange format holds, must still fail the plan)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *gt.n_groups = 0; if (!keep_overflow) *gt.overflow = 0; }
 }
 
 // Partial state layout (fixed capacity `pcap` groups): [u64 n_groups][keys n_keyw x pcap][lanes n_lanes x pcap]
@@ -131,7 +133,44 @@ __global__ void k_partial_export(GroupTable gt, AggPlan ap, uint64_t* dst, uint3
         for (int l = 0; l < ap.n_lanes; l++) dlanes[(size_t)l * pcap + pos] = gt.lanes[(size_t)l * cap + i];
     }
 }
-__global__ void k_partial_count(uint64_t* dst, const uint32_t* cursor) { dst[0] = *cursor; }
+__global__ void k_partial_count(uint64_t* dst, const uint32_t* cursor, uint32_t pcap) { dst[0] = *cursor < pcap ? *cursor : pcap; }
+
+// Compact partial state for the all-gather (the default multi-GPU merge): dst[0] = the number of groups this rank holds (its low
+// half doubles as the export cursor, so it may exceed `bound`), followed by min(groups, bound) rows of n_keyw + n_lanes words.
+// Only `1 + bound * row words` cross NVLink; `bound` follows the group counts seen in earlier runs (api.cu).
+__global__ void k_partial_export_rows(GroupTable gt, AggPlan ap, uint64_t* dst, uint32_t bound) {
+    const uint32_t cap = gt.cap_mask + 1;
+    const int rw = ap.n_keyw + ap.n_lanes;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        if (gt.state[i] != 2u) continue;
+        if (ap.n_keyw == 0 && gt.lanes[i] == 0) continue;  // no row reached the single group
+        const uint32_t pos = atomicAdd((uint32_t*)dst, 1u);
+        if (pos >= bound) continue;                         // (the merge sees count > bound and asks for a second, larger exchange)
+        uint64_t* row = dst + 1 + (size_t)pos * rw;
+        for (int w = 0; w < ap.n_keyw; w++) row[w] = gt.keys[(size_t)w * cap + i];
+        for (int l = 0; l < ap.n_lanes; l++) row[ap.n_keyw + l] = gt.lanes[(size_t)l * cap + i];
+    }
+}
+// K3 on the gathered rows: every rank folds the OTHER ranks' groups into its own table (its own groups are already there), so
+// nothing is re-initialised.  When some rank held more groups than `bound` nothing is merged anywhere (every rank reads the same
+// headers) and *max_count tells the host to repeat the exchange with a larger bound.
+__global__ void k_partial_merge_rows(GroupTable gt, AggPlan ap, const uint64_t* src, size_t words_per_rank, uint32_t bound, int nranks, int self, uint32_t* max_count) {
+    uint32_t mx = 0;
+    for (int r = 0; r < nranks; r++) { const uint32_t c = (uint32_t)src[(size_t)r * words_per_rank]; mx = c > mx ? c : mx; }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *max_count = mx;
+    if (mx > bound) return;
+    const int r = blockIdx.y;
+    if (r == self) return;
+    const uint64_t* base = src + (size_t)r * words_per_rank;
+    const uint32_t n = (uint32_t)base[0];
+    const int rw = ap.n_keyw + ap.n_lanes;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint64_t* row = base + 1 + (size_t)i * rw;
+        uint64_t key[MAX_KEYW];
+        for (int w = 0; w < ap.n_keyw; w++) key[w] = row[w];
+        merge_group(ap, gt, key, [&](int l, uint64_t& v) { v = row[ap.n_keyw + l]; return true; });
+    }
+}
 
 // ---- merge over NVLink peer memory (option "peer_merge"): export, exchange and merge without a collective library call ----
 // Every rank owns one buffer [2 parities][nranks segments of the partial-state layout] + [2][nranks] sequence flags, mapped into
@@ -219,7 +258,7 @@ __global__ void k_partial_counts(uint64_t* dst, size_t words_per_seg, const uint
 __global__ void k_partial_merge(GroupTable gt, AggPlan ap, const uint64_t* src, size_t words_per_rank, uint32_t pcap, int nranks) {
     for (int r = 0; r < nranks; r++) {
         const uint64_t* base = src + (size_t)r * words_per_rank;
-        const uint32_t n = (uint32_t)base[0];
+        const uint32_t n = (uint32_t)base[0] < pcap ? (uint32_t)base[0] : pcap;   // (a count beyond the segment's capacity never indexes past it)
         const uint64_t* skeys = base + 1;
         const uint64_t* slanes = skeys + (size_t)ap.n_keyw * pcap;
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -494,10 +533,24 @@ cudaError_t launch_join_build(const DevCol& key, int from_prim, int cast_prim_, 
     k_join_build<<<grid, 256, 0, s>>>(key, from_prim, cast_prim_, nrows, keys, rows, cap_mask);
     return cudaGetLastError();
 }
-cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStream_t s) {
+cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStream_t s, int keep_overflow) {
     const uint32_t cap = gt.cap_mask + 1;
     int grid = (int)((cap + 255) / 256); if (grid > 1184) grid = 1184;
-    k_table_init<<<grid, 256, 0, s>>>(gt, ap);
+    k_table_init<<<grid, 256, 0, s>>>(gt, ap, keep_overflow);
+    return cudaGetLastError();
+}
+cudaError_t launch_partial_export_rows(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, uint32_t bound, cudaStream_t s) {
+    const uint32_t cap = gt.cap_mask + 1;
+    int grid = (int)((cap + 255) / 256); if (grid > 1184) grid = 1184;
+    cudaError_t e = cudaMemsetAsync(dst, 0, 8, s);
+    if (e != cudaSuccess) return e;
+    k_partial_export_rows<<<grid, 256, 0, s>>>(gt, ap, dst, bound);
+    return cudaGetLastError();
+}
+cudaError_t launch_partial_merge_rows(const GroupTable& gt, const AggPlan& ap, const uint64_t* src, size_t words_per_rank, uint32_t bound, int nranks, int self,
+                                      uint32_t* max_count, cudaStream_t s) {
+    int gx = (int)((bound + 255) / 256); if (gx > 64) gx = 64; if (gx < 1) gx = 1;
+    k_partial_merge_rows<<<dim3((unsigned)gx, (unsigned)nranks), 256, 0, s>>>(gt, ap, src, words_per_rank, bound, nranks, self, max_count);
     return cudaGetLastError();
 }
 cudaError_t launch_partial_export(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, uint32_t pcap, uint32_t* cursor, cudaStream_t s) {
@@ -506,7 +559,7 @@ cudaError_t launch_partial_export(const GroupTable& gt, const AggPlan& ap, uint6
     cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
     k_partial_export<<<grid, 256, 0, s>>>(gt, ap, dst, pcap, cursor);
-    k_partial_count<<<1, 1, 0, s>>>(dst, cursor);
+    k_partial_count<<<1, 1, 0, s>>>(dst, cursor, pcap);
     return cudaGetLastError();
 }
 cudaError_t launch_partial_export_parts(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, size_t words_per_seg, uint32_t pcap, uint32_t* cursors, int nranks, cudaStream_t s) {

@@ -7,7 +7,12 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../include/bkgpu.h"
 #include "agg.h"
@@ -62,6 +67,10 @@ struct bkgpu_plan {
     uint32_t* d_cursor = nullptr;
     uint64_t* d_partial = nullptr;  // export buffer (this rank)
     uint64_t* d_gather = nullptr;   // nranks export buffers
+    size_t d_partial_words = 0, d_gather_words = 0;
+    std::vector<uint8_t*> bounce[2]; size_t bounce_rows = 0; cudaEvent_t bounce_done[2] = {nullptr, nullptr}; bool bounce_busy[2] = {false, false};
+    int no_bounce = 0;            // 1 = pageable host input goes straight to cudaMemcpyAsync (A/B of the bounce path)
+    uint32_t merge_bound = 0, merge_bound_used = 0;   // groups per rank the all-gather is sized for (learned from earlier runs)
     uint32_t* d_part_cursors = nullptr; int repartition = 0;   // hash repartition of the groups across ranks (option "repartition")
     // merge over NVLink peer memory (option "peer_merge"): this rank's buffer, the peers' mappings of theirs, step counter
     int peer_merge = 0, peer_rank = -1; bool peer_ready = false;
@@ -114,7 +123,12 @@ struct bkgpu_plan {
 
 #define CK(plan, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (plan)->cuda_fail(e__, #call); } while (0)
 
-static int thread_fail(int code, const char* msg) { g_thread_error = msg; return code; }
+static int thread_fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_thread_error = buf;
+    return code;
+}
 
 // ------------------------------------------------------------------ library
 extern "C" const char* bkgpu_version(void) { return "bkgpu 0.1 (sm_100a)"; }
@@ -218,6 +232,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "no_lean_nulls") p->no_lean_nulls = v != 0;
     else if (k == "no_lean_mm") p->no_lean_mm = v != 0;
     else if (k == "use_wp") p->use_wp = v != 0;
+    else if (k == "no_bounce") p->no_bounce = v != 0;
     else if (k == "wp_warps") { if (v != 0 && v != 8 && v != 12 && v != 16) return p->fail(BKGPU_EINVAL, "wp_warps: 0, 8, 12 or 16"); p->wp_warps = (int)v; }
     else if (k == "wp_kt_log2") { if (v < 0 || v > 14) return p->fail(BKGPU_EINVAL, "wp_kt_log2 out of range"); p->wp_kt_log2 = (int)v; }
     else if (k == "output_on_device") p->output_on_device = v != 0;
@@ -475,7 +490,79 @@ static int ensure_stage(bkgpu_plan* p, const std::vector<ColRef>& want, size_t r
     return BKGPU_OK;
 }
 
+// pinned bounce buffers for pageable input: one per staging buffer set and column
+static int ensure_bounce(bkgpu_plan* p, const std::vector<ColRef>& want, size_t rows) {
+    if (p->bounce_rows >= rows && p->bounce[0].size() >= want.size()) return BKGPU_OK;
+    for (int b = 0; b < 2; b++) {
+        for (uint8_t* q : p->bounce[b]) if (q) cudaFreeHost(q);
+        p->bounce[b].assign(want.size(), nullptr);
+        for (size_t i = 0; i < want.size(); i++) {
+            const size_t bytes = rows * (size_t)storage_bytes(prim_storage(want[i].prim));
+            if (cudaHostAlloc((void**)&p->bounce[b][i], bytes ? bytes : 8, cudaHostAllocDefault) != cudaSuccess) return p->fail(BKGPU_ENOMEM, "pinned bounce buffer of %zu bytes", bytes);
+        }
+        if (!p->bounce_done[b]) CK(p, cudaEventCreateWithFlags(&p->bounce_done[b], cudaEventDisableTiming));
+        p->bounce_busy[b] = false;
+    }
+    p->bounce_rows = rows;
+    return BKGPU_OK;
+}
+
 typedef int (*BatchFn)(bkgpu_plan*, const DevCol*, int64_t nrows, int64_t row_base, bool vec_ok);
+
+// ---- host-side copy workers: pageable input (what an Arrow RecordBatch of RocksdbVectorizedReader hands over) is copied into
+// pinned bounce buffers by several threads — cudaMemcpyAsync from pageable memory goes through the driver's single staging buffer
+// at a fraction of the link rate ----
+namespace {
+class CopyPool {
+  public:
+    explicit CopyPool(int n) { for (int i = 0; i < n; i++) th_.emplace_back([this] { run(); }); }
+    ~CopyPool() { { std::lock_guard<std::mutex> g(mu_); stop_ = true; } cv_.notify_all(); for (auto& t : th_) t.join(); }
+    int size() const { return (int)th_.size(); }
+    // runs fn(0) .. fn(n - 1) on the workers and the caller; returns when all are done
+    void parallel(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            fn_ = &fn; next_ = 0; total_ = n; done_ = 0; gen_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> g(mu_);
+        done_cv_.wait(g, [this] { return done_ == total_; });
+        fn_ = nullptr;
+    }
+  private:
+    void work() {
+        for (;;) {
+            int i;
+            const std::function<void(int)>* f;
+            { std::lock_guard<std::mutex> g(mu_); if (!fn_ || next_ >= total_) return; i = next_++; f = fn_; }
+            (*f)(i);
+            { std::lock_guard<std::mutex> g(mu_); if (++done_ == total_) done_cv_.notify_all(); }
+        }
+    }
+    void run() {
+        uint64_t seen = 0;
+        for (;;) {
+            { std::unique_lock<std::mutex> g(mu_); cv_.wait(g, [&] { return stop_ || gen_ != seen; }); if (stop_) return; seen = gen_; }
+            work();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_; std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int next_ = 0, total_ = 0, done_ = 0; uint64_t gen_ = 0; bool stop_ = false;
+};
+CopyPool& copy_pool() {
+    static CopyPool pool(std::max(1, std::min(15, (int)std::thread::hardware_concurrency() - 1)));
+    return pool;
+}
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+}  // namespace
 
 // feed a batch: device-resident columns go straight to the kernels; host columns stream through
 // two sets of device staging buffers (H2D of chunk i+1 overlaps the kernel on chunk i)
@@ -495,15 +582,32 @@ static int feed(bkgpu_plan* p, const std::vector<ColRef>& want, const bkgpu_colu
     }
     const int64_t chunk = std::min<int64_t>(p->chunk_rows, std::max<int64_t>((nrows + 7) & ~7ll, 8));
     if ((rc = ensure_stage(p, want, (size_t)chunk))) return rc;
+    bool pageable = false;
+    for (size_t i = 0; i < want.size() && !p->no_bounce; i++) pageable = pageable || is_pageable(bound[i]->values);
+    if (pageable && (rc = ensure_bounce(p, want, (size_t)chunk))) return rc;
     int buf = 0;
+    cudaEvent_t last_ready = nullptr;
     for (int64_t off = 0; off < nrows; off += chunk, buf ^= 1) {
         if (p->cancelled.load()) return p->fail(BKGPU_ECANCELLED, "cancelled");
         const int64_t n = std::min(chunk, nrows - off);
         CK(p, cudaStreamWaitEvent(p->copy_stream, p->stage_free[buf], 0));
+        if (pageable) {   // bounce: worker threads fill this buffer set's pinned copy of the chunk, the link then runs at the pinned rate
+            if (p->bounce_busy[buf]) { CK(p, cudaEventSynchronize(p->bounce_done[buf])); p->bounce_busy[buf] = false; }
+            struct Piece { uint8_t* dst; const uint8_t* src; size_t bytes; };
+            std::vector<Piece> pieces;
+            const size_t slice = (size_t)4 << 20;
+            for (size_t i = 0; i < want.size(); i++) {
+                const size_t eb = (size_t)storage_bytes(prim_storage(want[i].prim)), bytes = (size_t)n * eb;
+                const uint8_t* src = (const uint8_t*)bound[i]->values + (size_t)off * eb;
+                for (size_t o = 0; o < bytes; o += slice) pieces.push_back({p->bounce[buf][i] + o, src + o, std::min(slice, bytes - o)});
+            }
+            copy_pool().parallel((int)pieces.size(), [&](int k) { memcpy(pieces[(size_t)k].dst, pieces[(size_t)k].src, pieces[(size_t)k].bytes); });
+        }
         for (size_t i = 0; i < want.size(); i++) {
             const int st = prim_storage(want[i].prim);
             const size_t eb = (size_t)storage_bytes(st);
-            CK(p, cudaMemcpyAsync(p->stage[buf][i], (const uint8_t*)bound[i]->values + (size_t)off * eb, (size_t)n * eb, cudaMemcpyHostToDevice, p->copy_stream));
+            const void* hsrc = pageable ? (const void*)p->bounce[buf][i] : (const void*)((const uint8_t*)bound[i]->values + (size_t)off * eb);
+            CK(p, cudaMemcpyAsync(p->stage[buf][i], hsrc, (size_t)n * eb, cudaMemcpyHostToDevice, p->copy_stream));
             p->stats.h2d_bytes += (int64_t)((size_t)n * eb);
             dc[i].values = p->stage[buf][i]; dc[i].stype = st; dc[i].prim = want[i].prim; dc[i].validity = nullptr;
             if (bound[i]->validity) {
@@ -513,10 +617,15 @@ static int feed(bkgpu_plan* p, const std::vector<ColRef>& want, const bkgpu_colu
             }
         }
         CK(p, cudaEventRecord(p->stage_ready[buf], p->copy_stream));
+        if (pageable) { CK(p, cudaEventRecord(p->bounce_done[buf], p->copy_stream)); p->bounce_busy[buf] = true; }
         CK(p, cudaStreamWaitEvent(p->stream, p->stage_ready[buf], 0));
         if ((rc = fn(p, dc.data(), n, off, true))) return rc;
         CK(p, cudaEventRecord(p->stage_free[buf], p->stream));
+        last_ready = p->stage_ready[buf];
     }
+    // the caller's host buffers are borrowed for the duration of the call only (bkgpu.h): the last host-to-device copy must have
+    // read them before bkgpu_push returns (the kernels read the staging buffers, they may still be running)
+    if (last_ready) CK(p, cudaEventSynchronize(last_ready));
     return BKGPU_OK;
 }
 
@@ -624,8 +733,10 @@ static int join_build_table(bkgpu_plan* p) {
     if (p->jb_vals.empty()) { p->jb_vals.assign(nc, nullptr); p->jb_nullbytes.assign(nc, nullptr); p->jb_bitmap.assign(nc, nullptr); p->jb_has_null.assign(nc, false); }
     int rc;
     for (size_t i = 0; i < nc; i++) {
-        if (c.col_side[i] != 1 || !p->jb_has_null[i]) continue;
+        if (c.col_side[i] != 1) continue;
+        // (a bitmap kept from an earlier run of the plan must not mask this run's rows: a column without NULLs has none)
         dev_free(p, p->jb_bitmap[i]); p->jb_bitmap[i] = nullptr;
+        if (!p->jb_has_null[i]) continue;
         if ((rc = dev_alloc(p, (void**)&p->jb_bitmap[i], (size_t)(p->jb_rows + 7) / 8 + 8))) return rc;
         CK(p, launch_pack_validity(p->jb_nullbytes[i], p->jb_rows, p->jb_bitmap[i], p->stream));
         p->stats.kernel_launches++;
@@ -861,51 +972,88 @@ static uint32_t eff_pcap(const bkgpu_plan* p) {
     return (uint32_t)std::min<int64_t>(p->partial_cap, table);
 }
 
+// grow-only device buffers of the multi-GPU exchange
+static int ensure_words(bkgpu_plan* p, uint64_t** buf, size_t* have, size_t want) {
+    if (*have >= want) return BKGPU_OK;
+    dev_free(p, *buf); *buf = nullptr; *have = 0;
+    int rc = dev_alloc(p, (void**)buf, want * 8);
+    if (rc) return rc;
+    *have = want;
+    return BKGPU_OK;
+}
+
+// the collective step of bkgpu_finish: regions -> one set per GPU, the per-GPU partial tables meet once and are folded by K3.
+// Default: compact rows, one ncclAllGather of 1 + bound x (key + lane words) per rank — `bound` = the largest group count any rank
+// held in earlier runs of this plan (2048 on the first run); the merge reports the true maximum and the exchange is repeated once
+// with a larger bound when it did not fit.  Options: peer_merge (NVLink peer memory), repartition (all-to-all by key owner).
+static int agg_collective(bkgpu_plan* p, bool* rows_mode) {
+    const AggPlan& ap = p->c.ap;
+    GroupTable& gt = p->gt;
+    *rows_mode = false;
+    const uint32_t pcap = eff_pcap(p);
+    int rc;
+    const bool repart = p->repartition && ap.n_keyw > 0;   // (a scalar aggregate has one group: nothing to partition)
+    EventPair* ep = timer_begin(p, p->timed_coll, 0);
+    if (!(p->peer_merge && !repart) && !repart) {
+        *rows_mode = true;
+        if (p->peer_rank < 0 && nccl_comm_rank(p->nccl_comm, &p->peer_rank) != 0) return p->fail(BKGPU_ENCCL, "ncclCommUserRank: %s", nccl_last_error());
+        uint32_t bound = p->merge_bound ? p->merge_bound : 2048u;
+        if (ap.n_keyw == 0) bound = 1;
+        bound = std::min<uint32_t>(bound, pcap);
+        const size_t rw = (size_t)(ap.n_keyw + ap.n_lanes);
+        const size_t words = 1 + rw * bound;
+        if ((rc = ensure_words(p, &p->d_partial, &p->d_partial_words, words))) return rc;
+        if ((rc = ensure_words(p, &p->d_gather, &p->d_gather_words, words * (size_t)p->nranks))) return rc;
+        CK(p, launch_partial_export_rows(gt, ap, p->d_partial, bound, p->stream));
+        if (nccl_all_gather(p->nccl_comm, p->d_partial, p->d_gather, words, p->stream) != 0) return p->fail(BKGPU_ENCCL, "ncclAllGather: %s", nccl_last_error());
+        CK(p, launch_partial_merge_rows(gt, ap, p->d_gather, words, bound, p->nranks, p->peer_rank, p->d_cursor + 1, p->stream));
+        p->merge_bound_used = bound;
+        p->stats.kernel_launches += 2;
+        timer_end(p, ep);
+        return BKGPU_OK;
+    }
+    const size_t words = 1 + (size_t)(ap.n_keyw + ap.n_lanes) * pcap;
+    if ((rc = ensure_words(p, &p->d_partial, &p->d_partial_words, words * (repart ? (size_t)p->nranks : 1)))) return rc;
+    if ((rc = ensure_words(p, &p->d_gather, &p->d_gather_words, words * (size_t)p->nranks))) return rc;
+    if (p->peer_merge && !repart && (rc = peer_setup(p, words))) return rc;
+    if (p->peer_merge && !repart) {
+        const uint64_t seq = ++p->peer_seq;
+        CK(p, launch_peer_exchange(gt, ap, p->d_peer_ptrs, p->peer_local, p->nranks, p->peer_rank, words, pcap, seq, p->d_cursor, p->d_peer_timeout, p->stream));
+        CK(p, launch_table_init(gt, ap, p->stream, 1));
+        CK(p, launch_partial_merge(gt, ap, p->peer_local + (size_t)(seq & 1) * (size_t)p->nranks * words, words, pcap, p->nranks, p->stream));
+        timer_end(p, ep);
+        p->stats.kernel_launches += 5;
+        if (p->h_pinned) CK(p, cudaMemcpyAsync(p->h_pinned + 12, p->d_peer_timeout, 4, cudaMemcpyDeviceToHost, p->stream));   // checked after the result's synchronisation
+        return BKGPU_OK;
+    }
+    // hash repartition: every rank keeps only the groups it owns — an all-to-all of per-owner segments instead of the
+    // all-gather; the merged table (and the result) of a rank is its partition, the union over ranks is the answer
+    if (!p->d_part_cursors && (rc = dev_alloc(p, (void**)&p->d_part_cursors, 4 * (size_t)p->nranks))) return rc;
+    CK(p, launch_partial_export_parts(gt, ap, p->d_partial, words, pcap, p->d_part_cursors, p->nranks, p->stream));
+    if (nccl_all_to_all(p->nccl_comm, p->d_partial, p->d_gather, words, p->nranks, p->stream) != 0) return p->fail(BKGPU_ENCCL, "all-to-all: %s", nccl_last_error());
+    CK(p, launch_table_init(gt, ap, p->stream, 1));   // (keeps the overflow flag an export beyond partial_capacity raised)
+    CK(p, launch_partial_merge(gt, ap, p->d_gather, words, pcap, p->nranks, p->stream));
+    timer_end(p, ep);
+    p->stats.kernel_launches += 4;
+    return BKGPU_OK;
+}
+
 static int agg_finish(bkgpu_plan* p) {
     const AggPlan& ap = p->c.ap;
     GroupTable& gt = p->gt;
     uint32_t host_counts[2] = {0, 0};
-    if (p->nccl_comm && p->nranks > 1) {
-        // regions -> one set per GPU; partial tables meet in ONE all-gather and are folded by K3
-        const uint32_t pcap = eff_pcap(p);
-        const size_t words = 1 + (size_t)(ap.n_keyw + ap.n_lanes) * pcap;
-        int rc;
-        const bool repart = p->repartition && ap.n_keyw > 0;   // (a scalar aggregate has one group: nothing to partition)
-        if (!p->d_partial && (rc = dev_alloc(p, (void**)&p->d_partial, words * 8 * (repart ? (size_t)p->nranks : 1)))) return rc;
-        if (!p->d_gather && (rc = dev_alloc(p, (void**)&p->d_gather, words * 8 * (size_t)p->nranks))) return rc;
-        if (p->peer_merge && !repart && (rc = peer_setup(p, words))) return rc;
-        EventPair* ep = timer_begin(p, p->timed_coll, 0);
-        if (p->peer_merge && !repart) {
-            const uint64_t seq = ++p->peer_seq;
-            CK(p, launch_peer_exchange(gt, ap, p->d_peer_ptrs, p->peer_local, p->nranks, p->peer_rank, words, pcap, seq, p->d_cursor, p->d_peer_timeout, p->stream));
-            CK(p, launch_table_init(gt, ap, p->stream));
-            CK(p, launch_partial_merge(gt, ap, p->peer_local + (size_t)(seq & 1) * (size_t)p->nranks * words, words, pcap, p->nranks, p->stream));
-            timer_end(p, ep);
-            p->stats.kernel_launches += 5;
-            if (p->h_pinned) CK(p, cudaMemcpyAsync(p->h_pinned + 12, p->d_peer_timeout, 4, cudaMemcpyDeviceToHost, p->stream));   // checked after the result's synchronisation
-        } else {
-        if (repart) {
-            // hash repartition: every rank keeps only the groups it owns — an all-to-all of per-owner segments instead of the
-            // all-gather; the merged table (and the result) of a rank is its partition, the union over ranks is the answer
-            if (!p->d_part_cursors && (rc = dev_alloc(p, (void**)&p->d_part_cursors, 4 * (size_t)p->nranks))) return rc;
-            CK(p, launch_partial_export_parts(gt, ap, p->d_partial, words, pcap, p->d_part_cursors, p->nranks, p->stream));
-            if (nccl_all_to_all(p->nccl_comm, p->d_partial, p->d_gather, words, p->nranks, p->stream) != 0) return p->fail(BKGPU_ENCCL, "all-to-all: %s", nccl_last_error());
-        } else {
-        CK(p, launch_partial_export(gt, ap, p->d_partial, pcap, p->d_cursor, p->stream));
-        if (nccl_all_gather(p->nccl_comm, p->d_partial, p->d_gather, words, p->stream) != 0) return p->fail(BKGPU_ENCCL, "ncclAllGather: %s", nccl_last_error());
-        }
-        CK(p, launch_table_init(gt, ap, p->stream));
-        CK(p, launch_partial_merge(gt, ap, p->d_gather, words, pcap, p->nranks, p->stream));
-        timer_end(p, ep);
-        p->stats.kernel_launches += 4;
-        }
-    }
+    uint64_t* finish_hv = nullptr; uint8_t* finish_hn = nullptr; uint32_t finish_n_out = 0, finish_out_cap = 0;
+    const bool multi = p->nccl_comm && p->nranks > 1;
+    bool rows_mode = false;
     // device images: one per group expr, per aggregate its final (+2 for an AVG blob)
     int n_img = ap.n_group;
     for (int k = 0; k < ap.n_agg; k++) if (!ap.agg[k].hidden) n_img += ap.agg[k].kind == AG_AVG ? 3 : 1;
     int rc;
-    uint32_t n_out = 0, out_cap = 0;
+  for (int mtry = 0; mtry < 3; mtry++) {   // (a second trip only when some rank held more groups than the exchange was sized for)
+    if (multi && (rc = agg_collective(p, &rows_mode))) return rc;
+    uint32_t n_out = 0, out_cap = 0, merge_max = 0;
     uint64_t* hv = nullptr; uint8_t* hn = nullptr;
+    bool redo_merge = false;
     for (int attempt = 0; attempt < 2; attempt++) {
         // speculative extraction into the buffers kept from earlier runs: counts, cursor and rows come back
         // in ONE synchronisation; only a result larger than the buffers costs a second round
@@ -934,17 +1082,33 @@ static int agg_finish(bkgpu_plan* p) {
         uint32_t* hc3 = p->h_pinned ? p->h_pinned + 8 : nullptr;   // [8] groups [9] overflow [10] rows extracted
         CK(p, cudaMemcpyAsync(hc3 ? hc3 : host_counts, gt.n_groups, 8, cudaMemcpyDeviceToHost, p->stream));
         CK(p, cudaMemcpyAsync(hc3 ? hc3 + 2 : &n_out, p->d_cursor, 4, cudaMemcpyDeviceToHost, p->stream));
+        if (rows_mode) CK(p, cudaMemcpyAsync(hc3 ? hc3 + 3 : &merge_max, p->d_cursor + 1, 4, cudaMemcpyDeviceToHost, p->stream));
         CK(p, cudaMemcpyAsync(hv, p->d_outv, n_words * 8, cudaMemcpyDeviceToHost, p->stream));
         CK(p, cudaMemcpyAsync(hn, p->d_outn, n_words, cudaMemcpyDeviceToHost, p->stream));
         CK(p, cudaStreamSynchronize(p->stream));
         if (hc3) { host_counts[0] = hc3[0]; host_counts[1] = hc3[1]; n_out = hc3[2]; }
         if (p->peer_ready && p->h_pinned && p->h_pinned[12]) return p->fail(BKGPU_ENCCL, "peer merge: a rank did not publish its partial state within the time limit");
+        if (rows_mode) {
+            const uint32_t mx = hc3 ? hc3[3] : merge_max;
+            if (mx > p->merge_bound_used) {   // nothing was merged (k_partial_merge_rows): exchange again, sized for what the ranks really hold
+                if (mx > eff_pcap(p)) return p->fail(BKGPU_ETOOBIG, "a rank holds %u groups, more than partial_capacity %lld: raise partial_capacity", mx, (long long)p->partial_cap);
+                p->merge_bound = (mx + 63u) & ~63u;
+                redo_merge = true;
+                break;
+            }
+            const uint32_t learned = (std::max<uint32_t>(mx, 1u) + 63u) & ~63u;
+            if (learned > p->merge_bound) p->merge_bound = learned;
+        }
         p->stats.d2h_bytes += (int64_t)(n_words * 9 + 12);
         if (host_counts[1]) return p->fail(BKGPU_ETOOBIG, "group table overflow (capacity 2^%d slots / partial_capacity %lld): raise group_capacity_log2",
                                            (int)gt.cap_log2, (long long)p->partial_cap);
         if (host_counts[0] > p->known_groups) p->known_groups = host_counts[0];
         if (n_out <= out_cap) break;   // everything fitted
     }
+    if (!redo_merge) { finish_hv = hv; finish_hn = hn; finish_n_out = n_out; finish_out_cap = out_cap; break; }
+    if (mtry == 2) return p->fail(BKGPU_ENCCL, "partial-state exchange did not converge");
+  }
+    uint64_t* hv = finish_hv; uint8_t* hn = finish_hn; uint32_t n_out = finish_n_out, out_cap = finish_out_cap;
     if (n_out > out_cap) n_out = out_cap;
     int64_t rows = n_out;
     int64_t skip = p->c.offset > 0 ? std::min<int64_t>(p->c.offset, rows) : 0;
@@ -1073,6 +1237,7 @@ extern "C" int bkgpu_reset(bkgpu_plan* p) {
         p->stats.kernel_launches++;
     }
     p->jb_rows = 0; p->jt_built = false; p->jt_generic = false; std::fill(p->jb_has_null.begin(), p->jb_has_null.end(), false);
+    for (size_t i = 0; i < p->jb_bitmap.size(); i++) { dev_free(p, p->jb_bitmap[i]); p->jb_bitmap[i] = nullptr; }   // build-side validity of the previous run
     if (p->sort) { int rc = sort_reset(p->sort, p->stream, p->last_error); if (rc) { g_thread_error = p->last_error; return rc; } }
     p->result.clear(); p->result_rows = 0; p->result_pos = 0;
     bkgpu_stats z{}; z.kernel_launches = p->stats.kernel_launches; p->stats = z;
@@ -1093,6 +1258,7 @@ extern "C" void bkgpu_close(bkgpu_plan* p) {
     for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
     for (void* q : p->dev_allocs) cudaFree(q);
     for (int i = 0; i < 2; i++) { if (p->stage_free[i]) cudaEventDestroy(p->stage_free[i]); if (p->stage_ready[i]) cudaEventDestroy(p->stage_ready[i]); }
+    for (int i = 0; i < 2; i++) { for (uint8_t* q : p->bounce[i]) if (q) cudaFreeHost(q); if (p->bounce_done[i]) cudaEventDestroy(p->bounce_done[i]); }
     if (p->h_pinned) cudaFreeHost(p->h_pinned);
     if (p->h_outv) cudaFreeHost(p->h_outv);
     if (p->h_outn) cudaFreeHost(p->h_outn);
@@ -1105,6 +1271,79 @@ extern "C" int bkgpu_get_stats(bkgpu_plan* p, bkgpu_stats* out) {
     if (!p || !out) return thread_fail(BKGPU_EINVAL, "bkgpu_get_stats: NULL argument");
     *out = p->stats;
     return BKGPU_OK;
+}
+
+// ------------------------------------------------------------------ resident regions
+// A region's columns can be registered once and stay in HBM across queries (the reference's analogue: its column store and parquet
+// cache keep hot regions decoded in memory, include/column/file_manager.h:252-272): 180 GB hold ~7e9 rows of the C2 shape, and a query
+// over a resident region moves no input over PCIe at all.  Keyed by (device, region id); re-registering an id replaces it.
+namespace {
+struct ResidentRegion { int64_t nrows = 0; size_t bytes = 0; std::vector<bkgpu_column> cols; std::vector<void*> allocs; };
+std::mutex g_region_mu;
+std::map<std::pair<int, int64_t>, ResidentRegion> g_regions;
+void free_region(ResidentRegion& r) { for (void* q : r.allocs) cudaFree(q); r.allocs.clear(); r.cols.clear(); r.bytes = 0; }
+}  // namespace
+
+extern "C" int bkgpu_region_register(int device, int64_t region_id, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device) {
+    if (!cols || ncols <= 0 || nrows < 0) return thread_fail(BKGPU_EINVAL, "bkgpu_region_register: bad arguments");
+    if (cudaSetDevice(device) != cudaSuccess) return thread_fail(BKGPU_ENODEV, "cudaSetDevice failed");
+    ResidentRegion r; r.nrows = nrows;
+    cudaStream_t st = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return thread_fail(BKGPU_ENODEV, "cudaStreamCreate failed");
+    int rc = BKGPU_OK;
+    for (int i = 0; i < ncols && rc == BKGPU_OK; i++) {
+        const bkgpu_column& c = cols[i];
+        const int stype = prim_storage(c.prim_type);
+        if (stype < 0 || c.length != nrows || (nrows > 0 && !c.values)) { rc = thread_fail(BKGPU_EINVAL, "bkgpu_region_register: column %d_%d is malformed", c.tuple_id, c.slot_id); break; }
+        const size_t vb = (size_t)nrows * (size_t)storage_bytes(stype), nb = c.validity ? (size_t)(nrows + 7) / 8 : 0;
+        void *dv = nullptr, *dn = nullptr;
+        if (cudaMalloc(&dv, vb + 64) != cudaSuccess) { rc = thread_fail(BKGPU_ENOMEM, "cudaMalloc of %zu bytes failed", vb); break; }
+        r.allocs.push_back(dv);
+        if (nb) { if (cudaMalloc(&dn, nb + 64) != cudaSuccess) { rc = thread_fail(BKGPU_ENOMEM, "cudaMalloc of %zu bytes failed", nb); break; } r.allocs.push_back(dn); }
+        const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (vb && cudaMemcpyAsync(dv, c.values, vb, k, st) != cudaSuccess) { rc = thread_fail(BKGPU_ENODEV, "copy of column %d_%d failed", c.tuple_id, c.slot_id); break; }
+        if (nb && cudaMemcpyAsync(dn, c.validity, nb, k, st) != cudaSuccess) { rc = thread_fail(BKGPU_ENODEV, "copy of column %d_%d failed", c.tuple_id, c.slot_id); break; }
+        bkgpu_column d = c; d.values = dv; d.validity = (const uint8_t*)dn;
+        r.cols.push_back(d); r.bytes += vb + nb;
+    }
+    if (rc == BKGPU_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = thread_fail(BKGPU_ENODEV, "bkgpu_region_register: copy failed");
+    cudaStreamDestroy(st);
+    if (rc != BKGPU_OK) { free_region(r); return rc; }
+    std::lock_guard<std::mutex> g(g_region_mu);
+    auto key = std::make_pair(device, region_id);
+    auto it = g_regions.find(key);
+    if (it != g_regions.end()) { free_region(it->second); g_regions.erase(it); }
+    g_regions.emplace(key, std::move(r));
+    return BKGPU_OK;
+}
+extern "C" int bkgpu_region_evict(int device, int64_t region_id) {
+    std::lock_guard<std::mutex> g(g_region_mu);
+    auto it = g_regions.find(std::make_pair(device, region_id));
+    if (it == g_regions.end()) return thread_fail(BKGPU_EINVAL, "region %lld is not resident on device %d", (long long)region_id, device);
+    cudaSetDevice(device);
+    free_region(it->second);
+    g_regions.erase(it);
+    return BKGPU_OK;
+}
+extern "C" int bkgpu_region_info(int device, int64_t region_id, int64_t* nrows, size_t* bytes) {
+    std::lock_guard<std::mutex> g(g_region_mu);
+    auto it = g_regions.find(std::make_pair(device, region_id));
+    if (it == g_regions.end()) return thread_fail(BKGPU_EINVAL, "region %lld is not resident on device %d", (long long)region_id, device);
+    if (nrows) *nrows = it->second.nrows;
+    if (bytes) *bytes = it->second.bytes;
+    return BKGPU_OK;
+}
+// child->get_next() over a resident region: the same as bkgpu_push of its columns with on_device = 1
+extern "C" int bkgpu_push_region(bkgpu_plan* p, int64_t region_id) {
+    if (!p) return thread_fail(BKGPU_EINVAL, "bkgpu_push_region: NULL plan");
+    std::vector<bkgpu_column> cols; int64_t nrows = 0;
+    {
+        std::lock_guard<std::mutex> g(g_region_mu);
+        auto it = g_regions.find(std::make_pair(p->device, region_id));
+        if (it == g_regions.end()) return p->fail(BKGPU_EINVAL, "region %lld is not resident on device %d", (long long)region_id, p->device);
+        cols = it->second.cols; nrows = it->second.nrows;
+    }
+    return bkgpu_push(p, cols.data(), (int)cols.size(), nrows, 1);
 }
 
 // ------------------------------------------------------------------ partial state
@@ -1122,11 +1361,15 @@ extern "C" int bkgpu_partial_export(bkgpu_plan* p, void* dev_dst, size_t bytes) 
     if (bytes < need) return p->fail(BKGPU_EINVAL, "partial buffer too small: %zu < %zu", bytes, need);
     CK(p, cudaSetDevice(p->device));
     if (p->c.kind == PK_SORT) { rc = sort_partial_export(p->sort, dev_dst, p->stream, p->last_error); if (rc) g_thread_error = p->last_error; return rc; }
-    CK(p, launch_partial_export(p->gt, p->c.ap, (uint64_t*)dev_dst, eff_pcap(p), p->d_cursor, p->stream));
-    p->stats.kernel_launches += 2;
+    // compact rows (the layout the in-library all-gather ships): [u64 groups][groups x (key words + lane words)]
+    CK(p, launch_partial_export_rows(p->gt, p->c.ap, (uint64_t*)dev_dst, eff_pcap(p), p->stream));
+    p->stats.kernel_launches += 1;
+    uint64_t held = 0; uint32_t ov = 0;
+    CK(p, cudaMemcpyAsync(&held, dev_dst, 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(p, cudaMemcpyAsync(&ov, p->gt.overflow, 4, cudaMemcpyDeviceToHost, p->stream));
     CK(p, cudaStreamSynchronize(p->stream));
-    uint32_t ov = 0; CK(p, cudaMemcpy(&ov, p->gt.overflow, 4, cudaMemcpyDeviceToHost));
-    if (ov) return p->fail(BKGPU_ETOOBIG, "more than partial_capacity=%lld groups on this rank", (long long)p->partial_cap);
+    if (ov) return p->fail(BKGPU_ETOOBIG, "group table overflow (capacity 2^%d slots): raise group_capacity_log2", (int)p->gt.cap_log2);
+    if (held > eff_pcap(p)) return p->fail(BKGPU_ETOOBIG, "this rank holds %llu groups, more than partial_capacity=%lld", (unsigned long long)held, (long long)p->partial_cap);
     return BKGPU_OK;
 }
 extern "C" int bkgpu_partial_merge(bkgpu_plan* p, const void* dev_src, size_t bytes_per_rank, int nranks) {
@@ -1145,8 +1388,8 @@ extern "C" int bkgpu_partial_merge(bkgpu_plan* p, const void* dev_src, size_t by
         p->result_rows = rows; p->result_pos = 0; p->stats.rows_returned = rows; p->state = S_FINISHED;
         return BKGPU_OK;
     }
-    CK(p, launch_table_init(p->gt, p->c.ap, p->stream));
-    CK(p, launch_partial_merge(p->gt, p->c.ap, (const uint64_t*)dev_src, need / 8, eff_pcap(p), nranks, p->stream));
+    CK(p, launch_table_init(p->gt, p->c.ap, p->stream, 1));
+    CK(p, launch_partial_merge_rows(p->gt, p->c.ap, (const uint64_t*)dev_src, need / 8, eff_pcap(p), nranks, -1 /* fold every segment */, p->d_cursor + 1, p->stream));
     p->stats.kernel_launches += 2;
     void* comm = p->nccl_comm; int nr = p->nranks; p->nccl_comm = nullptr; p->nranks = 1;  // already merged: finalize locally
     rc = agg_finish(p);
@@ -1159,13 +1402,13 @@ extern "C" int bkgpu_partial_merge(bkgpu_plan* p, const void* dev_src, size_t by
 // ------------------------------------------------------------------ NCCL plumbing
 extern "C" int bkgpu_nccl_unique_id(uint8_t id_out[128]) {
     if (!id_out) return thread_fail(BKGPU_EINVAL, "bkgpu_nccl_unique_id: NULL");
-    if (nccl_unique_id(id_out) != 0) return thread_fail(BKGPU_ENCCL, nccl_last_error());
+    if (nccl_unique_id(id_out) != 0) return thread_fail(BKGPU_ENCCL, "%s", nccl_last_error());
     return BKGPU_OK;
 }
 extern "C" int bkgpu_nccl_comm_create(void** comm_out, const uint8_t id[128], int nranks, int rank, int device) {
     if (!comm_out || !id) return thread_fail(BKGPU_EINVAL, "bkgpu_nccl_comm_create: NULL");
     if (cudaSetDevice(device) != cudaSuccess) return thread_fail(BKGPU_ENODEV, "cudaSetDevice failed");
-    if (nccl_comm_create(comm_out, id, nranks, rank) != 0) return thread_fail(BKGPU_ENCCL, nccl_last_error());
+    if (nccl_comm_create(comm_out, id, nranks, rank) != 0) return thread_fail(BKGPU_ENCCL, "%s", nccl_last_error());
     return BKGPU_OK;
 }
 extern "C" void bkgpu_nccl_comm_destroy(void* comm) { if (comm) nccl_comm_destroy(comm); }

@@ -916,6 +916,7 @@ int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& er
             if (ok && limit_node) { out.limit = limit_node->limit; out.offset = limit_node->offset; }
         } else if (c && c->node_type == BK_JOIN_NODE && !filter) {
             ok = lower_join_agg(in, out, *top, *c, under_packet);
+            if (ok && limit_node) { out.limit = limit_node->limit; out.offset = limit_node->offset; }   // LimitNode over the joined aggregate
         } else { err = "AGG child must be [FILTER ->] SCAN or JOIN"; return BKGPU_EUNSUPPORTED; }
     } else if (top->node_type == BK_SORT_NODE) {
         const HNode* c = top->ch.empty() ? nullptr : skip_passthrough(&top->ch[0], nullptr);
@@ -923,7 +924,13 @@ int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& er
         if (is_filter(c)) { filter = c; c = c->ch.empty() ? nullptr : skip_passthrough(&c->ch[0], nullptr); }
         if (!c || c->node_type != BK_SCAN_NODE) { err = "SORT child must be [FILTER ->] SCAN"; return BKGPU_EUNSUPPORTED; }
         ok = lower_sort(in, out, *top, filter, *c);
-        if (ok && limit_node) { out.offset = limit_node->offset; if (out.limit < 0 || limit_node->limit + limit_node->offset < out.limit) out.limit = limit_node->limit + limit_node->offset; }
+        if (ok && limit_node) {
+            out.offset = limit_node->offset;
+            if (limit_node->limit >= 0) {   // (limit -1 = OFFSET only: the sort keeps every row)
+                const int64_t lim = limit_node->limit + limit_node->offset;
+                if (out.limit < 0 || lim < out.limit) out.limit = lim;
+            }
+        }
     } else if (is_filter(top) || top->node_type == BK_SCAN_NODE) {
         const HNode* c = top;
         if (is_filter(c)) c = c->ch.empty() ? nullptr : skip_passthrough(&c->ch[0], nullptr);

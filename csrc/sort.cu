@@ -332,8 +332,9 @@ __global__ void __launch_bounds__(1024) k_select_rank(const uint64_t* key, const
     __syncthreads();
     if (threadIdx.x == 0) {
         uint64_t tk = s_res[0], ti = s_res[1];
-        if (cap_thr && comp_lt(cap_thr[0], cap_thr[1], tk, ti)) { tk = cap_thr[0]; ti = cap_thr[1]; }   // never looser than the k-th row kept so far
-        rank_out[0] = tk; rank_out[1] = ti; rank_out[2] = n;
+        uint64_t capped = 0;
+        if (cap_thr && comp_lt(cap_thr[0], cap_thr[1], tk, ti)) { tk = cap_thr[0]; ti = cap_thr[1]; capped = 1ull << 62; }   // never looser than the k-th row kept so far
+        rank_out[0] = tk; rank_out[1] = ti; rank_out[2] = (uint64_t)n | capped;   // bit 62: the threshold in force is the pool's k-th key
     }
 }
 
@@ -656,10 +657,16 @@ int select_topk_class(SortState* s, const RowArgs& ra, int cls, cudaStream_t st,
         stats->kernel_launches += 3;
         if (!s->h_counts) SCK(cudaHostAlloc((void**)&s->h_counts, 64, cudaHostAllocDefault));
         SCK(cudaMemcpyAsync(s->h_counts, cnt, 32, cudaMemcpyDeviceToHost, st));
+        if (big && pool_thr) SCK(cudaMemcpyAsync(s->h_counts + 8, thr + 2, 8, cudaMemcpyDeviceToHost, st));
         SCK(cudaStreamSynchronize(st));
         memcpy(h, s->h_counts, 32);
         const uint32_t c1 = h[1], c2 = h[2], cls_rows = h[3], c3 = h[5];
-        const bool ok1 = c1 <= s->cand_cap && (c1 >= k || c1 >= cls_rows || pool_thr != nullptr);
+        // fewer than k candidates are complete only when the threshold in force was the pool's k-th key (every row at or below it
+        // was collected); a tighter SAMPLE threshold may have cut rows that belong between it and the pool's key: widen and retry
+        uint64_t thr_info = 0;
+        if (big && pool_thr) memcpy(&thr_info, s->h_counts + 8, 8);
+        const bool pool_in_force = pool_thr != nullptr && (!big || ((thr_info >> 62) & 1ull));
+        const bool ok1 = c1 <= s->cand_cap && (c1 >= k || c1 >= cls_rows || pool_in_force);
         const bool ok2 = c2 <= s->cand_cap && (c2 >= std::min(k, c1));
         const bool ok3 = c3 <= room && (c3 >= std::min(k, c2));
         if (ok1 && ok2 && ok3) { P.cur = nxt; P.n = h[4]; return 0; }

@@ -111,13 +111,18 @@ int   bkgpu_init(bkgpu_plan** out, const uint8_t* plan_desc, size_t len,
  *                          instead of gathered by NCCL (opt-in)
  *   "repartition"          with a communicator: groups are hash-partitioned across the ranks by one all-to-all (ncclSend/ncclRecv)
  *                          instead of gathered everywhere; each rank then returns only the groups it owns (high-cardinality GROUP BY)
- *   "force_generic" / "no_lean" / "no_lean_nulls" / "no_lean_mm" / "no_fused_probe"   pin the kernel variant (tests, A/B measurements) */
+ *   "force_generic" / "no_lean" / "no_lean_nulls" / "no_lean_mm" / "no_fused_probe"   pin the kernel variant (tests, A/B measurements)
+ *   "use_wp" / "wp_warps" / "wp_kt_log2"   opt into the warp-private (atomics-free) aggregate kernel and size it (csrc/agg_wp.cuh)
+ *   "no_bounce"            pageable host input goes straight to cudaMemcpyAsync instead of the threaded pinned bounce buffers (A/B) */
 int   bkgpu_set_option(bkgpu_plan*, const char* key, int64_t value);
 /* ExecNode::open(RuntimeState*) (exec_node.h:140): allocate tables. */
 int   bkgpu_open(bkgpu_plan*);
 /* child->get_next() inverted: feed one column batch of the scan tuple the columns
- * name.  Buffers are borrowed for the duration of the call.  on_device != 0 means
- * `values`/`validity` are device pointers on the plan's device. */
+ * name.  HOST buffers (on_device == 0) are borrowed for the duration of the call: every host-to-device copy has
+ * read them when bkgpu_push returns (pinned or pageable alike).  on_device != 0 means `values`/`validity` are
+ * device pointers on the plan's device; the kernels read them asynchronously on the plan's stream, so DEVICE
+ * buffers must stay valid and unmodified until bkgpu_finish has returned (or until work the caller orders after
+ * the plan's stream has run). */
 int   bkgpu_push(bkgpu_plan*, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device);
 /* End of input: drain, run the cross-GPU merge when a communicator was given,
  * finalize aggregates (AggFnCall::finalize, src/expr/agg_fn_call.cpp:927-990). */
@@ -135,6 +140,15 @@ void  bkgpu_cancel(bkgpu_plan*);
 /* ExecNode::close + destroy_tree. */
 void  bkgpu_close(bkgpu_plan*);
 int   bkgpu_get_stats(bkgpu_plan*, bkgpu_stats* out);
+
+/* ---- resident regions (the column store / parquet cache analogue, include/column/file_manager.h:252-272) ----
+ * A region's columns are copied to HBM once (host or device source) and stay there across queries, keyed by
+ * (device, region_id); bkgpu_push_region feeds them to a plan exactly like bkgpu_push(..., on_device = 1) — a query
+ * over a resident region moves no input over PCIe.  Registering an id again replaces the region. */
+int   bkgpu_region_register(int device, int64_t region_id, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device);
+int   bkgpu_region_evict(int device, int64_t region_id);
+int   bkgpu_region_info(int device, int64_t region_id, int64_t* nrows, size_t* bytes);
+int   bkgpu_push_region(bkgpu_plan*, int64_t region_id);
 
 /* ---- per-GPU partial state (MERGE_AGG / merge-sort on the db side) ---- */
 /* After bkgpu_finish on a plan WITHOUT a communicator the caller may move the

@@ -63,6 +63,15 @@ def main():
     whole = datagen.c2_table(0, n_region * world, n_groups=500)
     want = oracle.execute(queries.c2_filter_groupby().serialize(), whole)
     assert_same_rows(got, want.columns, ["0_1"])      # every rank holds the merged result
+    # ---- more groups per rank than the first exchange is sized for (2048): the merge reports it and the exchange runs again ----
+    mid = datagen.c2_table(rank * n_region, n_region, n_groups=6000)
+    got_m, stats_m = run_plan(queries.c2_filter_groupby(), mid, comm, dev, {})
+    assert_same_rows(got_m, oracle.execute(queries.c2_filter_groupby().serialize(), datagen.c2_table(0, n_region * world, n_groups=6000)).columns, ["0_1"])
+    # ---- more groups than partial_capacity: ETOOBIG on every rank, never a truncated result ----
+    st_big = RuntimeState(device=dev, nccl_comm=comm.value, options={"partial_capacity": 1000})
+    node_big = GpuExecNode(); node_big.init(queries.c2_filter_groupby()); node_big.add_child(ColumnSource([mid]))
+    assert node_big.open(st_big) == _lib.ETOOBIG, (st_big.error_code, st_big.error_msg)
+    node_big.close(st_big)
     # ---- the same merge over NVLink peer memory (CUDA IPC buffers, no collective call on the data path) ----
     got_p, stats_p = run_plan(queries.c2_filter_groupby(), region, comm, dev, {"peer_merge": 1})
     assert stats_p.collective_ms > 0
