@@ -48,11 +48,13 @@ def exchange_and_merge(node, world):
     nbytes = ctypes.c_size_t(0)
     _lib.check(L.bkgpu_partial_capacity(h, ctypes.byref(nbytes)), h)
     mine = torch.zeros(nbytes.value, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()                                # (the library works on its own stream: torch's fill must have run)
     _lib.check(L.bkgpu_partial_export(h, ctypes.c_void_p(mine.data_ptr()), nbytes.value), h)
     torch.cuda.synchronize()
     parts = [torch.zeros(nbytes.value, dtype=torch.uint8) for _ in range(world)]
     dist.all_gather(parts, mine.cpu())                      # gloo moves the partial states
     allp = torch.cat(parts).cuda()
+    torch.cuda.synchronize()
     _lib.check(L.bkgpu_partial_merge(h, ctypes.c_void_p(allp.data_ptr()), nbytes.value, world), h)
     torch.cuda.synchronize()
     return allp
@@ -105,6 +107,7 @@ def main():
     exchange_and_merge(node, world)
     got5 = fetch(node, st)
     want5 = oracle.execute(queries.c5_topk(1000).serialize(), whole5)
+    assert len(got5[0]) == len(want5.columns[0]) == 1000, (rank, len(got5), [len(c) for c in got5], [len(c) for c in want5.columns])
     assert_same_rows(got5, want5.columns, None)
     node.close(st)
     dist.barrier()
