@@ -464,6 +464,9 @@ def main():
 
     # ---- value: device-resident columns ----
     r = timed(lambda: step(dcols, 1), args.steps, max(args.warmup, 3))
+    if os.environ.get("BKGPU_BENCH_TRACE"):   # per-rank view of the timed region (stderr)
+        sys.stderr.write(f"[rank {rank}] step {r['ms'] / args.steps:.4f} ms  kernel {r['kernel_ms'] / max(r['kernel_launches'], 1):.4f} ms  "
+                         f"collective {r['coll_ms'] / args.steps:.4f} ms  launches/step {r['launches'] / args.steps:.1f}\n")
     total_rows = rows * world
     value = total_rows * args.steps / (r["ms"] / 1e3)
     ngroups_out = r["res"][0]

@@ -119,13 +119,28 @@ __global__ void k_table_init(GroupTable gt, AggPlan ap, int keep_overflow) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { *gt.n_groups = 0; if (!keep_overflow) *gt.overflow = 0; }
 }
 
+// walk the groups a table holds: the occupied list of a GROUP BY table (slots in insertion order), slot 0 of a scalar aggregate
+#define BK_FOR_EACH_GROUP(gt, ap, i)                                                                                   \
+    const uint32_t bk_n_ = (ap).n_keyw == 0 ? 1u : *(gt).n_groups;                                                    \
+    for (uint32_t bk_j_ = blockIdx.x * blockDim.x + threadIdx.x, i = 0; bk_j_ < bk_n_ && ((i = (ap).n_keyw == 0 ? 0u : (gt).n_groups[GT_OCC_OFF + bk_j_]), true); bk_j_ += gridDim.x * blockDim.x)
+
+// re-initialisation of a table whose `n` occupied slots are known (bkgpu_reset after a finished run): touches n slots, not the capacity
+__global__ void k_table_clear(GroupTable gt, AggPlan ap, uint32_t n) {
+    const uint32_t cap = gt.cap_mask + 1;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = gt.n_groups[GT_OCC_OFF + j];
+        gt.state[i] = 0u;
+        for (int l = 0; l < ap.n_lanes; l++) gt.lanes[(size_t)l * cap + i] = lane_identity(ap.lane_op[l]);
+    }
+}
+__global__ void k_table_clear_done(GroupTable gt) { *gt.n_groups = 0; *gt.overflow = 0; }
+
 // Partial state layout (fixed capacity `pcap` groups): [u64 n_groups][keys n_keyw x pcap][lanes n_lanes x pcap]
 __global__ void k_partial_export(GroupTable gt, AggPlan ap, uint64_t* dst, uint32_t pcap, uint32_t* cursor) {
     const uint32_t cap = gt.cap_mask + 1;
     uint64_t* dkeys = dst + 1;
     uint64_t* dlanes = dkeys + (size_t)ap.n_keyw * pcap;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        if (gt.state[i] != 2u) continue;
+    BK_FOR_EACH_GROUP(gt, ap, i) {
         if (ap.n_keyw == 0 && gt.lanes[i] == 0) continue;  // no row reached the single group
         const uint32_t pos = atomicAdd(cursor, 1u);
         if (pos >= pcap) { atomicExch(gt.overflow, 1u); continue; }
@@ -141,8 +156,7 @@ __global__ void k_partial_count(uint64_t* dst, const uint32_t* cursor, uint32_t 
 __global__ void k_partial_export_rows(GroupTable gt, AggPlan ap, uint64_t* dst, uint32_t bound) {
     const uint32_t cap = gt.cap_mask + 1;
     const int rw = ap.n_keyw + ap.n_lanes;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        if (gt.state[i] != 2u) continue;
+    BK_FOR_EACH_GROUP(gt, ap, i) {
         if (ap.n_keyw == 0 && gt.lanes[i] == 0) continue;  // no row reached the single group
         const uint32_t pos = atomicAdd((uint32_t*)dst, 1u);
         if (pos >= bound) continue;                         // (the merge sees count > bound and asks for a second, larger exchange)
@@ -181,8 +195,7 @@ __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) { asm vo
 __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) { uint64_t v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __global__ void k_peer_export(GroupTable gt, AggPlan ap, uint64_t* const* peers, int nranks, int rank, size_t seg_words, size_t parity_off, uint32_t pcap, uint32_t* cursor) {
     const uint32_t cap = gt.cap_mask + 1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        if (gt.state[i] != 2u) continue;
+    BK_FOR_EACH_GROUP(gt, ap, i) {
         if (ap.n_keyw == 0 && gt.lanes[i] == 0) continue;
         const uint32_t pos = atomicAdd(cursor, 1u);
         if (pos >= pcap) { atomicExch(gt.overflow, 1u); continue; }
@@ -236,8 +249,7 @@ __device__ __forceinline__ uint32_t owner_of(const uint64_t* key, int kw, int nr
 }
 __global__ void k_partial_export_parts(GroupTable gt, AggPlan ap, uint64_t* dst, size_t words_per_seg, uint32_t pcap, uint32_t* cursors, int nranks) {
     const uint32_t cap = gt.cap_mask + 1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        if (gt.state[i] != 2u) continue;
+    BK_FOR_EACH_GROUP(gt, ap, i) {
         uint64_t key[MAX_KEYW];
         for (int w = 0; w < ap.n_keyw; w++) key[w] = gt.keys[(size_t)w * cap + i];
         const uint32_t o = owner_of(key, ap.n_keyw, nranks);
@@ -274,8 +286,7 @@ __global__ void k_partial_merge(GroupTable gt, AggPlan ap, const uint64_t* src, 
 // for AVG, the intermediate {sum, count} pair (AggFnCall::finalize, agg_fn_call.cpp:927-990).
 __global__ void k_extract(GroupTable gt, AggPlan ap, uint64_t* outv, uint8_t* outn, uint32_t out_cap, uint32_t* cursor, int emit_default) {
     const uint32_t cap = gt.cap_mask + 1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        if (gt.state[i] != 2u) continue;
+    BK_FOR_EACH_GROUP(gt, ap, i) {
         const uint64_t nrows = gt.lanes[i];
         if (ap.n_keyw == 0 && nrows == 0 && !emit_default) continue;
         const uint32_t pos = atomicAdd(cursor, 1u);
@@ -539,9 +550,14 @@ cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStrea
     k_table_init<<<grid, 256, 0, s>>>(gt, ap, keep_overflow);
     return cudaGetLastError();
 }
+cudaError_t launch_table_clear(const GroupTable& gt, const AggPlan& ap, uint32_t n_occupied, cudaStream_t s) {
+    if (n_occupied) { int grid = (int)((n_occupied + 255) / 256); if (grid > 1184) grid = 1184; k_table_clear<<<grid, 256, 0, s>>>(gt, ap, n_occupied); }
+    k_table_clear_done<<<1, 1, 0, s>>>(gt);
+    return cudaGetLastError();
+}
 cudaError_t launch_partial_export_rows(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, uint32_t bound, cudaStream_t s) {
     const uint32_t cap = gt.cap_mask + 1;
-    int grid = (int)((cap + 255) / 256); if (grid > 1184) grid = 1184;
+    int grid = (int)((cap + 255) / 256); if (grid > 148) grid = 148;   // (the kernel walks the occupied list, grid-stride)
     cudaError_t e = cudaMemsetAsync(dst, 0, 8, s);
     if (e != cudaSuccess) return e;
     k_partial_export_rows<<<grid, 256, 0, s>>>(gt, ap, dst, bound);
@@ -579,7 +595,7 @@ cudaError_t launch_partial_merge(const GroupTable& gt, const AggPlan& ap, const 
 }
 cudaError_t launch_extract(const GroupTable& gt, const AggPlan& ap, uint64_t* outv, uint8_t* outn, uint32_t out_cap, uint32_t* cursor, int emit_default, cudaStream_t s) {
     const uint32_t cap = gt.cap_mask + 1;
-    int grid = (int)((cap + 255) / 256); if (grid > 1184) grid = 1184;
+    int grid = (int)((cap + 255) / 256); if (grid > 148) grid = 148;   // (the kernel walks the occupied list, grid-stride)
     cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
     k_extract<<<grid, 256, 0, s>>>(gt, ap, outv, outn, out_cap, cursor, emit_default);

@@ -4,6 +4,8 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 #include <string.h>
 #include <algorithm>
 #include <atomic>
@@ -38,6 +40,12 @@ struct HostCol {  // one materialised result column (host memory owned by the pl
 
 struct EventPair { cudaEvent_t a, b; int64_t bytes; };
 
+// BKGPU_TRACE=1: wall-clock time the HOST spends in each phase of a request (summed per plan, printed by bkgpu_close)
+struct HostClock {
+    double reset = 0, push = 0, collective = 0, extract_wait = 0, finish = 0; int64_t n = 0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6; }
+};
+
 }  // namespace
 
 struct bkgpu_plan {
@@ -68,8 +76,10 @@ struct bkgpu_plan {
     uint64_t* d_partial = nullptr;  // export buffer (this rank)
     uint64_t* d_gather = nullptr;   // nranks export buffers
     size_t d_partial_words = 0, d_gather_words = 0;
+    HostClock hclk; bool trace = getenv("BKGPU_TRACE") != nullptr;
     std::vector<uint8_t*> bounce[2]; size_t bounce_rows = 0; cudaEvent_t bounce_done[2] = {nullptr, nullptr}; bool bounce_busy[2] = {false, false};
     int no_bounce = 0;            // 1 = pageable host input goes straight to cudaMemcpyAsync (A/B of the bounce path)
+    int64_t finish_groups = -1;   // groups in the table when the last finish read the result back (-1 = unknown: full re-initialisation)
     uint32_t merge_bound = 0, merge_bound_used = 0;   // groups per rank the all-gather is sized for (learned from earlier runs)
     uint32_t* d_part_cursors = nullptr; int repartition = 0;   // hash repartition of the groups across ranks (option "repartition")
     // merge over NVLink peer memory (option "peer_merge"): this rank's buffer, the peers' mappings of theirs, step counter
@@ -251,7 +261,7 @@ static int alloc_group_table(bkgpu_plan* p) {
     if ((rc = dev_alloc(p, (void**)&gt.state, cap * 4))) return rc;
     if ((rc = dev_alloc(p, (void**)&gt.keys, cap * 8 * (size_t)std::max(ap.n_keyw, 1)))) return rc;
     if ((rc = dev_alloc(p, (void**)&gt.lanes, cap * 8 * (size_t)ap.n_lanes))) return rc;
-    if ((rc = dev_alloc(p, (void**)&gt.n_groups, 8))) return rc;
+    if ((rc = dev_alloc(p, (void**)&gt.n_groups, 4 * ((size_t)GT_OCC_OFF + cap)))) return rc;   // counter, overflow flag, occupied list
     gt.overflow = gt.n_groups + 1;
     if ((rc = dev_alloc(p, (void**)&p->d_rows_passed, 8))) return rc;
     if ((rc = dev_alloc(p, (void**)&p->d_cursor, 8))) return rc;
@@ -554,7 +564,7 @@ class CopyPool {
     int next_ = 0, total_ = 0, done_ = 0; uint64_t gen_ = 0; bool stop_ = false;
 };
 CopyPool& copy_pool() {
-    static CopyPool pool(std::max(1, std::min(15, (int)std::thread::hardware_concurrency() - 1)));
+    static CopyPool pool(std::max(1, std::min(23, (int)std::thread::hardware_concurrency() / 2 - 1)));
     return pool;
 }
 bool is_pageable(const void* p) {
@@ -580,10 +590,13 @@ static int feed(bkgpu_plan* p, const std::vector<ColRef>& want, const bkgpu_colu
         }
         return fn(p, dc.data(), nrows, 0, vec_ok);
     }
-    const int64_t chunk = std::min<int64_t>(p->chunk_rows, std::max<int64_t>((nrows + 7) & ~7ll, 8));
-    if ((rc = ensure_stage(p, want, (size_t)chunk))) return rc;
     bool pageable = false;
     for (size_t i = 0; i < want.size() && !p->no_bounce; i++) pageable = pageable || is_pageable(bound[i]->values);
+    // (pageable input adds a CPU copy stage of about the link's speed in front of the H2D copy: smaller chunks keep the fill / drain
+    //  of that three-stage pipeline at ~2 % of the batch instead of ~8 %)
+    const int64_t chunk_cap = pageable ? std::min<int64_t>(p->chunk_rows, (int64_t)2 << 20) : p->chunk_rows;
+    const int64_t chunk = std::min<int64_t>(chunk_cap, std::max<int64_t>((nrows + 7) & ~7ll, 8));
+    if ((rc = ensure_stage(p, want, (size_t)chunk))) return rc;
     if (pageable && (rc = ensure_bounce(p, want, (size_t)chunk))) return rc;
     int buf = 0;
     cudaEvent_t last_ready = nullptr;
@@ -595,7 +608,7 @@ static int feed(bkgpu_plan* p, const std::vector<ColRef>& want, const bkgpu_colu
             if (p->bounce_busy[buf]) { CK(p, cudaEventSynchronize(p->bounce_done[buf])); p->bounce_busy[buf] = false; }
             struct Piece { uint8_t* dst; const uint8_t* src; size_t bytes; };
             std::vector<Piece> pieces;
-            const size_t slice = (size_t)4 << 20;
+            const size_t slice = (size_t)1 << 20;
             for (size_t i = 0; i < want.size(); i++) {
                 const size_t eb = (size_t)storage_bytes(prim_storage(want[i].prim)), bytes = (size_t)n * eb;
                 const uint8_t* src = (const uint8_t*)bound[i]->values + (size_t)off * eb;
@@ -891,7 +904,14 @@ static int join_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t
     return feed(p, p->probe_want, cols, ncols, nrows, on_device, join_probe_batch);
 }
 
+static int bkgpu_push_impl(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device);
 extern "C" int bkgpu_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device) {
+    const double t0 = HostClock::now();
+    const int rc = bkgpu_push_impl(p, cols, ncols, nrows, on_device);
+    if (p) p->hclk.push += HostClock::now() - t0;
+    return rc;
+}
+static int bkgpu_push_impl(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device) {
     if (!p) return thread_fail(BKGPU_EINVAL, "bkgpu_push: NULL plan");
     if (p->state != S_OPEN) return p->fail(BKGPU_ESTATE, "bkgpu_push needs an open, unfinished plan");
     if (p->cancelled.load()) return p->fail(BKGPU_ECANCELLED, "cancelled");
@@ -1050,7 +1070,7 @@ static int agg_finish(bkgpu_plan* p) {
     for (int k = 0; k < ap.n_agg; k++) if (!ap.agg[k].hidden) n_img += ap.agg[k].kind == AG_AVG ? 3 : 1;
     int rc;
   for (int mtry = 0; mtry < 3; mtry++) {   // (a second trip only when some rank held more groups than the exchange was sized for)
-    if (multi && (rc = agg_collective(p, &rows_mode))) return rc;
+    { const double t0 = HostClock::now(); if (multi && (rc = agg_collective(p, &rows_mode))) return rc; p->hclk.collective += HostClock::now() - t0; }
     uint32_t n_out = 0, out_cap = 0, merge_max = 0;
     uint64_t* hv = nullptr; uint8_t* hn = nullptr;
     bool redo_merge = false;
@@ -1085,7 +1105,7 @@ static int agg_finish(bkgpu_plan* p) {
         if (rows_mode) CK(p, cudaMemcpyAsync(hc3 ? hc3 + 3 : &merge_max, p->d_cursor + 1, 4, cudaMemcpyDeviceToHost, p->stream));
         CK(p, cudaMemcpyAsync(hv, p->d_outv, n_words * 8, cudaMemcpyDeviceToHost, p->stream));
         CK(p, cudaMemcpyAsync(hn, p->d_outn, n_words, cudaMemcpyDeviceToHost, p->stream));
-        CK(p, cudaStreamSynchronize(p->stream));
+        { const double t0 = HostClock::now(); CK(p, cudaStreamSynchronize(p->stream)); p->hclk.extract_wait += HostClock::now() - t0; }
         if (hc3) { host_counts[0] = hc3[0]; host_counts[1] = hc3[1]; n_out = hc3[2]; }
         if (p->peer_ready && p->h_pinned && p->h_pinned[12]) return p->fail(BKGPU_ENCCL, "peer merge: a rank did not publish its partial state within the time limit");
         if (rows_mode) {
@@ -1103,6 +1123,7 @@ static int agg_finish(bkgpu_plan* p) {
         if (host_counts[1]) return p->fail(BKGPU_ETOOBIG, "group table overflow (capacity 2^%d slots / partial_capacity %lld): raise group_capacity_log2",
                                            (int)gt.cap_log2, (long long)p->partial_cap);
         if (host_counts[0] > p->known_groups) p->known_groups = host_counts[0];
+        p->finish_groups = host_counts[0];
         if (n_out <= out_cap) break;   // everything fitted
     }
     if (!redo_merge) { finish_hv = hv; finish_hn = hn; finish_n_out = n_out; finish_out_cap = out_cap; break; }
@@ -1159,7 +1180,14 @@ static void resolve_timers(bkgpu_plan* p) {
     p->timed_coll.clear();
 }
 
+static int bkgpu_finish_impl(bkgpu_plan* p);
 extern "C" int bkgpu_finish(bkgpu_plan* p) {
+    const double t0 = HostClock::now();
+    const int rc = bkgpu_finish_impl(p);
+    if (p) { p->hclk.finish += HostClock::now() - t0; p->hclk.n++; }
+    return rc;
+}
+static int bkgpu_finish_impl(bkgpu_plan* p) {
     if (!p) return thread_fail(BKGPU_EINVAL, "bkgpu_finish: NULL plan");
     if (p->state != S_OPEN) return p->fail(BKGPU_ESTATE, "bkgpu_finish needs an open plan");
     if (p->cancelled.load()) return p->fail(BKGPU_ECANCELLED, "cancelled");
@@ -1226,14 +1254,25 @@ extern "C" int bkgpu_get_next(bkgpu_plan* p, bkgpu_column* out_cols, int* ncols,
 
 // Re-arm an executed plan for the next request of the same fragment (prepared-statement reuse): tables
 // are cleared, allocations, streams and staging buffers are kept.
+static int bkgpu_reset_impl(bkgpu_plan* p);
 extern "C" int bkgpu_reset(bkgpu_plan* p) {
+    const double t0 = HostClock::now();
+    const int rc = bkgpu_reset_impl(p);
+    if (p) p->hclk.reset += HostClock::now() - t0;
+    return rc;
+}
+static int bkgpu_reset_impl(bkgpu_plan* p) {
     if (!p) return thread_fail(BKGPU_EINVAL, "bkgpu_reset: NULL plan");
     if (p->state != S_OPEN && p->state != S_FINISHED) return p->fail(BKGPU_ESTATE, "bkgpu_reset needs an opened plan");
     CK(p, cudaSetDevice(p->device));
     p->cancelled.store(0);
     if (p->c.kind == PK_AGG || p->c.kind == PK_JOIN_AGG) {
         CK(p, cudaMemsetAsync(p->d_rows_passed, 0, 8, p->stream));
-        CK(p, launch_table_init(p->gt, p->c.ap, p->stream));
+        // a finished run knows how many groups its table holds (the count came back with the result): clear those slots through the
+        // occupied list instead of re-initialising the whole capacity (2^20 slots = 44 MB by default)
+        if (p->state == S_FINISHED && p->finish_groups >= 0 && p->c.ap.n_keyw > 0) CK(p, launch_table_clear(p->gt, p->c.ap, (uint32_t)p->finish_groups, p->stream));
+        else CK(p, launch_table_init(p->gt, p->c.ap, p->stream));
+        p->finish_groups = -1;
         p->stats.kernel_launches++;
     }
     p->jb_rows = 0; p->jt_built = false; p->jt_generic = false; std::fill(p->jb_has_null.begin(), p->jb_has_null.end(), false);
@@ -1249,6 +1288,11 @@ extern "C" void bkgpu_cancel(bkgpu_plan* p) { if (p) p->cancelled.store(1); }
 
 extern "C" void bkgpu_close(bkgpu_plan* p) {
     if (!p) return;
+    if (p->trace && p->hclk.n) {
+        const double n = (double)p->hclk.n;
+        fprintf(stderr, "[bkgpu trace dev %d] %lld requests: host ms per request  reset %.4f  push %.4f  finish %.4f (collective enqueue %.4f, wait for the result %.4f)\n",
+                p->device, (long long)p->hclk.n, p->hclk.reset / n, p->hclk.push / n, p->hclk.finish / n, p->hclk.collective / n, p->hclk.extract_wait / n);
+    }
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);

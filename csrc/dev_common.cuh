@@ -237,7 +237,7 @@ __device__ __forceinline__ int table_upsert(uint32_t* state, uint64_t* keys, uin
             if (old == 0u) {
                 for (int i = 0; i < kw; i++) keys[(size_t)i * cap + slot] = key[i];
                 TableMem<SHARED>::publish(state + slot);
-                if (n_groups) atomicAdd(n_groups, 1u);
+                if (n_groups) n_groups[GT_OCC_OFF + atomicAdd(n_groups, 1u)] = slot;   // (global table only: the occupied list)
                 return (int)slot;
             }
             s = old;

@@ -152,8 +152,10 @@ struct GroupTable {
     uint64_t* lanes;     // [n_lanes][cap]
     uint32_t cap_mask;   // cap - 1 (cap is a power of two)
     uint32_t cap_log2;
-    uint32_t* n_groups;  // number of occupied slots
-    uint32_t* overflow;  // set when an insert could not find a free slot
+    uint32_t* n_groups;  // number of occupied slots; n_groups[GT_OCC_OFF + i] = slot of the i-th inserted group (the "occupied list":
+                         // re-initialisation, export and result extraction walk the groups that exist, not the table's capacity)
+    uint32_t* overflow;  // = n_groups + 1: set when an insert could not find a free slot
 };
+constexpr int GT_OCC_OFF = 4;
 
 }  // namespace bk
