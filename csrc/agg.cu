@@ -116,7 +116,8 @@ __global__ void k_table_init(GroupTable gt, AggPlan ap, int keep_overflow) {
     }
     // (re-initialisation between the export of a partial state and the merge keeps the overflow flag: a table that overflowed
     //  while rows were pushed, or an export that met more groups than the exchange format holds, must still fail the plan)
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *gt.n_groups = 0; if (!keep_overflow) *gt.overflow = 0; }
+    if (blockIdx.x == 0 && threadIdx.x < GT_OCC_OFF && !keep_overflow) gt.n_groups[threadIdx.x] = 0;   // fresh request: every counter of the block
+    if (blockIdx.x == 0 && threadIdx.x == 0 && keep_overflow) *gt.n_groups = 0;                          // mid-request re-initialisation (multi-GPU merge): the group count only
 }
 
 // walk the groups a table holds: the occupied list of a GROUP BY table (slots in insertion order), slot 0 of a scalar aggregate
@@ -132,8 +133,9 @@ __global__ void k_table_clear(GroupTable gt, AggPlan ap, uint32_t n) {
         gt.state[i] = 0u;
         for (int l = 0; l < ap.n_lanes; l++) gt.lanes[(size_t)l * cap + i] = lane_identity(ap.lane_op[l]);
     }
+    // (the counters can go in the same launch: nobody here reads them — `n` came by value, the occupied list sits behind them)
+    if (blockIdx.x == 0 && threadIdx.x < GT_OCC_OFF) gt.n_groups[threadIdx.x] = 0;
 }
-__global__ void k_table_clear_done(GroupTable gt) { *gt.n_groups = 0; *gt.overflow = 0; }
 
 // Partial state layout (fixed capacity `pcap` groups): [u64 n_groups][keys n_keyw x pcap][lanes n_lanes x pcap]
 __global__ void k_partial_export(GroupTable gt, AggPlan ap, uint64_t* dst, uint32_t pcap, uint32_t* cursor) {
@@ -356,6 +358,10 @@ cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t
     const bool grouped = a.plan.n_keyw > 0;
     const size_t smem = grouped ? agg_smem_bytes(a.smem_keyw, a.n_smem_lanes, a.smem_cap_log2) : 0;
     if (a.nrows <= 0) return cudaSuccess;
+    if (direct && !grouped && a.scalar_tma) {
+        cudaError_t e = cudaSuccess;
+        if (launch_count_where_tma(a, sm_count, s, &e)) { *kernel_name = "k_count_where_tma"; return e; }
+    }
     if (direct) {
         const size_t dsmem = grouped ? direct_smem_bytes(a.smem_keyw, a.n_smem_lanes, a.smem_cap_log2, a.direct.n_vals) : 0;
         *kernel_name = grouped ? "k_agg_group_direct" : "k_agg_scalar_direct";
@@ -551,8 +557,8 @@ cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStrea
     return cudaGetLastError();
 }
 cudaError_t launch_table_clear(const GroupTable& gt, const AggPlan& ap, uint32_t n_occupied, cudaStream_t s) {
-    if (n_occupied) { int grid = (int)((n_occupied + 255) / 256); if (grid > 1184) grid = 1184; k_table_clear<<<grid, 256, 0, s>>>(gt, ap, n_occupied); }
-    k_table_clear_done<<<1, 1, 0, s>>>(gt);
+    int grid = (int)((n_occupied + 255) / 256); if (grid > 1184) grid = 1184; if (grid < 1) grid = 1;
+    k_table_clear<<<grid, 256, 0, s>>>(gt, ap, n_occupied);
     return cudaGetLastError();
 }
 cudaError_t launch_partial_export_rows(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, uint32_t bound, cudaStream_t s) {

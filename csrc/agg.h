@@ -52,6 +52,7 @@ struct AggArgs {
     int32_t lean_nulls;      // lean kernel: some predicate / value column of this batch carries a validity bitmap
     int32_t lean_mm;         // lean kernel: some value column feeds MIN / MAX lanes or more than one lane
     // warp-private kernel (agg_wp.cuh): chosen by the host for the plainest lean batches
+    int32_t scalar_tma;      // 1 = try the TMA-staged scalar kernel (scalar_tma.cu)
     int32_t wp;              // 1 = launch k_agg_group_wp
     int32_t wp_gcap;         // dense group ids per warp table (multiple of 32)
     int32_t wp_kt_log2;      // log2 words of the CTA's key -> id table
@@ -65,6 +66,8 @@ inline size_t wp_warp_bytes(int na, uint32_t gcap) { return ((size_t)gcap * (8u 
 inline size_t wp_smem_bytes(int na, uint32_t gcap, int kt_log2, int warps) { return (kt_log2 < 0 ? 0 : ((size_t)8 << kt_log2)) + 16 + wp_warp_bytes(na, gcap) * (size_t)warps; }
 
 size_t agg_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2);
+// scalar_tma.cu: TMA-staged COUNT(*) WHERE int32 <cmp> c (experiment, option "scalar_tma"); false = not this kernel's shape
+bool launch_count_where_tma(const AggArgs& a, int sm_count, cudaStream_t s, cudaError_t* err);
 cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t s, const char** kernel_name);
 cudaError_t launch_direct_np0(const AggArgs& a, int na, int sm_count, size_t smem, cudaStream_t s, bool grouped);
 cudaError_t launch_direct_np1(const AggArgs& a, int na, int sm_count, size_t smem, cudaStream_t s, bool grouped);

@@ -78,7 +78,9 @@ struct bkgpu_plan {
     size_t d_partial_words = 0, d_gather_words = 0;
     HostClock hclk; bool trace = getenv("BKGPU_TRACE") != nullptr;
     std::vector<uint8_t*> bounce[2]; size_t bounce_rows = 0; cudaEvent_t bounce_done[2] = {nullptr, nullptr}; bool bounce_busy[2] = {false, false};
+    int scalar_tma = 0;           // 1 = COUNT(*) WHERE int32 <cmp> c runs the TMA-staged kernel (scalar_tma.cu) — A/B experiment
     int no_bounce = 0;            // 1 = pageable host input goes straight to cudaMemcpyAsync (A/B of the bounce path)
+    uint64_t rows_passed_host = 0;
     int64_t finish_groups = -1;   // groups in the table when the last finish read the result back (-1 = unknown: full re-initialisation)
     uint32_t merge_bound = 0, merge_bound_used = 0;   // groups per rank the all-gather is sized for (learned from earlier runs)
     uint32_t* d_part_cursors = nullptr; int repartition = 0;   // hash repartition of the groups across ranks (option "repartition")
@@ -243,6 +245,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "no_lean_mm") p->no_lean_mm = v != 0;
     else if (k == "use_wp") p->use_wp = v != 0;
     else if (k == "no_bounce") p->no_bounce = v != 0;
+    else if (k == "scalar_tma") p->scalar_tma = v != 0;
     else if (k == "wp_warps") { if (v != 0 && v != 8 && v != 12 && v != 16) return p->fail(BKGPU_EINVAL, "wp_warps: 0, 8, 12 or 16"); p->wp_warps = (int)v; }
     else if (k == "wp_kt_log2") { if (v < 0 || v > 14) return p->fail(BKGPU_EINVAL, "wp_kt_log2 out of range"); p->wp_kt_log2 = (int)v; }
     else if (k == "output_on_device") p->output_on_device = v != 0;
@@ -263,9 +266,9 @@ static int alloc_group_table(bkgpu_plan* p) {
     if ((rc = dev_alloc(p, (void**)&gt.lanes, cap * 8 * (size_t)ap.n_lanes))) return rc;
     if ((rc = dev_alloc(p, (void**)&gt.n_groups, 4 * ((size_t)GT_OCC_OFF + cap)))) return rc;   // counter, overflow flag, occupied list
     gt.overflow = gt.n_groups + 1;
-    if ((rc = dev_alloc(p, (void**)&p->d_rows_passed, 8))) return rc;
-    if ((rc = dev_alloc(p, (void**)&p->d_cursor, 8))) return rc;
-    CK(p, cudaMemsetAsync(p->d_rows_passed, 0, 8, p->stream));
+    p->d_cursor = gt.n_groups + 2;                       // [2] result cursor [3] merge info
+    p->d_rows_passed = (uint64_t*)(gt.n_groups + 4);     // [4..5] rows that passed the filter
+    CK(p, cudaMemsetAsync(gt.n_groups, 0, 4 * GT_OCC_OFF, p->stream));
     CK(p, launch_table_init(gt, ap, p->stream));
     p->stats.kernel_launches++;
     return BKGPU_OK;
@@ -419,6 +422,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
     if (jp) { if (!a.lean) return 1; a.jp = *jp; }
     // warp-private tables (agg_wp.cuh): the plainest lean batches whose groups fit one table per warp.  The capacity follows the
     // cardinality learned from earlier batches / runs of this plan; an unknown cardinality starts with the largest table.
+    a.scalar_tma = p->scalar_tma;
     a.wp = 0;
     if (a.lean && !a.lean_nulls && !a.lean_mm && p->use_wp && c.direct.n_vals <= 2) {
         const int np = c.direct.n_terms, na = c.direct.n_vals;
@@ -1043,7 +1047,7 @@ static int agg_collective(bkgpu_plan* p, bool* rows_mode) {
         CK(p, launch_partial_merge(gt, ap, p->peer_local + (size_t)(seq & 1) * (size_t)p->nranks * words, words, pcap, p->nranks, p->stream));
         timer_end(p, ep);
         p->stats.kernel_launches += 5;
-        if (p->h_pinned) CK(p, cudaMemcpyAsync(p->h_pinned + 12, p->d_peer_timeout, 4, cudaMemcpyDeviceToHost, p->stream));   // checked after the result's synchronisation
+        if (p->h_pinned) CK(p, cudaMemcpyAsync(p->h_pinned + 6, p->d_peer_timeout, 4, cudaMemcpyDeviceToHost, p->stream));   // checked after the result's synchronisation
         return BKGPU_OK;
     }
     // hash repartition: every rank keeps only the groups it owns — an all-to-all of per-owner segments instead of the
@@ -1080,10 +1084,10 @@ static int agg_finish(bkgpu_plan* p) {
         uint32_t want = std::max<uint32_t>(std::max<uint32_t>(p->known_groups, 1), attempt ? std::max<uint32_t>(host_counts[0], 1) : 1);
         if (ap.n_keyw == 0) want = 1;
         if (p->out_cap_alloc < want) {
-            dev_free(p, p->d_outv); dev_free(p, p->d_outn); p->d_outv = nullptr; p->d_outn = nullptr;
+            dev_free(p, p->d_outv); p->d_outv = nullptr; p->d_outn = nullptr;
             size_t cap = std::max<size_t>(want, 2048);
-            if ((rc = dev_alloc(p, (void**)&p->d_outv, cap * 8 * (size_t)n_img))) return rc;
-            if ((rc = dev_alloc(p, (void**)&p->d_outn, cap * (size_t)n_img))) return rc;
+            if ((rc = dev_alloc(p, (void**)&p->d_outv, cap * 9 * (size_t)n_img + 64))) return rc;   // values, then the null bytes: ONE copy brings both back
+            p->d_outn = (uint8_t*)(p->d_outv + cap * (size_t)n_img);
             p->out_cap_alloc = cap;
         }
         out_cap = (uint32_t)p->out_cap_alloc;
@@ -1092,24 +1096,27 @@ static int agg_finish(bkgpu_plan* p) {
         const size_t n_words = (size_t)out_cap * (size_t)n_img;
         if (p->h_out_cap < n_words) {   // pinned: the four copies below are truly asynchronous and land in one synchronisation
             if (p->h_outv) cudaFreeHost(p->h_outv);
-            if (p->h_outn) cudaFreeHost(p->h_outn);
             p->h_outv = nullptr; p->h_outn = nullptr; p->h_out_cap = 0;
-            CK(p, cudaHostAlloc((void**)&p->h_outv, n_words * 8, cudaHostAllocDefault));
-            CK(p, cudaHostAlloc((void**)&p->h_outn, n_words, cudaHostAllocDefault));
+            CK(p, cudaHostAlloc((void**)&p->h_outv, n_words * 9 + 64, cudaHostAllocDefault));
             p->h_out_cap = n_words;
         }
-        hv = p->h_outv; hn = p->h_outn;
-        uint32_t* hc3 = p->h_pinned ? p->h_pinned + 8 : nullptr;   // [8] groups [9] overflow [10] rows extracted
-        CK(p, cudaMemcpyAsync(hc3 ? hc3 : host_counts, gt.n_groups, 8, cudaMemcpyDeviceToHost, p->stream));
-        CK(p, cudaMemcpyAsync(hc3 ? hc3 + 2 : &n_out, p->d_cursor, 4, cudaMemcpyDeviceToHost, p->stream));
-        if (rows_mode) CK(p, cudaMemcpyAsync(hc3 ? hc3 + 3 : &merge_max, p->d_cursor + 1, 4, cudaMemcpyDeviceToHost, p->stream));
-        CK(p, cudaMemcpyAsync(hv, p->d_outv, n_words * 8, cudaMemcpyDeviceToHost, p->stream));
-        CK(p, cudaMemcpyAsync(hn, p->d_outn, n_words, cudaMemcpyDeviceToHost, p->stream));
+        hv = p->h_outv; hn = p->h_outn = (uint8_t*)(p->h_outv + n_words);
+        // two copies, one synchronisation: the 32-byte counter block (groups, overflow, rows extracted, merge info, rows passed) and
+        // the extracted rows (values + null bytes, contiguous on both sides)
+        uint32_t local_ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t* hc3 = p->h_pinned ? p->h_pinned + 8 : local_ctr;   // [8] groups [9] overflow [10] rows extracted [11] merge info [12..13] rows passed
+        CK(p, cudaMemcpyAsync(hc3, gt.n_groups, 32, cudaMemcpyDeviceToHost, p->stream));
+        if ((const uint8_t*)p->d_outn == (const uint8_t*)(p->d_outv + n_words)) CK(p, cudaMemcpyAsync(hv, p->d_outv, n_words * 9, cudaMemcpyDeviceToHost, p->stream));
+        else {
+            CK(p, cudaMemcpyAsync(hv, p->d_outv, n_words * 8, cudaMemcpyDeviceToHost, p->stream));
+            CK(p, cudaMemcpyAsync(hn, p->d_outn, n_words, cudaMemcpyDeviceToHost, p->stream));
+        }
         { const double t0 = HostClock::now(); CK(p, cudaStreamSynchronize(p->stream)); p->hclk.extract_wait += HostClock::now() - t0; }
-        if (hc3) { host_counts[0] = hc3[0]; host_counts[1] = hc3[1]; n_out = hc3[2]; }
-        if (p->peer_ready && p->h_pinned && p->h_pinned[12]) return p->fail(BKGPU_ENCCL, "peer merge: a rank did not publish its partial state within the time limit");
+        host_counts[0] = hc3[0]; host_counts[1] = hc3[1]; n_out = hc3[2]; merge_max = hc3[3];
+        memcpy(&p->rows_passed_host, hc3 + 4, 8);
+        if (p->peer_ready && p->h_pinned && p->h_pinned[6]) return p->fail(BKGPU_ENCCL, "peer merge: a rank did not publish its partial state within the time limit");
         if (rows_mode) {
-            const uint32_t mx = hc3 ? hc3[3] : merge_max;
+            const uint32_t mx = merge_max;
             if (mx > p->merge_bound_used) {   // nothing was merged (k_partial_merge_rows): exchange again, sized for what the ranks really hold
                 if (mx > eff_pcap(p)) return p->fail(BKGPU_ETOOBIG, "a rank holds %u groups, more than partial_capacity %lld: raise partial_capacity", mx, (long long)p->partial_cap);
                 p->merge_bound = (mx + 63u) & ~63u;
@@ -1197,9 +1204,7 @@ static int bkgpu_finish_impl(bkgpu_plan* p) {
         case PK_AGG: case PK_JOIN_AGG: {
             rc = agg_finish(p);
             if (!rc) {
-                uint64_t passed = 0;
-                CK(p, cudaMemcpy(&passed, p->d_rows_passed, 8, cudaMemcpyDeviceToHost));
-                p->stats.rows_filtered = p->stats.rows_scanned - (int64_t)passed;
+                p->stats.rows_filtered = p->stats.rows_scanned - (int64_t)p->rows_passed_host;   // (came back with the counter block)
             }
         } break;
         case PK_SORT: case PK_FILTER: {
@@ -1267,7 +1272,6 @@ static int bkgpu_reset_impl(bkgpu_plan* p) {
     CK(p, cudaSetDevice(p->device));
     p->cancelled.store(0);
     if (p->c.kind == PK_AGG || p->c.kind == PK_JOIN_AGG) {
-        CK(p, cudaMemsetAsync(p->d_rows_passed, 0, 8, p->stream));
         // a finished run knows how many groups its table holds (the count came back with the result): clear those slots through the
         // occupied list instead of re-initialising the whole capacity (2^20 slots = 44 MB by default)
         if (p->state == S_FINISHED && p->finish_groups >= 0 && p->c.ap.n_keyw > 0) CK(p, launch_table_clear(p->gt, p->c.ap, (uint32_t)p->finish_groups, p->stream));
@@ -1305,7 +1309,6 @@ extern "C" void bkgpu_close(bkgpu_plan* p) {
     for (int i = 0; i < 2; i++) { for (uint8_t* q : p->bounce[i]) if (q) cudaFreeHost(q); if (p->bounce_done[i]) cudaEventDestroy(p->bounce_done[i]); }
     if (p->h_pinned) cudaFreeHost(p->h_pinned);
     if (p->h_outv) cudaFreeHost(p->h_outv);
-    if (p->h_outn) cudaFreeHost(p->h_outn);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;

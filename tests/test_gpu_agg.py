@@ -251,3 +251,19 @@ def test_group_table_overflow_is_an_error():
     with pytest.raises(BkgpuError) as ei:
         execute(_agg_plan([P.slot_ref(0, 1, T.INT32)], aggs, [T.INT64]), cols, options={"group_capacity_log2": 10})
     assert ei.value.code == ETOOBIG
+
+
+@pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 70_001, 1_000_003])
+@pytest.mark.parametrize("op,c", [("lt", 1 << 19), ("le", 0), ("gt", (1 << 31) - 1), ("ge", -(1 << 31)), ("eq", 77), ("ne", 77)])
+def test_count_where_tma_staged_kernel(n, op, c):
+    """the TMA-staged variant of C1's scan (csrc/scalar_tma.cu: cp.async.bulk tiles + mbarrier ring): same counts as the oracle at sizes
+    around the 4096-row tile, every comparison operator"""
+    rng = np.random.default_rng(n % 1000 + len(op))
+    vals = rng.integers(0, 1 << 20, n)
+    vals[rng.integers(0, n, max(1, n // 50))] = 77
+    cols = [make_column(0, 1, T.INT32, vals)]
+    aggs = [P.agg_expr("count_star", 1, 1)]
+    root = P.agg(P.where(P.scan(0), getattr(P, op)(P.slot_ref(0, 1, T.INT32), P.int_lit(c))), 1, [], aggs)
+    pl = P.Plan(P.packet(root), {0: [(1, T.INT32)], 1: P.agg_tuple_slots(aggs, [T.INT64])})
+    _, stats, _ = run_both(pl, cols, keys=[], options={"scalar_tma": 1})
+    assert stats.main_kernel_name.decode() == "k_count_where_tma"
