@@ -78,7 +78,7 @@ struct bkgpu_plan {
     size_t d_partial_words = 0, d_gather_words = 0;
     HostClock hclk; bool trace = getenv("BKGPU_TRACE") != nullptr;
     std::vector<uint8_t*> bounce[2]; size_t bounce_rows = 0; cudaEvent_t bounce_done[2] = {nullptr, nullptr}; bool bounce_busy[2] = {false, false};
-    int scalar_tma = 0;           // 1 = COUNT(*) WHERE int32 <cmp> c runs the TMA-staged kernel (scalar_tma.cu) — A/B experiment
+    int scalar_tma = 1;           // COUNT(*) WHERE int32 <cmp> c runs the TMA-staged kernel (scalar_tma.cu): 0.97 vs 0.78 of HBM (profiles/r02_tma_scalar.md); 0 = the LDG kernel
     int no_bounce = 0;            // 1 = pageable host input goes straight to cudaMemcpyAsync (A/B of the bounce path)
     uint64_t rows_passed_host = 0;
     int64_t finish_groups = -1;   // groups in the table when the last finish read the result back (-1 = unknown: full re-initialisation)

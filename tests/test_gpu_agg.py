@@ -15,7 +15,9 @@ def test_c1_count_where():
     got, stats, want = run_both(queries.c1_count_where(), cols, keys=[])
     assert got[0].to_list() == [int((cols[0].values < (1 << 19)).sum())]
     assert stats.rows_filtered == want.rows_filtered
-    assert stats.main_kernel_name.decode() == "k_agg_scalar_direct"
+    assert stats.main_kernel_name.decode() == "k_count_where_tma"
+    got, stats, _ = run_both(queries.c1_count_where(), cols, keys=[], options={"scalar_tma": 0})
+    assert stats.main_kernel_name.decode() == "k_agg_scalar_direct" and stats.rows_filtered == want.rows_filtered
 
 
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 127, 128, 129, 1000, 65537, 300_003])
