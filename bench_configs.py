@@ -130,6 +130,16 @@ def main():
         ts = [gen(n, s, 5) for s in specs]
         run("C5 ORDER BY int64 LIMIT 1000 (one region of 125M rows)", queries.c5_topk(1000), [(cols_array(specs, ts), 2, n)], n, 8 * n, a.steps, a.warmup)
         del ts
+    if "c5full" in a.configs:   # ORDER BY without LIMIT: the device radix sort (Sorter, src/runtime/sorter.cpp:54-114) — 8-bit passes x 24 B/row
+        n = int(125_000_000 * a.scale)
+        specs = [(0, 1, T.INT64, 3, 1, 0, 0, 1.0), (0, 2, T.INT32, 0, 2, 0, 1 << 30, 1.0)]
+        ts = [gen(n, s, 5) for s in specs]
+        from baikaldb_b200 import plan as P
+        plan = P.Plan(P.sort(P.scan(0), [P.slot_ref(0, 1, T.INT64)], [True], tuple_id=0), {0: [(1, T.INT64), (2, T.INT32)]})
+        run("C5full ORDER BY int64 (no LIMIT), 125M rows: stable LSD radix sort of (key, row id) pairs; main_kernel_ms = the sort on the device, "
+            "the step also gathers the payload and copies 1.5 GB of sorted rows to the host", plan, [(cols_array(specs, ts), 2, n)], n,
+            (8 + 8 * 24) * n, max(1, a.steps // 5), 1)
+        del ts
     if "c3" in a.configs:
         nf, nd = int(100_000_000 * a.scale), int(10_000_000 * a.scale)
         fs = [(0, 1, T.INT32, 0, 1, 0, nd, 1.0), (0, 2, T.DOUBLE, 1, 2, 0, 0, 1.0)]

@@ -460,66 +460,157 @@ __global__ void k_sort_images(RowArgs a, int key_reg, int vclass, int desc, int 
         if (rid) rid[row] = (uint32_t)row;
     }
 }
-// one radix pass over `digit_shift`: warp w of block b owns the contiguous sub-tile [tile0, tile1)
-constexpr int RS_TILE = 2048;  // elements per warp sub-tile
-__global__ void __launch_bounds__(256) k_radix_hist(const uint64_t* key, const uint32_t* perm, uint32_t n, int shift, uint32_t* hist, uint32_t ntiles) {
-    const uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tile >= ntiles) return;
+// ------------------------------------------------------------------------------------------------------------
+// Full ORDER BY (Sorter::sort, src/runtime/sorter.cpp:54-114): stable LSD radix sort of (key image, row id) PAIRS, 8 bits per
+// pass, one read and one write of the pairs per pass ("Onesweep": chained scan with decoupled look-back):
+//   k_rs_hist : ONE pass over the images gives the histograms of all eight digits; a digit whose histogram has a single
+//               non-empty bin is skipped (small-range keys, the NULL-rank image, descending flags ...)
+//   k_rs_pass : a CTA takes the next 4096-pair tile (atomic ticket: tiles start in order, so the look-back never waits for a
+//               tile that has not started), ranks its pairs per digit (warp match + per-warp counters: stable), publishes the
+//               tile's digit counts, looks back over the preceding tiles' published counts for its scatter bases, reorders the
+//               tile through shared memory and writes digit-contiguous (coalesced) runs
+// The previous version gathered key[perm[i]] (a random 8-byte read per element and pass) and scattered 32 elements at a time.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 pairs per CTA tile (48 KB of shared memory for the reorder)
+constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_PREFIX = 2u << 30, RS_VAL_MASK = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(256) k_rs_hist(const uint64_t* key, uint32_t n, uint32_t* hist /* [8][256] */) {
     __shared__ uint32_t h[8][256];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i = lane; i < 256; i += 32) h[w][i] = 0;
-    __syncwarp();
-    const uint32_t t0 = tile * RS_TILE, t1 = min(t0 + RS_TILE, n);
-    for (uint32_t i = t0 + lane; i < t1; i += 32) atomicAdd(&h[w][(key[perm ? perm[i] : i] >> shift) & 0xFF], 1u);
-    __syncwarp();
-    for (int i = lane; i < 256; i += 32) hist[(size_t)i * ntiles + tile] = h[w][i];  // digit-major: a scan over it yields scatter bases
-}
-__global__ void k_scan_u32(uint32_t* data, uint64_t n, uint32_t* block_sums, int phase) {
-    // phase 0: per-block (1024 elements per thread-block chunk of 256 threads x 4) inclusive->exclusive scan, write block sums
-    // phase 1: add scanned block sums
-    const uint64_t base = (uint64_t)blockIdx.x * 1024;
-    if (phase == 1) {
-        const uint32_t add = block_sums[blockIdx.x];
-        for (int k = 0; k < 4; k++) { const uint64_t i = base + threadIdx.x * 4 + k; if (i < n) data[i] += add; }
-        return;
-    }
-    uint32_t v[4]; uint32_t s = 0;
-    for (int k = 0; k < 4; k++) { const uint64_t i = base + threadIdx.x * 4 + k; v[k] = i < n ? data[i] : 0; s += v[k]; }
-    uint32_t x = s;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
-    __shared__ uint32_t ws[8];
-    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&h[0][0])[i] = 0;
     __syncthreads();
-    uint32_t wpre = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) wpre += ws[w];
-    uint32_t run = wpre + x - s;
-    for (int k = 0; k < 4; k++) { const uint64_t i = base + threadIdx.x * 4 + k; if (i < n) data[i] = run; run += v[k]; }
-    if (threadIdx.x == 255) block_sums[blockIdx.x] = run;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint64_t k = key[i];
+#pragma unroll
+        for (int d = 0; d < 8; d++) atomicAdd(&h[d][(k >> (8 * d)) & 0xFF], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) { const uint32_t v = (&h[0][0])[i]; if (v) atomicAdd(hist + i, v); }
 }
-__global__ void __launch_bounds__(256) k_radix_scatter(const uint64_t* key, const uint32_t* perm_in, uint32_t* perm_out, uint32_t n, int shift,
-                                                        const uint32_t* bases, uint32_t ntiles) {
-    const uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tile >= ntiles) return;
-    __shared__ uint32_t cur[8][256];
+// per digit: exclusive scan of its histogram -> global scatter bases; active[d] = more than one non-empty bin
+__global__ void k_rs_bases(const uint32_t* hist, uint32_t* bases, uint32_t* active) {
+    const int d = blockIdx.x;
+    __shared__ uint32_t s[256];
+    const uint32_t v = hist[d * 256 + threadIdx.x];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0, nz = 0;
+        for (int i = 0; i < 256; i++) { const uint32_t c = s[i]; s[i] = run; run += c; nz += c != 0; }
+        active[d] = nz > 1;
+    }
+    __syncthreads();
+    bases[d * 256 + threadIdx.x] = s[threadIdx.x];
+}
+// null BYTES (1 = NULL) of a retained column -> Arrow validity bitmap (bit set = valid)
+__global__ void k_pack_null_bytes(const uint8_t* nb, int64_t n, uint8_t* bitmap) {
+    const int64_t nbytes = (n + 7) / 8;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbytes; b += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        for (int j = 0; j < 8; j++) { const int64_t r = b * 8 + j; if (r < n && !nb[r]) v |= 1u << j; }
+        bitmap[b] = (uint8_t)v;
+    }
+}
+__global__ void k_rs_iota(uint32_t* ids, uint32_t n) { for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ids[i] = i; }
+__global__ void k_rs_gather_u64(const uint64_t* src, const uint32_t* ids, uint64_t* dst, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[ids[i]];
+}
+__global__ void k_rs_gather_bytes(const uint8_t* src, const uint32_t* ids, uint8_t* dst, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[ids[i]];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_pass(const uint64_t* key_in, const uint32_t* id_in, uint64_t* key_out, uint32_t* id_out, uint32_t n, int shift,
+                                                        const uint32_t* global_base /* [256] of this digit */, uint32_t* status /* [ntiles][256], zeroed */,
+                                                        uint32_t* ticket) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint64_t* s_key = (uint64_t*)rs_smem;                        // [RS_TILE]
+    uint32_t* s_id = (uint32_t*)(s_key + RS_TILE);               // [RS_TILE]
+    uint32_t* wcnt = s_id + RS_TILE;                             // [8][256] per-warp digit counters -> per-warp offsets
+    uint32_t* dstart = wcnt + 8 * 256;                           // [256] start of the digit inside the reordered tile
+    uint32_t* tbase = dstart + 256;                              // [256] global address of the tile's first pair of the digit
+    __shared__ uint32_t s_tile;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i = lane; i < 256; i += 32) cur[w][i] = bases[(size_t)i * ntiles + tile];
-    __syncwarp();
-    const uint32_t t0 = tile * RS_TILE, t1 = min(t0 + RS_TILE, n);
-    for (uint32_t b = t0; b < t1; b += 32) {   // in order: stability comes from processing the sub-tile front to back
-        const uint32_t i = b + lane;
-        const bool live = i < t1;
-        const uint32_t src = live ? (perm_in ? perm_in[i] : i) : 0;
-        const uint32_t d = live ? (uint32_t)((key[src] >> shift) & 0xFF) : 0xFFFFFFFFu;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < 8 * 256; i += RS_THREADS) wcnt[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t t0 = tile * RS_TILE;
+    const uint32_t tile_n = min((uint32_t)RS_TILE, n - t0);
+    // ---- load: warp w owns the contiguous chunk [t0 + w * 512, + 512), 16 rounds of 32 consecutive pairs ----
+    uint64_t k[RS_ITEMS]; uint32_t id[RS_ITEMS]; uint32_t rank[RS_ITEMS];
+    const uint32_t c0 = w * (RS_ITEMS * 32);
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t li = c0 + r * 32 + lane;
+        if (li < tile_n) { k[r] = key_in[t0 + li]; id[r] = id_in[t0 + li]; } else { k[r] = ~0ull; id[r] = 0; }
+    }
+    // ---- rank inside the warp's chunk, in element order (stable): peers of a digit in this round + the digit's running count ----
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t li = c0 + r * 32 + lane;
+        const bool live = li < tile_n;
+        const uint32_t d = live ? (uint32_t)((k[r] >> shift) & 0xFF) : 256u;      // (pairs past the end match only each other)
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-        if (live) {
-            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            const uint32_t pos = cur[w][d] + rank;
-            perm_out[pos] = src;
+        uint32_t before = 0;
+        if (live) before = wcnt[w * 256 + d];
+        __syncwarp();
+        rank[r] = before + __popc(peers & ((1u << lane) - 1u));
+        if (live && lane == (31 - __clz(peers))) wcnt[w * 256 + d] = before + __popc(peers);   // one lane per digit group advances the counter
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- thread d: the digit's count per warp -> per-warp offsets, tile count; publish, look back, scatter bases ----
+    {
+        const int d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < 8; ww++) { const uint32_t c = wcnt[ww * 256 + d]; wcnt[ww * 256 + d] = run; run += c; }
+        const uint32_t cnt = run;
+        // exclusive scan of the tile's digit counts over the 256 digits -> where the digit starts in the reordered tile
+        uint32_t x = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+        __shared__ uint32_t wsum[8];
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        uint32_t wpre = 0;
+        for (int ww = 0; ww < w; ww++) wpre += wsum[ww];
+        dstart[d] = wpre + x - cnt;
+        // chained scan with decoupled look-back over the preceding tiles (they all started before this one: ticket order)
+        volatile uint32_t* st = status + (size_t)tile * 256 + d;
+        uint32_t excl = 0;
+        if (tile == 0) { __threadfence(); *st = RS_FLAG_PREFIX | cnt; }
+        else {
+            __threadfence(); *st = RS_FLAG_AGG | cnt;
+            for (int64_t p = (int64_t)tile - 1; p >= 0; p--) {
+                volatile const uint32_t* ps = status + (size_t)p * 256 + d;
+                uint32_t v;
+                do { v = *ps; } while ((v & ~RS_VAL_MASK) == 0);
+                excl += v & RS_VAL_MASK;
+                if (v & RS_FLAG_PREFIX) break;
+            }
+            __threadfence(); *st = RS_FLAG_PREFIX | (excl + cnt);
         }
-        __syncwarp();
-        if (live && lane == (31 - __clz(peers))) cur[w][d] += __popc(peers);  // the last lane of each digit group advances the cursor
-        __syncwarp();
+        tbase[d] = global_base[d] + excl;
+    }
+    __syncthreads();
+    // ---- reorder the tile through shared memory: digit-major, element order kept inside a digit ----
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t li = c0 + r * 32 + lane;
+        if (li < tile_n) {
+            const uint32_t d = (uint32_t)((k[r] >> shift) & 0xFF);
+            const uint32_t pos = dstart[d] + wcnt[w * 256 + d] + rank[r];
+            s_key[pos] = k[r]; s_id[pos] = id[r];
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tile_n; i += RS_THREADS) {
+        const uint64_t kk = s_key[i];
+        const uint32_t d = (uint32_t)((kk >> shift) & 0xFF);
+        const uint32_t dst = tbase[d] + (i - dstart[d]);
+        key_out[dst] = kk; id_out[dst] = s_id[i];
     }
 }
 
@@ -746,14 +837,11 @@ int copy_out(SortState* s, uint8_t* const* vals, uint8_t* const* nulls, const ui
             g.cols[0].values = sv; g.cols[0].validity = nullptr; g.cols[0].stype = prim_storage(cr.prim); g.cols[0].prim = cr.prim;
             g.n_cols = 1; g.dst_vals[0] = tv; g.dst_null[0] = tn;
             k_gather_sel<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(g, perm_dev + skip, (uint64_t)n, 0);
-            // null bytes travel separately (k_gather_sel read validity bitmaps, retained columns hold null BYTES)
+            // null bytes travel separately (k_gather_sel reads validity bitmaps, retained columns hold null BYTES)
+            k_rs_gather_bytes<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(sn, perm_dev + skip, tn, (uint64_t)n);
             SCK(cudaMemcpyAsync(oc.values.data(), tv, (size_t)n * oc.elem, cudaMemcpyDeviceToHost, st));
+            SCK(cudaMemcpyAsync(nb.data(), tn, (size_t)n, cudaMemcpyDeviceToHost, st));
             SCK(cudaStreamSynchronize(st));
-            std::vector<uint8_t> all_nulls((size_t)s->ret_rows);
-            SCK(cudaMemcpy(all_nulls.data(), sn, (size_t)s->ret_rows, cudaMemcpyDeviceToHost));
-            std::vector<uint32_t> hp((size_t)n);
-            SCK(cudaMemcpy(hp.data(), perm_dev + skip, (size_t)n * 4, cudaMemcpyDeviceToHost));
-            for (int64_t i = 0; i < n; i++) nb[(size_t)i] = all_nulls[hp[(size_t)i]];
             dfree(s, tv); dfree(s, tn);
         } else if (n > 0) {
             SCK(cudaMemcpyAsync(oc.values.data(), sv + (size_t)skip * oc.elem, (size_t)n * oc.elem, cudaMemcpyDeviceToHost, st));
@@ -836,7 +924,7 @@ int sort_push(SortState* s, const DevCol* cols, int64_t nrows, cudaStream_t stre
         snprintf(stats->main_kernel_name, sizeof stats->main_kernel_name, "%s", s->used_vec ? "topk_select(k_collect_rows_vec)" : "topk_select(k_collect_rows)");
     } else {
         rc = retain_batch(s, ra, stream, stats, err);
-        snprintf(stats->main_kernel_name, sizeof stats->main_kernel_name, "%s", s->c.kind == PK_FILTER ? "k_filter_write" : "k_radix_scatter");
+        snprintf(stats->main_kernel_name, sizeof stats->main_kernel_name, "%s", s->c.kind == PK_FILTER ? "k_filter_write" : "radix_sort(k_rs_pass)");
     }
     s->row_base += (uint64_t)nrows; s->total_seen += nrows;
     return rc;
@@ -1019,65 +1107,81 @@ int sort_finish(SortState* s, void* nccl_comm, int nranks, cudaStream_t st, bkgp
         *nrows = n;
         return copy_out(s, s->ret_vals.data(), s->ret_null.data(), nullptr, n, skip, st, out, err);
     }
-    // ---- full ORDER BY: LSD radix sort of the retained rows, least significant key first ----
+    // ---- full ORDER BY: stable LSD radix sort of (key image, row id) pairs, least significant ORDER BY key first ----
     const int64_t n = s->ret_rows;
-    if (n > 0xFFFFFFF0ll) return fail(err, BKGPU_EUNSUPPORTED, "full sort is limited to 2^32 rows per GPU");
+    if (n >= (int64_t)RS_VAL_MASK) return fail(err, BKGPU_EUNSUPPORTED, "full sort is limited to 2^30 rows per GPU");
     if (n == 0) { *nrows = 0; return copy_out(s, s->ret_vals.data(), s->ret_null.data(), nullptr, 0, 0, st, out, err); }
-    uint64_t* img = nullptr; uint32_t *perm[2] = {nullptr, nullptr}, *hist = nullptr, *bsum = nullptr, *bsum2 = nullptr; int rc;
     const uint32_t un = (uint32_t)n;
     const uint32_t ntiles = (un + RS_TILE - 1) / RS_TILE;
-    const uint64_t hist_n = (uint64_t)ntiles * 256;
-    const uint32_t nb1 = (uint32_t)((hist_n + 1023) / 1024), nb2 = (nb1 + 1023) / 1024;
-    if ((rc = dalloc(s, &img, (size_t)n * 8, err))) return rc;
-    if ((rc = dalloc(s, &perm[0], (size_t)n * 4, err))) return rc;
-    if ((rc = dalloc(s, &perm[1], (size_t)n * 4, err))) return rc;
-    if ((rc = dalloc(s, &hist, (size_t)hist_n * 4, err))) return rc;
-    if ((rc = dalloc(s, &bsum, (size_t)(nb1 + 1024) * 4, err))) return rc;
-    if ((rc = dalloc(s, &bsum2, (size_t)(nb2 + 1024) * 4, err))) return rc;
-    if (nb2 > 1024) return fail(err, BKGPU_EUNSUPPORTED, "full sort: too many radix tiles");
+    uint64_t *img_row = nullptr, *img[2] = {nullptr, nullptr}; uint32_t *ids[2] = {nullptr, nullptr}, *hist = nullptr, *status = nullptr; int rc;
+    if ((rc = dalloc(s, &img_row, (size_t)n * 8, err))) return rc;
+    if ((rc = dalloc(s, &img[0], (size_t)n * 8, err))) return rc;
+    if ((rc = dalloc(s, &img[1], (size_t)n * 8, err))) return rc;
+    if ((rc = dalloc(s, &ids[0], (size_t)n * 4, err))) return rc;
+    if ((rc = dalloc(s, &ids[1], (size_t)n * 4, err))) return rc;
+    if ((rc = dalloc(s, &hist, (size_t)(8 * 256 * 2 + 8 + 8) * 4, err))) return rc;       // histograms, bases, active flags, tickets
+    if ((rc = dalloc(s, &status, (size_t)ntiles * 256 * 8 * 4, err))) return rc;           // one look-back array per pass
+    uint32_t* bases = hist + 8 * 256; uint32_t* active = bases + 8 * 256; uint32_t* tickets = active + 8;
+    const size_t rs_smem = (size_t)RS_TILE * 12 + (8 * 256 + 256 + 256) * 4;
+    SCK(cudaFuncSetAttribute(k_rs_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
     RowArgs ra; memset(&ra, 0, sizeof ra);
     for (int c = 0; c < s->ncols; c++) { ra.cols[c].values = s->ret_vals[(size_t)c]; ra.cols[c].validity = nullptr; ra.cols[c].stype = prim_storage(s->c.cols[(size_t)c].prim); ra.cols[c].prim = s->c.cols[(size_t)c].prim; }
-    // retained columns carry null BYTES: rebuild bitmaps so the program sees NULLs
+    // retained columns carry null BYTES: pack them into bitmaps on the device so the key program sees NULLs
     std::vector<uint8_t*> bitmaps((size_t)s->ncols, nullptr);
     for (int c = 0; c < s->ncols; c++) {
-        std::vector<uint8_t> nbytes((size_t)n);
-        SCK(cudaMemcpy(nbytes.data(), s->ret_null[(size_t)c], (size_t)n, cudaMemcpyDeviceToHost));
-        bool any = false; for (auto b : nbytes) any |= b != 0;
-        if (!any) continue;
-        std::vector<uint8_t> bm((size_t)(n + 7) / 8 + 8, 0xFF);
-        for (int64_t i = 0; i < n; i++) if (nbytes[(size_t)i]) bm[(size_t)i >> 3] &= (uint8_t)~(1u << (i & 7));
-        if ((rc = dalloc(s, &bitmaps[(size_t)c], bm.size(), err))) return rc;
-        SCK(cudaMemcpy(bitmaps[(size_t)c], bm.data(), bm.size(), cudaMemcpyHostToDevice));
+        if ((rc = dalloc(s, &bitmaps[(size_t)c], (size_t)(n + 7) / 8 + 64, err))) return rc;
+        k_pack_null_bytes<<<grid_for((n + 7) / 8, 256, s->sm_count), 256, 0, st>>>(s->ret_null[(size_t)c], n, bitmaps[(size_t)c]);
         ra.cols[c].validity = bitmaps[(size_t)c];
     }
     ra.n_cols = s->ncols; ra.nrows = n; ra.prog = s->c.prog; ra.key.pred_out = -1;
+    k_rs_iota<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(ids[0], un);
     int cur = 0; bool first = true;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    int64_t pass_bytes = 0;
+    // sorts the pairs (img[cur], ids[cur]) by the 64-bit image: one histogram pass, then one Onesweep pass per digit that varies
+    auto sort_pairs = [&]() -> int {
+        SCK(cudaMemsetAsync(hist, 0, (size_t)(8 * 256 * 2 + 8 + 8) * 4, st));
+        k_rs_hist<<<std::min(s->sm_count * 4, (int)((un + 1023) / 1024)), 256, 0, st>>>(img[cur], un, hist);
+        k_rs_bases<<<8, 256, 0, st>>>(hist, bases, active);
+        uint32_t h_active[8];
+        SCK(cudaMemcpyAsync(h_active, active, 32, cudaMemcpyDeviceToHost, st));
+        SCK(cudaStreamSynchronize(st));
+        int n_active = 0;
+        for (int d = 0; d < 8; d++) n_active += h_active[d] != 0;
+        if (n_active) SCK(cudaMemsetAsync(status, 0, (size_t)ntiles * 256 * 4 * (size_t)n_active, st));
+        stats->kernel_launches += 2; pass_bytes += (int64_t)n * 8;
+        int slot = 0;
+        for (int d = 0; d < 8; d++) {
+            if (!h_active[d]) continue;
+            k_rs_pass<<<ntiles, RS_THREADS, rs_smem, st>>>(img[cur], ids[cur], img[cur ^ 1], ids[cur ^ 1], un, 8 * d, bases + 256 * d,
+                                                        status + (size_t)slot * ntiles * 256, tickets + d);
+            cur ^= 1; slot++;
+            stats->kernel_launches++; pass_bytes += (int64_t)n * 24;
+        }
+        return 0;
+    };
     for (int ki = (int)s->c.sort_keys.size() - 1; ki >= 0; ki--) {
         const SortKey& sk = s->c.sort_keys[(size_t)ki];
-      for (int mode = 0; mode < 2; mode++) {
-        k_sort_images<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(ra, sk.out_reg, host_prim_class(sk.prim), sk.asc ? 0 : 1, sk.null_first ? 1 : 0, mode, img, first ? perm[cur] : nullptr);
-        first = false;
-        for (int pass = 0; pass < (mode == 0 ? 8 : 1); pass++) {
-            k_radix_hist<<<(ntiles + 7) / 8, 256, 0, st>>>(img, perm[cur], un, pass * 8, hist, ntiles);
-            k_scan_u32<<<nb1, 256, 0, st>>>(hist, hist_n, bsum, 0);
-            k_scan_u32<<<nb2, 256, 0, st>>>(bsum, nb1, bsum2, 0);
-            if (nb2 > 1) { // third level on the host-sized tail (nb2 <= 1024): one block
-                k_scan_u32<<<1, 256, 0, st>>>(bsum2, nb2, bsum2 + 1024, 0);
-                k_scan_u32<<<nb2, 256, 0, st>>>(bsum, nb1, bsum2, 1);
-            }
-            k_scan_u32<<<nb1, 256, 0, st>>>(hist, hist_n, bsum, 1);
-            k_radix_scatter<<<(ntiles + 7) / 8, 256, 0, st>>>(img, perm[cur], perm[cur ^ 1], un, pass * 8, hist, ntiles);
-            cur ^= 1;
-            stats->kernel_launches += 5;
+        for (int mode = 0; mode < 2; mode++) {   // the key's value image first, then its NULL rank (stable: NULLs end up strictly first / last)
+            uint64_t* dst = first ? img[cur] : img_row;
+            k_sort_images<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(ra, sk.out_reg, host_prim_class(sk.prim), sk.asc ? 0 : 1, sk.null_first ? 1 : 0, mode, dst, nullptr);
+            if (!first) k_rs_gather_u64<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(img_row, ids[cur], img[cur], un);   // images in the current order
+            first = false;
+            stats->kernel_launches += 2;
+            if ((rc = sort_pairs())) return rc;
         }
-      }
     }
+    cudaEventRecord(e1, st);
     SCK(cudaStreamSynchronize(st));
+    { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); stats->main_kernel_ms += ms; stats->main_kernel_launches += 1; stats->main_kernel_bytes += pass_bytes; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    snprintf(stats->main_kernel_name, sizeof stats->main_kernel_name, "%s", "radix_sort(k_rs_pass)");
     int64_t keep = n; if (s->k >= 0 && keep > s->k) keep = s->k;
     int64_t skip = std::min<int64_t>(s->c.offset, keep); keep -= skip;
     *nrows = keep;
-    rc = copy_out(s, s->ret_vals.data(), s->ret_null.data(), perm[cur], keep, skip, st, out, err);
-    dfree(s, img); dfree(s, perm[0]); dfree(s, perm[1]); dfree(s, hist); dfree(s, bsum); dfree(s, bsum2);
+    rc = copy_out(s, s->ret_vals.data(), s->ret_null.data(), ids[cur], keep, skip, st, out, err);
+    dfree(s, img_row); dfree(s, img[0]); dfree(s, img[1]); dfree(s, ids[0]); dfree(s, ids[1]); dfree(s, hist); dfree(s, status);
     for (auto b : bitmaps) dfree(s, b);
     return rc;
 }
