@@ -329,6 +329,32 @@ __global__ void k_extract(GroupTable gt, AggPlan ap, uint64_t* outv, uint8_t* ou
     }
 }
 
+// The aggregate's extracted rows (canonical 64-bit images + null bytes, column-major with stride out_cap) as typed Arrow-layout
+// columns on the device: the input of the post fragment ([LIMIT ->] [SORT ->] [HAVING ->] above the aggregate).
+__global__ void k_images_to_columns(const uint64_t* outv, const uint8_t* outn, uint32_t out_cap, uint32_t n, PostCols pc) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        for (int c = 0; c < pc.n; c++) {
+            const int img = pc.img[c];
+            const uint64_t v = outv[(size_t)img * out_cap + r];
+            pc.null_bytes[c][r] = outn[(size_t)img * out_cap + r];
+            switch (pc.stype[c]) {
+                case ST_I32: ((int32_t*)pc.values[c])[r] = (int32_t)(int64_t)v; break;
+                case ST_U32: ((uint32_t*)pc.values[c])[r] = (uint32_t)v; break;
+                case ST_F32: ((float*)pc.values[c])[r] = (float)bits_f64(v); break;
+                case ST_U8: ((uint8_t*)pc.values[c])[r] = v ? 1 : 0; break;
+                case ST_BLOB16: ((uint64_t*)pc.values[c])[2 * (size_t)r] = v; ((uint64_t*)pc.values[c])[2 * (size_t)r + 1] = outv[(size_t)(img + 1) * out_cap + r]; break;
+                default: ((uint64_t*)pc.values[c])[r] = v; break;
+            }
+        }
+    }
+}
+cudaError_t launch_images_to_columns(const uint64_t* outv, const uint8_t* outn, uint32_t out_cap, uint32_t n, const PostCols& pc, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    int grid = (int)((n + 255) / 256); if (grid > 1184) grid = 1184;
+    k_images_to_columns<<<grid, 256, 0, s>>>(outv, outn, out_cap, n, pc);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------

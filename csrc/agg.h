@@ -65,6 +65,9 @@ struct AggArgs {
 inline size_t wp_warp_bytes(int na, uint32_t gcap) { return ((size_t)gcap * (8u * (uint32_t)na + 4u) + 15) & ~(size_t)15; }
 inline size_t wp_smem_bytes(int na, uint32_t gcap, int kt_log2, int warps) { return (kt_log2 < 0 ? 0 : ((size_t)8 << kt_log2)) + 16 + wp_warp_bytes(na, gcap) * (size_t)warps; }
 
+// typed columns built from the aggregate's extracted images (input of the post fragment)
+struct PostCols { int32_t n; int32_t img[MAX_COLS]; int32_t stype[MAX_COLS]; uint8_t* values[MAX_COLS]; uint8_t* null_bytes[MAX_COLS]; };
+cudaError_t launch_images_to_columns(const uint64_t* outv, const uint8_t* outn, uint32_t out_cap, uint32_t n, const PostCols& pc, cudaStream_t s);
 size_t agg_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2);
 // scalar_tma.cu: TMA-staged COUNT(*) WHERE int32 <cmp> c (experiment, option "scalar_tma"); false = not this kernel's shape
 bool launch_count_where_tma(const AggArgs& a, int sm_count, cudaStream_t s, cudaError_t* err);

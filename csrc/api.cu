@@ -80,6 +80,8 @@ struct bkgpu_plan {
     std::vector<uint8_t*> bounce[2]; size_t bounce_rows = 0; cudaEvent_t bounce_done[2] = {nullptr, nullptr}; bool bounce_busy[2] = {false, false};
     int scalar_tma = 1;           // COUNT(*) WHERE int32 <cmp> c runs the TMA-staged kernel (scalar_tma.cu): 0.97 vs 0.78 of HBM (profiles/r02_tma_scalar.md); 0 = the LDG kernel
     int no_bounce = 0;            // 1 = pageable host input goes straight to cudaMemcpyAsync (A/B of the bounce path)
+    SortState* post_sort = nullptr;                         // the post fragment above the aggregate (Compiled::post)
+    std::vector<uint8_t*> post_vals, post_nullb, post_bitmap; size_t post_cap = 0;
     uint64_t rows_passed_host = 0;
     int64_t finish_groups = -1;   // groups in the table when the last finish read the result back (-1 = unknown: full re-initialisation)
     uint32_t merge_bound = 0, merge_bound_used = 0;   // groups per rank the all-gather is sized for (learned from earlier runs)
@@ -288,6 +290,7 @@ extern "C" int bkgpu_open(bkgpu_plan* p) {
     int rc = BKGPU_OK;
     if (p->c.kind == PK_AGG || p->c.kind == PK_JOIN_AGG) rc = alloc_group_table(p);
     if (!rc && (p->c.kind == PK_SORT || p->c.kind == PK_FILTER)) rc = sort_open(p->c, p->device, p->stream, p->region_base, &p->sort, p->last_error);
+    if (!rc && p->c.post) rc = sort_open(*p->c.post, p->device, p->stream, 0, &p->post_sort, p->last_error);
     if (rc) { g_thread_error = p->last_error; return rc; }
     p->state = S_OPEN;
     return BKGPU_OK;
@@ -1062,6 +1065,53 @@ static int agg_collective(bkgpu_plan* p, bool* rows_mode) {
     return BKGPU_OK;
 }
 
+// [LIMIT ->] [SORT ->] [HAVING ->] above the aggregate: the extracted rows (still on the device) become typed columns and run through
+// the post fragment's sort / filter kernels; only the final rows travel to the host
+static int agg_post(bkgpu_plan* p, uint32_t n_out, uint32_t out_cap) {
+    const Compiled& pc = *p->c.post;
+    const size_t nc = pc.cols.size();
+    int rc;
+    if (p->post_cap < std::max<size_t>(n_out, 1) || p->post_vals.size() != nc) {
+        for (auto& v : {&p->post_vals, &p->post_nullb, &p->post_bitmap}) { for (uint8_t* q : *v) dev_free(p, q); v->assign(nc, nullptr); }
+        const size_t cap = std::max<size_t>(n_out, 2048);
+        for (size_t c = 0; c < nc; c++) {
+            if ((rc = dev_alloc(p, (void**)&p->post_vals[c], cap * (size_t)storage_bytes(prim_storage(pc.cols[c].prim)) + 64))) return rc;
+            if ((rc = dev_alloc(p, (void**)&p->post_nullb[c], cap + 64))) return rc;
+            if ((rc = dev_alloc(p, (void**)&p->post_bitmap[c], cap / 8 + 64))) return rc;
+        }
+        p->post_cap = cap;
+    }
+    PostCols pcs; memset(&pcs, 0, sizeof pcs);
+    pcs.n = (int)nc;
+    int img = 0;
+    for (size_t c = 0; c < nc; c++) {   // (post columns = the aggregate's output columns, in order: plan.cpp::lower_post)
+        pcs.img[c] = img; pcs.stype[c] = prim_storage(pc.cols[c].prim); pcs.values[c] = p->post_vals[c]; pcs.null_bytes[c] = p->post_nullb[c];
+        img += p->c.out_cols[c].kind == 1 ? 2 : 1;
+    }
+    CK(p, launch_images_to_columns(p->d_outv, p->d_outn, out_cap, n_out, pcs, p->stream));
+    std::vector<DevCol> dc(std::max<size_t>(nc, 1));
+    for (size_t c = 0; c < nc; c++) {
+        if (n_out) CK(p, launch_pack_validity(p->post_nullb[c], n_out, p->post_bitmap[c], p->stream));
+        dc[c].values = p->post_vals[c]; dc[c].validity = p->post_bitmap[c]; dc[c].stype = prim_storage(pc.cols[c].prim); dc[c].prim = pc.cols[c].prim;
+    }
+    p->stats.kernel_launches += 1 + (int64_t)nc;
+    if ((rc = sort_reset(p->post_sort, p->stream, p->last_error))) { g_thread_error = p->last_error; return rc; }
+    bkgpu_stats scratch{};   // (the post fragment's kernels are not the request's "main kernel")
+    if (n_out && (rc = sort_push(p->post_sort, dc.data(), n_out, p->stream, &scratch, p->last_error))) { g_thread_error = p->last_error; return rc; }
+    std::vector<SortOutCol> cols; int64_t rows = 0;
+    if ((rc = sort_finish(p->post_sort, nullptr, 1, p->stream, &scratch, cols, &rows, p->last_error))) { g_thread_error = p->last_error; return rc; }
+    p->stats.kernel_launches += scratch.kernel_launches;
+    p->result.clear();
+    for (size_t c = 0; c < cols.size(); c++) {
+        SortOutCol& sc = cols[c];
+        HostCol hc; hc.desc = p->c.out_cols[c]; hc.elem = sc.elem;
+        hc.values = std::move(sc.values); hc.validity = std::move(sc.validity);
+        p->result.push_back(std::move(hc));
+    }
+    p->result_rows = rows; p->result_pos = 0;
+    return BKGPU_OK;
+}
+
 static int agg_finish(bkgpu_plan* p) {
     const AggPlan& ap = p->c.ap;
     GroupTable& gt = p->gt;
@@ -1138,6 +1188,7 @@ static int agg_finish(bkgpu_plan* p) {
   }
     uint64_t* hv = finish_hv; uint8_t* hn = finish_hn; uint32_t n_out = finish_n_out, out_cap = finish_out_cap;
     if (n_out > out_cap) n_out = out_cap;
+    if (p->c.post) return agg_post(p, n_out, out_cap);
     int64_t rows = n_out;
     int64_t skip = p->c.offset > 0 ? std::min<int64_t>(p->c.offset, rows) : 0;
     int64_t lim = p->c.agg_limit;   // AggNode::get_next stops at its limit (agg_node.cpp:555)
@@ -1302,6 +1353,7 @@ extern "C" void bkgpu_close(bkgpu_plan* p) {
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
     resolve_timers(p);
     if (p->sort) sort_close(p->sort);
+    if (p->post_sort) sort_close(p->post_sort);
     for (size_t r = 0; r < p->peer_ptr.size(); r++) if ((int)r != p->peer_rank && p->peer_ptr[r]) cudaIpcCloseMemHandle(p->peer_ptr[r]);
     for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
     for (void* q : p->dev_allocs) cudaFree(q);

@@ -853,6 +853,8 @@ static void explain(Compiled& c) {
         snprintf(buf, sizeof buf, "rows: pred_out=%d limit=%lld offset=%lld direct=%d\n", c.ap.pred_out, (long long)c.limit, (long long)c.offset, (int)c.has_direct); s += buf;
         for (auto& k : c.sort_keys) { snprintf(buf, sizeof buf, "  order key: out=%d prim=%d asc=%d null_first=%d\n", k.out_reg, k.prim, (int)k.asc, (int)k.null_first); s += buf; }
     }
+    if (c.post) { snprintf(buf, sizeof buf, "post fragment above the aggregate: kind=%d keys=%zu pred_out=%d limit=%lld offset=%lld\n", c.post->kind, c.post->sort_keys.size(),
+                           c.post->ap.pred_out, (long long)c.post->limit, (long long)c.post->offset); s += buf; }
     snprintf(buf, sizeof buf, "program: %d instr, %d outputs\n", c.prog.n_instr, c.prog.n_out); s += buf;
     for (int i = 0; i < c.prog.n_instr; i++) {
         const Instr& in = c.prog.code[i];
@@ -866,6 +868,7 @@ static void explain(Compiled& c) {
 bool lower_sort(Infer& in, Compiled& out, const HNode& sort, const HNode* filter, const HNode& scan);
 bool lower_filter(Infer& in, Compiled& out, const HNode* limit_node, const HNode& filter_or_scan, const HNode& scan);
 bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& join, bool under_packet);
+bool lower_post(Infer& in, Compiled& out, const HNode* sort, const HNode* having, const HNode* limit_node);
 
 static bool infer_node(Infer& in, HNode& n) {
     for (auto& e : n.conjuncts) if (!infer_expr(in, e)) return false;
@@ -903,6 +906,16 @@ int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& er
     bool ok = false;
     const HNode* limit_node = nullptr;
     if (top->node_type == BK_LIMIT_NODE && !top->ch.empty()) { limit_node = top; top = skip_passthrough(&top->ch[0], &under_packet); }
+    // the db-side chain above an aggregate: [LIMIT ->] [SORT ->] [HAVING_FILTER ->] (MERGE_)AGG (separate.cpp:241-260): the operators
+    // above the aggregate become a post fragment over the aggregate's output rows
+    const HNode *post_sort = nullptr, *post_having = nullptr;
+    {
+        const HNode* t = top;
+        const HNode *ps = nullptr, *ph = nullptr;
+        if (t->node_type == BK_SORT_NODE && !t->ch.empty()) { ps = t; t = skip_passthrough(&t->ch[0], nullptr); }
+        if (t && (is_filter(t) || t->node_type == BK_HAVING_FILTER_NODE) && !t->ch.empty()) { ph = t; t = skip_passthrough(&t->ch[0], nullptr); }
+        if (t && (ps || ph) && (t->node_type == BK_AGG_NODE || t->node_type == BK_MERGE_AGG_NODE)) { post_sort = ps; post_having = ph; top = t; }
+    }
     if (top->node_type == BK_AGG_NODE || top->node_type == BK_MERGE_AGG_NODE) {
         if (top->ch.empty()) { err = "AGG node without a child"; return BKGPU_EINVAL; }
         const HNode* c = skip_passthrough(&top->ch[0], nullptr);
@@ -913,11 +926,12 @@ int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& er
             std::vector<const HExpr*> conj;
             if (filter) for (auto& e : filter->conjuncts) conj.push_back(&e);
             ok = lower_agg(in, out, *top, conj, c->tuple_id, under_packet, true);
-            if (ok && limit_node) { out.limit = limit_node->limit; out.offset = limit_node->offset; }
+            if (ok && limit_node && !post_sort && !post_having) { out.limit = limit_node->limit; out.offset = limit_node->offset; }
         } else if (c && c->node_type == BK_JOIN_NODE && !filter) {
             ok = lower_join_agg(in, out, *top, *c, under_packet);
-            if (ok && limit_node) { out.limit = limit_node->limit; out.offset = limit_node->offset; }   // LimitNode over the joined aggregate
+            if (ok && limit_node && !post_sort && !post_having) { out.limit = limit_node->limit; out.offset = limit_node->offset; }   // LimitNode over the joined aggregate
         } else { err = "AGG child must be [FILTER ->] SCAN or JOIN"; return BKGPU_EUNSUPPORTED; }
+        if (ok && (post_sort || post_having)) ok = lower_post(in, out, post_sort, post_having, limit_node);
     } else if (top->node_type == BK_SORT_NODE) {
         const HNode* c = top->ch.empty() ? nullptr : skip_passthrough(&top->ch[0], nullptr);
         const HNode* filter = nullptr;
@@ -1021,6 +1035,61 @@ bool lower_filter(Infer& in, Compiled& out, const HNode* limit_node, const HNode
     int reg = 0;
     if (!lower_predicate(in, lw, filter, out.ap, reg)) return false;
     p.n_out = reg;
+    return true;
+}
+
+// [LIMIT ->] [SORT ->] [HAVING ->] over an aggregate: a fragment of kind PK_SORT / PK_FILTER whose input rows are the aggregate's
+// output columns (SortNode::open src/exec/sort_node.cpp:278-346, FilterNode::get_next src/exec/filter_node.cpp:726-795 over the
+// rows AggNode::get_next emits).  The AVG intermediate blobs ride along as 16-byte payload columns.
+bool lower_post(Infer& in, Compiled& out, const HNode* sort, const HNode* having, const HNode* limit_node) {
+    auto post = std::make_shared<Compiled>();
+    Compiled& pc = *post;
+    pc.kind = sort ? PK_SORT : PK_FILTER;
+    pc.tuples = out.tuples;
+    pc.scan_tuple = -1;
+    Program& p = pc.prog; memset(&p, 0, sizeof p);
+    memset(&pc.ap, 0, sizeof pc.ap);
+    Lower lw{&pc, &in, &p, {}};
+    if (out.out_cols.size() > (size_t)MAX_COLS) return in.fail(BKGPU_EUNSUPPORTED, "more than %d aggregate output columns under a SORT / HAVING", MAX_COLS);
+    for (const OutCol& oc : out.out_cols) {
+        const int prim = oc.kind == 1 ? BK_STRING : oc.prim;
+        const int ci = lw.intern_col(oc.tuple_id, oc.slot_id, prim);
+        if (ci != (int)pc.out_cols.size()) return in.fail(BKGPU_EUNSUPPORTED, "aggregate output columns %d_%d appear twice", oc.tuple_id, oc.slot_id);
+        pc.out_cols.push_back({oc.tuple_id, oc.slot_id, prim, oc.kind});
+    }
+    const size_t n_payload = pc.cols.size();
+    int reg = 0;
+    if (having && having->limit != -1 && sort) return in.fail(BKGPU_EUNSUPPORTED, "LIMIT on a HAVING filter below a sort is order dependent");
+    if (!lower_predicate(in, lw, having, pc.ap, reg)) return false;
+    if (sort) {
+        pc.limit = sort->limit;
+        if (sort->order_exprs.empty()) return in.fail(BKGPU_EINVAL, "SORT node without order expressions");
+        if (sort->order_exprs.size() > 4) return in.fail(BKGPU_EUNSUPPORTED, "more than 4 ORDER BY expressions");
+        for (size_t i = 0; i < sort->order_exprs.size(); i++) {
+            const HExpr& e = sort->order_exprs[i];
+            if (e.col_type == BK_STRING) return in.fail(BKGPU_EUNSUPPORTED, "ORDER BY over a STRING key is outside the GPU path");
+            int depth = 0;
+            if (!lw.expr(e, depth)) return false;
+            pc.sort_keys.push_back({reg, e.col_type, sort->is_asc[i] != 0, sort->is_null_first[i] != 0});
+            if (!lw.out_reg(reg++)) return false;
+        }
+        if (limit_node) {
+            pc.offset = limit_node->offset;
+            if (limit_node->limit >= 0) { const int64_t lim = limit_node->limit + limit_node->offset; if (pc.limit < 0 || lim < pc.limit) pc.limit = lim; }
+        }
+    } else {
+        pc.limit = having ? having->limit : -1;
+        pc.offset = 0;
+        if (limit_node) {
+            pc.offset = limit_node->offset;
+            const int64_t lim = limit_node->limit < 0 ? -1 : limit_node->limit + limit_node->offset;
+            if (lim >= 0 && (pc.limit < 0 || lim < pc.limit)) pc.limit = lim;
+        }
+    }
+    p.n_out = reg;
+    if (pc.cols.size() != n_payload) return in.fail(BKGPU_EUNSUPPORTED, "SORT / HAVING above an aggregate references a column the aggregate does not output");
+    pc.has_direct = false;
+    out.post = post;
     return true;
 }
 

@@ -85,6 +85,9 @@ struct Compiled {
     // to probe-row alignment first); usable while every probe row has exactly one match
     std::shared_ptr<Compiled> jfast;
     std::vector<int> jfast_of_main;    // for every column of jfast->cols: index of the same column in this->cols
+    // operators ABOVE the aggregate ([LIMIT ->] [SORT ->] [HAVING ->] AGG, exec_node.cpp:347-394): a second, small fragment of kind
+    // PK_SORT / PK_FILTER whose "scan tuple" is the aggregate's output row (its columns = this->out_cols, in order)
+    std::shared_ptr<Compiled> post;
     std::string explain;
 };
 

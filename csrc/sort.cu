@@ -356,7 +356,7 @@ __global__ void k_gather_topk(GatherArgs g, const uint64_t* idx, const uint32_t*
             for (uint32_t j = 0; j < g.old_n; j++) if (g.old_idx[j] == id) { src = j; break; }
         }
         for (int c = 0; c < g.n_cols; c++) {
-            const int eb = g.cols[c].stype == ST_U8 ? 1 : ((g.cols[c].stype == ST_I32 || g.cols[c].stype == ST_U32 || g.cols[c].stype == ST_F32) ? 4 : 8);
+            const int eb = g.cols[c].stype == ST_U8 ? 1 : (g.cols[c].stype == ST_BLOB16 ? 16 : ((g.cols[c].stype == ST_I32 || g.cols[c].stype == ST_U32 || g.cols[c].stype == ST_F32) ? 4 : 8));
             const uint8_t* sv; uint8_t isnull;
             if (from_batch) { sv = (const uint8_t*)g.cols[c].values + (size_t)src * eb; isnull = elem_is_null(g.cols[c], src) ? 1 : 0; }
             else { sv = g.old_vals[c] + (size_t)src * eb; isnull = g.old_null[c][src]; }
@@ -438,10 +438,12 @@ __global__ void k_gather_sel(GatherArgs g, const uint32_t* sel, uint64_t n, uint
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const int64_t src = sel[i];
         for (int c = 0; c < g.n_cols; c++) {
-            const int eb = g.cols[c].stype == ST_U8 ? 1 : ((g.cols[c].stype == ST_I32 || g.cols[c].stype == ST_U32 || g.cols[c].stype == ST_F32) ? 4 : 8);
+            const int eb = g.cols[c].stype == ST_U8 ? 1 : (g.cols[c].stype == ST_BLOB16 ? 16 : ((g.cols[c].stype == ST_I32 || g.cols[c].stype == ST_U32 || g.cols[c].stype == ST_F32) ? 4 : 8));
             const uint8_t* sv = (const uint8_t*)g.cols[c].values + (size_t)src * eb;
             uint8_t* dv = g.dst_vals[c] + (size_t)(dst_off + i) * eb;
-            if (eb == 8) *(uint64_t*)dv = *(const uint64_t*)sv; else if (eb == 4) *(uint32_t*)dv = *(const uint32_t*)sv; else *dv = *sv;
+            if (eb == 8) *(uint64_t*)dv = *(const uint64_t*)sv; else if (eb == 4) *(uint32_t*)dv = *(const uint32_t*)sv;
+            else if (eb == 16) { ((uint64_t*)dv)[0] = ((const uint64_t*)sv)[0]; ((uint64_t*)dv)[1] = ((const uint64_t*)sv)[1]; }   // AVG intermediate blob (payload only)
+            else *dv = *sv;
             g.dst_null[c][dst_off + i] = elem_is_null(g.cols[c], src) ? 1 : 0;
         }
     }
