@@ -23,13 +23,16 @@ namespace bk {
 // ------------------------------------------------------------------------------------------
 // one (possibly joined) row through the program into the tables
 struct InterpCtx { SmemTable st; bool grouped, use_smem; uint32_t gcap; };
-__device__ __forceinline__ uint32_t interp_row(const AggArgs& a, const InterpCtx& cx, int64_t row, int64_t brow) {
+// how: 0 = filter, then aggregate the row; 1 = filter only (SEMI / ANTI probe: does the joined row satisfy the conditions?);
+//      2 = aggregate without the filter (the NULL-extended / preserved rows of the join's tail)
+__device__ __forceinline__ uint32_t interp_row(const AggArgs& a, const InterpCtx& cx, int64_t row, int64_t brow, int how = 0) {
     const AggPlan& ap = a.plan;
     const GroupTable& gt = a.gt;
     uint64_t out[MAX_GROUP + MAX_AGG + 1];
     uint32_t out_null;
     run_program(a.prog, a.cols, row, out, out_null, brow);
-    if (ap.pred_out >= 0 && (((out_null >> ap.pred_out) & 1u) || out[ap.pred_out] == 0)) return 0;
+    if (how != 2 && ap.pred_out >= 0 && (((out_null >> ap.pred_out) & 1u) || out[ap.pred_out] == 0)) return 0;
+    if (how == 1) return 1;
     auto arg = [&](int i, uint64_t& v, bool& isnull) {
         const int r = ap.agg[i].arg_out;
         if (r == 0xFF) { v = 0; isnull = true; return; }
@@ -71,6 +74,13 @@ __global__ void __launch_bounds__(256) k_agg_interp(const __grid_constant__ AggA
     cx.st = SmemTable{};
     if (cx.use_smem) cx.st = smem_table_init(smem_raw, a);
     uint32_t passed = 0;
+    if (a.join.enabled && a.join.tail) {   // after the last probe batch: the preserved (build) side's rows the join type asks for
+        const int jt = a.join.join_type;
+        for (int64_t br = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; br < a.join.n_build; br += (int64_t)gridDim.x * blockDim.x) {
+            const bool m = a.join.matched[br] != 0;
+            if (jt == 4 /*SEMI*/ ? m : !m) passed += interp_row(a, cx, -1, br, 2);
+        }
+    } else
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.nrows; row += (int64_t)gridDim.x * blockDim.x) {
         if (!a.join.enabled) { passed += interp_row(a, cx, row, -1); continue; }
         // K4 probe: every build row whose cast key equals this row's (Joiner::encode_hash_key + FlatMap seek,
@@ -82,7 +92,11 @@ __global__ void __launch_bounds__(256) k_agg_interp(const __grid_constant__ AggA
         for (;;) {
             const uint32_t br = a.join.rows[slot];
             if (br == 0xFFFFFFFFu) break;
-            if (a.join.keys[slot] == img) passed += interp_row(a, cx, row, (int64_t)br);
+            if (a.join.keys[slot] == img) {
+                if (a.join.join_type == 3 /*INNER*/ || !a.join.matched) passed += interp_row(a, cx, row, (int64_t)br);
+                else if (a.join.join_type == 1 /*LEFT*/) { if (interp_row(a, cx, row, (int64_t)br)) { passed++; a.join.matched[br] = 1; } }
+                else if (interp_row(a, cx, row, (int64_t)br, 1)) a.join.matched[br] = 1;   // SEMI / ANTI_SEMI: only whether a partner exists
+            }
             slot = (slot + 1) & a.join.cap_mask;
         }
     }

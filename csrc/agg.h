@@ -13,6 +13,13 @@ struct JoinArgs {
     int32_t enabled;
     int32_t probe_col;       // index into cols of the probe key
     int32_t probe_prim, cast_prim;
+    // LEFT / SEMI / ANTI_SEMI (the build side = the reference's outer / driver table is the preserved side, join_node.cpp:1200-1276,
+    // joiner.cpp:633-685): `matched[build row]` is set by the probe; the TAIL launch (tail = 1) walks the n_build build rows and emits the
+    // unmatched ones NULL-extended (LEFT), the matched ones (SEMI) or the unmatched ones (ANTI_SEMI)
+    int32_t join_type;       // pb::JoinType: 1 LEFT, 3 INNER, 4 SEMI, 5 ANTI_SEMI (RIGHT arrives as LEFT with the children swapped)
+    int32_t tail;
+    uint8_t* matched;
+    int64_t n_build;
 };
 
 // FK -> PK join fused into the lean aggregate: the GROUP BY key is a build-side (dimension) attribute reached through

@@ -80,6 +80,7 @@ struct bkgpu_plan {
     std::vector<uint8_t*> bounce[2]; size_t bounce_rows = 0; cudaEvent_t bounce_done[2] = {nullptr, nullptr}; bool bounce_busy[2] = {false, false};
     int scalar_tma = 1;           // COUNT(*) WHERE int32 <cmp> c runs the TMA-staged kernel (scalar_tma.cu): 0.97 vs 0.78 of HBM (profiles/r02_tma_scalar.md); 0 = the LDG kernel
     int no_bounce = 0;            // 1 = pageable host input goes straight to cudaMemcpyAsync (A/B of the bounce path)
+    uint8_t* jb_matched = nullptr; size_t jb_matched_cap = 0; bool join_tail_launch = false;   // LEFT / SEMI / ANTI: build rows that found a partner
     SortState* post_sort = nullptr;                         // the post fragment above the aggregate (Compiled::post)
     std::vector<uint8_t*> post_vals, post_nullb, post_bitmap; size_t post_cap = 0;
     uint64_t rows_passed_host = 0;
@@ -319,6 +320,8 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
     if (c.kind == PK_JOIN_AGG) {
         a.join.enabled = 1; a.join.keys = p->jt_keys; a.join.rows = p->jt_rows; a.join.cap_mask = p->jt_mask;
         a.join.probe_col = c.probe_key_col; a.join.probe_prim = c.cols[(size_t)c.probe_key_col].prim; a.join.cast_prim = c.join_key_prim;
+        a.join.join_type = c.join_type; a.join.matched = c.join_type == BK_INNER_JOIN ? nullptr : p->jb_matched; a.join.n_build = p->jb_rows;
+        a.join.tail = p->join_tail_launch ? 1 : 0;
     }
     const bool direct = c.has_direct && vec_ok && !p->force_generic && c.kind == PK_AGG;   // (the join's fast-path plan is lowered as PK_AGG)
     const int ncols = (int)c.cols.size();
@@ -823,6 +826,10 @@ static int join_generic_table(bkgpu_plan* p) {
     key.values = p->jb_vals[ki]; key.validity = p->jb_bitmap[ki]; key.stype = prim_storage(c.cols[ki].prim); key.prim = c.cols[ki].prim;
     CK(p, launch_join_build(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, p->jt_keys, p->jt_rows, p->jt_mask, p->stream));
     p->stats.kernel_launches++;
+    if (c.join_type != BK_INNER_JOIN) {   // one "found a partner" byte per build row
+        if ((rc = ensure_buf(p, (void**)&p->jb_matched, &p->jb_matched_cap, (size_t)std::max<int64_t>(p->jb_rows, 1)))) return rc;
+        CK(p, cudaMemsetAsync(p->jb_matched, 0, (size_t)std::max<int64_t>(p->jb_rows, 1), p->stream));
+    }
     p->jt_generic = true;
     return BKGPU_OK;
 }
@@ -899,6 +906,25 @@ static int join_probe_batch(bkgpu_plan* p, const DevCol* probe_cols, int64_t nro
     }
     { int rc = join_generic_table(p); if (rc) return rc; }
     return launch_agg_batch(p, c, all.data(), nrows, false);
+}
+
+// LEFT / SEMI / ANTI_SEMI: once every probe batch has run, the preserved (build) side's rows the join type asks for go through the
+// aggregate — unmatched rows NULL-extended (LEFT), matched rows (SEMI), unmatched rows (ANTI_SEMI); join_node.cpp:1200-1276
+static int join_tail(bkgpu_plan* p) {
+    const Compiled& c = p->c;
+    if (p->jb_rows == 0) return BKGPU_OK;
+    int rc;
+    if (!p->jt_built && (rc = join_build_table(p))) return rc;
+    if ((rc = join_generic_table(p))) return rc;
+    std::vector<DevCol> all(c.cols.size());
+    for (size_t i = 0; i < c.cols.size(); i++) {
+        all[i].stype = prim_storage(c.cols[i].prim); all[i].prim = c.cols[i].prim;
+        if (c.col_side[i] == 1) { all[i].values = p->jb_vals[i]; all[i].validity = p->jb_bitmap[i]; }   // (probe-side columns are never read: row = -1 is NULL)
+    }
+    p->join_tail_launch = true;
+    rc = launch_agg_batch(p, c, all.data(), p->jb_rows, false);
+    p->join_tail_launch = false;
+    return rc;
 }
 
 static int join_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device) {
@@ -1253,6 +1279,7 @@ static int bkgpu_finish_impl(bkgpu_plan* p) {
     int rc = BKGPU_OK;
     switch (p->c.kind) {
         case PK_AGG: case PK_JOIN_AGG: {
+            if (p->c.kind == PK_JOIN_AGG && p->c.join_type != BK_INNER_JOIN && (rc = join_tail(p))) break;
             rc = agg_finish(p);
             if (!rc) {
                 p->stats.rows_filtered = p->stats.rows_scanned - (int64_t)p->rows_passed_host;   // (came back with the counter block)

@@ -1099,16 +1099,22 @@ bool lower_post(Infer& in, Compiled& out, const HNode* sort, const HNode* having
 // Filters of both children and the residual join conditions become one predicate over the joined row — for an
 // INNER join that is the same set of rows.
 bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& join, bool under_packet) {
-    if (join.join_type != BK_INNER_JOIN) return in.fail(BKGPU_EUNSUPPORTED, "only INNER JOIN is fused with the aggregate on the GPU path");
+    int jt = join.join_type;
+    if (jt != BK_INNER_JOIN && jt != BK_LEFT_JOIN && jt != BK_RIGHT_JOIN && jt != BK_SEMI_JOIN && jt != BK_ANTI_SEMI_JOIN)
+        return in.fail(BKGPU_EUNSUPPORTED, "join type %d (FULL / NULL) is outside the GPU path", jt);
     if (join.ch.size() != 2) return in.fail(BKGPU_EINVAL, "JOIN node needs two children");
     const HNode* side[2]; const HNode* filt[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; i++) {
-        const HNode* c = skip_passthrough(&join.ch[(size_t)i], nullptr);
+        // RIGHT JOIN: the reference swaps the roles — the right child becomes the outer (preserved, driver) table (join_node.cpp:151-156)
+        const HNode* c = skip_passthrough(&join.ch[(size_t)(jt == BK_RIGHT_JOIN ? 1 - i : i)], nullptr);
         if (is_filter(c)) { filt[i] = c; c = c->ch.empty() ? nullptr : skip_passthrough(&c->ch[0], nullptr); }
         if (!c || c->node_type != BK_SCAN_NODE) return in.fail(BKGPU_EUNSUPPORTED, "JOIN children must be [FILTER ->] SCAN");
         if (filt[i] && filt[i]->limit != -1) return in.fail(BKGPU_EUNSUPPORTED, "LIMIT below a join is order dependent");
         side[i] = c;
     }
+    if (jt == BK_RIGHT_JOIN) jt = BK_LEFT_JOIN;
+    // the fused predicate (child filters + residual conditions over the joined row) equals filter-then-join only for INNER joins
+    if (jt != BK_INNER_JOIN && (filt[0] || filt[1])) return in.fail(BKGPU_EUNSUPPORTED, "LEFT / SEMI / ANTI join over filtered children is outside the GPU path");
     const int build_tuple = side[0]->tuple_id, probe_tuple = side[1]->tuple_id;
     out.build_tuple = build_tuple;
     std::vector<const HExpr*> conj;
@@ -1133,14 +1139,14 @@ bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& joi
     if (cast == BK_STRING || is_double_t(cast)) return in.fail(BKGPU_EUNSUPPORTED, "join key type %d is outside the GPU path", cast);
     if (!lower_agg(in, out, agg, conj, probe_tuple, under_packet, false)) return false;
     out.kind = PK_JOIN_AGG;
-    out.join_type = join.join_type; out.join_key_prim = cast;
+    out.join_type = jt; out.join_key_prim = cast;
     Program dummy; memset(&dummy, 0, sizeof dummy);
     Lower lw{&out, &in, &dummy, {}};
     out.build_key_col = lw.intern_col(bk->tuple_id, bk->slot_id, in.slot_type(bk->tuple_id, bk->slot_id));
     out.probe_key_col = lw.intern_col(pk->tuple_id, pk->slot_id, in.slot_type(pk->tuple_id, pk->slot_id));
     if ((int)out.cols.size() > MAX_COLS) return in.fail(BKGPU_EUNSUPPORTED, "more than %d columns referenced", MAX_COLS);
     // fast path: lower the same aggregate again with every column treated as a column of ONE (virtual, joined) tuple
-    {
+    if (jt == BK_INNER_JOIN) {
         auto jf = std::make_shared<Compiled>();
         jf->tuples = out.tuples; jf->build_tuple = -1;
         Infer in2{}; in2.tuples = &jf->tuples;

@@ -1136,6 +1136,9 @@ static JoinBucket* join_seek(JoinState* s, const uint8_t* key, size_t klen, int 
 static int join_open(Ctx* c, Node* n) { /* join_node.cpp:920-1022, joiner.cpp:166-217,624-631 */
     JoinState* s = (JoinState*)calloc(1, sizeof *s); n->st = s;
     if (n->nchildren != 2) { snprintf(c->err, c->errlen, "join needs two children"); return -1; }
+    if (n->join_type == J_RIGHT) { /* join_node.cpp:151-156: the right child becomes the outer (preserved, driver) table */
+        Node* t = n->children[0]; n->children[0] = n->children[1]; n->children[1] = t; n->join_type = J_LEFT;
+    }
     collect_tuples(n->children[0], s->outer_tuple); collect_tuples(n->children[1], s->inner_tuple);
     s->outer_eq = (Expr**)calloc((size_t)n->n_conj + 1, sizeof(Expr*)); s->inner_eq = (Expr**)calloc((size_t)n->n_conj + 1, sizeof(Expr*));
     s->cast_types = (int*)calloc((size_t)n->n_conj + 1, sizeof(int)); s->other = (Expr**)calloc((size_t)n->n_conj + 1, sizeof(Expr*));

@@ -94,7 +94,7 @@ def test_sort_and_having_over_joined_aggregate():
     h = _having(a, P.gt(P.slot_ref(2, 1, T.INT64), P.int_lit(390)))
     pl = P.Plan(P.limit(P.sort(h, [P.slot_ref(2, 2, T.DOUBLE)], [False], tuple_id=2), 30),
                 {0: [(1, T.INT32), (2, T.DOUBLE)], 1: [(1, T.INT32), (2, T.INT32)], 2: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE])})
-    run_both(pl, [dim, fact], keys=None)
+    run_both(pl, dim + fact, keys=None, batches=[dim, fact])
     # LIMIT directly over the joined aggregate (the limit used to be dropped): any 11 groups
     pl2 = P.Plan(P.limit(a, 11), {0: [(1, T.INT32), (2, T.DOUBLE)], 1: [(1, T.INT32), (2, T.INT32)], 2: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE])})
     from baikaldb_b200.exec_node import execute

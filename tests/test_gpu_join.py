@@ -119,3 +119,72 @@ def test_fused_probe_with_a_fact_side_filter(nf):
     _, stats, _ = run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact])
     assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
     run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact], options={"no_fused_probe": 1})
+
+
+def _outer_join_tables(seed, nd=2_500, nf=40_000):
+    """a dimension with duplicate and NULL keys and keys no fact row refers to; facts with NULL keys and keys without a dimension row"""
+    rng = np.random.default_rng(seed)
+    dim = [make_column(1, 1, T.INT32, rng.integers(0, 1_200, nd), rng.random(nd) > 0.04), make_column(1, 2, T.INT32, rng.integers(0, 12, nd)),
+           make_column(1, 3, T.DOUBLE, rng.normal(size=nd))]
+    fact = [make_column(0, 1, T.INT32, rng.integers(400, 1_500, nf), rng.random(nf) > 0.05), make_column(0, 2, T.DOUBLE, rng.random(nf), rng.random(nf) > 0.1),
+            make_column(0, 3, T.INT32, rng.integers(0, 100, nf))]
+    tuples = {0: [(1, T.INT32), (2, T.DOUBLE), (3, T.INT32)], 1: [(1, T.INT32), (2, T.INT32), (3, T.DOUBLE)]}
+    return dim, fact, tuples
+
+
+@pytest.mark.parametrize("residual", [False, True])
+@pytest.mark.parametrize("jt", ["LEFT_JOIN", "RIGHT_JOIN"])
+def test_outer_joins_keep_every_preserved_row(jt, residual):
+    """LEFT (RIGHT = roles swapped, join_node.cpp:151-156): every row of the preserved table reaches the aggregate — with each partner
+    that satisfies the conditions, or once NULL-extended (join_node.cpp:1200-1276, Joiner::construct_null_result_batch):
+    COUNT(*) counts the NULL-extended rows, COUNT(fact col) / SUM(fact col) do not"""
+    dim, fact, tuples = _outer_join_tables(7 + residual)
+    aggs = [P.agg_expr("count_star", 2, 1), P.agg_expr("count", 2, 2, None, P.slot_ref(0, 2, T.DOUBLE)), P.agg_expr("sum", 2, 3, None, P.slot_ref(0, 2, T.DOUBLE)),
+            P.agg_expr("min", 2, 4, None, P.slot_ref(0, 3, T.INT32)), P.agg_expr("sum", 2, 5, None, P.slot_ref(1, 3, T.DOUBLE))]
+    conds = [P.eq(P.slot_ref(1, 1, T.INT32), P.slot_ref(0, 1, T.INT32))]
+    if residual:
+        conds.append(P.gt(P.add(P.slot_ref(0, 3, T.INT32), P.slot_ref(1, 2, T.INT32)), P.int_lit(40)))
+    children = (P.scan(1), P.scan(0)) if jt == "LEFT_JOIN" else (P.scan(0), P.scan(1))   # the dimension is the preserved side either way
+    j = P.join(children[0], children[1], conds, join_type=getattr(P.JoinType, jt))
+    tuples[2] = P.agg_tuple_slots(aggs, [T.INT64, T.INT64, T.DOUBLE, T.INT32, T.DOUBLE])
+    pl = P.Plan(P.agg(j, 2, [P.slot_ref(1, 2, T.INT32)], aggs), tuples)
+    got, _, _ = run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact])
+    by = {c.name: c for c in got}
+    assert sum(by["2_1"].to_list()) > sum(by["2_2"].to_list())          # NULL-extended rows exist and count only in COUNT(*)
+
+
+@pytest.mark.parametrize("residual", [False, True])
+@pytest.mark.parametrize("jt", ["SEMI_JOIN", "ANTI_SEMI_JOIN"])
+def test_semi_and_anti_joins_emit_outer_rows_once(jt, residual):
+    """SEMI: outer rows with at least one partner, each once whatever the number of partners; ANTI_SEMI: outer rows without one
+    (joiner.cpp:655-685) — NULL keys never find a partner"""
+    dim, fact, tuples = _outer_join_tables(11 + residual)
+    aggs = [P.agg_expr("count_star", 2, 1), P.agg_expr("sum", 2, 2, None, P.slot_ref(1, 3, T.DOUBLE)), P.agg_expr("max", 2, 3, None, P.slot_ref(1, 1, T.INT32))]
+    conds = [P.eq(P.slot_ref(1, 1, T.INT32), P.slot_ref(0, 1, T.INT32))]
+    if residual:
+        conds.append(P.lt(P.slot_ref(0, 3, T.INT32), P.multiplies(P.slot_ref(1, 2, T.INT32), P.int_lit(6))))
+    j = P.join(P.scan(1), P.scan(0), conds, join_type=getattr(P.JoinType, jt))
+    tuples[2] = P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE, T.INT32])
+    for group in ([P.slot_ref(1, 2, T.INT32)], []):
+        pl = P.Plan(P.packet(P.agg(j, 2, group, aggs)), tuples)
+        got, _, _ = run_both(pl, fact + dim, keys=["1_2"] if group else [], batches=[dim, fact])
+    total = {c.name: c for c in got}["2_1"].to_list()[0]
+    assert 0 < total < len(dim[0])
+
+
+def test_outer_join_with_an_empty_probe_side_and_unsupported_shapes():
+    dim, fact, tuples = _outer_join_tables(3)
+    aggs = [P.agg_expr("count_star", 2, 1), P.agg_expr("sum", 2, 2, None, P.slot_ref(0, 2, T.DOUBLE))]
+    tuples[2] = P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE])
+    j = P.join(P.scan(1), P.scan(0), [P.eq(P.slot_ref(1, 1, T.INT32), P.slot_ref(0, 1, T.INT32))], join_type=P.JoinType.LEFT_JOIN)
+    pl = P.Plan(P.agg(j, 2, [P.slot_ref(1, 2, T.INT32)], aggs), tuples)
+    no_fact = [make_column(c.tuple_id, c.slot_id, c.prim_type, c.values[:0]) for c in fact]
+    got, _, _ = run_both(pl, no_fact + dim, keys=["1_2"], batches=[dim, no_fact])     # every dimension row once, NULL-extended
+    assert sum({c.name: c for c in got}["2_1"].to_list()) == len(dim[0])
+    from baikaldb_b200._lib import BkgpuError, EUNSUPPORTED
+    from baikaldb_b200.exec_node import execute
+    filtered = P.join(P.where(P.scan(1), P.gt(P.slot_ref(1, 2, T.INT32), P.int_lit(3))), P.scan(0),
+                      [P.eq(P.slot_ref(1, 1, T.INT32), P.slot_ref(0, 1, T.INT32))], join_type=P.JoinType.LEFT_JOIN)
+    with pytest.raises(BkgpuError) as e:   # filter-then-join is not the fused predicate's meaning for an outer join: rejected, never wrong
+        execute(P.Plan(P.agg(filtered, 2, [P.slot_ref(1, 2, T.INT32)], aggs), tuples), [dim, fact])
+    assert e.value.code == EUNSUPPORTED

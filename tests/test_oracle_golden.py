@@ -361,3 +361,40 @@ def test_order_by_null_placement_row_oracle_equals_acero(asc):
     assert keys == ac.column("0_1").to_pylist()
     nn = int((~cols[0].valid).sum())
     assert (keys[:nn] == [None] * nn) if asc else (keys[-nn:] == [None] * nn)
+
+
+@pytest.mark.parametrize("jt", ["LEFT_JOIN", "RIGHT_JOIN", "SEMI_JOIN", "ANTI_SEMI_JOIN"])
+def test_row_oracle_outer_semi_anti_joins_equal_acero(jt):
+    """the row restatement of LEFT / RIGHT / SEMI / ANTI_SEMI (join_node.cpp:151-156,1200-1276; joiner.cpp:633-685) against the
+    Acero hashjoin the reference's vectorized engine declares for them (join_node.cpp:853-868: LEFT_OUTER / LEFT_SEMI / LEFT_ANTI,
+    outer side first) — duplicate keys, NULL keys on both sides, outer rows without a partner"""
+    import pyarrow.acero as ac
+    from baikaldb_b200 import plan as P
+    from baikaldb_b200.column import make_column
+    from baikaldb_b200.plan import PrimitiveType as T
+    from oracle import acero_oracle as A, oracle
+    rng = np.random.default_rng(5)
+    nd, nf = 2_500, 40_000
+    dim = [make_column(1, 1, T.INT32, rng.integers(0, 1_200, nd), rng.random(nd) > 0.04), make_column(1, 2, T.INT32, rng.integers(0, 12, nd))]
+    fact = [make_column(0, 1, T.INT32, rng.integers(400, 1_500, nf), rng.random(nf) > 0.05), make_column(0, 2, T.DOUBLE, rng.random(nf), rng.random(nf) > 0.1)]
+    semi = "SEMI" in jt
+    aggs = [P.agg_expr("count_star", 2, 1)] + ([] if semi else [P.agg_expr("count", 2, 2, None, P.slot_ref(0, 2, T.DOUBLE)), P.agg_expr("sum", 2, 3, None, P.slot_ref(0, 2, T.DOUBLE))])
+    ch = (P.scan(0), P.scan(1)) if jt == "RIGHT_JOIN" else (P.scan(1), P.scan(0))
+    j = P.join(ch[0], ch[1], [P.eq(P.slot_ref(1, 1, T.INT32), P.slot_ref(0, 1, T.INT32))], join_type=getattr(P.JoinType, jt))
+    pl = P.Plan(P.agg(j, 2, [P.slot_ref(1, 2, T.INT32)], aggs), {0: [(1, T.INT32), (2, T.DOUBLE)], 1: [(1, T.INT32), (2, T.INT32)],
+                                                                   2: P.agg_tuple_slots(aggs, [T.INT64] if semi else [T.INT64, T.INT64, T.DOUBLE])})
+    r = oracle.execute(pl.serialize(), fact + dim)
+    mine = {c.name: c.to_list() for c in r.columns}
+    at = {"LEFT_JOIN": "left outer", "RIGHT_JOIN": "left outer", "SEMI_JOIN": "left semi", "ANTI_SEMI_JOIN": "left anti"}[jt]
+    jd = ac.Declaration("hashjoin", ac.HashJoinNodeOptions(at, ["1_1"], ["0_1"]),
+                        inputs=[ac.Declaration("table_source", ac.TableSourceNodeOptions(A.to_table(dim))), ac.Declaration("table_source", ac.TableSourceNodeOptions(A.to_table(fact)))])
+    specs = [([], "hash_count_all", None, "c")] + ([] if semi else [("0_2", "hash_count", None, "n"), ("0_2", "hash_sum", None, "s")])
+    t = ac.Declaration("aggregate", ac.AggregateNodeOptions(specs, keys=["1_2"]), inputs=[jd]).to_table()
+    want = {k: i for i, k in enumerate(t.column("1_2").to_pylist())}
+    assert sorted(mine["1_2"]) == sorted(want)
+    for i, k in enumerate(mine["1_2"]):
+        assert mine["2_1"][i] == t.column("c")[want[k]].as_py()
+        if not semi:
+            assert mine["2_2"][i] == t.column("n")[want[k]].as_py()
+            a, b = mine["2_3"][i], t.column("s")[want[k]].as_py()
+            assert (a is None and b is None) or abs(a - b) <= 1e-9 * max(1.0, abs(b))
