@@ -474,8 +474,8 @@ __global__ void k_sort_images(RowArgs a, int key_reg, int vclass, int desc, int 
 // The previous version gathered key[perm[i]] (a random 8-byte read per element and pass) and scattered 32 elements at a time.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 pairs per CTA tile (48 KB of shared memory for the reorder)
+constexpr int RS_ITEMS = 12;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 3072 pairs per CTA tile (36 KB of shared memory for the reorder): four CTAs per SM
 constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_PREFIX = 2u << 30, RS_VAL_MASK = (1u << 30) - 1u;
 
 __global__ void __launch_bounds__(256) k_rs_hist(const uint64_t* key, uint32_t n, uint32_t* hist /* [8][256] */) {
@@ -506,13 +506,20 @@ __global__ void k_rs_bases(const uint32_t* hist, uint32_t* bases, uint32_t* acti
     bases[d * 256 + threadIdx.x] = s[threadIdx.x];
 }
 // null BYTES (1 = NULL) of a retained column -> Arrow validity bitmap (bit set = valid)
-__global__ void k_pack_null_bytes(const uint8_t* nb, int64_t n, uint8_t* bitmap) {
+__global__ void k_pack_null_bytes(const uint8_t* nb, int64_t n, uint8_t* bitmap, uint32_t* any_null) {
     const int64_t nbytes = (n + 7) / 8;
+    bool seen = false;
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbytes; b += (int64_t)gridDim.x * blockDim.x) {
         uint32_t v = 0;
-        for (int j = 0; j < 8; j++) { const int64_t r = b * 8 + j; if (r < n && !nb[r]) v |= 1u << j; }
+        for (int j = 0; j < 8; j++) { const int64_t r = b * 8 + j; if (r < n) { if (!nb[r]) v |= 1u << j; else seen = true; } }
         bitmap[b] = (uint8_t)v;
     }
+    if (seen) *any_null = 1u;   // (lets the sort skip the NULL-rank pass of a key column without NULLs)
+}
+// key image of a plain column key, without the expression interpreter
+__global__ void k_sort_images_direct(DevCol c, int64_t n, int vclass, int desc, uint64_t* img) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x)
+        img[row] = elem_is_null(c, row) ? 0ull : key_image(load_elem(c, row), vclass, desc);
 }
 __global__ void k_rs_iota(uint32_t* ids, uint32_t n) { for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ids[i] = i; }
 __global__ void k_rs_gather_u64(const uint64_t* src, const uint32_t* ids, uint64_t* dst, uint32_t n) {
@@ -522,7 +529,7 @@ __global__ void k_rs_gather_bytes(const uint8_t* src, const uint32_t* ids, uint8
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[ids[i]];
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_pass(const uint64_t* key_in, const uint32_t* id_in, uint64_t* key_out, uint32_t* id_out, uint32_t n, int shift,
+__global__ void __launch_bounds__(RS_THREADS, 4) k_rs_pass(const uint64_t* key_in, const uint32_t* id_in, uint64_t* key_out, uint32_t* id_out, uint32_t n, int shift,
                                                         const uint32_t* global_base /* [256] of this digit */, uint32_t* status /* [ntiles][256], zeroed */,
                                                         uint32_t* ticket) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
@@ -539,7 +546,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_pass(const uint64_t* key_in, 
     const uint32_t tile = s_tile;
     const uint32_t t0 = tile * RS_TILE;
     const uint32_t tile_n = min((uint32_t)RS_TILE, n - t0);
-    // ---- load: warp w owns the contiguous chunk [t0 + w * 512, + 512), 16 rounds of 32 consecutive pairs ----
+    // ---- load: warp w owns the contiguous chunk [t0 + w * 32 * RS_ITEMS, + 32 * RS_ITEMS), RS_ITEMS rounds of 32 consecutive pairs ----
     uint64_t k[RS_ITEMS]; uint32_t id[RS_ITEMS]; uint32_t rank[RS_ITEMS];
     const uint32_t c0 = w * (RS_ITEMS * 32);
 #pragma unroll
@@ -582,9 +589,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_pass(const uint64_t* key_in, 
         // chained scan with decoupled look-back over the preceding tiles (they all started before this one: ticket order)
         volatile uint32_t* st = status + (size_t)tile * 256 + d;
         uint32_t excl = 0;
-        if (tile == 0) { __threadfence(); *st = RS_FLAG_PREFIX | cnt; }
+        // (flag and count travel in ONE word: no fence is needed around the publication)
+        if (tile == 0) *st = RS_FLAG_PREFIX | cnt;
         else {
-            __threadfence(); *st = RS_FLAG_AGG | cnt;
+            *st = RS_FLAG_AGG | cnt;
             for (int64_t p = (int64_t)tile - 1; p >= 0; p--) {
                 volatile const uint32_t* ps = status + (size_t)p * 256 + d;
                 uint32_t v;
@@ -592,7 +600,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_pass(const uint64_t* key_in, 
                 excl += v & RS_VAL_MASK;
                 if (v & RS_FLAG_PREFIX) break;
             }
-            __threadfence(); *st = RS_FLAG_PREFIX | (excl + cnt);
+            *st = RS_FLAG_PREFIX | (excl + cnt);
         }
         tbase[d] = global_base[d] + excl;
     }
@@ -1130,11 +1138,17 @@ int sort_finish(SortState* s, void* nccl_comm, int nranks, cudaStream_t st, bkgp
     for (int c = 0; c < s->ncols; c++) { ra.cols[c].values = s->ret_vals[(size_t)c]; ra.cols[c].validity = nullptr; ra.cols[c].stype = prim_storage(s->c.cols[(size_t)c].prim); ra.cols[c].prim = s->c.cols[(size_t)c].prim; }
     // retained columns carry null BYTES: pack them into bitmaps on the device so the key program sees NULLs
     std::vector<uint8_t*> bitmaps((size_t)s->ncols, nullptr);
+    uint32_t* null_flags = nullptr;
+    if ((rc = dalloc(s, &null_flags, sizeof(uint32_t) * MAX_COLS, err))) return rc;
+    SCK(cudaMemsetAsync(null_flags, 0, sizeof(uint32_t) * MAX_COLS, st));
     for (int c = 0; c < s->ncols; c++) {
         if ((rc = dalloc(s, &bitmaps[(size_t)c], (size_t)(n + 7) / 8 + 64, err))) return rc;
-        k_pack_null_bytes<<<grid_for((n + 7) / 8, 256, s->sm_count), 256, 0, st>>>(s->ret_null[(size_t)c], n, bitmaps[(size_t)c]);
+        k_pack_null_bytes<<<grid_for((n + 7) / 8, 256, s->sm_count), 256, 0, st>>>(s->ret_null[(size_t)c], n, bitmaps[(size_t)c], null_flags + c);
         ra.cols[c].validity = bitmaps[(size_t)c];
     }
+    uint32_t h_null_flags[MAX_COLS] = {0};
+    SCK(cudaMemcpyAsync(h_null_flags, null_flags, sizeof(uint32_t) * (size_t)s->ncols, cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
     ra.n_cols = s->ncols; ra.nrows = n; ra.prog = s->c.prog; ra.key.pred_out = -1;
     k_rs_iota<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(ids[0], un);
     int cur = 0; bool first = true;
@@ -1165,8 +1179,14 @@ int sort_finish(SortState* s, void* nccl_comm, int nranks, cudaStream_t st, bkgp
     };
     for (int ki = (int)s->c.sort_keys.size() - 1; ki >= 0; ki--) {
         const SortKey& sk = s->c.sort_keys[(size_t)ki];
+        // a plain column key (config C5's shape): its image comes straight from the column, and without NULLs in it the NULL-rank pass is void
+        const bool direct_key = s->c.has_direct && s->c.sort_keys.size() == 1 && !s->c.direct_cols.empty();
+        const int dcol = direct_key ? s->c.direct_cols[0] : -1;
         for (int mode = 0; mode < 2; mode++) {   // the key's value image first, then its NULL rank (stable: NULLs end up strictly first / last)
+            if (mode == 1 && direct_key && !h_null_flags[dcol]) continue;
             uint64_t* dst = first ? img[cur] : img_row;
+            if (mode == 0 && direct_key) k_sort_images_direct<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(ra.cols[dcol], n, host_prim_class(sk.prim), sk.asc ? 0 : 1, dst);
+            else
             k_sort_images<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(ra, sk.out_reg, host_prim_class(sk.prim), sk.asc ? 0 : 1, sk.null_first ? 1 : 0, mode, dst, nullptr);
             if (!first) k_rs_gather_u64<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(img_row, ids[cur], img[cur], un);   // images in the current order
             first = false;
@@ -1185,6 +1205,7 @@ int sort_finish(SortState* s, void* nccl_comm, int nranks, cudaStream_t st, bkgp
     rc = copy_out(s, s->ret_vals.data(), s->ret_null.data(), ids[cur], keep, skip, st, out, err);
     dfree(s, img_row); dfree(s, img[0]); dfree(s, img[1]); dfree(s, ids[0]); dfree(s, ids[1]); dfree(s, hist); dfree(s, status);
     for (auto b : bitmaps) dfree(s, b);
+    dfree(s, null_flags);
     return rc;
 }
 
