@@ -48,6 +48,10 @@ class ExprNodeType(IntEnum):  # proto/expr.proto:6-37
     AND_PREDICATE = 13
     OR_PREDICATE = 14
     XOR_PREDICATE = 15
+    TIMESTAMP_LITERAL = 16
+    DATETIME_LITERAL = 17
+    DATE_LITERAL = 18
+    TIME_LITERAL = 20
     IS_TRUE_PREDICATE = 19
     ROW_EXPR = 22
 
@@ -191,6 +195,13 @@ class Expr:
             out.w64(v)
         elif nt == ExprNodeType.DOUBLE_LITERAL:
             out.f64(self.value)
+        elif nt == ExprNodeType.STRING_LITERAL:
+            out.s(self.value)
+        elif nt in (ExprNodeType.TIMESTAMP_LITERAL, ExprNodeType.DATETIME_LITERAL, ExprNodeType.DATE_LITERAL, ExprNodeType.TIME_LITERAL):
+            v = int(self.value)     # DeriveExprNode.int_val: the image (literal.h:95-114)
+            if v >= 1 << 63:
+                v -= 1 << 64
+            out.w64(v)
         elif nt == ExprNodeType.AGG_EXPR:
             out.s(self.name)
             out.w(self.tuple_id)
@@ -227,6 +238,27 @@ def double_lit(v: float) -> Expr:
 
 def bool_lit(v: bool) -> Expr:
     return Expr(ExprNodeType.BOOL_LITERAL, T.BOOL, value=bool(v))
+
+
+def str_lit(text: str) -> Expr:
+    """a STRING literal; the GPU path takes it only where type inference folds it into a date/time image"""
+    return Expr(ExprNodeType.STRING_LITERAL, T.STRING, value=text)
+
+
+def datetime_lit(image: int) -> Expr:
+    return Expr(ExprNodeType.DATETIME_LITERAL, T.DATETIME, value=int(image))
+
+
+def timestamp_lit(seconds: int) -> Expr:
+    return Expr(ExprNodeType.TIMESTAMP_LITERAL, T.TIMESTAMP, value=int(seconds))
+
+
+def date_lit(image: int) -> Expr:
+    return Expr(ExprNodeType.DATE_LITERAL, T.DATE, value=int(image))
+
+
+def time_lit(image: int) -> Expr:
+    return Expr(ExprNodeType.TIME_LITERAL, T.TIME, value=int(image))
 
 
 def null_lit() -> Expr:

@@ -157,7 +157,7 @@ __global__ void __maxnreg__(wp_regs(WARPS)) k_agg_group_wp(const __grid_constant
     const size_t wbytes = wp_warp_bytes_dev(NA, G);
     unsigned char* acc0 = (unsigned char*)(next_id + 4);
     // ---- init: key table EMPTY, every warp zeroes its own accumulators (the identity of ADD and of the row count) ----
-    if (!DENSE) { for (uint32_t i = threadIdx.x; i < kt_cap; i += blockDim.x) kt[i] = ~0ull; }
+    if constexpr (!DENSE) { for (uint32_t i = threadIdx.x; i < kt_cap; i += blockDim.x) kt[i] = ~0ull; }
     if (threadIdx.x == 0) *next_id = 0;
     {
         uint32_t* w = (uint32_t*)(acc0 + wbytes * warp);

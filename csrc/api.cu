@@ -333,7 +333,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
     for (int k = 0; k < a.plan.n_agg; k++) {
         AggSpec& s = a.plan.agg[k];
         if (s.kind == AG_COUNT_STAR) continue;
-        bool nullable = c.arg_can_null[(size_t)k];
+        bool nullable = c.arg_can_null[(size_t)k] || p->join_tail_launch;   // (the tail's probe-side columns are NULL on every row)
         for (int i = 0; i < ncols; i++) if ((c.arg_cols_mask[(size_t)k] >> i) & 1) nullable = nullable || cols[i].validity != nullptr;
         s.nullable = nullable ? 1 : 0;
         if (s.cnt_lane && s.cnt_owner) {

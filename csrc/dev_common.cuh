@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include "dev_types.h"
 #include "../include/bkgpu_plan.h"
+#include "datetime.h"
 
 namespace bk {
 
@@ -158,6 +159,7 @@ __device__ __forceinline__ uint64_t f64_to_u64_x86(double d) {
 }
 // ExprValue::cast_to (include/common/expr_value.h:502-611) for the numeric types
 __device__ __forceinline__ uint64_t cast_prim(uint64_t v, int from, int to) {
+    if (from != to && dt_is_family(from) && dt_is_family(to)) return dt_family_cast(v, from, to);   // DATE <-> DATETIME <-> TIMESTAMP (-> TIME)
     int fc = prim_class(from);
     if (to == BK_DOUBLE || to == BK_FLOAT) {
         double d = fc == VC_F64 ? bits_f64(v) : (fc == VC_U64 ? (double)v : (double)(int64_t)v);

@@ -15,6 +15,7 @@
 #include <string.h>
 #include <map>
 #include "../include/bkgpu.h"
+#include "datetime.h"
 
 namespace bk {
 
@@ -55,6 +56,7 @@ static double bitsd(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
 // ExprValue::cast_to on canonical images, executed with the host's (x86-64) conversion semantics —
 // the same ones the reference binary gets from its static_casts (expr_value.h:340-410,502-611).
 uint64_t host_cast_prim(uint64_t v, int from, int to) {
+    if (from != to && dt_is_family(from) && dt_is_family(to)) return dt_family_cast(v, from, to);   // (callers reject TIME sources first)
     int fc = host_prim_class(from);
     if (to == BK_DOUBLE || to == BK_FLOAT) {
         double d = fc == VC_F64 ? bitsd(v) : (fc == VC_U64 ? (double)v : (double)(int64_t)v);
@@ -100,7 +102,9 @@ struct Reader {
     void bad(const char* m) { if (!fail) { fail = true; err = m; } }
 };
 
-static bool is_literal_node(int nt) { return nt >= BK_NULL_LITERAL && nt <= BK_STRING_LITERAL; }
+static bool is_literal_node(int nt) {
+    return (nt >= BK_NULL_LITERAL && nt <= BK_STRING_LITERAL) || nt == BK_TIMESTAMP_LITERAL || nt == BK_DATETIME_LITERAL || nt == BK_DATE_LITERAL || nt == BK_TIME_LITERAL;
+}
 
 static void parse_enode(Reader& r, HExpr& e, int& remaining, int depth) {
     if (remaining <= 0 || depth > 64) { r.bad("expr node list does not match its node count"); return; }
@@ -113,6 +117,12 @@ static void parse_enode(Reader& r, HExpr& e, int& remaining, int depth) {
         case BK_BOOL_LITERAL: e.lit_bits = r.rd() ? 1 : 0; e.lit_prim = BK_BOOL; break;
         case BK_INT_LITERAL: e.lit_bits = (uint64_t)r.rd64(); e.lit_prim = BK_INT64; break;
         case BK_DOUBLE_LITERAL: e.lit_bits = (uint64_t)r.rd64(); e.lit_prim = BK_DOUBLE; break;
+        case BK_STRING_LITERAL: e.lit_str = r.rdstr(); e.lit_prim = BK_STRING; break;   // (only where inference folds it into a date/time image)
+        // DeriveExprNode.int_val carries the image (Literal::init, include/expr/literal.h:95-114)
+        case BK_DATETIME_LITERAL: e.lit_bits = (uint64_t)r.rd64(); e.lit_prim = BK_DATETIME; break;
+        case BK_TIMESTAMP_LITERAL: e.lit_bits = (uint64_t)(uint32_t)r.rd64(); e.lit_prim = BK_TIMESTAMP; break;
+        case BK_DATE_LITERAL: e.lit_bits = (uint64_t)(uint32_t)r.rd64(); e.lit_prim = BK_DATE; break;
+        case BK_TIME_LITERAL: e.lit_bits = (uint64_t)(int64_t)(int32_t)r.rd64(); e.lit_prim = BK_TIME; break;
         case BK_AGG_EXPR:
             e.name = r.rdstr(); e.tuple_id = r.rd(); e.final_slot = r.rd(); e.inter_slot = r.rd(); break;
         case BK_FUNCTION_CALL: case BK_IS_NULL_PREDICATE: case BK_IN_PREDICATE: case BK_NOT_PREDICATE:
@@ -123,8 +133,8 @@ static void parse_enode(Reader& r, HExpr& e, int& remaining, int depth) {
             for (int i = 0; i < na; i++) e.arg_types.push_back(r.rd());
             e.return_type = r.rd();
         } break;
-        case BK_STRING_LITERAL: case BK_LIKE_PREDICATE: case BK_ROW_EXPR:
-            r.bad("STRING / LIKE / ROW expressions are outside the GPU path"); return;
+        case BK_LIKE_PREDICATE: case BK_ROW_EXPR:
+            r.bad("LIKE / ROW expressions are outside the GPU path"); return;
         default: r.bad("unknown expr node type"); return;
     }
     if (nch < 0 || nch > 1024) { r.bad("bad expr num_children"); return; }
@@ -194,6 +204,29 @@ static bool expr_constant(const HExpr& e) {
 }
 static void complete(HExpr& e, int nargs, int at, int rt) { e.arg_types.assign((size_t)nargs, at); e.return_type = rt; }
 
+// A literal's value as the image of type `to` — ExprValue::cast_to (include/common/expr_value.h:502-611) on the host.
+// `via_text`: Literal::cast_to_col_type (include/expr/literal.h:204-210) — a numeric literal that meets a date/time type is first
+// written out in decimal and then read as a date ("20240131" -> 2024-01-31); a plain cast_to reinterprets the number as the image.
+static bool fold_literal(Infer& in, HExpr& c, int to, bool via_text) {
+    if (c.lit_null || to == BK_INVALID_TYPE || to == BK_NULL_TYPE) return true;
+    if (c.lit_prim == BK_TIME && dt_is_family(to) && to != BK_TIME)
+        return in.fail(BKGPU_EUNSUPPORTED, "a TIME value as DATE/DATETIME/TIMESTAMP depends on the current date: outside the GPU path");
+    if (dt_is_family(to) && c.lit_prim != BK_STRING && !dt_is_family(c.lit_prim) && via_text) {
+        if (is_double_t(c.lit_prim)) return in.fail(BKGPU_EUNSUPPORTED, "a DOUBLE literal compared as a date/time goes through its text form: outside the GPU path");
+        char buf[32];
+        if (is_uint_t(c.lit_prim)) snprintf(buf, sizeof buf, "%llu", (unsigned long long)c.lit_bits);
+        else snprintf(buf, sizeof buf, "%lld", (long long)c.lit_bits);   // std::to_string, expr_value.h:709-726 (BOOL prints 0 / 1)
+        c.lit_str = buf; c.lit_prim = BK_STRING;
+    }
+    if (c.lit_prim == BK_STRING) {
+        if (to == BK_STRING) return true;
+        if (!dt_is_family(to)) return in.fail(BKGPU_EUNSUPPORTED, "a STRING literal outside a date/time comparison is outside the GPU path");
+        c.lit_bits = parse_literal(c.lit_str.c_str(), c.lit_str.size(), to);
+    } else c.lit_bits = host_cast_prim(c.lit_bits, c.lit_prim, to);
+    c.lit_prim = to;
+    return true;
+}
+
 static bool infer_expr(Infer& in, HExpr& e) {
     for (auto& c : e.ch) if (!infer_expr(in, c)) return false;
     e.is_constant = expr_constant(e);
@@ -213,6 +246,11 @@ static bool infer_expr(Infer& in, HExpr& e) {
         case BK_BOOL_LITERAL: if (!e.col_type) e.col_type = BK_BOOL; return true;
         case BK_INT_LITERAL: if (!e.col_type) e.col_type = BK_INT64; return true;
         case BK_DOUBLE_LITERAL: if (!e.col_type) e.col_type = BK_DOUBLE; return true;
+        case BK_STRING_LITERAL: if (!e.col_type) e.col_type = BK_STRING; return true;
+        case BK_DATETIME_LITERAL: if (!e.col_type) e.col_type = BK_DATETIME; return true;
+        case BK_TIMESTAMP_LITERAL: if (!e.col_type) e.col_type = BK_TIMESTAMP; return true;
+        case BK_DATE_LITERAL: if (!e.col_type) e.col_type = BK_DATE; return true;
+        case BK_TIME_LITERAL: if (!e.col_type) e.col_type = BK_TIME; return true;
         case BK_AGG_EXPR: {  // agg_fn_call.cpp:87-122
             int ct = e.ch.empty() ? BK_INVALID_TYPE : e.ch[0].col_type;
             if (e.name == "count_star" || e.name == "count") e.col_type = BK_INT64;
@@ -239,11 +277,22 @@ static bool infer_expr(Infer& in, HExpr& e) {
             std::vector<int> types = {e.ch[0].col_type, e.ch[1].col_type};
             int map_type;
             if (all_int(types)) map_type = BK_INT64;
-            else if (has(types, is_datetime_family)) return in.fail(BKGPU_EUNSUPPORTED, "IN over date/time types is outside the GPU path");
+            else if (has_eq(types, BK_DATETIME)) map_type = BK_DATETIME;     // InPredicate::singel_open, predicate.cpp:102-119
+            else if (has_eq(types, BK_TIMESTAMP)) map_type = BK_TIMESTAMP;
+            else if (has_eq(types, BK_DATE)) map_type = BK_DATE;
+            else if (has_eq(types, BK_TIME)) map_type = BK_TIME;
             else if (has(types, is_double_t) || has(types, is_int_t)) map_type = BK_DOUBLE;
             else return in.fail(BKGPU_EUNSUPPORTED, "IN over STRING is outside the GPU path");
-            for (size_t i = 1; i < e.ch.size(); i++)
-                if (!is_literal_node(e.ch[i].node_type)) return in.fail(BKGPU_EUNSUPPORTED, "IN list entries must be literals");
+            if (e.ch[0].col_type == BK_STRING) return in.fail(BKGPU_EUNSUPPORTED, "IN over a STRING operand is outside the GPU path");
+            if (e.ch[0].col_type == BK_TIME && map_type != BK_TIME && dt_is_family(map_type))
+                return in.fail(BKGPU_EUNSUPPORTED, "a TIME value as DATE/DATETIME/TIMESTAMP depends on the current date: outside the GPU path");
+            for (size_t i = 1; i < e.ch.size(); i++) {
+                HExpr& c = e.ch[i];
+                if (!is_literal_node(c.node_type)) return in.fail(BKGPU_EUNSUPPORTED, "IN list entries must be literals");
+                // Literal::get_value casts to the literal's col_type, then the set takes value.cast_to(_map_type) (predicate.cpp:120-136)
+                if (!fold_literal(in, c, c.col_type, false) || !fold_literal(in, c, map_type, false)) return false;
+                if (!c.lit_null) c.col_type = map_type;
+            }
             e.arg_types.assign(1, map_type);
             if (!e.col_type) e.col_type = BK_BOOL;
             return true;
@@ -342,18 +391,19 @@ static bool infer_expr(Infer& in, HExpr& e) {
         for (size_t i = 0; i < e.arg_types.size() && i < e.ch.size(); i++) {
             HExpr& c = e.ch[i];
             if (is_literal_node(c.node_type) && !c.lit_null) {
-                if (is_datetime_family(e.arg_types[i]))
-                    return in.fail(BKGPU_EUNSUPPORTED, "numeric literal compared as date/time needs string parsing: outside the GPU path");
-                c.lit_bits = host_cast_prim(c.lit_bits, c.lit_prim, e.arg_types[i]); c.lit_prim = e.arg_types[i];
+                if (!fold_literal(in, c, e.arg_types[i], true)) return false;
+                c.col_type = e.arg_types[i];   // value_to_node_type: the literal now is of the argument's type (literal.h:296-310)
             }
         }
     }
     if (e.ch.size() < e.arg_types.size()) return in.fail(BKGPU_EINVAL, "function has fewer children than arg_types");
     for (int at : e.arg_types)
         if (at == BK_STRING) return in.fail(BKGPU_EUNSUPPORTED, "STRING-domain comparison is outside the GPU path");
-    for (size_t i = 0; i < e.arg_types.size(); i++)
-        if (is_datetime_family(e.arg_types[i]) && e.ch[i].col_type != e.arg_types[i])
-            return in.fail(BKGPU_EUNSUPPORTED, "date/time casts are outside the GPU path (only same-type comparisons)");
+    for (size_t i = 0; i < e.arg_types.size(); i++) {
+        if (e.ch[i].col_type == BK_TIME && e.arg_types[i] != BK_TIME && dt_is_family(e.arg_types[i]))
+            return in.fail(BKGPU_EUNSUPPORTED, "a TIME value as DATE/DATETIME/TIMESTAMP depends on the current date: outside the GPU path");
+        if (e.ch[i].col_type == BK_STRING) return in.fail(BKGPU_EUNSUPPORTED, "STRING operands are outside the GPU path");
+    }
     return true;
 }
 
@@ -389,6 +439,7 @@ struct Lower {
     // ExprValue::cast_to between canonical images: a no-op when the image does not change
     bool cast(int from, int to) {
         if (from == to || to == BK_INVALID_TYPE || from == BK_NULL_TYPE) return true;
+        if (dt_is_family(from) && dt_is_family(to)) return emit(OP_CAST, (uint8_t)from, (uint8_t)to);   // calendar conversion (datetime.h)
         bool from_int = is_int_t(from) || from == BK_BOOL || is_datetime_family(from);
         if (from_int && (to == BK_INT64 || to == BK_UINT64 || to == BK_DATETIME)) return true;  // sign/zero-extended image reinterpreted
         if (from == BK_FLOAT && to == BK_DOUBLE) return true;                                    // floats travel widened
@@ -409,7 +460,11 @@ struct Lower {
                 return cast(st, e.col_type);
             }
             case BK_NULL_LITERAL: { int k = add_const(0, true); if (k < 0) return false; depth++; return emit(OP_CONST, (uint8_t)k); }
-            case BK_BOOL_LITERAL: case BK_INT_LITERAL: case BK_DOUBLE_LITERAL: {
+            case BK_BOOL_LITERAL: case BK_INT_LITERAL: case BK_DOUBLE_LITERAL: case BK_STRING_LITERAL:
+            case BK_DATETIME_LITERAL: case BK_TIMESTAMP_LITERAL: case BK_DATE_LITERAL: case BK_TIME_LITERAL: {
+                if (e.lit_prim == BK_STRING) return in->fail(BKGPU_EUNSUPPORTED, "a STRING literal outside a date/time comparison is outside the GPU path");
+                if (e.lit_prim == BK_TIME && e.col_type != BK_TIME && dt_is_family(e.col_type))
+                    return in->fail(BKGPU_EUNSUPPORTED, "a TIME value as DATE/DATETIME/TIMESTAMP depends on the current date: outside the GPU path");
                 // Literal::get_value: _value.cast_to(_col_type)
                 uint64_t bits = e.col_type ? host_cast_prim(e.lit_bits, e.lit_prim, e.col_type) : e.lit_bits;
                 int k = add_const(bits, false); if (k < 0) return false;
@@ -774,7 +829,8 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
                 if (st != col->col_type) { ok = false; break; }
                 int cc = host_prim_class(st), ac = host_prim_class(at);
                 if ((cc == VC_F64) != (ac == VC_F64)) { ok = false; break; }  // would need an int<->double conversion per row
-                if (is_datetime_family(at)) { ok = false; break; }
+                if (is_datetime_family(at) && st != at) { ok = false; break; }   // (a change of type inside the family is a calendar conversion: generic path)
+                if (lit->lit_prim == BK_STRING) { ok = false; break; }
                 // Literal::get_value casts to its col_type, ScalarFnCall casts that to the arg type
                 uint64_t bits = lit->col_type ? host_cast_prim(lit->lit_bits, lit->lit_prim, lit->col_type) : lit->lit_bits;
                 bits = host_cast_prim(bits, lit->col_type ? lit->col_type : lit->lit_prim, at);

@@ -22,6 +22,7 @@ struct HExpr {
     bool lit_null = false;
     uint64_t lit_bits = 0;
     int lit_prim = 0;
+    std::string lit_str;              // STRING literal text (lit_prim == BK_STRING) until type inference folds it into an image
     int final_slot = 0, inter_slot = 0;
     bool is_constant = false;
 };
@@ -96,6 +97,8 @@ int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& er
 
 // host-side ExprValue::cast_to on canonical images (x86 semantics == the reference's build)
 uint64_t host_cast_prim(uint64_t v, int from, int to);
+// literal.cpp: the text of a literal as a DATETIME / TIMESTAMP / DATE / TIME image (ExprValue::cast_to from STRING)
+uint64_t parse_literal(const char* text, size_t length, int to_prim);
 int host_prim_class(int prim);
 int prim_storage(int prim);       // SType of the column buffer carrying `prim`
 int storage_bytes(int stype);

@@ -142,6 +142,17 @@ void  bkgpu_cancel(bkgpu_plan*);
 void  bkgpu_close(bkgpu_plan*);
 int   bkgpu_get_stats(bkgpu_plan*, bkgpu_stats* out);
 
+/* ---- date/time literals ----
+ * The text of a literal as the image the plan compares against: ExprValue::cast_to from STRING (include/common/expr_value.h:534-573
+ * -> str_to_datetime / str_to_time, src/common/datetime.cpp:149-263,477-560), for a binding that folds `col >= '2024-01-31'`
+ * itself.  prim_type: BK_DATETIME, BK_TIMESTAMP, BK_DATE or BK_TIME; *image: the 64-bit canonical image (TIMESTAMP / DATE
+ * zero-extended, TIME sign-extended).  Text that is not a date gives the zero image, as in the reference.  Needs no GPU. */
+int   bkgpu_parse_datetime(const char* text, size_t length, int prim_type, uint64_t* image);
+/* ExprValue::cast_to (include/common/expr_value.h:502-611) between two non-STRING primitive types, on canonical images — the
+ * conversion plan compilation applies to literals (DATE <-> DATETIME <-> TIMESTAMP in the reference's fixed UTC+8 zone included).
+ * BKGPU_EUNSUPPORTED for a TIME source with another date/time target (relative to the current date in the reference). */
+int   bkgpu_cast_image(uint64_t image, int from_prim, int to_prim, uint64_t* out);
+
 /* ---- resident regions (the column store / parquet cache analogue, include/column/file_manager.h:252-272) ----
  * A region's columns are copied to HBM once (host or device source) and stay there across queries, keyed by
  * (device, region_id); bkgpu_push_region feeds them to a plan exactly like bkgpu_push(..., on_device = 1) — a query

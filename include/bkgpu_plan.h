@@ -30,6 +30,9 @@
  *     BOOL_LITERAL    : value
  *     INT_LITERAL     : value64
  *     DOUBLE_LITERAL  : ieee754-bits64
+ *     STRING_LITERAL  : str (taken only where it meets a DATE / DATETIME / TIMESTAMP / TIME operand: folded into that type's image
+ *                       the way ExprValue::cast_to parses it, include/common/expr_value.h:534-573)
+ *     DATETIME_LITERAL, TIMESTAMP_LITERAL, DATE_LITERAL, TIME_LITERAL : value64 = the image (DeriveExprNode.int_val, literal.h:95-114)
  *     FUNCTION_CALL, *_PREDICATE : fn_op STR(name) n_arg_types arg_type* return_type   pb::Function
  *                       (n_arg_types == 0 / return_type == 0: not yet completed; the library
  *                        then runs the reference's type inference itself —
@@ -59,7 +62,8 @@ enum bkgpu_expr_node_type {
     BK_BOOL_LITERAL = 5, BK_INT_LITERAL = 6, BK_DOUBLE_LITERAL = 7, BK_STRING_LITERAL = 8,
     BK_IS_NULL_PREDICATE = 9, BK_IN_PREDICATE = 10, BK_LIKE_PREDICATE = 11,
     BK_NOT_PREDICATE = 12, BK_AND_PREDICATE = 13, BK_OR_PREDICATE = 14,
-    BK_XOR_PREDICATE = 15, BK_IS_TRUE_PREDICATE = 19, BK_ROW_EXPR = 22
+    BK_XOR_PREDICATE = 15, BK_TIMESTAMP_LITERAL = 16, BK_DATETIME_LITERAL = 17, BK_DATE_LITERAL = 18,
+    BK_IS_TRUE_PREDICATE = 19, BK_TIME_LITERAL = 20, BK_ROW_EXPR = 22
 };
 
 /* pb::PrimitiveType — proto/common.proto:46-72 */

@@ -28,10 +28,12 @@
  * of <= 1024 rows, one ExprValue per value access, byte-string group keys.
  */
 #include "bk_oracle.h"
+#include <ctype.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 /* ---- enum values: the reference's (see include/bkgpu_plan.h for the citations) ---- */
 enum { T_INVALID = 0, T_NULL = 1, T_BOOL = 2, T_INT8 = 3, T_INT16 = 4, T_INT32 = 5, T_INT64 = 6,
@@ -42,7 +44,8 @@ enum { N_SCAN = 1, N_SORT = 2, N_AGG = 4, N_MERGE_AGG = 5, N_TABLE_FILTER = 6, N
        N_LIMIT = 11, N_WHERE_FILTER = 12, N_HAVING_FILTER = 13, N_PACKET = 14, N_SELECT_MANAGER = 25 };
 enum { E_SLOT_REF = 1, E_FUNCTION_CALL = 2, E_AGG_EXPR = 3, E_NULL_LITERAL = 4, E_BOOL_LITERAL = 5,
        E_INT_LITERAL = 6, E_DOUBLE_LITERAL = 7, E_STRING_LITERAL = 8, E_IS_NULL = 9, E_IN = 10,
-       E_LIKE = 11, E_NOT = 12, E_AND = 13, E_OR = 14, E_XOR = 15, E_IS_TRUE = 19, E_ROW_EXPR = 22 };
+       E_LIKE = 11, E_NOT = 12, E_AND = 13, E_OR = 14, E_XOR = 15, E_TIMESTAMP_LITERAL = 16, E_DATETIME_LITERAL = 17,
+       E_DATE_LITERAL = 18, E_IS_TRUE = 19, E_TIME_LITERAL = 20, E_ROW_EXPR = 22 };
 enum { FT_COMMON = 0, FT_AGG = 1, FT_BIT_NOT = 2, FT_LOGIC_NOT = 3, FT_UMINUS = 4, FT_ADD = 5,
        FT_MINUS = 6, FT_MULTIPLIES = 7, FT_DIVIDES = 8, FT_MOD = 9, FT_LS = 10, FT_RS = 11,
        FT_BIT_AND = 12, FT_BIT_OR = 13, FT_BIT_XOR = 14, FT_EQ = 15, FT_NE = 16, FT_GT = 17,
@@ -64,6 +67,7 @@ typedef struct ExprValue {
         float float_val; double double_val;
     } u;
     AvgIntermediate avg; /* the 16-byte STRING blob AVG keeps in its intermediate slot */
+    const char* str;     /* STRING literal (NUL-terminated, owned by its Expr); NULL for the AVG blob */
 } ExprValue;
 
 static ExprValue ev_null(void) { ExprValue v; memset(&v, 0, sizeof v); v.type = T_NULL; return v; }
@@ -106,28 +110,262 @@ static int num_bool(const ExprValue* v) { /* static_cast<bool>: non-zero -> true
     }
 }
 
-/* cast_to, expr_value.h:502-611 — numeric targets only; the date/time/string families are
- * outside the GPU path and are rejected when the plan is built. */
+/* =========================== date / time encodings ===========================
+ * include/common/datetime.h:28-33,56-68 (layouts) and src/common/datetime.cpp (conversions; the reference fixes the
+ * zone at UTC+8 without DST: mktime_fixed_r / localtime_fixed_r default tz_offset_hours = 8).
+ *   DATETIME  u64: (year*13+month)<<46 | day<<41 | hour<<36 | minute<<30 | second<<24 | microsecond
+ *   DATE      u32: DATETIME >> 41          TIMESTAMP u32: seconds since the epoch
+ *   TIME      i32: sign * (hour<<12 | minute<<6 | second) */
+static int64_t dt_div_floor(int64_t a, int64_t b) { return (a >= 0 ? a : a + 1 - b) / b; }             /* datetime.cpp:24-26 */
+static int64_t dt_days_from_civil(int64_t y, unsigned m, unsigned d) {                                 /* datetime.cpp:31-38 */
+    y -= m <= 2;
+    const int64_t era = dt_div_floor(y, 400);
+    const unsigned yoe = (unsigned)(y - era * 400);
+    const unsigned doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+    const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    return era * 146097 + (int64_t)doe - 719468;
+}
+static int64_t dt_mktime_fixed(int year, unsigned mon, unsigned mday, int hour, int min, int sec, int tz) { /* datetime.cpp:41-52 */
+    return dt_days_from_civil(year, mon, mday) * 86400LL + hour * 3600LL + min * 60LL + sec - tz * 3600LL;
+}
+typedef struct { int year, mon, mday, hour, min, sec; } DtCivil;
+static DtCivil dt_localtime_fixed(int64_t timep, int tz) {                                             /* datetime.cpp:54-98 */
+    int64_t t = timep + tz * 3600LL, days = t / 86400LL, rem = t % 86400LL;
+    if (rem < 0) { rem += 86400LL; --days; }
+    const int64_t z = days + 719468, era = dt_div_floor(z, 146097);
+    const unsigned doe = (unsigned)(z - era * 146097);
+    const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    int year = (int)(yoe + era * 400);
+    const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const unsigned mp = (5 * doy + 2) / 153;
+    DtCivil c;
+    c.mday = (int)(doy - (153 * mp + 2) / 5 + 1);
+    c.mon = (int)(mp + (mp < 10 ? 3 : -9));
+    c.year = year + (c.mon <= 2);
+    c.hour = (int)(rem / 3600); rem %= 3600; c.min = (int)(rem / 60); c.sec = (int)(rem % 60);
+    return c;
+}
+static uint64_t dt_pack(uint64_t year, uint64_t month, uint64_t day, uint64_t hour, uint64_t minute, uint64_t second, uint64_t macrosec) {
+    return ((year * 13 + month) << 46) | (day << 41) | (hour << 36) | (minute << 30) | (second << 24) | macrosec;
+}
+/* str_to_datetime_internal, datetime.cpp:149-263 (the sscanf formats are the reference's) */
+static uint64_t dt_str_to_datetime(const char* str_time, size_t length, int* is_full_datetime) {
+    int is_full = 0;
+    while (*str_time == ' ') str_time++;
+    enum { max_time_size = 26 };
+    size_t len = length < max_time_size ? length : max_time_size;
+    char buf[max_time_size + 1]; memset(buf, 0, sizeof buf);
+    memcpy(buf, str_time, strnlen(str_time, len));
+    int has_delim = 1, delim_cnt = 0;
+    if (isdigit((unsigned char)buf[2]) && isdigit((unsigned char)buf[4])) has_delim = 0;
+    if (buf[3] == '-') has_delim = 1;
+    int32_t year_length = -1; uint32_t idx = 0;
+    for (; idx < len; ++idx) {
+        if (has_delim) {
+            if (!isdigit((unsigned char)buf[idx])) { delim_cnt++; if (year_length == -1) year_length = (int32_t)idx; }
+            if (delim_cnt > 5 && buf[idx] == '.') break;
+        } else if (buf[idx] == '.') break;
+    }
+    if (idx < len) for (uint32_t i = idx + 1; i <= idx + 6 && i < max_time_size; ++i) if (!isdigit((unsigned char)buf[i])) buf[i] = '0';
+    unsigned long year = 0, month = 0, day = 0, hour = 0, minute = 0, second = 0, macrosec = 0;
+    if (has_delim) {
+        sscanf(buf, "%4lu%*[^0-9a-z]%2lu%*[^0-9a-z]%2lu%*[^0-9a-z]%2lu%*[^0-9a-z]%2lu%*[^0-9a-z]%2lu.%6lu",
+               &year, &month, &day, &hour, &minute, &second, &macrosec);
+        is_full = 1;
+    } else {
+        if (idx <= 6) { sscanf(buf, "%2lu%2lu%2lu", &year, &month, &day); year_length = 2; }
+        else if (idx == 8) sscanf(buf, "%4lu%2lu%2lu", &year, &month, &day);
+        else if (idx == 12) { sscanf(buf, "%2lu%2lu%2lu%2lu%2lu%2lu.%6lu", &year, &month, &day, &hour, &minute, &second, &macrosec); is_full = 1; year_length = 2; }
+        else if (idx <= 13) { sscanf(buf, "%2lu%2lu%2lu%2lu%2lu%2lu", &year, &month, &day, &hour, &minute, &second); is_full = 1; year_length = 2; }
+        else if (idx >= 14) { sscanf(buf, "%4lu%2lu%2lu%2lu%2lu%2lu.%6lu", &year, &month, &day, &hour, &minute, &second, &macrosec); is_full = 1; }
+        else return 0;
+    }
+    if (year_length == 2) { if (year >= 70 && year < 100) year += 1900; else if (year < 70 && year > 0) year += 2000; }
+    if (month > 12 || day > 31 || hour > 23 || minute > 59 || second > 59) return 0;
+    if (is_full_datetime) *is_full_datetime = is_full;
+    return dt_pack(year, month, day, hour, minute, second, macrosec);
+}
+static int64_t dt_datetime_to_timestamp(uint64_t datetime) {                                           /* datetime.cpp:304-331 */
+    if (datetime == 0) return 0;
+    const int year_month = (int)((datetime >> 46) & 0x1FFFF);
+    const int year = year_month / 13, mon = year_month % 13, mday = (int)((datetime >> 41) & 0x1F);
+    if (mon == 0 || mday == 0) return 0;
+    const int64_t t = dt_mktime_fixed(year, (unsigned)mon, (unsigned)mday, (int)((datetime >> 36) & 0x1F), (int)((datetime >> 30) & 0x3F), (int)((datetime >> 24) & 0x3F), 8);
+    return t <= 0 ? 0 : t;
+}
+static uint64_t dt_timestamp_to_datetime(int64_t timestamp) {                                          /* datetime.cpp:352-373 */
+    if (timestamp == 0) return 0;
+    const DtCivil c = dt_localtime_fixed(timestamp, 8);
+    return dt_pack((uint64_t)c.year, (uint64_t)c.mon, (uint64_t)c.mday, (uint64_t)c.hour, (uint64_t)c.min, (uint64_t)c.sec, 0);
+}
+static uint32_t dt_datetime_to_date(uint64_t datetime) { return (uint32_t)((datetime >> 41) & 0x3FFFFF); } /* datetime.h:62-64 */
+static uint64_t dt_date_to_datetime(uint32_t date) { return (uint64_t)date << 41; }                         /* datetime.h:65-67 */
+static int32_t dt_datetime_to_time(uint64_t datetime) {                                                /* datetime.cpp:410-419 */
+    return (int32_t)(((datetime >> 24) & 0x3F) | (((datetime >> 30) & 0x3F) << 6) | (((datetime >> 36) & 0x1F) << 12));
+}
+static uint64_t dt_time_to_datetime(int32_t tm) {                       /* datetime.cpp:420-442 — relative to today's date */
+    int64_t now = (int64_t)time(NULL);
+    now = ((now + 28800) / 86400) * 86400;
+    int minus = 0; if (tm < 0) { minus = 1; tm = -tm; }
+    int32_t delta = (int32_t)(((tm >> 12) & 0x3FF) * 3600 + ((tm >> 6) & 0x3F) * 60 + (tm & 0x3F));
+    if (minus) delta = -delta;
+    return dt_timestamp_to_datetime(now - 28800 + delta);
+}
+static int32_t dt_str_to_time(const char* str_time, size_t length) {                                   /* datetime.cpp:477-560 */
+    while (*str_time == ' ') { str_time++; length--; }
+    int minus = 0;
+    if (str_time[0] == '-') { minus = 1; str_time++; length--; }
+    size_t len = length < 20 ? length : 20;
+    int day = 0, hour = 0, minute = 0, second = 0; int32_t tm = 0;
+    int has_blank = 0, has_delim = 0; uint32_t idx = 0;
+    for (; idx < len; ++idx) {
+        if (str_time[idx] == ' ') { has_blank = 1; has_delim = 1; }
+        if (str_time[idx] == ':') has_delim = 1;
+        if (str_time[idx] == '.') break;
+    }
+    if (idx >= 12) {
+        int full = 0; uint64_t d = dt_str_to_datetime(str_time, length, &full);
+        if (full) return dt_datetime_to_time(d);
+    }
+    if (has_blank) sscanf(str_time, "%d %u:%2u:%2u", &day, (unsigned*)&hour, (unsigned*)&minute, (unsigned*)&second);
+    else if (has_delim) sscanf(str_time, "%d:%2u:%2u", &hour, (unsigned*)&minute, (unsigned*)&second);
+    else {
+        char t[24];
+        if (idx >= 4) {
+            idx -= 2; memcpy(t, str_time + idx, 2); t[2] = 0; second = (int)strtoll(t, NULL, 10);
+            idx -= 2; memcpy(t, str_time + idx, 2); t[2] = 0; minute = (int)strtoll(t, NULL, 10);
+            memcpy(t, str_time, idx); t[idx] = 0; hour = (int)strtoll(t, NULL, 10);
+        } else if (idx >= 2) {
+            idx -= 2; memcpy(t, str_time + idx, 2); t[2] = 0; second = (int)strtoll(t, NULL, 10);
+            memcpy(t, str_time, idx); t[idx] = 0; minute = (int)strtoll(t, NULL, 10);
+        } else { memcpy(t, str_time, idx); t[idx] = 0; second = (int)strtoll(t, NULL, 10); }
+    }
+    if (day < 0 || hour < 0 || minute < 0 || minute > 59 || second < 0 || second > 59) return 0;
+    hour += day * 24;
+    tm |= second; tm |= (minute << 6); tm |= (hour << 12);
+    return minus ? -tm : tm;
+}
+/* formatting, only to pin the restatement against the reference's own test vectors (test/test_date_time.cpp) */
+static void dt_datetime_to_str(uint64_t d, int precision_len, char out[32]) {                          /* datetime.cpp:117-139 */
+    const int ym = (int)((d >> 46) & 0x1FFFF), macrosec = (int)(d & 0xFFFFFF);
+    snprintf(out, 32, "%04d-%02d-%02d %02d:%02d:%02d.%06d", ym / 13, ym % 13, (int)((d >> 41) & 0x1F), (int)((d >> 36) & 0x1F), (int)((d >> 30) & 0x3F), (int)((d >> 24) & 0x3F), macrosec);
+    if (precision_len > 0 && precision_len <= 6) out[20 + precision_len] = 0;
+    else if (precision_len == 0 || macrosec == 0) out[19] = 0;
+    else out[26] = 0;
+}
+static void dt_timestamp_to_str(int64_t ts, char out[32]) {                                            /* datetime.cpp:100-114 */
+    if (ts <= 0) { snprintf(out, 32, "0000-00-00 00:00:00"); return; }
+    const DtCivil c = dt_localtime_fixed(ts, 8);
+    snprintf(out, 32, "%04d-%02d-%02d %02d:%02d:%02d", c.year, c.mon, c.mday, c.hour, c.min, c.sec);
+}
+static void dt_time_to_str(int32_t tm, char out[32]) {                                                 /* datetime.cpp:443-455 */
+    int minus = 0; if (tm < 0) { minus = 1; tm = -tm; }
+    snprintf(out, 32, "%s%02d:%02d:%02d", minus ? "-" : "", (tm >> 12) & 0x3FF, (tm >> 6) & 0x3F, tm & 0x3F);
+}
+/* test entry points (ctypes): op 0 str->DATETIME, 1 str->TIMESTAMP (str_to_timestamp = datetime_to_timestamp(str_to_datetime), datetime.cpp:116),
+ * 2 str->DATE, 3 str->TIME; *_to_str: kind 0 DATETIME (precision in `arg`), 1 TIMESTAMP, 2 TIME */
+uint64_t bk_oracle_parse_datetime(const char* s, int64_t len, int op) {
+    switch (op) {
+        case 0: return dt_str_to_datetime(s, (size_t)len, NULL);
+        case 1: return (uint64_t)(uint32_t)dt_datetime_to_timestamp(dt_str_to_datetime(s, (size_t)len, NULL));   /* stored in uint32_val, expr_value.h:551 */
+        case 2: return dt_datetime_to_date(dt_str_to_datetime(s, (size_t)len, NULL));
+        default: return (uint64_t)(int64_t)dt_str_to_time(s, (size_t)len);
+    }
+}
+void bk_oracle_datetime_to_str(uint64_t v, int kind, int arg, char* out) {
+    if (kind == 0) dt_datetime_to_str(v, arg, out); else if (kind == 1) dt_timestamp_to_str((int64_t)v, out); else dt_time_to_str((int32_t)v, out);
+}
+
+static int is_dt_family(int t) { return t == T_DATETIME || t == T_TIMESTAMP || t == T_DATE || t == T_TIME; }
+static ExprValue* ev_cast_to(ExprValue* v, int t);
+/* the value as a DATETIME image: the `case pb::DATETIME` arm of cast_to, expr_value.h:534-548 */
+static uint64_t ev_as_datetime(const ExprValue* o) {
+    switch (o->type) {
+        case T_STRING: return o->str ? dt_str_to_datetime(o->str, strlen(o->str), NULL) : 0;
+        case T_TIMESTAMP: return dt_timestamp_to_datetime((int64_t)o->u.uint32_val);
+        case T_DATE: return dt_date_to_datetime(o->u.uint32_val);
+        case T_TIME: return dt_time_to_datetime(o->u.int32_val);
+        case T_DATETIME: return o->u.uint64_val;
+        default: return num_u64(o);
+    }
+}
+static int ev_is_numberic(const ExprValue* v) { return is_int(v->type) || v->type == T_BOOL || is_double(v->type); } /* expr_value.h:1059-1061 */
+
+/* cast_to, expr_value.h:502-611 (STRING sources: literals only; a STRING -> integer cast is strtoull, -> double strtod) */
 static ExprValue* ev_cast_to(ExprValue* v, int t) {
     if (ev_is_null(v) || v->type == T_MAXVALUE || v->type == t) return v;
     ExprValue o = *v;
     memset(&v->u, 0, sizeof v->u);
+    if (o.type == T_STRING && o.str && !is_dt_family(t) && t != T_STRING) {   /* get_numberic<T> of a STRING, expr_value.h:373-383 */
+        if (is_double(t)) { o.type = T_DOUBLE; o.u.double_val = strtod(o.str, NULL); }
+        else { o.type = T_UINT64; o.u.uint64_val = strtoull(o.str, NULL, 10); }
+        o.str = NULL;
+    }
     switch (t) {
         case T_BOOL: v->u.bool_val = (uint8_t)num_bool(&o); break;
         case T_INT8: v->u.int8_val = num_i8(&o); break;
         case T_INT16: v->u.int16_val = num_i16(&o); break;
-        case T_INT32: case T_TIME: v->u.int32_val = num_i32(&o); break;
+        case T_INT32: v->u.int32_val = num_i32(&o); break;
         case T_INT64: v->u.int64_val = num_i64(&o); break;
         case T_UINT8: v->u.uint8_val = num_u8(&o); break;
         case T_UINT16: v->u.uint16_val = num_u16(&o); break;
-        case T_UINT32: case T_TIMESTAMP: case T_DATE: v->u.uint32_val = num_u32(&o); break;
-        case T_UINT64: case T_DATETIME: v->u.uint64_val = num_u64(&o); break;
+        case T_UINT32: v->u.uint32_val = num_u32(&o); break;
+        case T_UINT64: v->u.uint64_val = num_u64(&o); break;
+        case T_DATETIME: v->u.uint64_val = ev_as_datetime(&o); break;
+        case T_TIMESTAMP: v->u.uint32_val = ev_is_numberic(&o) ? num_u32(&o) : (uint32_t)dt_datetime_to_timestamp(ev_as_datetime(&o)); break;
+        case T_DATE: v->u.uint32_val = ev_is_numberic(&o) ? num_u32(&o) : dt_datetime_to_date(ev_as_datetime(&o)); break;
+        case T_TIME:
+            if (ev_is_numberic(&o)) v->u.int32_val = num_i32(&o);
+            else if (o.type == T_STRING) v->u.int32_val = o.str ? dt_str_to_time(o.str, strlen(o.str)) : 0;
+            else v->u.int32_val = dt_datetime_to_time(ev_as_datetime(&o));
+            break;
         case T_FLOAT: v->u.float_val = num_f32(&o); break;
         case T_DOUBLE: v->u.double_val = num_f64(&o); break;
         default: v->u = o.u; break;
     }
+    if (t != T_STRING) v->str = NULL;
     v->type = t;
     return v;
+}
+/* test entry point: cast_to between two non-STRING types on the 64-bit canonical images the GPU library uses */
+uint64_t bk_oracle_cast_image(uint64_t image, int from, int to) {
+    ExprValue v = ev_typed(from);
+    switch (from) {
+        case T_BOOL: v.u.bool_val = image != 0; break;
+        case T_INT8: v.u.int8_val = (int8_t)image; break;
+        case T_INT16: v.u.int16_val = (int16_t)image; break;
+        case T_INT32: case T_TIME: v.u.int32_val = (int32_t)image; break;
+        case T_INT64: v.u.int64_val = (int64_t)image; break;
+        case T_UINT8: v.u.uint8_val = (uint8_t)image; break;
+        case T_UINT16: v.u.uint16_val = (uint16_t)image; break;
+        case T_UINT32: case T_TIMESTAMP: case T_DATE: v.u.uint32_val = (uint32_t)image; break;
+        case T_FLOAT: { double d; memcpy(&d, &image, 8); v.u.float_val = (float)d; } break;
+        case T_DOUBLE: memcpy(&v.u.double_val, &image, 8); break;
+        default: v.u.uint64_val = image; break;
+    }
+    ev_cast_to(&v, to);
+    switch (to) {
+        case T_BOOL: return v.u.bool_val;
+        case T_INT8: return (uint64_t)(int64_t)v.u.int8_val;
+        case T_INT16: return (uint64_t)(int64_t)v.u.int16_val;
+        case T_INT32: case T_TIME: return (uint64_t)(int64_t)v.u.int32_val;
+        case T_UINT8: return v.u.uint8_val;
+        case T_UINT16: return v.u.uint16_val;
+        case T_UINT32: case T_TIMESTAMP: case T_DATE: return v.u.uint32_val;
+        case T_FLOAT: { double d = (double)v.u.float_val; uint64_t b; memcpy(&b, &d, 8); return b; }
+        case T_DOUBLE: { uint64_t b; memcpy(&b, &v.u.double_val, 8); return b; }
+        default: return v.u.uint64_val;
+    }
+}
+
+/* Literal::cast_to_col_type, literal.h:204-210: a numeric literal meeting a date/time type goes through its decimal string */
+static void lit_cast_to_col_type(ExprValue* v, int t, char* scratch /* >= 32 bytes, lives as long as v */) {
+    if (is_dt_family(t) && ev_is_numberic(v) && !is_double(v->type)) {
+        if (is_uint(v->type)) snprintf(scratch, 32, "%llu", (unsigned long long)num_u64(v));
+        else snprintf(scratch, 32, "%lld", (long long)num_i64(v));           /* std::to_string, expr_value.h:709-726 */
+        memset(&v->u, 0, sizeof v->u); v->type = T_STRING; v->str = scratch;
+    }
+    ev_cast_to(v, t);
 }
 
 /* add, expr_value.h:840-881 (the BOOL arm mutates the argument in the reference; kept) */
@@ -249,6 +487,7 @@ typedef struct Expr {
     struct Expr** children;
     int tuple_id, slot_id;            /* SLOT_REF / AGG_EXPR */
     ExprValue lit;                    /* literals */
+    char* str_lit; char lit_scratch[32];  /* STRING literal bytes; decimal image of a numeric literal cast to a date/time type */
     int fn_op; char name[64];
     int n_arg_types, arg_types[4], return_type;
     int agg_type, final_slot, inter_slot;
@@ -294,6 +533,17 @@ static Expr* parse_enode(Reader* r, int* remaining) {
         case E_BOOL_LITERAL: e->lit = ev_bool(rd(r)); break;
         case E_INT_LITERAL: e->lit = ev_typed(T_INT64); e->lit.u.int64_val = rd64(r); break;
         case E_DOUBLE_LITERAL: { int64_t b = rd64(r); e->lit = ev_typed(T_DOUBLE); memcpy(&e->lit.u.double_val, &b, 8); } break;
+        case E_STRING_LITERAL: { /* literal.h:69-73 */
+            int32_t len = r->pos < r->n ? r->w[r->pos] : -1;
+            if (len < 0 || len > 4096) { set_err(r, "bad string literal"); break; }
+            e->str_lit = (char*)calloc((size_t)len + 1, 1);
+            rdstr(r, e->str_lit, (size_t)len + 1);
+            e->lit = ev_typed(T_STRING); e->lit.str = e->str_lit;
+        } break;
+        case E_DATETIME_LITERAL: e->lit = ev_typed(T_DATETIME); e->lit.u.uint64_val = (uint64_t)rd64(r); break;  /* literal.h:95-114 */
+        case E_TIME_LITERAL: e->lit = ev_typed(T_TIME); e->lit.u.int32_val = (int32_t)rd64(r); break;
+        case E_TIMESTAMP_LITERAL: e->lit = ev_typed(T_TIMESTAMP); e->lit.u.uint32_val = (uint32_t)rd64(r); break;
+        case E_DATE_LITERAL: e->lit = ev_typed(T_DATE); e->lit.u.uint32_val = (uint32_t)rd64(r); break;
         case E_AGG_EXPR:
             rdstr(r, e->name, sizeof e->name);
             e->tuple_id = rd(r); e->final_slot = rd(r); e->inter_slot = rd(r);
@@ -470,7 +720,8 @@ static int expr_constant(const Expr* e) {
     return 1;
 }
 static int expr_is_literal(const Expr* e) {
-    return e->node_type >= E_NULL_LITERAL && e->node_type <= E_STRING_LITERAL;
+    return (e->node_type >= E_NULL_LITERAL && e->node_type <= E_STRING_LITERAL) || e->node_type == E_TIMESTAMP_LITERAL ||
+           e->node_type == E_DATETIME_LITERAL || e->node_type == E_DATE_LITERAL || e->node_type == E_TIME_LITERAL;
 }
 static int all_int2(const int* t, int n) { for (int i = 0; i < n; i++) if (!is_int(t[i])) return 0; return 1; }
 static int has_t(const int* t, int n, int (*f)(int)) { for (int i = 0; i < n; i++) if (f(t[i])) return 1; return 0; }
@@ -495,6 +746,11 @@ static int type_infer(Ctx* c, Expr* e) {
         case E_BOOL_LITERAL: if (e->col_type == T_INVALID) e->col_type = T_BOOL; return 0;
         case E_INT_LITERAL: if (e->col_type == T_INVALID) e->col_type = T_INT64; return 0;
         case E_DOUBLE_LITERAL: if (e->col_type == T_INVALID) e->col_type = T_DOUBLE; return 0;
+        case E_STRING_LITERAL: if (e->col_type == T_INVALID) e->col_type = T_STRING; return 0;
+        case E_DATETIME_LITERAL: if (e->col_type == T_INVALID) e->col_type = T_DATETIME; return 0;
+        case E_TIMESTAMP_LITERAL: if (e->col_type == T_INVALID) e->col_type = T_TIMESTAMP; return 0;
+        case E_DATE_LITERAL: if (e->col_type == T_INVALID) e->col_type = T_DATE; return 0;
+        case E_TIME_LITERAL: if (e->col_type == T_INVALID) e->col_type = T_TIME; return 0;
         case E_AGG_EXPR: {
             int ct = e->nchildren ? e->children[0]->col_type : T_INVALID;
             switch (e->agg_type) {
@@ -514,9 +770,11 @@ static int type_infer(Ctx* c, Expr* e) {
             for (int i = 1; i < e->nchildren; i++) if (e->children[i]->is_constant) e->children[i]->col_type = e->children[0]->col_type;
         int types[2] = { e->children[0]->col_type, e->children[1]->col_type };
         if (all_int2(types, 2)) e->map_type = T_INT64;
-        else if (has_eq(types, 2, T_DATETIME) || has_eq(types, 2, T_TIMESTAMP) || has_eq(types, 2, T_DATE) || has_eq(types, 2, T_TIME)) {
-            snprintf(c->err, c->errlen, "date/time IN outside the path"); return -1;
-        } else if (has_t(types, 2, is_double) || has_t(types, 2, is_int)) e->map_type = T_DOUBLE;
+        else if (has_eq(types, 2, T_DATETIME)) e->map_type = T_DATETIME;
+        else if (has_eq(types, 2, T_TIMESTAMP)) e->map_type = T_TIMESTAMP;
+        else if (has_eq(types, 2, T_DATE)) e->map_type = T_DATE;
+        else if (has_eq(types, 2, T_TIME)) e->map_type = T_TIME;
+        else if (has_t(types, 2, is_double) || has_t(types, 2, is_int)) e->map_type = T_DOUBLE;
         else { snprintf(c->err, c->errlen, "string IN outside the path"); return -1; }
         e->int_set = (int64_t*)calloc((size_t)e->nchildren, sizeof(int64_t));
         e->dbl_set = (double*)calloc((size_t)e->nchildren, sizeof(double));
@@ -526,7 +784,7 @@ static int type_infer(Ctx* c, Expr* e) {
             ExprValue v = expr_value(c, e->children[i], NULL);
             if (ev_is_null(&v)) { e->has_null = 1; continue; }
             ev_cast_to(&v, e->map_type);
-            if (e->map_type == T_INT64) e->int_set[e->set_n++] = num_i64(&v); else e->dbl_set[e->set_n++] = num_f64(&v);
+            if (e->map_type != T_DOUBLE) e->int_set[e->set_n++] = num_i64(&v); else e->dbl_set[e->set_n++] = num_f64(&v);   /* predicate.cpp:128-136 */
         }
         if (e->col_type == T_INVALID) e->col_type = T_BOOL;
         return 0;
@@ -613,7 +871,11 @@ static int type_infer(Ctx* c, Expr* e) {
     if (e->col_type == T_INVALID) e->col_type = e->return_type;
     /* Literal type cast, scalar_fn_call.cpp:113-117 + Literal::cast_to_col_type */
     for (int i = 0; i < e->n_arg_types && i < e->nchildren; i++)
-        if (expr_is_literal(e->children[i])) ev_cast_to(&e->children[i]->lit, e->arg_types[i]);
+        if (expr_is_literal(e->children[i])) {
+            Expr* l = e->children[i];
+            lit_cast_to_col_type(&l->lit, e->arg_types[i], l->lit_scratch);
+            if (!ev_is_null(&l->lit)) l->col_type = l->lit.type;   /* value_to_node_type: _col_type = _value.type */
+        }
     return 0;
 }
 
@@ -718,7 +980,8 @@ static ExprValue expr_value(const Ctx* c, Expr* e, const MemRow* row) {
             ev_cast_to(&v, e->col_type); return v;
         }
         case E_NULL_LITERAL: return ev_null();
-        case E_BOOL_LITERAL: case E_INT_LITERAL: case E_DOUBLE_LITERAL: { /* literal.h:204-206 */
+        case E_BOOL_LITERAL: case E_INT_LITERAL: case E_DOUBLE_LITERAL: case E_STRING_LITERAL:
+        case E_DATETIME_LITERAL: case E_TIMESTAMP_LITERAL: case E_DATE_LITERAL: case E_TIME_LITERAL: { /* literal.h:204-206 */
             ExprValue v = e->lit; ev_cast_to(&v, e->col_type); return v;
         }
         case E_AND: { /* predicate.h:25-45 */
@@ -755,7 +1018,7 @@ static ExprValue expr_value(const Ctx* c, Expr* e, const MemRow* row) {
             ExprValue v = expr_value(c, e->children[0], row);
             if (ev_is_null(&v)) return ev_null();
             ev_cast_to(&v, e->map_type);
-            if (e->map_type == T_INT64 ? in_int(e, num_i64(&v)) : in_dbl(e, num_f64(&v))) return ev_bool(1);
+            if (e->map_type != T_DOUBLE ? in_int(e, num_i64(&v)) : in_dbl(e, num_f64(&v))) return ev_bool(1);
             return e->has_null ? ev_null() : ev_bool(0);
         }
         case E_FUNCTION_CALL: { /* scalar_fn_call.cpp:194-225 */

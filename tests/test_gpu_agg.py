@@ -269,3 +269,17 @@ def test_count_where_tma_staged_kernel(n, op, c):
     pl = P.Plan(P.packet(root), {0: [(1, T.INT32)], 1: P.agg_tuple_slots(aggs, [T.INT64])})
     _, stats, _ = run_both(pl, cols, keys=[], options={"scalar_tma": 1})
     assert stats.main_kernel_name.decode() == "k_count_where_tma"
+
+
+@pytest.mark.parametrize("variant", ["direct", "generic"])
+def test_literal_wider_than_the_column_keeps_its_value(variant):
+    """`int32_col < 3000000000`: the comparison runs in INT64 and the literal takes the ARGUMENT's type (Literal::cast_to_col_type,
+    include/expr/literal.h:204-210 -> value_to_node_type), it is not narrowed to the column's INT32 first — every non-NULL row passes"""
+    rng = np.random.default_rng(3)
+    n = 50_000
+    cols = [make_column(0, 1, T.INT32, rng.integers(-(1 << 31), 1 << 31, n), rng.random(n) > 0.1), make_column(0, 2, T.INT32, rng.integers(0, 9, n))]
+    aggs = [P.agg_expr("count_star", 1, 1)]
+    pl = P.Plan(P.agg(P.where(P.scan(0), P.lt(P.slot_ref(0, 1, T.INT32), P.int_lit(3_000_000_000))), 1, [P.slot_ref(0, 2, T.INT32)], aggs),
+                {0: [(1, T.INT32), (2, T.INT32)], 1: [(1, T.INT64)]})
+    got, _, _ = run_both(pl, cols, keys=["0_2"], options={"force_generic": 1} if variant == "generic" else None)
+    assert sum({c.name: c for c in got}["1_1"].to_list()) == int(cols[0].valid.sum())
