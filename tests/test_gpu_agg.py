@@ -222,18 +222,6 @@ def test_single_int64_key_direct():
     assert stats.main_kernel_name.decode() == "k_agg_group_direct"  # nullable key column: not the lean shape
 
 
-def test_literal_takes_column_type_quirk():
-    """`int32_col < 3000000000`: the literal is cast to the column's type first (scalar_fn_call.cpp:57-67,
-    literal.h:204-206), so it wraps to a negative INT32 — mirrored bit for bit."""
-    n = 1000
-    cols = [make_column(0, 1, T.INT32, np.arange(n, dtype=np.int32) - 500)]
-    aggs = [P.agg_expr("count_star", 1, 1)]
-    root = P.agg(P.where(P.scan(0), P.lt(P.slot_ref(0, 1, T.INT32), P.int_lit(3_000_000_000))), 1, [], aggs)
-    pl = P.Plan(P.packet(root), {0: [(1, T.INT32)], 1: P.agg_tuple_slots(aggs, [T.INT64])})
-    got, _, _ = run_both(pl, cols, keys=[])
-    assert got[0].to_list() == [0]
-
-
 def test_high_cardinality_global_table():
     rng = np.random.default_rng(5)
     n = 400_000
