@@ -535,10 +535,11 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_rs_pass(const uint64_t* key_i
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint64_t* s_key = (uint64_t*)rs_smem;                        // [RS_TILE]
     uint32_t* s_id = (uint32_t*)(s_key + RS_TILE);               // [RS_TILE]
-    uint32_t* wcnt = s_id + RS_TILE;                             // [8][256] per-warp digit counters -> per-warp offsets
+    uint32_t* wcnt = s_id + RS_TILE;                             // [8][256] per-warp digit counts -> running offsets inside the digit's run
     uint32_t* dstart = wcnt + 8 * 256;                           // [256] start of the digit inside the reordered tile
     uint32_t* tbase = dstart + 256;                              // [256] global address of the tile's first pair of the digit
     __shared__ uint32_t s_tile;
+    __shared__ uint32_t wsum[8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < 8 * 256; i += RS_THREADS) wcnt[i] = 0;
@@ -547,75 +548,89 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_rs_pass(const uint64_t* key_i
     const uint32_t t0 = tile * RS_TILE;
     const uint32_t tile_n = min((uint32_t)RS_TILE, n - t0);
     // ---- load: warp w owns the contiguous chunk [t0 + w * 32 * RS_ITEMS, + 32 * RS_ITEMS), RS_ITEMS rounds of 32 consecutive pairs ----
-    uint64_t k[RS_ITEMS]; uint32_t id[RS_ITEMS]; uint32_t rank[RS_ITEMS];
+    uint64_t k[RS_ITEMS]; uint32_t id[RS_ITEMS];
     const uint32_t c0 = w * (RS_ITEMS * 32);
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++) {
         const uint32_t li = c0 + r * 32 + lane;
         if (li < tile_n) { k[r] = key_in[t0 + li]; id[r] = id_in[t0 + li]; } else { k[r] = ~0ull; id[r] = 0; }
     }
-    // ---- rank inside the warp's chunk, in element order (stable): peers of a digit in this round + the digit's running count ----
+    // ---- early counts: the warp's digit histogram (order-free atomics), so the tile's counts are published BEFORE the ranking and the
+    //      following tiles' look-back finds them sooner ----
+    uint32_t* wc = wcnt + w * 256;
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const uint32_t li = c0 + r * 32 + lane;
-        const bool live = li < tile_n;
-        const uint32_t d = live ? (uint32_t)((k[r] >> shift) & 0xFF) : 256u;      // (pairs past the end match only each other)
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-        uint32_t before = 0;
-        if (live) before = wcnt[w * 256 + d];
-        __syncwarp();
-        rank[r] = before + __popc(peers & ((1u << lane) - 1u));
-        if (live && lane == (31 - __clz(peers))) wcnt[w * 256 + d] = before + __popc(peers);   // one lane per digit group advances the counter
-        __syncwarp();
-    }
+    for (int r = 0; r < RS_ITEMS; r++)
+        if (c0 + r * 32 + lane < tile_n) atomicAdd(wc + (uint32_t)((k[r] >> shift) & 0xFF), 1u);
     __syncthreads();
-    // ---- thread d: the digit's count per warp -> per-warp offsets, tile count; publish, look back, scatter bases ----
+    // ---- thread d: the digit's count per warp -> per-warp offsets, tile count; publish; where the digit starts in the reordered tile ----
+    const int d_own = threadIdx.x;
+    uint32_t cnt;
+    volatile uint32_t* st = status + (size_t)tile * 256 + d_own;
     {
-        const int d = threadIdx.x;
         uint32_t run = 0;
 #pragma unroll
-        for (int ww = 0; ww < 8; ww++) { const uint32_t c = wcnt[ww * 256 + d]; wcnt[ww * 256 + d] = run; run += c; }
-        const uint32_t cnt = run;
-        // exclusive scan of the tile's digit counts over the 256 digits -> where the digit starts in the reordered tile
+        for (int ww = 0; ww < 8; ww++) { const uint32_t c = wcnt[ww * 256 + d_own]; wcnt[ww * 256 + d_own] = run; run += c; }
+        cnt = run;
+        *st = (tile == 0 ? RS_FLAG_PREFIX : RS_FLAG_AGG) | cnt;   // (flag and count travel in ONE word: no fence around the publication)
         uint32_t x = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
-        __shared__ uint32_t wsum[8];
         if (lane == 31) wsum[w] = x;
         __syncthreads();
         uint32_t wpre = 0;
         for (int ww = 0; ww < w; ww++) wpre += wsum[ww];
-        dstart[d] = wpre + x - cnt;
-        // chained scan with decoupled look-back over the preceding tiles (they all started before this one: ticket order)
-        volatile uint32_t* st = status + (size_t)tile * 256 + d;
+        dstart[d_own] = wpre + x - cnt;
+    }
+    __syncthreads();
+    // ---- rank in element order (stable) and place: peers of the digit in this round + the digit's running offset.  The peer mask
+    //      comes from eight ballots, one per digit bit: MATCH.ANY kept the XU pipe 72 % busy (profiles/r02_radix_history.md) ----
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const bool live = c0 + r * 32 + lane < tile_n;
+        const uint32_t d = (uint32_t)((k[r] >> shift) & 0xFF);
+        uint32_t peers = __ballot_sync(0xFFFFFFFFu, live);
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const uint32_t bit = (d >> b) & 1u;
+            peers &= ~(__ballot_sync(0xFFFFFFFFu, bit != 0) ^ (0u - bit));
+        }
+        uint32_t before = 0;
+        if (live) before = wc[d];
+        __syncwarp();
+        const uint32_t mine = __popc(peers & lt_mask);
+        if (live) {
+            if ((peers >> lane) == 1u) wc[d] = before + mine + 1u;   // the highest peer lane advances the offset by the group's size
+            const uint32_t pos = dstart[d] + before + mine;
+            s_key[pos] = k[r]; s_id[pos] = id[r];
+        }
+        __syncwarp();
+    }
+    // ---- chained scan with decoupled look-back over the preceding tiles (they all started before this one: ticket order) ----
+    {
         uint32_t excl = 0;
-        // (flag and count travel in ONE word: no fence is needed around the publication)
-        if (tile == 0) *st = RS_FLAG_PREFIX | cnt;
-        else {
-            *st = RS_FLAG_AGG | cnt;
-            for (int64_t p = (int64_t)tile - 1; p >= 0; p--) {
-                volatile const uint32_t* ps = status + (size_t)p * 256 + d;
-                uint32_t v;
-                do { v = *ps; } while ((v & ~RS_VAL_MASK) == 0);
-                excl += v & RS_VAL_MASK;
-                if (v & RS_FLAG_PREFIX) break;
+        if (tile != 0) {
+            // four predecessors per round trip: the loads are independent, the walk consumes them nearest first
+            for (int64_t p = (int64_t)tile - 1;;) {
+                uint32_t v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = p - j >= 0 ? *(volatile const uint32_t*)(status + (size_t)(p - j) * 256 + d_own) : RS_FLAG_PREFIX;
+                int j = 0; bool done = false;
+#pragma unroll
+                for (; j < 4; j++) {
+                    if ((v[j] & ~RS_VAL_MASK) == 0) break;            // not published yet: poll again from this tile
+                    excl += v[j] & RS_VAL_MASK;
+                    if (v[j] & RS_FLAG_PREFIX) { done = true; break; }
+                }
+                if (done) break;
+                p -= j;
             }
             *st = RS_FLAG_PREFIX | (excl + cnt);
         }
-        tbase[d] = global_base[d] + excl;
+        tbase[d_own] = global_base[d_own] + excl;
     }
     __syncthreads();
-    // ---- reorder the tile through shared memory: digit-major, element order kept inside a digit ----
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const uint32_t li = c0 + r * 32 + lane;
-        if (li < tile_n) {
-            const uint32_t d = (uint32_t)((k[r] >> shift) & 0xFF);
-            const uint32_t pos = dstart[d] + wcnt[w * 256 + d] + rank[r];
-            s_key[pos] = k[r]; s_id[pos] = id[r];
-        }
-    }
-    __syncthreads();
+    // ---- write the digit-contiguous runs ----
     for (uint32_t i = threadIdx.x; i < tile_n; i += RS_THREADS) {
         const uint64_t kk = s_key[i];
         const uint32_t d = (uint32_t)((kk >> shift) & 0xFF);
