@@ -80,6 +80,7 @@ struct bkgpu_plan {
     std::vector<uint8_t*> bounce[2]; size_t bounce_rows = 0; cudaEvent_t bounce_done[2] = {nullptr, nullptr}; bool bounce_busy[2] = {false, false};
     int scalar_tma = 1;           // COUNT(*) WHERE int32 <cmp> c runs the TMA-staged kernel (scalar_tma.cu): 0.97 vs 0.78 of HBM (profiles/r02_tma_scalar.md); 0 = the LDG kernel
     int no_bounce = 0;            // 1 = pageable host input goes straight to cudaMemcpyAsync (A/B of the bounce path)
+    int no_stream_copy = 0;       // 1 = the bounce copy uses memcpy instead of non-temporal stores (A/B, hostcopy.cpp)
     uint8_t* jb_matched = nullptr; size_t jb_matched_cap = 0; bool join_tail_launch = false;   // LEFT / SEMI / ANTI: build rows that found a partner
     SortState* post_sort = nullptr;                         // the post fragment above the aggregate (Compiled::post)
     std::vector<uint8_t*> post_vals, post_nullb, post_bitmap; size_t post_cap = 0;
@@ -240,6 +241,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "chunk_rows") { if (v < 1024) return p->fail(BKGPU_EINVAL, "chunk_rows too small"); p->chunk_rows = (v + 7) & ~7ll; }
     else if (k == "partial_capacity") { if (v < 1) return p->fail(BKGPU_EINVAL, "partial_capacity must be positive"); p->partial_cap = v; }
     else if (k == "force_generic") p->force_generic = v != 0;
+    else if (k == "no_stream_copy") p->no_stream_copy = v != 0;
     else if (k == "no_lean") p->no_lean = v != 0;
     else if (k == "no_fused_probe") p->no_fused_probe = v != 0;
     else if (k == "repartition") p->repartition = v != 0;
@@ -532,6 +534,7 @@ typedef int (*BatchFn)(bkgpu_plan*, const DevCol*, int64_t nrows, int64_t row_ba
 // ---- host-side copy workers: pageable input (what an Arrow RecordBatch of RocksdbVectorizedReader hands over) is copied into
 // pinned bounce buffers by several threads — cudaMemcpyAsync from pageable memory goes through the driver's single staging buffer
 // at a fraction of the link rate ----
+namespace bk { void stream_copy(void* dst, const void* src, size_t bytes); }   // hostcopy.cpp
 namespace {
 class CopyPool {
   public:
@@ -624,7 +627,11 @@ static int feed(bkgpu_plan* p, const std::vector<ColRef>& want, const bkgpu_colu
                 const uint8_t* src = (const uint8_t*)bound[i]->values + (size_t)off * eb;
                 for (size_t o = 0; o < bytes; o += slice) pieces.push_back({p->bounce[buf][i] + o, src + o, std::min(slice, bytes - o)});
             }
-            copy_pool().parallel((int)pieces.size(), [&](int k) { memcpy(pieces[(size_t)k].dst, pieces[(size_t)k].src, pieces[(size_t)k].bytes); });
+            const bool nt = !p->no_stream_copy;
+            copy_pool().parallel((int)pieces.size(), [&](int k) {
+                const Piece& pc = pieces[(size_t)k];
+                if (nt) stream_copy(pc.dst, pc.src, pc.bytes); else memcpy(pc.dst, pc.src, pc.bytes);
+            });
         }
         for (size_t i = 0; i < want.size(); i++) {
             const int st = prim_storage(want[i].prim);

@@ -114,7 +114,8 @@ int   bkgpu_init(bkgpu_plan** out, const uint8_t* plan_desc, size_t len,
  *   "force_generic" / "no_lean" / "no_lean_nulls" / "no_lean_mm" / "no_fused_probe"   pin the kernel variant (tests, A/B measurements)
  *   "use_wp" / "wp_warps" / "wp_kt_log2"   opt into the warp-private (atomics-free) aggregate kernel and size it (csrc/agg_wp.cuh)
  *   "scalar_tma"           0 = COUNT(*) WHERE int32 <cmp> c takes the LDG kernel instead of the TMA-staged one (csrc/scalar_tma.cu; default 1)
- *   "no_bounce"            pageable host input goes straight to cudaMemcpyAsync instead of the threaded pinned bounce buffers (A/B) */
+ *   "no_bounce"            pageable host input goes straight to cudaMemcpyAsync instead of the threaded pinned bounce buffers (A/B)
+ *   "no_stream_copy"       the bounce copy uses memcpy instead of non-temporal stores (A/B) */
 int   bkgpu_set_option(bkgpu_plan*, const char* key, int64_t value);
 /* ExecNode::open(RuntimeState*) (exec_node.h:140): allocate tables. */
 int   bkgpu_open(bkgpu_plan*);

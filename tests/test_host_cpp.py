@@ -127,3 +127,12 @@ def test_cpp_row_engine_child_through_chunk_adapter(host_bin, rows, capacity):
         for nm in g:
             assert (g[nm] is None and w[nm] is None) or _same(g[nm], w[nm]), (nm, g, w)
     assert "scan_rows=%d" % rows in r.stderr
+
+
+def test_stream_copy_is_a_byte_exact_copy(tmp_path):
+    """the non-temporal bounce copy of the pageable-input path (csrc/hostcopy.cpp): every size / alignment combination equals memcpy and
+    writes nothing outside its range"""
+    exe = str(tmp_path / "stream_copy_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "cpp", "stream_copy_check.cpp"), os.path.join(ROOT, "csrc", "hostcopy.cpp"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout + r.stderr
