@@ -299,6 +299,17 @@ def abs_(a): return common("abs", a)
 def floor_(a): return common("floor", a)
 def ceil_(a): return common("ceil", a)
 def round_(a, bits: Optional[Expr] = None): return common("round", a) if bits is None else common("round", a, bits)
+def sqrt_(a): return common("sqrt", a)
+def sign_(a): return common("sign", a)
+def ln_(a): return common("ln", a)
+def log_(base, a): return common("log", base, a)
+def pow_(a, b): return common("pow", a, b)
+def fmod_(a, b): return common("mod", a, b)
+def greatest(*xs): return common("greatest", *xs)
+def least(*xs): return common("least", *xs)
+def bit_count(a): return common("bit_count", a)
+def pi_(): return common("pi")
+def trig(name, a): return common(name, a)   # sin asin cos acos tan cot atan
 def cast_to_signed(a): return common("cast_to_signed", a)
 def cast_to_unsigned(a): return common("cast_to_unsigned", a)
 def cast_to_double(a): return common("cast_to_double", a)

@@ -64,8 +64,12 @@ enum Op : uint8_t {
     OP_SELECT,       // pops [cond, a, b]: cond non-NULL true ? a : b      if_ / case_when (internal_functions.cpp:2351-2388)
     OP_IFNULL,       // pops [a, b]: a NULL ? b : a                           ifnull (internal_functions.cpp:2390-2395)
     OP_MATH,         // a = MathFn on a DOUBLE image, b = constant index (round: 10^bits)   internal_functions.cpp:52-99
+    OP_MATH2,        // a = Math2Fn: pops [x, y] DOUBLE images, NULL if either is or outside the domain   internal_functions.cpp:114-127,234-317
 };
-enum MathFn : uint8_t { MF_ABS = 0, MF_FLOOR = 1, MF_CEIL = 2, MF_ROUND = 3 };
+enum MathFn : uint8_t { MF_ABS = 0, MF_FLOOR = 1, MF_CEIL = 2, MF_ROUND = 3,
+                        // one DOUBLE argument, NULL outside the domain (internal_functions.cpp:101-232); SIGN and BIT_COUNT leave an INT64 image
+                        MF_SQRT = 4, MF_SIGN = 5, MF_SIN = 6, MF_ASIN = 7, MF_COS = 8, MF_ACOS = 9, MF_TAN = 10, MF_COT = 11, MF_ATAN = 12, MF_LN = 13, MF_BIT_COUNT = 14 };
+enum Math2Fn : uint8_t { MF2_FMOD = 0, MF2_LOG = 1, MF2_POW = 2, MF2_GREATEST = 3, MF2_LEAST = 4 };   // two DOUBLE arguments (OP_MATH2)
 struct Instr { uint8_t op, a, b, c; };
 
 struct Program {

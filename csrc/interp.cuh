@@ -143,20 +143,48 @@ static __device__ __noinline__ void run_program(const Program& p, const DevCol* 
                 break;
             case OP_MATH:
                 if (!((nul >> (sp - 1)) & 1u)) {
+                    if (in.a == MF_BIT_COUNT) { st[sp - 1] = (uint64_t)__popcll(st[sp - 1]); break; }   // (UINT64 image in, INT64 image out)
                     const double x = bits_f64(st[sp - 1]);
                     double r;
+                    bool null_out = false;
                     switch (in.a) {
                         case MF_ABS: r = x < 0 ? -x : x; break;
                         case MF_FLOOR: r = floor(x); break;
                         case MF_CEIL: r = ceil(x); break;
+                        case MF_SQRT: null_out = x < 0; r = sqrt(x); break;
+                        case MF_SIGN: st[sp - 1] = (uint64_t)(int64_t)(x > 0 ? 1 : (x < 0 ? -1 : 0)); continue;   // INT64 image
+                        case MF_SIN: r = sin(x); break;
+                        case MF_COS: r = cos(x); break;
+                        case MF_TAN: r = tan(x); break;
+                        case MF_ATAN: r = atan(x); break;
+                        case MF_ASIN: null_out = x < -1 || x > 1; r = asin(x); break;
+                        case MF_ACOS: null_out = x < -1 || x > 1; r = acos(x); break;
+                        case MF_COT: { const double s = sin(x), c = cos(x); null_out = fabs(s) < 1e-9; r = __ddiv_rn(c, s); } break;   // float_equal(sin, 0), common.h:1604
+                        case MF_LN: null_out = x <= 0; r = log(x); break;
                         default: {   // round half away from zero at `bits` decimals: -::round(-x * base) / base for x < 0
                             const double base = bits_f64(p.cbits[in.b]);
                             r = base > 0 ? (x < 0 ? -__ddiv_rn(round(__dmul_rn(-x, base)), base) : __ddiv_rn(round(__dmul_rn(x, base)), base)) : 0.0;
                         } break;
                     }
                     st[sp - 1] = f64_bits(r);
+                    if (null_out) nul |= 1u << (sp - 1);
                 }
                 break;
+            case OP_MATH2: {
+                sp--;
+                bool n = ((nul >> sp) | (nul >> (sp - 1))) & 1u;
+                const double x = bits_f64(st[sp - 1]), y = bits_f64(st[sp]);
+                double r = 0;
+                if (!n) switch (in.a) {
+                    case MF2_FMOD: n = fabs(y) < 1e-9; r = fmod(x, y); break;                                  // mod(): float_equal(rhs, 0) -> NULL
+                    case MF2_LOG: n = x <= 0 || y <= 0 || x == 1; r = __ddiv_rn(log(y), log(x)); break;         // log(base, value)
+                    case MF2_POW: r = pow(x, y); break;
+                    case MF2_GREATEST: r = y > x ? y : x; break;
+                    default: r = y < x ? y : x; break;
+                }
+                st[sp - 1] = f64_bits(r);
+                nul = n ? (nul | (1u << (sp - 1))) : (nul & ~(1u << (sp - 1)));
+            } break;
             case OP_OUT:
                 sp--;
                 out[in.a] = st[sp];

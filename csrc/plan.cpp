@@ -204,6 +204,19 @@ static bool expr_constant(const HExpr& e) {
 }
 static void complete(HExpr& e, int nargs, int at, int rt) { e.arg_types.assign((size_t)nargs, at); e.return_type = rt; }
 
+// named builtins of one / two DOUBLE arguments (src/expr/internal_functions.cpp:101-317,336-350) -> MathFn / Math2Fn, -1 = not one
+static int math1_fn(const std::string& n) {
+    static const std::pair<const char*, int> t[] = {{"sqrt", MF_SQRT}, {"sign", MF_SIGN}, {"sin", MF_SIN}, {"asin", MF_ASIN}, {"cos", MF_COS}, {"acos", MF_ACOS},
+                                                    {"tan", MF_TAN}, {"cot", MF_COT}, {"atan", MF_ATAN}, {"ln", MF_LN}, {"bit_count", MF_BIT_COUNT}};
+    for (auto& p : t) if (n == p.first) return p.second;
+    return -1;
+}
+static int math2_fn(const std::string& n) {
+    static const std::pair<const char*, int> t[] = {{"mod", MF2_FMOD}, {"log", MF2_LOG}, {"pow", MF2_POW}, {"power", MF2_POW}, {"greatest", MF2_GREATEST}, {"least", MF2_LEAST}};
+    for (auto& p : t) if (n == p.first) return p.second;
+    return -1;
+}
+
 // A literal's value as the image of type `to` — ExprValue::cast_to (include/common/expr_value.h:502-611) on the host.
 // `via_text`: Literal::cast_to_col_type (include/expr/literal.h:204-210) — a numeric literal that meets a date/time type is first
 // written out in decimal and then read as a date ("20240131" -> 2024-01-31); a plain cast_to reinterprets the number as the image.
@@ -354,8 +367,8 @@ static bool infer_expr(Infer& in, HExpr& e) {
                     if (n < 2) return in.fail(BKGPU_EINVAL, "case_when needs a WHEN/THEN pair");
                     for (size_t i = 1; i < n; i++) if (i % 2 == 1 || i + 1 == n) merge.push_back(types[i]);
                 }
-                else if (e.name == "abs" || e.name == "round" || e.name == "cast_to_double") e.return_type = BK_DOUBLE;
-                else if (e.name == "floor" || e.name == "ceil" || e.name == "cast_to_signed") e.return_type = BK_INT64;
+                else if (e.name == "abs" || e.name == "round" || e.name == "cast_to_double" || math1_fn(e.name) >= 0 || math2_fn(e.name) >= 0 || e.name == "pi") e.return_type = BK_DOUBLE;
+                else if (e.name == "floor" || e.name == "ceil" || e.name == "ceiling" || e.name == "cast_to_signed") e.return_type = BK_INT64;
                 else if (e.name == "cast_to_unsigned") e.return_type = BK_UINT64;
                 else return in.fail(BKGPU_EUNSUPPORTED, "function '%s' is outside the GPU path", e.name.c_str());
                 if (!merge.empty()) {   // has_merged_type (include/common/type_utils.h:502-560)
@@ -377,8 +390,12 @@ static bool infer_expr(Infer& in, HExpr& e) {
                     if (e.return_type == BK_STRING || is_datetime_family(e.return_type))
                         return in.fail(BKGPU_EUNSUPPORTED, "%s returning type %d is outside the GPU path", e.name.c_str(), e.return_type);
                 }
-                if ((e.name == "abs" || e.name == "floor" || e.name == "ceil" || e.name.rfind("cast_to_", 0) == 0) && n != 1)
+                if (e.name == "sign" || e.name == "bit_count") e.return_type = BK_INT64;   // return_type_map, fn_manager.cpp:105-128
+                if ((e.name == "abs" || e.name == "floor" || e.name == "ceil" || e.name == "ceiling" || e.name.rfind("cast_to_", 0) == 0 || math1_fn(e.name) >= 0) && n != 1)
                     return in.fail(BKGPU_EINVAL, "%s() needs one argument", e.name.c_str());
+                if (e.name == "pi" && n != 0) return in.fail(BKGPU_EINVAL, "pi() takes no argument");
+                if (math2_fn(e.name) >= 0 && (e.name == "greatest" || e.name == "least" ? n < 1 : n != 2))
+                    return in.fail(BKGPU_EINVAL, "%s() needs %s", e.name.c_str(), e.name == "greatest" || e.name == "least" ? "an argument" : "two arguments");
                 if (e.name == "round" && (n < 1 || n > 2 || (n == 2 && (!is_literal_node(e.ch[1].node_type) || e.ch[1].lit_null))))
                     return in.fail(BKGPU_EUNSUPPORTED, "round() needs a literal number of decimals");
                 for (auto& c : e.ch)
@@ -565,15 +582,33 @@ struct Lower {
             depth = d0 + 1;
             return true;
         }
+        if (e.name == "pi") {
+            const double pi = 3.14159265358979323846; uint64_t b; memcpy(&b, &pi, 8);
+            int k = add_const(b, false); if (k < 0) return false;
+            depth++;
+            return emit(OP_CONST, (uint8_t)k) && cast(BK_DOUBLE, ct);
+        }
+        if (const int m2 = math2_fn(e.name); m2 >= 0) {   // arguments read with get_numberic<double>(); greatest / least fold left to right
+            if (!expr(e.ch[0], depth) || !cast(e.ch[0].col_type, BK_DOUBLE)) return false;
+            for (size_t i = 1; i < e.ch.size(); i++) {
+                if (!expr(e.ch[i], depth) || !cast(e.ch[i].col_type, BK_DOUBLE) || !emit(OP_MATH2, (uint8_t)m2)) return false;
+                depth--;
+            }
+            depth = d0 + 1;
+            return cast(BK_DOUBLE, ct);
+        }
         if (!expr(e.ch[0], depth)) return false;
         const int at = e.ch[0].col_type;
+        if (e.name == "bit_count") return cast(at, BK_UINT64) && emit(OP_MATH, MF_BIT_COUNT) && cast(BK_INT64, ct);
         if (e.name == "cast_to_signed") return cast(at, BK_INT64) && cast(BK_INT64, ct);
         if (e.name == "cast_to_unsigned") return cast(at, BK_UINT64) && cast(BK_UINT64, ct);
         if (e.name == "cast_to_double") return cast(at, BK_DOUBLE) && cast(BK_DOUBLE, ct);
         if (!cast(at, BK_DOUBLE)) return false;   // get_numberic<double>()
         if (e.name == "abs") return emit(OP_MATH, MF_ABS) && cast(BK_DOUBLE, ct);
         if (e.name == "floor") return emit(OP_MATH, MF_FLOOR) && emit(OP_CAST, (uint8_t)BK_DOUBLE, (uint8_t)BK_INT64) && cast(BK_INT64, ct);
-        if (e.name == "ceil") return emit(OP_MATH, MF_CEIL) && emit(OP_CAST, (uint8_t)BK_DOUBLE, (uint8_t)BK_INT64) && cast(BK_INT64, ct);
+        if (e.name == "ceil" || e.name == "ceiling") return emit(OP_MATH, MF_CEIL) && emit(OP_CAST, (uint8_t)BK_DOUBLE, (uint8_t)BK_INT64) && cast(BK_INT64, ct);
+        if (e.name == "sign") return emit(OP_MATH, MF_SIGN) && cast(BK_INT64, ct);
+        if (const int m1 = math1_fn(e.name); m1 >= 0) return emit(OP_MATH, (uint8_t)m1) && cast(BK_DOUBLE, ct);
         if (e.name == "round") {
             int bits = 0;
             if (e.ch.size() == 2) {   // input[1].get_numberic<int>() of the literal (cast to its col_type first, literal.h:204-206)
@@ -881,8 +916,8 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
 // ---------------------------------------------------------------- explain
 static const char* op_name(int op) {
     static const char* n[] = {"END", "LOAD_COL", "CONST", "CAST", "CMP", "ARITH", "DIV_F64", "MOD", "BIT", "BIT_NOT", "NEG",
-                              "LOGIC_NOT", "AND", "OR", "XOR", "NOT3", "IS_NULL", "IS_TRUE", "IN", "OUT", "SELECT", "IFNULL", "MATH"};
-    return op >= 0 && op <= OP_MATH ? n[op] : "?";
+                              "LOGIC_NOT", "AND", "OR", "XOR", "NOT3", "IS_NULL", "IS_TRUE", "IN", "OUT", "SELECT", "IFNULL", "MATH", "MATH2"};
+    return op >= 0 && op <= OP_MATH2 ? n[op] : "?";
 }
 static void explain(Compiled& c) {
     char buf[256];

@@ -843,7 +843,12 @@ static int type_infer(Ctx* c, Expr* e) {
             else if (!strcmp(e->name, "ifnull")) { if (nn != 2) { snprintf(c->err, c->errlen, "ifnull() needs 2 arguments"); return -1; } merge[nm++] = e->children[0]->col_type; merge[nm++] = e->children[1]->col_type; }
             else if (!strcmp(e->name, "case_when")) { for (int i = 1; i < nn; i++) if (i % 2 == 1 || i + 1 == nn) merge[nm++] = e->children[i]->col_type; }
             else if (!strcmp(e->name, "abs") || !strcmp(e->name, "round") || !strcmp(e->name, "cast_to_double")) e->return_type = T_DOUBLE;
-            else if (!strcmp(e->name, "floor") || !strcmp(e->name, "ceil") || !strcmp(e->name, "cast_to_signed")) e->return_type = T_INT64;
+            else if (!strcmp(e->name, "floor") || !strcmp(e->name, "ceil") || !strcmp(e->name, "ceiling") || !strcmp(e->name, "cast_to_signed") ||
+                     !strcmp(e->name, "sign") || !strcmp(e->name, "bit_count")) e->return_type = T_INT64;
+            else if (!strcmp(e->name, "sqrt") || !strcmp(e->name, "mod") || !strcmp(e->name, "sin") || !strcmp(e->name, "asin") || !strcmp(e->name, "cos") ||
+                     !strcmp(e->name, "acos") || !strcmp(e->name, "tan") || !strcmp(e->name, "cot") || !strcmp(e->name, "atan") || !strcmp(e->name, "ln") ||
+                     !strcmp(e->name, "log") || !strcmp(e->name, "pi") || !strcmp(e->name, "pow") || !strcmp(e->name, "power") || !strcmp(e->name, "greatest") ||
+                     !strcmp(e->name, "least")) e->return_type = T_DOUBLE;   /* return_type_map, fn_manager.cpp:105-128 */
             else if (!strcmp(e->name, "cast_to_unsigned")) e->return_type = T_UINT64;
             else { snprintf(c->err, c->errlen, "unsupported function %s", e->name); return -1; }
             if (nm) { /* has_merged_type, include/common/type_utils.h:502-560 */
@@ -892,14 +897,55 @@ static ExprValue call_common(const Expr* e, ExprValue* a, int n) {
         for (int i = 0; i < n / 2; i++) if (!ev_is_null(&a[2 * i]) && num_bool(&a[2 * i])) return a[2 * i + 1];
         return n % 2 == 0 ? ev_null() : a[n - 1];
     }
+    if (!strcmp(e->name, "pi")) { r = ev_typed(T_DOUBLE); r.u.double_val = M_PI; return r; }                         /* :259-263 */
+    if (!strcmp(e->name, "greatest") || !strcmp(e->name, "least")) {                                                 /* :265-317 */
+        const int gt = e->name[0] == 'g'; double ret = 0; int found = 0;
+        for (int i = 0; i < n; i++) {
+            if (ev_is_null(&a[i])) return ev_null();
+            const double v = num_f64(&a[i]);
+            if (!found) { found = 1; ret = v; } else if (gt ? v > ret : v < ret) ret = v;
+        }
+        if (!found) return ev_null();
+        r = ev_typed(T_DOUBLE); r.u.double_val = ret; return r;
+    }
+    if (!strcmp(e->name, "mod") || !strcmp(e->name, "log") || !strcmp(e->name, "pow") || !strcmp(e->name, "power")) {
+        if (n < 2 || ev_is_null(&a[0]) || ev_is_null(&a[1])) return ev_null();
+        const double p = num_f64(&a[0]), q = num_f64(&a[1]);
+        r = ev_typed(T_DOUBLE);
+        if (e->name[0] == 'm') { if (fabs(q - 0) < 1e-9) return ev_null(); r.u.double_val = fmod(p, q); }            /* mod :114-127, float_equal(rhs, 0) */
+        else if (e->name[0] == 'l') { if (p <= 0 || q <= 0 || p == 1) return ev_null(); r.u.double_val = log(q) / log(p); } /* log(base, val) :234-246 */
+        else r.u.double_val = pow(p, q);                                                                             /* :248-257 */
+        return r;
+    }
+    if (!strcmp(e->name, "bit_count")) {                                                                             /* :336-350 */
+        if (n != 1 || ev_is_null(&a[0])) return ev_null();
+        ExprValue t = a[0]; ev_cast_to(&t, T_UINT64);
+        r = ev_typed(T_INT64);
+        for (uint64_t v = t.u.uint64_val; v; v >>= 1) r.u.int64_val += (int64_t)(v & 1);
+        return r;
+    }
     if (n < 1 || ev_is_null(&a[0])) return ev_null();
+    {   /* one-argument DOUBLE functions :101-232: sqrt, sign, sin, asin, cos, acos, tan, cot, atan, ln */
+        const double v = num_f64(&a[0]);
+        r = ev_typed(T_DOUBLE);
+        if (!strcmp(e->name, "sqrt")) { if (v < 0) return ev_null(); r.u.double_val = sqrt(v); return r; }
+        if (!strcmp(e->name, "sign")) { r = ev_typed(T_INT64); r.u.int64_val = v > 0 ? 1 : (v < 0 ? -1 : 0); return r; }
+        if (!strcmp(e->name, "sin")) { r.u.double_val = sin(v); return r; }
+        if (!strcmp(e->name, "cos")) { r.u.double_val = cos(v); return r; }
+        if (!strcmp(e->name, "tan")) { r.u.double_val = tan(v); return r; }
+        if (!strcmp(e->name, "atan")) { r.u.double_val = atan(v); return r; }
+        if (!strcmp(e->name, "asin")) { if (v < -1 || v > 1) return ev_null(); r.u.double_val = asin(v); return r; }
+        if (!strcmp(e->name, "acos")) { if (v < -1 || v > 1) return ev_null(); r.u.double_val = acos(v); return r; }
+        if (!strcmp(e->name, "cot")) { const double s = sin(v), c = cos(v); if (fabs(s - 0) < 1e-9) return ev_null(); r.u.double_val = c / s; return r; }
+        if (!strcmp(e->name, "ln")) { if (v <= 0) return ev_null(); r.u.double_val = log(v); return r; }
+    }
     if (!strcmp(e->name, "cast_to_signed")) { r = a[0]; ev_cast_to(&r, T_INT64); return r; }
     if (!strcmp(e->name, "cast_to_unsigned")) { r = a[0]; ev_cast_to(&r, T_UINT64); return r; }
     if (!strcmp(e->name, "cast_to_double")) { r = a[0]; ev_cast_to(&r, T_DOUBLE); return r; }
     double x = num_f64(&a[0]);
     if (!strcmp(e->name, "abs")) { r = ev_typed(T_DOUBLE); r.u.double_val = x < 0 ? -x : x; return r; }
     if (!strcmp(e->name, "floor")) { r = ev_typed(T_INT64); r.u.int64_val = (int64_t)floor(x); return r; }
-    if (!strcmp(e->name, "ceil")) { r = ev_typed(T_INT64); r.u.int64_val = (int64_t)ceil(x); return r; }
+    if (!strcmp(e->name, "ceil") || !strcmp(e->name, "ceiling")) { r = ev_typed(T_INT64); r.u.int64_val = (int64_t)ceil(x); return r; }
     if (!strcmp(e->name, "round")) {
         int bits = n == 2 ? num_i32(&a[1]) : 0;
         double base = pow(10, bits);

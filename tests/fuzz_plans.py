@@ -1,5 +1,6 @@
 """Deterministic random fragments for the fuzz tests: expressions over a 5-column nullable table drawn from the operator surface the
-GPU path claims (arithmetic, comparisons, three-valued logic, IN, IS NULL, IF / IFNULL / CASE WHEN, ABS / FLOOR / CEIL / ROUND, casts),
+GPU path claims (arithmetic, comparisons, three-valued logic, IN, IS NULL, IF / IFNULL / CASE WHEN, ABS / FLOOR / CEIL / ROUND, SQRT / LN / POW /
+MOD / SIGN / GREATEST / LEAST, casts),
 used as filters, GROUP BY keys and aggregate arguments."""
 import numpy as np
 
@@ -44,7 +45,7 @@ class Gen:
         """numeric-valued expression"""
         if d <= 0 or self.r.random() < 0.25:
             return self.col() if self.r.random() < 0.7 else self.lit()
-        k = int(self.r.integers(0, 12))
+        k = int(self.r.integers(0, 17))
         a, b = self.num(d - 1), self.num(d - 1)
         if k == 0: return P.add(a, b)
         if k == 1: return P.minus(a, b)
@@ -57,6 +58,11 @@ class Gen:
         if k == 8: return self.pick([P.abs_, P.floor_, P.ceil_, P.round_])(a)
         if k == 9: return P.round_(a, P.int_lit(int(self.r.integers(0, 3))))
         if k == 10: return self.pick([P.cast_to_signed, P.cast_to_double])(a)
+        if k == 11: return P.ifnull(self.pick([P.sqrt_, P.ln_])(a), b)
+        if k == 12: return self.pick([P.greatest, P.least])(a, b, self.lit())
+        if k == 13: return P.sign_(a)
+        if k == 14: return P.fmod_(a, self.pick([P.int_lit(3), P.double_lit(2.5), self.col()]))
+        if k == 15: return P.pow_(P.divides(a, P.int_lit(50)), P.int_lit(int(self.r.integers(0, 4))))
         return P.uminus(a)
 
     def pred(self, d):

@@ -65,6 +65,29 @@ def test_oracle_known_answers():
     assert ev(P.cast_to_double(i64), T.DOUBLE) == [10.0, 20.0, 30.0, 40.0]
 
 
+def test_oracle_known_answers_of_the_remaining_numeric_builtins():
+    """sqrt / sign / ln / log / pow / mod / greatest / least / bit_count / pi / trigonometry (internal_functions.cpp:101-350): NULL outside
+    the domain, DOUBLE arithmetic on get_numberic<double>() of the arguments"""
+    cols = [make_column(0, 1, T.INT32, [4, -9, 0, 5], [True, True, True, False]), make_column(0, 2, T.DOUBLE, [2.0, -0.5, 1.0, 7.0], [True, True, True, True]),
+            make_column(0, 3, T.INT64, [10, 20, 30, 40]), make_column(0, 4, T.UINT64, [1, 255, (1 << 64) - 1, 0])]
+    a, d, i64, u64 = _c(1), _c(2), _c(3), _c(4)
+    ev = lambda e, t: _scalar_rows(e, t, cols)[0]
+    assert ev(P.sqrt_(a), T.DOUBLE) == [2.0, None, 0.0, None]                       # negative -> NULL
+    assert ev(P.sign_(d), T.INT64) == [1, -1, 1, 1] and ev(P.sign_(a), T.INT64) == [1, -1, 0, None]
+    assert ev(P.ln_(d), T.DOUBLE) == [math.log(2.0), None, 0.0, math.log(7.0)]      # <= 0 -> NULL
+    assert ev(P.log_(P.int_lit(2), i64), T.DOUBLE) == [math.log(10) / math.log(2), math.log(20) / math.log(2), math.log(30) / math.log(2), math.log(40) / math.log(2)]
+    assert ev(P.log_(d, i64), T.DOUBLE)[1:3] == [None, None]                         # base <= 0, base == 1 -> NULL
+    assert ev(P.pow_(d, P.int_lit(3)), T.DOUBLE) == [8.0, -0.125, 1.0, 343.0]
+    assert ev(P.fmod_(i64, d), T.DOUBLE) == [0.0, 0.0, 0.0, 5.0] and ev(P.fmod_(i64, P.int_lit(0)), T.DOUBLE) == [None] * 4
+    assert ev(P.fmod_(P.uminus(i64), P.int_lit(7)), T.DOUBLE) == [-3.0, -6.0, -2.0, -5.0]   # std::fmod keeps the dividend's sign
+    assert ev(P.greatest(a, d, P.int_lit(1)), T.DOUBLE) == [4.0, 1.0, 1.0, None] and ev(P.least(a, d, P.int_lit(1)), T.DOUBLE) == [1.0, -9.0, 0.0, None]
+    assert ev(P.bit_count(u64), T.INT64) == [1, 8, 64, 0] and ev(P.bit_count(P.uminus(P.int_lit(1))), T.INT64) == [64] * 4
+    assert ev(P.pi_(), T.DOUBLE) == [math.pi] * 4
+    assert ev(P.trig("asin", d), T.DOUBLE) == [None, math.asin(-0.5), math.asin(1.0), None] and ev(P.trig("cot", a), T.DOUBLE)[2] is None
+    got = ev(P.trig("sin", d), T.DOUBLE)
+    assert all(abs(g - math.sin(x)) < 1e-15 for g, x in zip(got, [2.0, -0.5, 1.0, 7.0]))
+
+
 def test_lowering_accepts_and_rejects():
     ok = _group_plan(P.floor_(P.divides(_c(2), P.int_lit(10))), T.INT64, P.if_(P.gt(_c(1), P.int_lit(0)), _c(2), P.int_lit(0)), T.DOUBLE)
     text = _lib.explain(ok.serialize())
@@ -85,6 +108,12 @@ CASES = [
     ("ceil_round", lambda: (P.ceil_(_c(2)), T.INT64, P.round_(_c(2), P.int_lit(1)), T.DOUBLE)),
     ("round0_neg", lambda: (P.cast_to_signed(P.round_(_c(2))), T.INT64, P.round_(P.multiplies(_c(2), P.double_lit(0.5))), T.DOUBLE)),
     ("casts", lambda: (P.cast_to_signed(_c(2)), T.INT64, P.cast_to_double(P.cast_to_unsigned(_c(3))), T.DOUBLE)),
+    ("sqrt_ln", lambda: (P.sign_(_c(2)), T.INT64, P.add(P.ifnull(P.sqrt_(_c(2)), P.double_lit(-1.0)), P.ifnull(P.ln_(_c(3)), P.double_lit(0.25))), T.DOUBLE)),
+    ("pow_log", lambda: (_c(1), T.INT32, P.add(P.pow_(P.divides(_c(2), P.int_lit(10)), P.int_lit(3)), P.ifnull(P.log_(P.int_lit(3), _c(3)), P.double_lit(0.0))), T.DOUBLE)),
+    ("fmod_greatest", lambda: (P.cast_to_signed(P.fmod_(_c(3), P.int_lit(5))), T.INT64, P.minus(P.greatest(_c(1), _c(2), P.int_lit(0)), P.least(_c(2), _c(3))), T.DOUBLE)),
+    ("bit_count_pi", lambda: (P.bit_count(_c(4)), T.INT64, P.multiplies(P.pi_(), P.bit_count(_c(3))), T.DOUBLE)),
+    ("trig", lambda: (_c(1), T.INT32, P.add(P.add(P.trig("sin", _c(2)), P.trig("cos", _c(3))), P.add(P.ifnull(P.trig("asin", P.divides(_c(1), P.int_lit(5))), P.double_lit(9.0)), P.trig("atan", _c(2)))), T.DOUBLE)),
+    ("tan_cot_acos", lambda: (_c(1), T.INT32, P.add(P.trig("tan", P.divides(_c(2), P.int_lit(40))), P.add(P.ifnull(P.trig("cot", _c(1)), P.double_lit(0.5)), P.ifnull(P.trig("acos", P.divides(_c(1), P.int_lit(6))), P.double_lit(4.0)))), T.DOUBLE)),
 ]
 
 
