@@ -454,7 +454,9 @@ __global__ void k_join_build_fast(DevCol key, int from_prim, int cast_to, int64_
         if (elem_is_null(key, r)) continue;   // a NULL key never matches
         const uint64_t img = cast_prim(load_elem(key, r), from_prim, cast_to);
         if (jf.mode == 1) {
-            if (atomicExch(dense_w + ((img ^ jf.bias) - jf.dense_min), (uint32_t)r) != 0xFFFFFFFFu) atomicExch(dup_flag, 1u);
+            const uint64_t off = (img ^ jf.bias) - jf.dense_min;
+            if (off >= jf.dense_size) { atomicExch(dup_flag + 2, 1u); continue; }   // outside the range learned from an earlier run of the plan: the host rebuilds
+            if (atomicExch(dense_w + off, (uint32_t)r) != 0xFFFFFFFFu) atomicExch(dup_flag, 1u);
         } else {
             const uint32_t k32 = (uint32_t)img;
             const uint64_t v = ((uint64_t)k32 << 32) | (uint32_t)r;
@@ -544,7 +546,7 @@ cudaError_t launch_join_minmax(const DevCol& key, int from_prim, int cast_prim_,
     return cudaGetLastError();
 }
 cudaError_t launch_join_build_fast(const DevCol& key, int from_prim, int cast_prim_, int64_t nrows, const JoinFast& jf, uint32_t* dense_w, uint64_t* packed_w, uint32_t* dup_flag, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(dup_flag, 0, 4, s);
+    cudaError_t e = cudaMemsetAsync(dup_flag, 0, 12, s);   // [0] duplicate key, [1] fused probe unusable (set by the compose step), [2] key outside the guessed range
     if (e != cudaSuccess) return e;
     if (jf.mode == 1) e = cudaMemsetAsync(dense_w, 0xFF, jf.dense_size * 4, s); else e = cudaMemsetAsync(packed_w, 0xFF, ((size_t)jf.packed_mask + 1) * 8, s);
     if (e != cudaSuccess || nrows == 0) return e;

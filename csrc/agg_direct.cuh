@@ -613,6 +613,140 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
     };
     if (q0 + lane < nquads) issue_loads(q0 + lane);
     uint32_t qhead = 0, qcount = 0;   // warp-uniform: ring start (a multiple of 32) and entries waiting in it
+    if constexpr (JOIN && !NULLS && !MM) {
+    if (a.jp.mode == 1) {
+        // ---- K4 fused, software-pipelined (profiles/r02_join_history.md): the dimension lookups of a trip are ISSUED, then the rows the
+        //      previous trip queued are drained while they fly (the table work hides the L2 round trip), then they are consumed and the
+        //      trip's rows queued.  The next trip's foreign keys load into the key registers as soon as the lookups have left.
+        const JoinProbe& jp = a.jp;
+#pragma unroll 1
+        for (;;) {
+            const bool last = q0 >= nquads;
+            const int64_t q = q0 + lane;
+            uint32_t pass = 0, g[4] = {0, 0, 0, 0}, pr4[4] = {0, 0, 0, 0};
+            if (!last) {
+                if (q < nquads) {
+                    pass = 0xFu;
+#pragma unroll
+                    for (int t = 0; t < NP; t++) {
+                        uint32_t r8[8];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) r8[j] = pr[t][j];
+                        pass &= term_mask_i32(tcmp[t], tconst[t], r8);
+                    }
+                }
+                uint32_t inr = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint64_t img = jp.key_signed ? (uint64_t)(int64_t)(int32_t)kr[j] : (uint64_t)kr[j];
+                    const uint64_t off = (img ^ jp.bias) - jp.dense_min;
+                    if (((pass >> j) & 1u) && off < jp.dense_size) {
+                        inr |= 1u << j;
+                        g[j] = __ldg(jp.attr + off);
+                        if (jp.present) pr4[j] = __ldg(jp.present + off);
+                    }
+                }
+                pass &= inr;
+                if (q + stride < nquads) {   // the keys of the next trip (the lookups above no longer need these registers)
+                    const U32x4 r = ldg128_u32(kptr + (q + stride) * 16);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) kr[j] = r.v[j];
+                }
+            }
+            // ---- drain what the previous trip queued ----
+            {
+                const uint32_t limit = (last || NP == 0) ? qcount : (qcount & ~31u);
+#pragma unroll 1
+                for (uint32_t e0 = 0; e0 < limit; e0 += 32) {
+                    if (e0 + lane >= limit) continue;
+                    uint32_t e = qhead + e0 + lane;
+                    if (NP > 0) e -= e >= LQ ? LQ : 0u;
+                    const uint64_t k0 = lds64(qkey + e * 8u);
+                    uint64_t v[NA > 0 ? NA : 1];
+#pragma unroll
+                    for (int s = 0; s < NA; s++) v[s] = lds64(qval + (s * LQ + e) * 8u);
+                    const uint32_t h = ((uint32_t)k0 ^ (uint32_t)(k0 >> 32)) * 0x9E3779B1u;
+                    int slot = -1;
+                    if (k0 != EMPTY_KEY) slot = smem32_upsert1(keys_addr, cap_mask, k0, h >> hash_shift);
+                    if (slot >= 0) {
+                        reds_inc32(lanes_addr + slot * 16u);
+                        int first = 0;
+                        if (pair2) {
+                            const uint32_t addr = acc_addr[0] + slot * 16u;
+                            uint64_t c0, c1;
+                            lds128(addr, c0, c1);
+                            for (;;) {
+                                uint64_t p0, p1;
+                                atoms_cas128(addr, c0, c1, f64_bits(bits_f64(c0) + bits_f64(v[0])), f64_bits(bits_f64(c1) + bits_f64(v[NA > 1 ? 1 : 0])), p0, p1);
+                                if (p0 == c0 && p1 == c1) break;
+                                c0 = p0; c1 = p1;
+                            }
+                            first = 2;
+                        }
+#pragma unroll
+                        for (int s = 0; s < NA; s++) {
+                            if (s < first) continue;
+                            if (acc_f64[s]) smem32_add_f64(acc_addr[s] + slot * 16u, bits_f64(v[s])); else smem32_add_u64(acc_addr[s] + slot * 16u, v[s]);
+                        }
+                    } else {
+                        uint64_t key[2] = {k0, 0ull};
+                        uint64_t gv[NA > 0 ? NA : 1];
+#pragma unroll
+                        for (int s = 0; s < NA; s++) gv[s] = lds64(qval + (s * LQ + e) * 8u);
+                        global_update_row<NA>(a, key, gv, 0u);
+                    }
+                }
+                if (NP > 0) { qhead = (qhead + limit) % LQ; qcount -= limit; } else qcount = 0;
+            }
+            __syncwarp();
+            if (last) break;
+            // ---- consume the lookups: rows without a partner leave the mask (inner join); queue the survivors ----
+            if (jp.present) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (pr4[j] == 0xFFFFFFFFu) pass &= ~(1u << j);
+            }
+            {
+                uint32_t bal[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) bal[j] = __ballot_sync(0xFFFFFFFFu, (pass >> j) & 1u);
+                uint32_t fresh = 0;
+                const uint32_t tail = qhead + qcount;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if ((pass >> j) & 1u) {
+                        uint32_t pos = tail + fresh + (uint32_t)__popc(bal[j] & lane_lt);
+                        if (NP > 0) pos -= pos >= LQ ? LQ : 0u;
+                        sts64(qkey + pos * 8u, (uint64_t)g[j] & kmask);
+#pragma unroll
+                        for (int s = 0; s < NA; s++) sts64(qval + (s * LQ + pos) * 8u, vr[s][j]);
+                    }
+                    fresh += __popc(bal[j]);
+                }
+                qcount += fresh;
+            }
+            passed += __popc(pass);
+            // ---- the other columns of the next trip (its keys are already on their way) ----
+            if (q + stride < nquads) {
+#pragma unroll
+                for (int t = 0; t < NP; t++) { const U32x4 r = ldg128_u32(tptr[t] + (q + stride) * 16);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) pr[t][j] = r.v[j]; }
+#pragma unroll
+                for (int s = 0; s < NA; s++) { const U64x4 r = ldg256_u64(vptr[s] + (q + stride) * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) vr[s][j] = r.v[j]; }
+            }
+            __syncwarp();
+            q0 += stride;
+        }
+        smem_table_flush(st, a);
+        if (blockIdx.x == 0 && threadIdx.x < (a.nrows & 3)) passed += direct_tail_row<NP, NA, JOIN>(a, (a.nrows & ~(int64_t)3) + threadIdx.x);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) passed += __shfl_xor_sync(0xFFFFFFFFu, passed, d);
+        if (lane == 0 && passed) atomicAdd((unsigned long long*)a.rows_passed, (unsigned long long)passed);
+        return;
+    }
+    }
 #pragma unroll 1
     for (;;) {
         const bool last = q0 >= nquads;   // (warp-uniform) one extra trip drains what is left in the ring

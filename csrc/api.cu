@@ -103,6 +103,7 @@ struct bkgpu_plan {
     int64_t jb_rows = 0, jb_cap = 0;
     uint64_t* jt_keys = nullptr; uint32_t* jt_rows = nullptr; uint32_t jt_mask = 0; bool jt_built = false, jt_generic = false;
     JoinFast jf{}; uint32_t* jf_dense = nullptr; uint64_t* jf_packed = nullptr;   // FK -> PK fast path (unique build keys)
+    bool jf_learned = false; uint64_t jf_learn_min = 0, jf_learn_max = 0;   // key range of the plan's previous build (skips the min/max pass + round trip)
     JoinProbe jp{}; uint32_t* jp_attr = nullptr; uint64_t* jp_packed = nullptr; int jp_key_pos = 0;   // ... fused into the lean aggregate
     size_t jf_dense_cap = 0, jf_packed_cap = 0, jp_attr_cap = 0, jp_packed_cap = 0, j_scratch_cap = 0;
     uint64_t* j_scratch = nullptr;   // [0..1] key min / max, then u32 flags: [4] duplicate build key, [5] fused probe unusable
@@ -780,15 +781,24 @@ static int join_build_table(bkgpu_plan* p) {
     if (p->jg_buf.empty()) p->jg_buf.assign(nc, nullptr);
     bool build_nulls = false;
     for (size_t i = 0; i < nc; i++) if (c.col_side[i] == 1 && p->jb_has_null[i]) build_nulls = true;   // gathered columns must be NULL-free
+    bool retry_measured = false;
+again:
     if (c.jfast && !build_nulls && p->jb_rows > 0) {
         const int cls = host_prim_class(c.join_key_prim);
         const uint64_t bias = cls == VC_I64 ? 0x8000000000000000ull : 0ull;
         if ((rc = ensure_buf(p, (void**)&p->j_scratch, &p->j_scratch_cap, 64))) return rc;
         uint64_t* mm = p->j_scratch; uint32_t* dup = (uint32_t*)(p->j_scratch + 2);
-        CK(p, launch_join_minmax(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, bias, mm, p->stream));
+        // the key range: measured (one pass over the keys + a round trip), or — when this plan has built before — the range it saw then,
+        // checked by the build kernel itself (a key outside it raises a flag and the build is redone with a measured range)
         uint64_t h_mm[2];
-        CK(p, cudaMemcpyAsync(h_mm, mm, 16, cudaMemcpyDeviceToHost, p->stream));
-        CK(p, cudaStreamSynchronize(p->stream));
+        bool guessed = p->jf_learned && !retry_measured;
+        if (guessed) { h_mm[0] = p->jf_learn_min; h_mm[1] = p->jf_learn_max; }
+        else {
+            CK(p, launch_join_minmax(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, bias, mm, p->stream));
+            CK(p, cudaMemcpyAsync(h_mm, mm, 16, cudaMemcpyDeviceToHost, p->stream));
+            CK(p, cudaStreamSynchronize(p->stream));
+            p->stats.kernel_launches++;
+        }
         JoinFast jf{}; jf.bias = bias;
         const uint64_t range = h_mm[1] >= h_mm[0] ? h_mm[1] - h_mm[0] + 1 : 0;
         const int kb = storage_bytes(prim_storage(c.join_key_prim));
@@ -804,15 +814,17 @@ static int join_build_table(bkgpu_plan* p) {
         }
         if (jf.mode) {
             CK(p, launch_join_build_fast(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, jf, p->jf_dense, p->jf_packed, dup, p->stream));
-            p->stats.kernel_launches += 2;
+            p->stats.kernel_launches += 1;
             p->jf = jf;
-            if ((rc = join_compose_probe(p, dup + 1))) return rc;   // enqueued behind the build: both flags come back in one round trip
-            uint32_t h_flags[2] = {0, 0};
-            CK(p, cudaMemcpyAsync(h_flags, dup, 8, cudaMemcpyDeviceToHost, p->stream));
+            if ((rc = join_compose_probe(p, dup + 1))) return rc;   // enqueued behind the build: all flags come back in one round trip
+            uint32_t h_flags[3] = {0, 0, 0};
+            CK(p, cudaMemcpyAsync(h_flags, dup, 12, cudaMemcpyDeviceToHost, p->stream));
             CK(p, cudaStreamSynchronize(p->stream));
+            if (h_flags[2] && guessed) { retry_measured = true; goto again; }   // this run's keys left the learned range
             if (h_flags[0]) { p->jf = JoinFast{}; p->jp = JoinProbe{}; }   // duplicate build keys: not a PK, the general probe runs
             else if (h_flags[1]) p->jp = JoinProbe{};
-        }
+            p->jf_learned = true; p->jf_learn_min = h_mm[0]; p->jf_learn_max = h_mm[1];
+        } else if (guessed) { retry_measured = true; goto again; }   // (the learned range no longer fits this row count)
     }
     return BKGPU_OK;
 }

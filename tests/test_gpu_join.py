@@ -188,3 +188,41 @@ def test_outer_join_with_an_empty_probe_side_and_unsupported_shapes():
     with pytest.raises(BkgpuError) as e:   # filter-then-join is not the fused predicate's meaning for an outer join: rejected, never wrong
         execute(P.Plan(P.agg(filtered, 2, [P.slot_ref(1, 2, T.INT32)], aggs), tuples), [dim, fact])
     assert e.value.code == EUNSUPPORTED
+
+
+def test_fused_build_reuses_the_learned_key_range_and_recovers_when_it_no_longer_fits():
+    """prepared-statement reuse of C3's plan: the second build skips the min/max pass and trusts the first run's key range (checked by the
+    build kernel); dimension keys that leave that range, and duplicate keys, must still give the oracle's rows"""
+    from baikaldb_b200.exec_node import ColumnSource, GpuExecNode, RowBatch, RuntimeState
+    from oracle import oracle
+    from tests.util import assert_same_rows
+    rng = np.random.default_rng(21)
+    pl = queries.c3_join_groupby()
+
+    def tables(lo, hi, nd, nf, dup=False):
+        keys = rng.permutation(np.arange(lo, hi, dtype=np.int64))[:nd]
+        if dup:
+            keys[: nd // 10] = keys[nd // 10: 2 * (nd // 10)]
+        dim = [make_column(1, 1, T.INT32, keys), make_column(1, 2, T.INT32, rng.integers(0, 50, nd))]
+        fact = [make_column(0, 1, T.INT32, rng.integers(lo - 5, hi + 5, nf)), make_column(0, 2, T.DOUBLE, rng.random(nf))]
+        return dim, fact
+
+    runs = [tables(0, 4000, 3000, 60_000), tables(100, 3900, 3000, 60_000), tables(-7000, 9000, 5000, 60_000), tables(0, 4000, 3000, 60_000, dup=True),
+            tables(1_000_000, 1_002_000, 1500, 60_000)]
+    node, st = GpuExecNode(), RuntimeState(device=0)
+    node.init(pl)
+    node.add_child(ColumnSource([runs[0][0], runs[0][1]]))
+    try:
+        assert node.open(st) == 0, st.error_msg
+        for i, (dim, fact) in enumerate(runs):
+            if i:
+                node.reset(); node.push(dim); node.push(fact); node.finish()
+            got, eos, rb = [], False, RowBatch()
+            while not eos:
+                rc, eos = node.get_next(st, rb)
+                assert rc == 0
+                got = got or list(rb.columns)
+            want = oracle.execute(pl.serialize(), fact + dim)
+            assert_same_rows(got, want.columns, ["1_2"])
+    finally:
+        node.close(st)
