@@ -958,7 +958,7 @@ static void explain(Compiled& c) {
 // ---------------------------------------------------------------- entry
 bool lower_sort(Infer& in, Compiled& out, const HNode& sort, const HNode* filter, const HNode& scan);
 bool lower_filter(Infer& in, Compiled& out, const HNode* limit_node, const HNode& filter_or_scan, const HNode& scan);
-bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& join, bool under_packet);
+bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& join, bool under_packet, const HNode* above);
 bool lower_post(Infer& in, Compiled& out, const HNode* sort, const HNode* having, const HNode* limit_node);
 
 static bool infer_node(Infer& in, HNode& n) {
@@ -1018,8 +1018,9 @@ int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& er
             if (filter) for (auto& e : filter->conjuncts) conj.push_back(&e);
             ok = lower_agg(in, out, *top, conj, c->tuple_id, under_packet, true);
             if (ok && limit_node && !post_sort && !post_having) { out.limit = limit_node->limit; out.offset = limit_node->offset; }
-        } else if (c && c->node_type == BK_JOIN_NODE && !filter) {
-            ok = lower_join_agg(in, out, *top, *c, under_packet);
+        } else if (c && c->node_type == BK_JOIN_NODE) {   // AGG -> [FILTER ->] JOIN: the store-side chain of a filtered join (separate.cpp:241-260)
+            if (filter && filter->limit != -1) { err = "LIMIT on a filter below an aggregate is order dependent: outside the GPU path"; return BKGPU_EUNSUPPORTED; }
+            ok = lower_join_agg(in, out, *top, *c, under_packet, filter);
             if (ok && limit_node && !post_sort && !post_having) { out.limit = limit_node->limit; out.offset = limit_node->offset; }   // LimitNode over the joined aggregate
         } else { err = "AGG child must be [FILTER ->] SCAN or JOIN"; return BKGPU_EUNSUPPORTED; }
         if (ok && (post_sort || post_having)) ok = lower_post(in, out, post_sort, post_having, limit_node);
@@ -1189,7 +1190,7 @@ bool lower_post(Infer& in, Compiled& out, const HNode* sort, const HNode* having
 // src/exec/joiner.cpp:624-631); the key is the cast equal-slot value (strip_out_equal_slots, joiner.cpp:166-217).
 // Filters of both children and the residual join conditions become one predicate over the joined row — for an
 // INNER join that is the same set of rows.
-bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& join, bool under_packet) {
+bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& join, bool under_packet, const HNode* above) {
     int jt = join.join_type;
     if (jt != BK_INNER_JOIN && jt != BK_LEFT_JOIN && jt != BK_RIGHT_JOIN && jt != BK_SEMI_JOIN && jt != BK_ANTI_SEMI_JOIN)
         return in.fail(BKGPU_EUNSUPPORTED, "join type %d (FULL / NULL) is outside the GPU path", jt);
@@ -1205,6 +1206,9 @@ bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& joi
     }
     if (jt == BK_RIGHT_JOIN) jt = BK_LEFT_JOIN;
     // the fused predicate (child filters + residual conditions over the joined row) equals filter-then-join only for INNER joins
+    // a filter ABOVE the join sees the joined row: for an INNER join it simply joins the residual conditions; above an outer join it would also
+    // have to judge the NULL-extended rows, after the match decision — a second predicate the probe does not carry
+    if (jt != BK_INNER_JOIN && above) return in.fail(BKGPU_EUNSUPPORTED, "a filter between the aggregate and a LEFT / SEMI / ANTI join is outside the GPU path");
     if (jt != BK_INNER_JOIN && (filt[0] || filt[1])) return in.fail(BKGPU_EUNSUPPORTED, "LEFT / SEMI / ANTI join over filtered children is outside the GPU path");
     const int build_tuple = side[0]->tuple_id, probe_tuple = side[1]->tuple_id;
     out.build_tuple = build_tuple;
@@ -1221,6 +1225,7 @@ bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& joi
     }
     if (!bk) return in.fail(BKGPU_EUNSUPPORTED, "join without an equality between the two tables (nested loop) is outside the GPU path");
     for (int i = 0; i < 2; i++) if (filt[i]) for (auto& e : filt[i]->conjuncts) conj.push_back(&e);
+    if (above) for (auto& e : above->conjuncts) conj.push_back(&e);
     int ot = bk->col_type, it = pk->col_type, cast;
     auto is_signed_t = [](int t) { return t >= BK_INT8 && t <= BK_INT64; };
     if (ot == it) cast = ot;

@@ -35,6 +35,9 @@ struct Expr {
     static Expr int_literal(int64_t v) { Expr e; e.node_type = BK_INT_LITERAL; e.col_type = BK_INT64; e.int_val = v; return e; }
     static Expr double_literal(double v) { Expr e; e.node_type = BK_DOUBLE_LITERAL; e.col_type = BK_DOUBLE; e.double_val = v; return e; }
     static Expr null_literal() { Expr e; e.node_type = BK_NULL_LITERAL; e.col_type = BK_NULL_TYPE; return e; }
+    // STRING_LITERAL (taken where it folds into a date/time image) and the typed date/time literals, whose int_val is the image (literal.h:95-114)
+    static Expr string_literal(std::string s) { Expr e; e.node_type = BK_STRING_LITERAL; e.col_type = BK_STRING; e.name = std::move(s); return e; }
+    static Expr datetime_literal(int node_type, int col_type, int64_t image) { Expr e; e.node_type = node_type; e.col_type = col_type; e.int_val = image; return e; }
     static Expr fn(int fn_op, const char* name, std::vector<Expr> args) { Expr e; e.node_type = BK_FUNCTION_CALL; e.fn_op = fn_op; e.name = name; e.children = std::move(args); return e; }
     static Expr predicate(int node_type, int fn_op, const char* name, std::vector<Expr> args) {
         Expr e; e.node_type = node_type; e.col_type = BK_BOOL; e.fn_op = fn_op; e.name = name; e.children = std::move(args); return e;
@@ -98,6 +101,8 @@ private:
             case BK_BOOL_LITERAL: w(e.bool_val ? 1 : 0); break;
             case BK_INT_LITERAL: w64(e.int_val); break;
             case BK_DOUBLE_LITERAL: f64(e.double_val); break;
+            case BK_STRING_LITERAL: str(e.name); break;
+            case BK_DATETIME_LITERAL: case BK_TIMESTAMP_LITERAL: case BK_DATE_LITERAL: case BK_TIME_LITERAL: w64(e.int_val); break;
             case BK_AGG_EXPR: str(e.name); w(e.tuple_id); w(e.final_slot_id); w(e.intermediate_slot_id); break;
             default: w(e.fn_op); str(e.name); w((int32_t)e.arg_types.size()); for (int a : e.arg_types) w(a); w(e.return_type); break;
         }

@@ -111,3 +111,22 @@ def test_having_over_scalar_aggregate():
     assert len(got[0]) == 1
     got, _, _ = run_both(P.Plan(P.packet(_having(a, P.gt(P.slot_ref(1, 1, T.INT64), P.int_lit(10**9)))), tuples), cols, keys=[])
     assert not got or len(got[0]) == 0
+
+
+def test_aggregate_over_a_filtered_join():
+    """AGG -> FILTER -> JOIN (the store-side chain of `... FROM a JOIN b ON ... WHERE f(a, b) GROUP BY ...`): the filter sees the joined row;
+    above an INNER join it joins the residual conditions, above an outer join it is refused"""
+    nd, nf = 4_000, 90_000
+    fact, dim = datagen.c3_fact(0, nf, nd), datagen.c3_dim(0, nd, nd, n_groups=60)
+    aggs = [P.agg_expr("count_star", 2, 1), P.agg_expr("sum", 2, 2, None, P.slot_ref(0, 2, T.DOUBLE))]
+    tuples = {0: [(1, T.INT32), (2, T.DOUBLE)], 1: [(1, T.INT32), (2, T.INT32)], 2: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE])}
+    on = [P.eq(P.slot_ref(1, 1, T.INT32), P.slot_ref(0, 1, T.INT32))]
+    where = [P.gt(P.add(P.slot_ref(0, 2, T.DOUBLE), P.slot_ref(1, 2, T.INT32)), P.double_lit(20.25)), P.ne(P.mod(P.slot_ref(1, 1, T.INT32), P.int_lit(7)), P.int_lit(0))]
+    a = P.agg(P.where(P.join(P.scan(1), P.scan(0), on), *where), 2, [P.slot_ref(1, 2, T.INT32)], aggs)
+    got, _, _ = run_both(P.Plan(a, tuples), dim + fact, keys=["1_2"], batches=[dim, fact])
+    assert 0 < len(got[0]) <= 60
+    from baikaldb_b200 import _lib
+    left = P.agg(P.where(P.join(P.scan(1), P.scan(0), on, join_type=P.JoinType.LEFT_JOIN), *where), 2, [P.slot_ref(1, 2, T.INT32)], aggs)
+    with pytest.raises(_lib.BkgpuError) as e:
+        _lib.explain(P.Plan(left, tuples).serialize())
+    assert e.value.code == _lib.EUNSUPPORTED
