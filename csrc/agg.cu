@@ -106,6 +106,54 @@ __global__ void __launch_bounds__(256) k_agg_interp(const __grid_constant__ AggA
     if ((threadIdx.x & 31) == 0 && passed) atomicAdd((unsigned long long*)a.rows_passed, (unsigned long long)passed);
 }
 
+// ---- a JOIN that returns rows (JoinNode::get_next_for_hash_inner_join / _other_join, join_node.cpp:1200-1326): the probe emits (probe row,
+// build row) pairs, a gather per output column follows.  LEFT: matched[] is set here, the tail emits (NONE, build row) for the rest.
+constexpr uint32_t JOIN_NO_ROW = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(256) k_join_pairs(const __grid_constant__ AggArgs a, uint32_t* pairs, uint32_t cap, uint32_t* cursor) {
+    InterpCtx cx; cx.grouped = false; cx.use_smem = false; cx.gcap = 0; cx.st = SmemTable{};
+    auto emit = [&](uint32_t prow, uint32_t brow) {
+        const uint32_t pos = atomicAdd(cursor, 1u);
+        if (pos < cap) { pairs[2 * (size_t)pos] = prow; pairs[2 * (size_t)pos + 1] = brow; }   // (past the capacity only the count matters: the host grows the buffer and reruns)
+    };
+    if (a.join.tail) {
+        for (int64_t br = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; br < a.join.n_build; br += (int64_t)gridDim.x * blockDim.x)
+            if (!a.join.matched[br]) emit(JOIN_NO_ROW, (uint32_t)br);
+        return;
+    }
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.nrows; row += (int64_t)gridDim.x * blockDim.x) {
+        const DevCol& pc = a.cols[a.join.probe_col];
+        if (elem_is_null(pc, row)) continue;
+        const uint64_t img = cast_prim(load_elem(pc, row), a.join.probe_prim, a.join.cast_prim);
+        uint32_t slot = hash_key1(img) & a.join.cap_mask;
+        for (;;) {
+            const uint32_t br = a.join.rows[slot];
+            if (br == 0xFFFFFFFFu) break;
+            if (a.join.keys[slot] == img && interp_row(a, cx, row, (int64_t)br, 1)) {
+                if (a.join.matched) a.join.matched[br] = 1;
+                emit((uint32_t)row, br);
+            }
+            slot = (slot + 1) & a.join.cap_mask;
+        }
+    }
+}
+// one output column of the joined rows: element `which` of each pair addresses `src`; JOIN_NO_ROW (the NULL-extended side) gives NULL
+__global__ void k_join_rows_gather(DevCol src, const uint32_t* pairs, int which, uint32_t n, int eb, uint8_t* dst, uint8_t* dst_null) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t r = pairs[2 * (size_t)i + which];
+        const bool isnull = r == JOIN_NO_ROW || elem_is_null(src, r);
+        dst_null[i] = isnull ? 1 : 0;
+        const uint8_t* s = (const uint8_t*)src.values + (size_t)r * eb;
+        uint8_t* d = dst + (size_t)i * eb;
+        if (isnull) { for (int b = 0; b < eb; b++) d[b] = 0; continue; }
+        switch (eb) {
+            case 1: *d = *s; break;
+            case 4: *(uint32_t*)d = *(const uint32_t*)s; break;
+            case 8: *(uint64_t*)d = *(const uint64_t*)s; break;
+            default: for (int b = 0; b < eb; b++) d[b] = s[b]; break;
+        }
+    }
+}
+
 // K4 build: insert (cast key image, row) of every non-NULL build row (Joiner::construct_hash_map, joiner.cpp:624-631)
 __global__ void k_join_build(DevCol key, int from_prim, int cast_to, int64_t nrows, uint64_t* keys, uint32_t* rows, uint32_t cap_mask) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
@@ -583,6 +631,20 @@ cudaError_t launch_pack_validity(const uint8_t* null_bytes, int64_t n, uint8_t* 
     if (n == 0) return cudaSuccess;
     int grid = (int)(((n + 7) / 8 + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
     k_pack_validity<<<grid, 256, 0, s>>>(null_bytes, n, bitmap);
+    return cudaGetLastError();
+}
+cudaError_t launch_join_pairs(const AggArgs& a, uint32_t* pairs, uint32_t cap, uint32_t* cursor, int sm_count, cudaStream_t s) {
+    const int64_t n = a.join.tail ? a.join.n_build : a.nrows;
+    if (n == 0) return cudaSuccess;
+    int64_t g64 = (n + 255) / 256; if (g64 > (int64_t)sm_count * 8) g64 = (int64_t)sm_count * 8;
+    const int grid = g64 < 1 ? 1 : (int)g64;
+    k_join_pairs<<<grid, 256, 0, s>>>(a, pairs, cap, cursor);
+    return cudaGetLastError();
+}
+cudaError_t launch_join_rows_gather(const DevCol& src, const uint32_t* pairs, int which, uint32_t n, int eb, uint8_t* dst, uint8_t* dst_null, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    int grid = (int)((n + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    k_join_rows_gather<<<grid, 256, 0, s>>>(src, pairs, which, n, eb, dst, dst_null);
     return cudaGetLastError();
 }
 cudaError_t launch_join_build(const DevCol& key, int from_prim, int cast_prim_, int64_t nrows, uint64_t* keys, uint32_t* rows, uint32_t cap_mask, cudaStream_t s) {

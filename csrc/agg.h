@@ -98,6 +98,9 @@ cudaError_t launch_join_gather(const DevCol& probe_key, int from_prim, int cast_
 cudaError_t launch_join_compose(const JoinFast& jf, const uint32_t* attr_by_row, uint32_t* attr_of_key, uint64_t* packed_attr, uint32_t* bad_flag, cudaStream_t s);
 cudaError_t launch_unpack_validity(const uint8_t* bitmap, int64_t n, uint8_t* null_bytes, cudaStream_t s);
 cudaError_t launch_pack_validity(const uint8_t* null_bytes, int64_t n, uint8_t* bitmap, cudaStream_t s);
+// a JOIN that returns rows: (probe row, build row) pairs of the joined rows that pass the conditions, then one gather per output column
+cudaError_t launch_join_pairs(const AggArgs& a, uint32_t* pairs, uint32_t cap, uint32_t* cursor, int sm_count, cudaStream_t s);
+cudaError_t launch_join_rows_gather(const DevCol& src, const uint32_t* pairs, int which, uint32_t n, int elem_bytes, uint8_t* dst, uint8_t* dst_null, cudaStream_t s);
 cudaError_t launch_table_init(const GroupTable& gt, const AggPlan& ap, cudaStream_t s, int keep_overflow = 0);
 cudaError_t launch_table_clear(const GroupTable& gt, const AggPlan& ap, uint32_t n_occupied, cudaStream_t s);
 cudaError_t launch_partial_export_rows(const GroupTable& gt, const AggPlan& ap, uint64_t* dst, uint32_t bound, cudaStream_t s);

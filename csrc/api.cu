@@ -81,6 +81,7 @@ struct bkgpu_plan {
     int scalar_tma = 1;           // COUNT(*) WHERE int32 <cmp> c runs the TMA-staged kernel (scalar_tma.cu): 0.97 vs 0.78 of HBM (profiles/r02_tma_scalar.md); 0 = the LDG kernel
     int no_bounce = 0;            // 1 = pageable host input goes straight to cudaMemcpyAsync (A/B of the bounce path)
     int no_stream_copy = 0;       // 1 = the bounce copy uses memcpy instead of non-temporal stores (A/B, hostcopy.cpp)
+    uint32_t* jr_pairs = nullptr; size_t jr_pairs_cap = 0; uint32_t* jr_cursor = nullptr; size_t jr_cursor_cap = 0;   // PK_JOIN: (probe row, build row) pairs of one batch
     uint8_t* jb_matched = nullptr; size_t jb_matched_cap = 0; bool join_tail_launch = false;   // LEFT / SEMI / ANTI: build rows that found a partner
     SortState* post_sort = nullptr;                         // the post fragment above the aggregate (Compiled::post)
     std::vector<uint8_t*> post_vals, post_nullb, post_bitmap; size_t post_cap = 0;
@@ -946,6 +947,100 @@ static int join_tail(bkgpu_plan* p) {
     return rc;
 }
 
+// ---- a JOIN that returns rows (PK_JOIN): pairs -> gather -> the sink fragment (p->post_sort) ----
+static int join_rows_emit(bkgpu_plan* p, const std::vector<DevCol>& all, int64_t n_probe, bool tail) {
+    const Compiled& c = p->c;
+    int rc;
+    AggArgs a; memset(&a, 0, sizeof a);
+    a.plan = c.ap; a.prog = c.prog; a.nrows = n_probe;
+    const int ncols = (int)c.cols.size();
+    for (int i = 0; i < ncols; i++) a.cols[i] = all[(size_t)i];
+    a.n_cols = ncols;
+    a.join.enabled = 1; a.join.keys = p->jt_keys; a.join.rows = p->jt_rows; a.join.cap_mask = p->jt_mask;
+    a.join.probe_col = c.probe_key_col; a.join.probe_prim = c.cols[(size_t)c.probe_key_col].prim; a.join.cast_prim = c.join_key_prim;
+    a.join.join_type = c.join_type; a.join.matched = c.join_type == BK_INNER_JOIN ? nullptr : p->jb_matched; a.join.n_build = p->jb_rows;
+    a.join.tail = tail ? 1 : 0;
+    if ((rc = ensure_buf(p, (void**)&p->jr_cursor, &p->jr_cursor_cap, 64))) return rc;
+    size_t want = (size_t)std::max<int64_t>(tail ? p->jb_rows : n_probe, 1 << 12);
+    uint32_t found = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {   // a batch with more pairs than the buffer holds is counted, the buffer grown, the batch rerun
+        if (want > 0x7FFFFFF0ull) return p->fail(BKGPU_ETOOBIG, "a probe batch joins to more than 2^31 rows: push smaller batches");
+        if ((rc = ensure_buf(p, (void**)&p->jr_pairs, &p->jr_pairs_cap, want * 8))) return rc;
+        CK(p, cudaMemsetAsync(p->jr_cursor, 0, 4, p->stream));
+        if (attempt && a.join.matched && !tail) {}   // (matched[] only ever gains flags: the rerun sets the same ones)
+        CK(p, launch_join_pairs(a, p->jr_pairs, (uint32_t)want, p->jr_cursor, p->sm_count, p->stream));
+        CK(p, cudaMemcpyAsync(&found, p->jr_cursor, 4, cudaMemcpyDeviceToHost, p->stream));
+        CK(p, cudaStreamSynchronize(p->stream));
+        p->stats.kernel_launches++;
+        if ((size_t)found <= want) break;
+        want = found;
+    }
+    if (!found) return BKGPU_OK;
+    const Compiled& pc = *c.post;
+    const size_t nc = pc.cols.size();
+    if (p->post_cap < found || p->post_vals.size() != nc) {
+        for (auto& v : {&p->post_vals, &p->post_nullb, &p->post_bitmap}) { for (uint8_t* q : *v) dev_free(p, q); v->assign(nc, nullptr); }
+        const size_t cap = std::max<size_t>((size_t)found + found / 4, 1 << 16);
+        for (size_t k = 0; k < nc; k++) {
+            if ((rc = dev_alloc(p, (void**)&p->post_vals[k], cap * (size_t)storage_bytes(prim_storage(pc.cols[k].prim)) + 64))) return rc;
+            if ((rc = dev_alloc(p, (void**)&p->post_nullb[k], cap + 64))) return rc;
+            if ((rc = dev_alloc(p, (void**)&p->post_bitmap[k], cap / 8 + 64))) return rc;
+        }
+        p->post_cap = cap;
+    }
+    std::vector<DevCol> dc(std::max<size_t>(nc, 1));
+    for (size_t k = 0; k < nc; k++) {   // sink column k = output column k = device column k of the join (plan.cpp::lower_join_rows)
+        const int st = prim_storage(pc.cols[k].prim);
+        CK(p, launch_join_rows_gather(all[k], p->jr_pairs, c.col_side[k] == 1 ? 1 : 0, found, storage_bytes(st), p->post_vals[k], p->post_nullb[k], p->stream));
+        CK(p, launch_pack_validity(p->post_nullb[k], found, p->post_bitmap[k], p->stream));
+        dc[k].values = p->post_vals[k]; dc[k].validity = p->post_bitmap[k]; dc[k].stype = st; dc[k].prim = pc.cols[k].prim;
+    }
+    p->stats.kernel_launches += 2 * (int64_t)nc;
+    p->rows_passed_host += found;
+    if ((rc = sort_push(p->post_sort, dc.data(), (int64_t)found, p->stream, &p->stats, p->last_error))) { g_thread_error = p->last_error; return rc; }
+    CK(p, cudaStreamSynchronize(p->stream));   // the gather buffers are reused by the next batch
+    return BKGPU_OK;
+}
+static void join_all_cols(bkgpu_plan* p, const DevCol* probe_cols, std::vector<DevCol>& all) {
+    const Compiled& c = p->c;
+    all.assign(c.cols.size(), DevCol{});
+    for (size_t i = 0; i < c.cols.size(); i++) {
+        all[i].stype = prim_storage(c.cols[i].prim); all[i].prim = c.cols[i].prim;
+        if (c.col_side[i] == 1) { all[i].values = p->jb_vals[i]; all[i].validity = p->jb_bitmap[i]; }
+    }
+    if (probe_cols) for (size_t w = 0; w < p->probe_map.size(); w++) all[(size_t)p->probe_map[w]] = probe_cols[w];
+}
+static int join_rows_batch(bkgpu_plan* p, const DevCol* probe_cols, int64_t nrows, int64_t, bool) {
+    int rc;
+    if ((rc = join_generic_table(p))) return rc;
+    std::vector<DevCol> all;
+    join_all_cols(p, probe_cols, all);
+    return join_rows_emit(p, all, nrows, false);
+}
+static int join_rows_finish(bkgpu_plan* p) {
+    const Compiled& c = p->c;
+    int rc;
+    if (c.join_type != BK_INNER_JOIN && p->jb_rows > 0) {   // LEFT: the preserved rows that found no partner, NULL-extended
+        if (!p->jt_built && (rc = join_build_table(p))) return rc;
+        if ((rc = join_generic_table(p))) return rc;
+        std::vector<DevCol> all;
+        join_all_cols(p, nullptr, all);
+        if ((rc = join_rows_emit(p, all, 0, true))) return rc;
+    }
+    std::vector<SortOutCol> cols; int64_t rows = 0;
+    if ((rc = sort_finish(p->post_sort, nullptr, 1, p->stream, &p->stats, cols, &rows, p->last_error))) { g_thread_error = p->last_error; return rc; }
+    p->result.clear();
+    for (size_t k = 0; k < cols.size(); k++) {
+        SortOutCol& sc = cols[k];
+        HostCol hc; hc.desc = c.out_cols[k]; hc.elem = sc.elem;
+        hc.values = std::move(sc.values); hc.validity = std::move(sc.validity);
+        p->result.push_back(std::move(hc));
+    }
+    p->result_rows = rows; p->result_pos = 0;
+    p->stats.rows_filtered = 0;
+    return BKGPU_OK;
+}
+
 static int join_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device) {
     const Compiled& c = p->c;
     bool is_build = false;
@@ -953,7 +1048,7 @@ static int join_push(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t
     if (is_build) return join_retain_build(p, cols, ncols, nrows, on_device);
     if (!p->jt_built) { int rc = join_build_table(p); if (rc) return rc; }
     if (p->probe_want.empty()) for (size_t i = 0; i < c.cols.size(); i++) if (c.col_side[i] == 0) { p->probe_want.push_back(c.cols[i]); p->probe_map.push_back((int)i); }
-    return feed(p, p->probe_want, cols, ncols, nrows, on_device, join_probe_batch);
+    return feed(p, p->probe_want, cols, ncols, nrows, on_device, c.kind == PK_JOIN ? join_rows_batch : join_probe_batch);
 }
 
 static int bkgpu_push_impl(bkgpu_plan* p, const bkgpu_column* cols, int ncols, int64_t nrows, int on_device);
@@ -979,7 +1074,7 @@ static int bkgpu_push_impl(bkgpu_plan* p, const bkgpu_column* cols, int ncols, i
                 CK(p, cudaMemcpyAsync(p->h_pinned, p->gt.n_groups, 4, cudaMemcpyDeviceToHost, p->stream));  // no sync: a stale value only costs speed
             return BKGPU_OK;
         }
-        case PK_JOIN_AGG: return join_push(p, cols, ncols, nrows, on_device);
+        case PK_JOIN_AGG: case PK_JOIN: return join_push(p, cols, ncols, nrows, on_device);
         case PK_SORT: case PK_FILTER: return feed(p, p->c.cols, cols, ncols, nrows, on_device, sort_batch);
         default: return p->fail(BKGPU_EUNSUPPORTED, "plan kind %d has no push path yet", p->c.kind);
     }
@@ -1304,6 +1399,7 @@ static int bkgpu_finish_impl(bkgpu_plan* p) {
                 p->stats.rows_filtered = p->stats.rows_scanned - (int64_t)p->rows_passed_host;   // (came back with the counter block)
             }
         } break;
+        case PK_JOIN: rc = join_rows_finish(p); break;
         case PK_SORT: case PK_FILTER: {
             std::vector<SortOutCol> cols; int64_t rows = 0;
             rc = sort_finish(p->sort, p->nccl_comm, p->nranks, p->stream, &p->stats, cols, &rows, p->last_error);
@@ -1379,6 +1475,7 @@ static int bkgpu_reset_impl(bkgpu_plan* p) {
     p->jb_rows = 0; p->jt_built = false; p->jt_generic = false; std::fill(p->jb_has_null.begin(), p->jb_has_null.end(), false);
     for (size_t i = 0; i < p->jb_bitmap.size(); i++) { dev_free(p, p->jb_bitmap[i]); p->jb_bitmap[i] = nullptr; }   // build-side validity of the previous run
     if (p->sort) { int rc = sort_reset(p->sort, p->stream, p->last_error); if (rc) { g_thread_error = p->last_error; return rc; } }
+    if (p->c.kind == PK_JOIN && p->post_sort) { int rc = sort_reset(p->post_sort, p->stream, p->last_error); if (rc) { g_thread_error = p->last_error; return rc; } }
     p->result.clear(); p->result_rows = 0; p->result_pos = 0;
     bkgpu_stats z{}; z.kernel_launches = p->stats.kernel_launches; p->stats = z;
     p->state = S_OPEN;

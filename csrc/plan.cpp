@@ -960,6 +960,7 @@ bool lower_sort(Infer& in, Compiled& out, const HNode& sort, const HNode* filter
 bool lower_filter(Infer& in, Compiled& out, const HNode* limit_node, const HNode& filter_or_scan, const HNode& scan);
 bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& join, bool under_packet, const HNode* above);
 bool lower_post(Infer& in, Compiled& out, const HNode* sort, const HNode* having, const HNode* limit_node);
+bool lower_join_rows(Infer& in, Compiled& out, const HNode& join, const HNode* above, const HNode* sort, const HNode* limit_node);
 
 static bool infer_node(Infer& in, HNode& n) {
     for (auto& e : n.conjuncts) if (!infer_expr(in, e)) return false;
@@ -968,6 +969,13 @@ static bool infer_node(Infer& in, HNode& n) {
     for (auto& e : n.order_exprs) if (!infer_expr(in, e)) return false;
     for (auto& c : n.ch) if (!infer_node(in, c)) return false;
     return true;
+}
+
+// [SORT ->] [FILTER ->] JOIN at the top of the fragment -> the JOIN node, else nullptr
+static const HNode* join_rows_shape(const HNode* t) {
+    if (t && t->node_type == BK_SORT_NODE && !t->ch.empty()) t = skip_passthrough(&t->ch[0], nullptr);
+    if (t && is_filter(t) && !t->ch.empty()) t = skip_passthrough(&t->ch[0], nullptr);
+    return t && t->node_type == BK_JOIN_NODE ? t : nullptr;
 }
 
 int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& err) {
@@ -1024,6 +1032,11 @@ int compile_plan(const uint8_t* desc, size_t len, Compiled& out, std::string& er
             if (ok && limit_node && !post_sort && !post_having) { out.limit = limit_node->limit; out.offset = limit_node->offset; }   // LimitNode over the joined aggregate
         } else { err = "AGG child must be [FILTER ->] SCAN or JOIN"; return BKGPU_EUNSUPPORTED; }
         if (ok && (post_sort || post_having)) ok = lower_post(in, out, post_sort, post_having, limit_node);
+    } else if (const HNode* jn = join_rows_shape(top)) {   // [SORT ->] [FILTER ->] JOIN: a join that returns its rows
+        const HNode* t = top; const HNode *js = nullptr, *jf = nullptr;
+        if (t->node_type == BK_SORT_NODE) { js = t; t = skip_passthrough(&t->ch[0], nullptr); }
+        if (is_filter(t)) jf = t;
+        ok = lower_join_rows(in, out, *jn, jf, js, limit_node);
     } else if (top->node_type == BK_SORT_NODE) {
         const HNode* c = top->ch.empty() ? nullptr : skip_passthrough(&top->ch[0], nullptr);
         const HNode* filter = nullptr;
@@ -1258,6 +1271,124 @@ bool lower_join_agg(Infer& in, Compiled& out, const HNode& agg, const HNode& joi
             if (ok) out.jfast = jf; else out.jfast_of_main.clear();
         }
     }
+    return true;
+}
+
+// A JOIN whose rows are the result ([LIMIT ->] [SORT ->] [FILTER ->] JOIN; JoinNode::get_next, join_node.cpp:1200-1326).  The joined rows that
+// pass the conditions are produced on the device batch by batch (pairs + one gather per column) and handed to a sink fragment
+// (Compiled::post, kind PK_FILTER without a predicate, or PK_SORT) whose "scan tuple" is the joined row: every slot of both tuples.
+// INNER: child filters, the residual conditions and a filter above the join are one predicate.  LEFT / RIGHT: the outer (build) side is
+// preserved, unmatched rows come out NULL-extended; filtered children or a filter above are refused (as in lower_join_agg).
+bool lower_join_rows(Infer& in, Compiled& out, const HNode& join, const HNode* above, const HNode* sort, const HNode* limit_node) {
+    int jt = join.join_type;
+    if (jt != BK_INNER_JOIN && jt != BK_LEFT_JOIN && jt != BK_RIGHT_JOIN)
+        return in.fail(BKGPU_EUNSUPPORTED, "a join of type %d that returns rows is outside the GPU path (INNER / LEFT / RIGHT are lowered)", jt);
+    if (join.ch.size() != 2) return in.fail(BKGPU_EINVAL, "JOIN node needs two children");
+    if (above && above->limit != -1) return in.fail(BKGPU_EUNSUPPORTED, "LIMIT on a filter above a join: use a LIMIT node");
+    const HNode* side[2]; const HNode* filt[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++) {
+        const HNode* c = skip_passthrough(&join.ch[(size_t)(jt == BK_RIGHT_JOIN ? 1 - i : i)], nullptr);
+        if (is_filter(c)) { filt[i] = c; c = c->ch.empty() ? nullptr : skip_passthrough(&c->ch[0], nullptr); }
+        if (!c || c->node_type != BK_SCAN_NODE) return in.fail(BKGPU_EUNSUPPORTED, "JOIN children must be [FILTER ->] SCAN");
+        if (filt[i] && filt[i]->limit != -1) return in.fail(BKGPU_EUNSUPPORTED, "LIMIT below a join is order dependent");
+        side[i] = c;
+    }
+    if (jt == BK_RIGHT_JOIN) jt = BK_LEFT_JOIN;
+    if (jt != BK_INNER_JOIN && (filt[0] || filt[1] || above)) return in.fail(BKGPU_EUNSUPPORTED, "LEFT join with filtered children or a filter above it is outside the GPU path");
+    const int build_tuple = side[0]->tuple_id, probe_tuple = side[1]->tuple_id;
+    out.kind = PK_JOIN; out.build_tuple = build_tuple; out.scan_tuple = probe_tuple; out.join_type = jt;
+    std::vector<const HExpr*> conj;
+    const HExpr *bk = nullptr, *pk = nullptr;
+    for (auto& e : join.conjuncts) {
+        bool taken = false;
+        if (!bk && e.node_type == BK_FUNCTION_CALL && e.fn_op == BK_FT_EQ && e.ch.size() == 2 && e.ch[0].node_type == BK_SLOT_REF && e.ch[1].node_type == BK_SLOT_REF) {
+            const HExpr *a = &e.ch[0], *b = &e.ch[1];
+            if (a->tuple_id == build_tuple && b->tuple_id == probe_tuple) { bk = a; pk = b; taken = true; }
+            else if (b->tuple_id == build_tuple && a->tuple_id == probe_tuple) { bk = b; pk = a; taken = true; }
+        }
+        if (!taken) conj.push_back(&e);
+    }
+    if (!bk) return in.fail(BKGPU_EUNSUPPORTED, "join without an equality between the two tables (nested loop) is outside the GPU path");
+    for (int i = 0; i < 2; i++) if (filt[i]) for (auto& e : filt[i]->conjuncts) conj.push_back(&e);
+    if (above) for (auto& e : above->conjuncts) conj.push_back(&e);
+    int ot = bk->col_type, it = pk->col_type, cast;
+    auto is_signed_t = [](int t) { return t >= BK_INT8 && t <= BK_INT64; };
+    if (ot == it) cast = ot;
+    else if (is_signed_t(ot) && is_signed_t(it)) cast = BK_INT64;
+    else if (is_uint_t(ot) && is_uint_t(it)) cast = BK_UINT64;
+    else return in.fail(BKGPU_EUNSUPPORTED, "join keys of types %d and %d are compared as STRING in the reference: outside the GPU path", ot, it);
+    if (cast == BK_STRING || is_double_t(cast)) return in.fail(BKGPU_EUNSUPPORTED, "join key type %d is outside the GPU path", cast);
+    out.join_key_prim = cast;
+    Program& p = out.prog; memset(&p, 0, sizeof p);
+    memset(&out.ap, 0, sizeof out.ap);
+    Lower lw{&out, &in, &p, {}};
+    // every slot of both tuples is an output column (and a device column): build tuple first, as the joined row lists them
+    for (int sd = 0; sd < 2; sd++) {
+        const int tid = sd == 0 ? build_tuple : probe_tuple;
+        const HTuple* t = nullptr;
+        for (auto& x : out.tuples) if (x.tuple_id == tid) t = &x;
+        if (!t || t->slots.empty()) return in.fail(BKGPU_EINVAL, "join tuple %d has no descriptor", tid);
+        for (auto& sl : t->slots) {
+            if (prim_storage(sl.second) < 0 || sl.second == BK_STRING) return in.fail(BKGPU_EUNSUPPORTED, "column %d_%d has type %d: outside the GPU path", tid, sl.first, sl.second);
+            if (lw.intern_col(tid, sl.first, sl.second) >= MAX_COLS) return in.fail(BKGPU_EUNSUPPORTED, "more than %d columns in the joined row", MAX_COLS);
+            out.out_cols.push_back({tid, sl.first, sl.second, 0});
+        }
+    }
+    const size_t n_payload = out.cols.size();
+    out.build_key_col = lw.intern_col(bk->tuple_id, bk->slot_id, in.slot_type(bk->tuple_id, bk->slot_id));
+    out.probe_key_col = lw.intern_col(pk->tuple_id, pk->slot_id, in.slot_type(pk->tuple_id, pk->slot_id));
+    int reg = 0;
+    out.ap.pred_out = -1;
+    if (!conj.empty()) {
+        if (conj.size() > 8) return in.fail(BKGPU_EUNSUPPORTED, "more than 8 conjuncts");
+        for (auto* c : conj) { int depth = 0; if (!lw.expr(*c, depth) || !lw.to_bool(*c)) return false; }
+        if (conj.size() > 1 && !lw.emit(OP_AND, (uint8_t)conj.size())) return false;
+        out.ap.pred_out = reg;
+        if (!lw.out_reg(reg++)) return false;
+    }
+    p.n_out = reg;
+    if (out.cols.size() != n_payload) return in.fail(BKGPU_EINVAL, "join conditions reference a slot that is in neither tuple descriptor");
+    // the sink over the joined rows
+    auto post = std::make_shared<Compiled>();
+    Compiled& pc = *post;
+    pc.kind = sort ? PK_SORT : PK_FILTER;
+    pc.tuples = out.tuples; pc.scan_tuple = -1;
+    Program& pp = pc.prog; memset(&pp, 0, sizeof pp);
+    memset(&pc.ap, 0, sizeof pc.ap);
+    pc.ap.pred_out = -1;
+    Infer in2{}; in2.tuples = &pc.tuples;
+    Lower lw2{&pc, &in2, &pp, {}};
+    for (const OutCol& oc : out.out_cols) { lw2.intern_col(oc.tuple_id, oc.slot_id, oc.prim); pc.out_cols.push_back(oc); }
+    int preg = 0;
+    if (sort) {
+        pc.limit = sort->limit;
+        if (sort->order_exprs.empty()) return in.fail(BKGPU_EINVAL, "SORT node without order expressions");
+        if (sort->order_exprs.size() > 4) return in.fail(BKGPU_EUNSUPPORTED, "more than 4 ORDER BY expressions");
+        for (size_t i = 0; i < sort->order_exprs.size(); i++) {
+            const HExpr& e = sort->order_exprs[i];
+            if (e.col_type == BK_STRING) return in.fail(BKGPU_EUNSUPPORTED, "ORDER BY over a STRING key is outside the GPU path");
+            int depth = 0;
+            if (!lw2.expr(e, depth)) { in.code = in2.code; in.err = in2.err; return false; }
+            pc.sort_keys.push_back({preg, e.col_type, sort->is_asc[i] != 0, sort->is_null_first[i] != 0});
+            if (!lw2.out_reg(preg++)) return false;
+        }
+        if (limit_node) {
+            pc.offset = limit_node->offset;
+            if (limit_node->limit >= 0) { const int64_t lim = limit_node->limit + limit_node->offset; if (pc.limit < 0 || lim < pc.limit) pc.limit = lim; }
+        }
+    } else {
+        pc.limit = join.limit; pc.offset = 0;
+        if (limit_node) {
+            pc.offset = limit_node->offset;
+            const int64_t lim = limit_node->limit < 0 ? -1 : limit_node->limit + limit_node->offset;
+            if (lim >= 0 && (pc.limit < 0 || lim < pc.limit)) pc.limit = lim;
+        }
+    }
+    pp.n_out = preg;
+    if (pc.cols.size() != out.out_cols.size()) return in.fail(BKGPU_EUNSUPPORTED, "ORDER BY above a join references a column outside the joined row");
+    pc.has_direct = false;
+    out.post = post;
+    out.limit = pc.limit; out.offset = pc.offset;
     return true;
 }
 
