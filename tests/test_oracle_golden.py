@@ -398,3 +398,30 @@ def test_row_oracle_outer_semi_anti_joins_equal_acero(jt):
             assert mine["2_2"][i] == t.column("n")[want[k]].as_py()
             a, b = mine["2_3"][i], t.column("s")[want[k]].as_py()
             assert (a is None and b is None) or abs(a - b) <= 1e-9 * max(1.0, abs(b))
+
+
+@pytest.mark.parametrize("jt", ["INNER_JOIN", "LEFT_JOIN", "RIGHT_JOIN"])
+def test_row_oracle_joined_rows_equal_acero(jt):
+    """a JOIN that returns its rows: the row restatement's joined rows are Acero's hashjoin rows (inner / left outer), as multisets —
+    duplicate keys and NULL keys on both sides"""
+    import pyarrow.acero as ac
+    from baikaldb_b200 import plan as P
+    from baikaldb_b200.column import make_column
+    from baikaldb_b200.plan import PrimitiveType as T
+    from oracle import acero_oracle as A, oracle
+    rng = np.random.default_rng(8)
+    nd, nf = 900, 12_000
+    dim = [make_column(1, 1, T.INT32, rng.integers(0, 500, nd), rng.random(nd) > 0.04), make_column(1, 2, T.INT32, rng.integers(0, 12, nd))]
+    fact = [make_column(0, 1, T.INT32, rng.integers(200, 700, nf), rng.random(nf) > 0.05), make_column(0, 2, T.DOUBLE, rng.random(nf), rng.random(nf) > 0.1)]
+    ch = (P.scan(0), P.scan(1)) if jt == "RIGHT_JOIN" else (P.scan(1), P.scan(0))
+    j = P.join(ch[0], ch[1], [P.eq(P.slot_ref(1, 1, T.INT32), P.slot_ref(0, 1, T.INT32))], join_type=getattr(P.JoinType, jt))
+    r = oracle.execute(P.Plan(P.packet(j), {0: [(1, T.INT32), (2, T.DOUBLE)], 1: [(1, T.INT32), (2, T.INT32)]}).serialize(), fact + dim)
+    names = ["0_1", "0_2", "1_1", "1_2"]
+    mine = {c.name: c.to_list() for c in r.columns}
+    key = lambda t: tuple((0, 0) if v is None else (1, v) for v in t)
+    got = sorted(zip(*[mine[n] for n in names]), key=key)
+    jd = ac.Declaration("hashjoin", ac.HashJoinNodeOptions("inner" if jt == "INNER_JOIN" else "left outer", ["1_1"], ["0_1"]),
+                        inputs=[ac.Declaration("table_source", ac.TableSourceNodeOptions(A.to_table(dim))), ac.Declaration("table_source", ac.TableSourceNodeOptions(A.to_table(fact)))])
+    t = jd.to_table()
+    want = sorted(zip(*[t.column(n).to_pylist() for n in names]), key=key)
+    assert len(got) == len(want) > 1000 and got == want
