@@ -48,6 +48,7 @@ SYMBOLS = [
     ("bkgpu_region_register", c_int, [c_int, c_int64, POINTER(BkgpuColumn), c_int, c_int64, c_int]),
     ("bkgpu_region_evict", c_int, [c_int, c_int64]),
     ("bkgpu_region_info", c_int, [c_int, c_int64, POINTER(c_int64), POINTER(c_size_t)]),
+    ("bkgpu_release_cache", None, []),
     ("bkgpu_parse_datetime", c_int, [c_char_p, c_size_t, c_int, POINTER(c_uint64)]),
     ("bkgpu_cast_image", c_int, [c_uint64, c_int, c_int, POINTER(c_uint64)]),
     ("bkgpu_push_region", c_int, [c_void_p, c_int64]),

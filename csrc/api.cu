@@ -128,7 +128,7 @@ struct bkgpu_plan {
     bkgpu_stats stats{};
     std::vector<EventPair> timed;
     std::vector<EventPair> timed_coll;
-    std::vector<void*> dev_allocs;
+    std::vector<std::pair<void*, size_t>> dev_allocs;   // (buffer, size class) — returned to the process-wide cache on free / close
 
     int fail(int code, const char* fmt, ...) {
         char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -169,16 +169,67 @@ extern "C" int bkgpu_plan_explain(const uint8_t* desc, size_t len, char* text, s
 }
 
 // ------------------------------------------------------------------ helpers
+// Device buffers come from a process-wide cache of freed buffers (per device, per size class): a store opens and closes one plan per
+// request (the reference builds its ExecNode tree per request, src/store/region.cpp:3072), and cudaMalloc / cudaFree of the 40 MB group
+// table cost milliseconds and a device-wide synchronisation each.  A buffer enters the cache only after the owning plan's streams have
+// drained.  BKGPU_NO_ALLOC_CACHE=1 turns the cache off; bkgpu_release_cache() returns its memory to the driver.
+namespace {
+struct DevCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> free_;
+    size_t held = 0;
+    const size_t limit = (size_t)8 << 30;
+    const bool off = getenv("BKGPU_NO_ALLOC_CACHE") && atoi(getenv("BKGPU_NO_ALLOC_CACHE")) != 0;
+    void* take(int device, size_t sc) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = free_.find({device, sc});
+        if (it == free_.end()) return nullptr;
+        void* q = it->second; free_.erase(it); held -= sc;
+        return q;
+    }
+    bool put(int device, size_t sc, void* q) {
+        std::lock_guard<std::mutex> g(mu);
+        if (off || held + sc > limit) return false;
+        free_.insert({{device, sc}, q}); held += sc;
+        return true;
+    }
+    void release_all() {   // (the caller has the right device current for none of them: cudaFree takes any device's pointer)
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : free_) cudaFree(kv.second);
+        free_.clear(); held = 0;
+    }
+};
+DevCache& dev_cache() { static DevCache c; return c; }
+size_t size_class(size_t b) {   // eight classes per power of two: at most 12.5 % slack
+    if (b < 256) return 256;
+    size_t p2 = 1; while (p2 < b) p2 <<= 1;
+    const size_t step = p2 >> 3;
+    return (b + step - 1) / step * step;
+}
+}  // namespace
+extern "C" void bkgpu_release_cache(void) { dev_cache().release_all(); }
+
 static int dev_alloc(bkgpu_plan* p, void** out, size_t bytes) {
-    cudaError_t e = cudaMalloc(out, bytes ? bytes : 8);
-    if (e != cudaSuccess) return p->cuda_fail(e, "cudaMalloc");
-    p->dev_allocs.push_back(*out);
+    const size_t sc = size_class(bytes ? bytes : 8);
+    void* q = dev_cache().take(p->device, sc);
+    if (!q) {
+        cudaError_t e = cudaMalloc(&q, sc);
+        if (e != cudaSuccess) { cudaGetLastError(); dev_cache().release_all(); e = cudaMalloc(&q, sc); }   // memory held by the cache is memory the device has
+        if (e != cudaSuccess) return p->cuda_fail(e, "cudaMalloc");
+    }
+    *out = q;
+    p->dev_allocs.push_back({q, sc});
     return BKGPU_OK;
 }
 static void dev_free(bkgpu_plan* p, void* ptr) {
     if (!ptr) return;
-    auto it = std::find(p->dev_allocs.begin(), p->dev_allocs.end(), ptr);
-    if (it != p->dev_allocs.end()) p->dev_allocs.erase(it);
+    size_t sc = 0;
+    for (auto it = p->dev_allocs.begin(); it != p->dev_allocs.end(); ++it) if (it->first == ptr) { sc = it->second; p->dev_allocs.erase(it); break; }
+    if (sc) {   // work queued on this plan's streams may still use the buffer
+        if (p->stream) cudaStreamSynchronize(p->stream);
+        if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
+        if (dev_cache().put(p->device, sc, ptr)) return;
+    }
     cudaFree(ptr);
 }
 // grow-only device buffer: plans are re-armed with bkgpu_reset and run again; cudaMalloc / cudaFree per run would
@@ -226,8 +277,7 @@ extern "C" int bkgpu_init(bkgpu_plan** out, const uint8_t* desc, size_t len, int
         if (nccl_comm_count(nccl_comm, &n) != 0 || n < 1) { g_thread_error = std::string("NCCL: ") + nccl_last_error(); delete p; return BKGPU_ENCCL; }
         p->nranks = n;
     }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
+    { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n > 0) p->sm_count = n; }   // (cudaGetDeviceProperties costs milliseconds per call)
     *out = p;
     return BKGPU_OK;
 }
@@ -1499,7 +1549,7 @@ extern "C" void bkgpu_close(bkgpu_plan* p) {
     if (p->post_sort) sort_close(p->post_sort);
     for (size_t r = 0; r < p->peer_ptr.size(); r++) if ((int)r != p->peer_rank && p->peer_ptr[r]) cudaIpcCloseMemHandle(p->peer_ptr[r]);
     for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
-    for (void* q : p->dev_allocs) cudaFree(q);
+    for (auto& q : p->dev_allocs) if (!dev_cache().put(p->device, q.second, q.first)) cudaFree(q.first);   // (both streams were drained above)
     for (int i = 0; i < 2; i++) { if (p->stage_free[i]) cudaEventDestroy(p->stage_free[i]); if (p->stage_ready[i]) cudaEventDestroy(p->stage_ready[i]); }
     for (int i = 0; i < 2; i++) { for (uint8_t* q : p->bounce[i]) if (q) cudaFreeHost(q); if (p->bounce_done[i]) cudaEventDestroy(p->bounce_done[i]); }
     if (p->h_pinned) cudaFreeHost(p->h_pinned);

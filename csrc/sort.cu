@@ -892,8 +892,7 @@ int sort_open(const Compiled& c, int device, cudaStream_t stream, int64_t region
     SortState* s = new SortState();
     s->c = c; s->device = device; s->ncols = (int)c.cols.size();
     s->row_base = s->region_base = (uint64_t)region_base;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+    { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n > 0) s->sm_count = n; }
     s->k = c.kind == PK_SORT ? c.limit : -1;
     s->topk = c.kind == PK_SORT && c.sort_keys.size() == 1 && s->k >= 0 && s->k <= 4096;
     s->ret_vals.assign((size_t)s->ncols, nullptr); s->ret_null.assign((size_t)s->ncols, nullptr);

@@ -143,6 +143,11 @@ void  bkgpu_cancel(bkgpu_plan*);
 void  bkgpu_close(bkgpu_plan*);
 int   bkgpu_get_stats(bkgpu_plan*, bkgpu_stats* out);
 
+/* Device buffers of closed plans are kept in a process-wide cache and handed to the next plan (a store opens one plan per request;
+ * cudaMalloc / cudaFree of the group table would cost milliseconds each).  This returns the cached memory to the driver.
+ * Environment BKGPU_NO_ALLOC_CACHE=1 disables the cache. */
+void  bkgpu_release_cache(void);
+
 /* ---- date/time literals ----
  * The text of a literal as the image the plan compares against: ExprValue::cast_to from STRING (include/common/expr_value.h:534-573
  * -> str_to_datetime / str_to_time, src/common/datetime.cpp:149-263,477-560), for a binding that folds `col >= '2024-01-31'`
