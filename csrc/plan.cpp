@@ -124,7 +124,12 @@ static void parse_enode(Reader& r, HExpr& e, int& remaining, int depth) {
         case BK_DATE_LITERAL: e.lit_bits = (uint64_t)(uint32_t)r.rd64(); e.lit_prim = BK_DATE; break;
         case BK_TIME_LITERAL: e.lit_bits = (uint64_t)(int64_t)(int32_t)r.rd64(); e.lit_prim = BK_TIME; break;
         case BK_AGG_EXPR:
-            e.name = r.rdstr(); e.tuple_id = r.rd(); e.final_slot = r.rd(); e.inter_slot = r.rd(); break;
+            e.name = r.rdstr(); e.tuple_id = r.rd(); e.final_slot = r.rd(); e.inter_slot = r.rd();
+            // count_distinct / sum_distinct / avg_distinct are COUNT / SUM / AVG (name_type_map, agg_fn_call.cpp:32-40) that a MERGE_AGG node UPDATES
+            // from its input rows instead of merging intermediates (AggFnCall::merge, agg_fn_call.cpp:719-727): the planner put the argument
+            // into the GROUP BY of the aggregate below (select_planner.cpp:640-667), so each distinct value arrives once
+            if (e.name == "count_distinct" || e.name == "sum_distinct" || e.name == "avg_distinct") { e.distinct = true; e.name.resize(e.name.size() - 9); }
+            break;
         case BK_FUNCTION_CALL: case BK_IS_NULL_PREDICATE: case BK_IN_PREDICATE: case BK_NOT_PREDICATE:
         case BK_AND_PREDICATE: case BK_OR_PREDICATE: case BK_XOR_PREDICATE: case BK_IS_TRUE_PREDICATE: {
             e.fn_op = r.rd(); e.name = r.rdstr();
@@ -681,7 +686,9 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
     // ---- predicate: all conjuncts non-NULL true (filter_node.cpp:726-734) ----
     ap.pred_out = -1;
     if (out.is_merge && !conjuncts.empty()) return in.fail(BKGPU_EUNSUPPORTED, "filter below MERGE_AGG_NODE");
-    if (out.is_merge && agg.group_exprs.empty() && !agg.agg_fns.empty()) {
+    bool any_distinct = false;
+    for (auto& f : agg.agg_fns) any_distinct = any_distinct || f.distinct;   // (a distinct aggregate is never "initial": is_initialize, agg_fn_call.cpp:322-328)
+    if (out.is_merge && agg.group_exprs.empty() && !agg.agg_fns.empty() && !any_distinct) {
         // a scalar merger skips input rows whose aggregates are all still "initial" (AggFnCall::all_is_initialize,
         // agg_node.cpp:519-522): pass = OR_k (count_k <> 0 | value_k IS NOT NULL), three-valued, NULL = skip
         for (size_t k = 0; k < agg.agg_fns.size(); k++) {
@@ -746,7 +753,7 @@ static bool lower_agg(Infer& in, Compiled& out, const HNode& agg, const std::vec
         const HExpr& f = agg.agg_fns[(size_t)k];
         AggSpec& a = ap.agg[k]; memset(&a, 0, sizeof a);
         a.arg_out = 0xFF; a.out_prim = (uint8_t)f.col_type;
-        if (out.is_merge) {
+        if (out.is_merge && !f.distinct) {
             // MERGE_AGG_NODE: the input rows carry the stores' intermediate slots; AggFnCall::merge (agg_fn_call.cpp:719-822)
             // adds counts and sums, folds MIN/MAX, and adds both halves of an AVG blob.  NULL intermediates are skipped.
             const int st = in.slot_type(f.tuple_id, f.inter_slot);

@@ -24,6 +24,7 @@ struct HExpr {
     int lit_prim = 0;
     std::string lit_str;              // STRING literal text (lit_prim == BK_STRING) until type inference folds it into an image
     int final_slot = 0, inter_slot = 0;
+    bool distinct = false;            // AGG_EXPR count_distinct / sum_distinct / avg_distinct: name holds the base function
     bool is_constant = false;
 };
 

@@ -494,6 +494,7 @@ typedef struct Expr {
     /* InPredicate */
     int map_type, has_null; int64_t* int_set; double* dbl_set; int set_n;
     int is_constant;
+    int is_distinct;                  /* AGG_EXPR *_distinct: a merger updates it from its input rows (no merge), agg_fn_call.cpp:719-727 */
 } Expr;
 
 typedef struct Node {
@@ -549,6 +550,9 @@ static Expr* parse_enode(Reader* r, int* remaining) {
             e->tuple_id = rd(r); e->final_slot = rd(r); e->inter_slot = rd(r);
             if (!strcmp(e->name, "count_star")) e->agg_type = A_COUNT_STAR;
             else if (!strcmp(e->name, "count")) e->agg_type = A_COUNT;
+            else if (!strcmp(e->name, "count_distinct")) { e->agg_type = A_COUNT; e->is_distinct = 1; }   /* name_type_map + _is_distinct, agg_fn_call.cpp:32-80 */
+            else if (!strcmp(e->name, "sum_distinct")) { e->agg_type = A_SUM; e->is_distinct = 1; }
+            else if (!strcmp(e->name, "avg_distinct")) { e->agg_type = A_AVG; e->is_distinct = 1; }
             else if (!strcmp(e->name, "sum")) e->agg_type = A_SUM;
             else if (!strcmp(e->name, "avg")) e->agg_type = A_AVG;
             else if (!strcmp(e->name, "min")) e->agg_type = A_MIN;
@@ -1267,6 +1271,7 @@ static void agg_finalize(const Ctx* c, Expr* a, MemRow* dst) { /* agg_fn_call.cp
 static int agg_all_initial(const Ctx* c, Node* n, const MemRow* row) { /* AggFnCall::all_is_initialize */
     for (int i = 0; i < n->n_agg; i++) {
         Expr* a = n->aggs[i];
+        if (a->is_distinct) return 0;   /* is_initialize: false for a distinct aggregate, agg_fn_call.cpp:322-328 */
         ExprValue v = memrow_get(c, row, a->tuple_id, a->inter_slot);
         if (a->agg_type == A_COUNT_STAR || a->agg_type == A_COUNT) { if (!ev_is_null(&v) && v.u.int64_val != 0) return 0; }
         else if (!ev_is_null(&v)) return 0;
@@ -1305,7 +1310,7 @@ static int agg_open(Ctx* c, Node* n, int under_packet) { /* agg_node.cpp:405-505
                 for (int k = 0; k < n->n_agg; k++) agg_initialize(c, n->aggs[k], &adopted, 0);
                 e = agg_insert(s, key.p, key.n, &adopted); first = 1;
             }
-            if (s->is_merger) { for (int k = 0; k < n->n_agg; k++) agg_merge(c, n->aggs[k], cur, &e->row, first); }
+            if (s->is_merger) { for (int k = 0; k < n->n_agg; k++) { if (n->aggs[k]->is_distinct) agg_update(c, n->aggs[k], cur, &e->row); else agg_merge(c, n->aggs[k], cur, &e->row, first); } }
             else for (int k = 0; k < n->n_agg; k++) agg_update(c, n->aggs[k], cur, &e->row);
         }
     } while (!eos);

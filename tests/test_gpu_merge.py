@@ -74,3 +74,39 @@ def test_scalar_merge_of_nothing_and_of_initial_rows():
     run_both(_minmax_plan(True, False), _concat([empty, empty, empty]), [])
     none = [c.__class__(c.tuple_id, c.slot_id, c.prim_type, c.values[:0], None) for c in empty]
     run_both(_minmax_plan(True, False), none, [])
+
+
+def _distinct_case(seed=1, n=60_000, nk=9, nx=300):
+    """COUNT(DISTINCT x), SUM(DISTINCT x), AVG(DISTINCT x), SUM(v), COUNT(*) GROUP BY k as the planner lays it out (select_planner.cpp:612-700):
+    a lower aggregate GROUP BY (k, x) with the ordinary aggregates, and above it a MERGE_AGG GROUP BY k whose *_distinct functions are
+    UPDATED from the (k, x) rows (AggFnCall::merge -> update for distinct aggregates, agg_fn_call.cpp:719-727) while the ordinary ones merge"""
+    import numpy as np
+    from baikaldb_b200 import plan as P
+    from baikaldb_b200.column import make_column
+    from baikaldb_b200.plan import PrimitiveType as T
+    rng = np.random.default_rng(seed)
+    k, x, v = rng.integers(0, nk, n), rng.integers(-50, nx, n), rng.random(n)
+    xv = rng.random(n) > 0.1
+    cols = [make_column(0, 1, T.INT32, k), make_column(0, 2, T.INT32, x, xv), make_column(0, 3, T.DOUBLE, v)]
+    low_aggs = [P.agg_expr("sum", 1, 1, None, P.slot_ref(0, 3, T.DOUBLE)), P.agg_expr("count_star", 1, 2)]
+    low = P.Plan(P.agg(P.scan(0), 1, [P.slot_ref(0, 1, T.INT32), P.slot_ref(0, 2, T.INT32)], low_aggs),
+                 {0: [(1, T.INT32), (2, T.INT32), (3, T.DOUBLE)], 1: P.agg_tuple_slots(low_aggs, [T.DOUBLE, T.INT64])})
+    top_aggs = [P.agg_expr("sum", 1, 1, None, P.slot_ref(0, 3, T.DOUBLE)), P.agg_expr("count_star", 1, 2), P.agg_expr("count_distinct", 1, 3, None, P.slot_ref(0, 2, T.INT32)),
+                P.agg_expr("sum_distinct", 1, 4, None, P.slot_ref(0, 2, T.INT32)), P.agg_expr("avg_distinct", 1, 5, 6, P.slot_ref(0, 2, T.INT32))]
+    top = P.Plan(P.agg(P.scan(0), 1, [P.slot_ref(0, 1, T.INT32)], top_aggs, merge=True),
+                 {0: [(1, T.INT32), (2, T.INT32)], 1: [(1, T.DOUBLE), (2, T.INT64), (3, T.INT64), (4, T.INT64), (5, T.DOUBLE), (6, T.STRING)]})
+    return (k, x, xv, v), cols, low, top
+
+
+def test_distinct_aggregates_two_level_plan():
+    import numpy as np
+    from baikaldb_b200.exec_node import execute
+    (k, x, xv, v), cols, low, top = _distinct_case()
+    mid, _, _ = run_both(low, cols, keys=["0_1", "0_2"])                 # GPU: GROUP BY (k, x), NULL x is its own group
+    got, _, _ = run_both(top, list(mid), keys=["0_1"])                   # GPU: the merger over those rows == oracle
+    by = {c.name: c.to_list() for c in got}
+    for i, kk in enumerate(by["0_1"]):                                   # ... and == an independent numpy computation
+        m = k == kk
+        dx = sorted(set(x[m & xv].tolist()))
+        assert by["1_3"][i] == len(dx) and by["1_4"][i] == sum(dx) and by["1_2"][i] == int(m.sum())
+        assert abs(by["1_5"][i] - sum(dx) / len(dx)) < 1e-9 and abs(by["1_1"][i] - v[m].sum()) < 1e-6 * max(1.0, v[m].sum())

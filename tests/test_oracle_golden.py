@@ -425,3 +425,19 @@ def test_row_oracle_joined_rows_equal_acero(jt):
     t = jd.to_table()
     want = sorted(zip(*[t.column(n).to_pylist() for n in names]), key=key)
     assert len(got) == len(want) > 1000 and got == want
+
+
+def test_row_oracle_distinct_aggregates_equal_numpy():
+    """COUNT / SUM / AVG (DISTINCT x) through the planner's two-level layout (tests/test_gpu_merge.py::_distinct_case): oracle rows == numpy sets"""
+    from oracle import oracle
+    from tests.test_gpu_merge import _distinct_case
+    (k, x, xv, v), cols, low, top = _distinct_case(seed=3, n=20_000)
+    mid = oracle.execute(low.serialize(), cols)
+    res = oracle.execute(top.serialize(), list(mid.columns))
+    by = {c.name: c.to_list() for c in res.columns}
+    assert sorted(by["0_1"]) == sorted(set(k.tolist()))
+    for i, kk in enumerate(by["0_1"]):
+        m = k == kk
+        dx = sorted(set(x[m & xv].tolist()))
+        assert by["1_3"][i] == len(dx) and by["1_4"][i] == sum(dx) and by["1_2"][i] == int(m.sum())
+        assert abs(by["1_5"][i] - sum(dx) / len(dx)) < 1e-9 and abs(by["1_1"][i] - v[m].sum()) < 1e-9 * max(1.0, v[m].sum())
