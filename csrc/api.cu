@@ -1017,7 +1017,7 @@ static int join_rows_emit(bkgpu_plan* p, const std::vector<DevCol>& all, int64_t
         if (want > 0x7FFFFFF0ull) return p->fail(BKGPU_ETOOBIG, "a probe batch joins to more than 2^31 rows: push smaller batches");
         if ((rc = ensure_buf(p, (void**)&p->jr_pairs, &p->jr_pairs_cap, want * 8))) return rc;
         CK(p, cudaMemsetAsync(p->jr_cursor, 0, 4, p->stream));
-        if (attempt && a.join.matched && !tail) {}   // (matched[] only ever gains flags: the rerun sets the same ones)
+        // (a rerun of a LEFT batch sets the same matched[] flags again: they only ever go from 0 to 1)
         CK(p, launch_join_pairs(a, p->jr_pairs, (uint32_t)want, p->jr_cursor, p->sm_count, p->stream));
         CK(p, cudaMemcpyAsync(&found, p->jr_cursor, 4, cudaMemcpyDeviceToHost, p->stream));
         CK(p, cudaStreamSynchronize(p->stream));
