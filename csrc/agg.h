@@ -60,6 +60,7 @@ struct AggArgs {
     int32_t lean_mm;         // lean kernel: some value column feeds MIN / MAX lanes or more than one lane
     // warp-private kernel (agg_wp.cuh): chosen by the host for the plainest lean batches
     int32_t scalar_tma;      // 1 = try the TMA-staged scalar kernel (scalar_tma.cu)
+    int32_t jp_pipeline;     // 1 = the fused probe issues its dimension lookups one drain ahead (agg_direct.cuh)
     int32_t wp;              // 1 = launch k_agg_group_wp
     int32_t wp_gcap;         // dense group ids per warp table (multiple of 32)
     int32_t wp_kt_log2;      // log2 words of the CTA's key -> id table

@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
     if (q0 + lane < nquads) issue_loads(q0 + lane);
     uint32_t qhead = 0, qcount = 0;   // warp-uniform: ring start (a multiple of 32) and entries waiting in it
     if constexpr (JOIN && !NULLS && !MM) {
-    if (a.jp.mode == 1) {
+    if (a.jp.mode == 1 && a.jp_pipeline) {
         // ---- K4 fused, software-pipelined (profiles/r02_join_history.md): the dimension lookups of a trip are ISSUED, then the rows the
         //      previous trip queued are drained while they fly (the table work hides the L2 round trip), then they are consumed and the
         //      trip's rows queued.  The next trip's foreign keys load into the key registers as soon as the lookups have left.

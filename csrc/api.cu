@@ -24,6 +24,11 @@
 
 using namespace bk;
 
+// Paths written after the round's last GPU window stay off until they have run on a GPU: BKGPU_EXPERIMENTAL=1 turns them on (the pipelined fused
+// probe, the learned build range, the device-buffer cache); tests/conftest.py keys the tests that exercise them on the same variable.
+static bool experimental_on() { static const bool on = getenv("BKGPU_EXPERIMENTAL") && atoi(getenv("BKGPU_EXPERIMENTAL")) != 0; return on; }
+
+
 namespace {
 
 thread_local std::string g_thread_error;
@@ -104,6 +109,7 @@ struct bkgpu_plan {
     int64_t jb_rows = 0, jb_cap = 0;
     uint64_t* jt_keys = nullptr; uint32_t* jt_rows = nullptr; uint32_t jt_mask = 0; bool jt_built = false, jt_generic = false;
     JoinFast jf{}; uint32_t* jf_dense = nullptr; uint64_t* jf_packed = nullptr;   // FK -> PK fast path (unique build keys)
+    int join_pipeline = experimental_on() ? 1 : 0, join_learn_range = experimental_on() ? 1 : 0;   // options of the same names
     bool jf_learned = false; uint64_t jf_learn_min = 0, jf_learn_max = 0;   // key range of the plan's previous build (skips the min/max pass + round trip)
     JoinProbe jp{}; uint32_t* jp_attr = nullptr; uint64_t* jp_packed = nullptr; int jp_key_pos = 0;   // ... fused into the lean aggregate
     size_t jf_dense_cap = 0, jf_packed_cap = 0, jp_attr_cap = 0, jp_packed_cap = 0, j_scratch_cap = 0;
@@ -179,7 +185,7 @@ struct DevCache {
     std::multimap<std::pair<int, size_t>, void*> free_;
     size_t held = 0;
     const size_t limit = (size_t)8 << 30;
-    const bool off = getenv("BKGPU_NO_ALLOC_CACHE") && atoi(getenv("BKGPU_NO_ALLOC_CACHE")) != 0;
+    const bool off = !experimental_on() || (getenv("BKGPU_NO_ALLOC_CACHE") && atoi(getenv("BKGPU_NO_ALLOC_CACHE")) != 0);
     void* take(int device, size_t sc) {
         std::lock_guard<std::mutex> g(mu);
         auto it = free_.find({device, sc});
@@ -294,6 +300,8 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "partial_capacity") { if (v < 1) return p->fail(BKGPU_EINVAL, "partial_capacity must be positive"); p->partial_cap = v; }
     else if (k == "force_generic") p->force_generic = v != 0;
     else if (k == "no_stream_copy") p->no_stream_copy = v != 0;
+    else if (k == "join_pipeline") p->join_pipeline = v != 0;
+    else if (k == "join_learn_range") p->join_learn_range = v != 0;
     else if (k == "no_lean") p->no_lean = v != 0;
     else if (k == "no_fused_probe") p->no_fused_probe = v != 0;
     else if (k == "repartition") p->repartition = v != 0;
@@ -479,7 +487,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
 
         }
     }
-    if (jp) { if (!a.lean) return 1; a.jp = *jp; }
+    if (jp) { if (!a.lean) return 1; a.jp = *jp; a.jp_pipeline = p->join_pipeline; }
     // warp-private tables (agg_wp.cuh): the plainest lean batches whose groups fit one table per warp.  The capacity follows the
     // cardinality learned from earlier batches / runs of this plan; an unknown cardinality starts with the largest table.
     a.scalar_tma = p->scalar_tma;
@@ -842,7 +850,7 @@ again:
         // the key range: measured (one pass over the keys + a round trip), or — when this plan has built before — the range it saw then,
         // checked by the build kernel itself (a key outside it raises a flag and the build is redone with a measured range)
         uint64_t h_mm[2];
-        bool guessed = p->jf_learned && !retry_measured;
+        bool guessed = p->jf_learned && !retry_measured && p->join_learn_range;
         if (guessed) { h_mm[0] = p->jf_learn_min; h_mm[1] = p->jf_learn_max; }
         else {
             CK(p, launch_join_minmax(key, c.cols[ki].prim, c.join_key_prim, p->jb_rows, bias, mm, p->stream));

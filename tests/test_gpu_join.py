@@ -190,6 +190,7 @@ def test_outer_join_with_an_empty_probe_side_and_unsupported_shapes():
     assert e.value.code == EUNSUPPORTED
 
 
+@pytest.mark.unverified
 def test_fused_build_reuses_the_learned_key_range_and_recovers_when_it_no_longer_fits():
     """prepared-statement reuse of C3's plan: the second build skips the min/max pass and trusts the first run's key range (checked by the
     build kernel); dimension keys that leave that range, and duplicate keys, must still give the oracle's rows"""
@@ -236,6 +237,7 @@ def _row_multiset(cols):
     return names, sorted((tuple(by[nm][i] for nm in names) for i in range(n)), key=key)
 
 
+@pytest.mark.unverified
 @pytest.mark.parametrize("jt", ["INNER_JOIN", "LEFT_JOIN", "RIGHT_JOIN"])
 @pytest.mark.parametrize("residual", [False, True])
 def test_join_that_returns_its_rows(jt, residual):
@@ -264,6 +266,7 @@ def test_join_that_returns_its_rows(jt, residual):
         assert any(r[fk] is None and r[gn.index("0_3")] is None for r in gr)          # NULL-extended rows exist
 
 
+@pytest.mark.unverified
 def test_join_rows_under_filter_sort_and_limit():
     from baikaldb_b200.exec_node import execute
     from oracle import oracle

@@ -98,6 +98,8 @@ def _distinct_case(seed=1, n=60_000, nk=9, nx=300):
     return (k, x, xv, v), cols, low, top
 
 
+@pytest.mark.gpu
+@pytest.mark.unverified
 def test_distinct_aggregates_two_level_plan():
     import numpy as np
     from baikaldb_b200.exec_node import execute
