@@ -61,6 +61,7 @@ struct AggArgs {
     // warp-private kernel (agg_wp.cuh): chosen by the host for the plainest lean batches
     int32_t scalar_tma;      // 1 = try the TMA-staged scalar kernel (scalar_tma.cu)
     int32_t jp_pipeline;     // 1 = the fused probe issues its dimension lookups one drain ahead (agg_direct.cuh)
+    int32_t lean_bank;       // 1 = the lean kernel's drain deals entries to lanes by the bank group of their home slot (option lean_bank)
     int32_t wp;              // 1 = launch k_agg_group_wp
     int32_t wp_gcap;         // dense group ids per warp table (multiple of 32)
     int32_t wp_kt_log2;      // log2 words of the CTA's key -> id table

@@ -529,7 +529,9 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 // aggregate: its sum gets +0 and its non-NULL counter no increment); the key column stays NULL-free in this kernel.
 // MM: value columns may feed MIN / MAX lanes (LDS -> compare -> ATOMS.CAS.64 only when the row improves the extreme: after the
 // first rows of a group that is one LDS per row) and up to three lanes each (SUM + MIN + MAX over one column).
-template <int NP, int NA, bool JOIN, bool NULLS = false, bool MM = false>
+// BANK (opt-in `lean_bank`, experimental): the drain re-deals the 32 entries of a pass so that lane L serves an entry whose home slot
+// is L mod 8 (mod the eight 16-byte bank groups): the 16-byte LDS / CAS of a quarter-warp then hit eight different bank groups.
+template <int NP, int NA, bool JOIN, bool NULLS = false, bool MM = false, bool BANK = false>
 __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid_constant__ AggArgs a) {
     constexpr int NS = NP + 1 + NA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -841,6 +843,69 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
         const uint32_t limit = (last || NP == 0) ? total : (total & ~31u);
         // (a two-entries-per-lane variant of this loop measured 17% slower: more registers, more idle
         //  lanes in the last pass — profiles/r01_agg_kernel_history.md)
+        if constexpr (BANK && !NULLS && !MM && !JOIN) {
+            auto update = [&](bool active, uint64_t k0, uint32_t e) {
+                if (!active) return;
+                uint64_t v[NA > 0 ? NA : 1];
+#pragma unroll
+                for (int s = 0; s < NA; s++) v[s] = lds64(qval + (s * LQ + e) * 8u);
+                const uint32_t h = ((uint32_t)k0 ^ (uint32_t)(k0 >> 32)) * 0x9E3779B1u;
+                int slot = -1;
+                if (k0 != EMPTY_KEY) slot = smem32_upsert1(keys_addr, cap_mask, k0, h >> hash_shift);
+                if (slot >= 0) {
+                    reds_inc32(lanes_addr + slot * 16u);
+                    int first = 0;
+                    if (pair2) {
+                        const uint32_t addr = acc_addr[0] + slot * 16u;
+                        uint64_t c0, c1;
+                        lds128(addr, c0, c1);
+                        for (;;) {
+                            uint64_t p0, p1;
+                            atoms_cas128(addr, c0, c1, f64_bits(bits_f64(c0) + bits_f64(v[0])), f64_bits(bits_f64(c1) + bits_f64(v[NA > 1 ? 1 : 0])), p0, p1);
+                            if (p0 == c0 && p1 == c1) break;
+                            c0 = p0; c1 = p1;
+                        }
+                        first = 2;
+                    }
+#pragma unroll
+                    for (int s = 0; s < NA; s++) {
+                        if (s < first) continue;
+                        if (acc_f64[s]) smem32_add_f64(acc_addr[s] + slot * 16u, bits_f64(v[s])); else smem32_add_u64(acc_addr[s] + slot * 16u, v[s]);
+                    }
+                } else {   // rare: re-read the entry so that v[] never needs an address (no local-memory copy per pass)
+                    uint64_t key[2] = {k0, 0ull};
+                    uint64_t gv[NA > 0 ? NA : 1];
+#pragma unroll
+                    for (int s = 0; s < NA; s++) gv[s] = lds64(qval + (s * LQ + e) * 8u);
+                    global_update_row<NA>(a, key, gv, 0u);
+                }
+            };
+#pragma unroll 1
+            for (uint32_t e0 = 0; e0 < limit; e0 += 32) {
+                const bool have = e0 + lane < limit;
+                uint32_t e = qhead + e0 + lane;
+                if (NP > 0) e -= e >= LQ ? LQ : 0u;
+                const uint64_t k0 = have ? lds64(qkey + e * 8u) : EMPTY_KEY;
+                const uint32_t b = ((((uint32_t)k0 ^ (uint32_t)(k0 >> 32)) * 0x9E3779B1u) >> hash_shift) & 7u;   // bank group of the home slot
+                const uint32_t act = __ballot_sync(0xFFFFFFFFu, have && k0 != EMPTY_KEY);
+                const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, b & 1u), m1 = __ballot_sync(0xFFFFFFFFu, b & 2u), m2 = __ballot_sync(0xFFFFFFFFu, b & 4u);
+                auto members = [&](uint32_t g) { return act & ((g & 1u) ? m0 : ~m0) & ((g & 2u) ? m1 : ~m1) & ((g & 4u) ? m2 : ~m2); };
+                const uint32_t rank = __popc(members(b) & lane_lt);
+                // lane L serves the (L / 8)-th entry of bank group L % 8
+                uint32_t dm = members((uint32_t)lane & 7u);
+                const int r = lane >> 3;
+                if (r > 0) dm &= dm - 1u;
+                if (r > 1) dm &= dm - 1u;
+                if (r > 2) dm &= dm - 1u;
+                const bool served = dm != 0u;
+                const int src = served ? __ffs(dm) - 1 : lane;
+                const uint64_t ks = __shfl_sync(0xFFFFFFFFu, k0, src);
+                uint32_t es = qhead + e0 + (uint32_t)src;
+                if (NP > 0) es -= es >= LQ ? LQ : 0u;
+                update(served, ks, es);
+                update(have && (k0 == EMPTY_KEY || rank >= 4u), k0, e);   // a fifth entry of a bank group, or the sentinel key: by its own lane
+            }
+        } else
 #pragma unroll 1
         for (uint32_t e0 = 0; e0 < limit; e0 += 32) {
             if (e0 + lane >= limit) continue;   // (only the final trip has a ragged pass)
@@ -1072,6 +1137,13 @@ static inline cudaError_t launch_direct(const AggArgs& a, int sm_count, size_t s
                 k_agg_group_lean<NP, NA, false, true><<<direct_grid(k_agg_group_lean<NP, NA, false, true>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
             }
             else if (a.jp.mode) k_agg_group_lean<NP, NA, true><<<grid, LEAN_THREADS, smem, s>>>(a);
+            else if (NA <= 2 && a.lean_bank) {
+                if constexpr (NA <= 2) {
+                    cudaError_t e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return e;
+                    k_agg_group_lean<NP, NA, false, false, false, true><<<direct_grid(k_agg_group_lean<NP, NA, false, false, false, true>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
+                }
+            }
             else k_agg_group_lean<NP, NA, false><<<grid, LEAN_THREADS, smem, s>>>(a);
         } else
         k_agg_group_direct<NP, NA><<<direct_grid(k_agg_group_direct<NP, NA>, smem, sm_count, a.nrows), DIRECT_THREADS, smem, s>>>(a);

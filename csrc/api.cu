@@ -110,6 +110,7 @@ struct bkgpu_plan {
     uint64_t* jt_keys = nullptr; uint32_t* jt_rows = nullptr; uint32_t jt_mask = 0; bool jt_built = false, jt_generic = false;
     JoinFast jf{}; uint32_t* jf_dense = nullptr; uint64_t* jf_packed = nullptr;   // FK -> PK fast path (unique build keys)
     int join_pipeline = experimental_on() ? 1 : 0, join_learn_range = experimental_on() ? 1 : 0;   // options of the same names
+    int lean_bank = 0;            // opt-in: bank-aware dealing of the lean kernel's drain (agg_direct.cuh, BANK)
     bool jf_learned = false; uint64_t jf_learn_min = 0, jf_learn_max = 0;   // key range of the plan's previous build (skips the min/max pass + round trip)
     JoinProbe jp{}; uint32_t* jp_attr = nullptr; uint64_t* jp_packed = nullptr; int jp_key_pos = 0;   // ... fused into the lean aggregate
     size_t jf_dense_cap = 0, jf_packed_cap = 0, jp_attr_cap = 0, jp_packed_cap = 0, j_scratch_cap = 0;
@@ -301,6 +302,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "force_generic") p->force_generic = v != 0;
     else if (k == "no_stream_copy") p->no_stream_copy = v != 0;
     else if (k == "join_pipeline") p->join_pipeline = v != 0;
+    else if (k == "lean_bank") p->lean_bank = v != 0;
     else if (k == "join_learn_range") p->join_learn_range = v != 0;
     else if (k == "no_lean") p->no_lean = v != 0;
     else if (k == "no_fused_probe") p->no_fused_probe = v != 0;
@@ -490,7 +492,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
     if (jp) { if (!a.lean) return 1; a.jp = *jp; a.jp_pipeline = p->join_pipeline; }
     // warp-private tables (agg_wp.cuh): the plainest lean batches whose groups fit one table per warp.  The capacity follows the
     // cardinality learned from earlier batches / runs of this plan; an unknown cardinality starts with the largest table.
-    a.scalar_tma = p->scalar_tma;
+    a.scalar_tma = p->scalar_tma; a.lean_bank = p->lean_bank;
     a.wp = 0;
     if (a.lean && !a.lean_nulls && !a.lean_mm && p->use_wp && c.direct.n_vals <= 2) {
         const int np = c.direct.n_terms, na = c.direct.n_vals;

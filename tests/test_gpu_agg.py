@@ -21,13 +21,13 @@ def test_c1_count_where():
 
 
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 127, 128, 129, 1000, 65537, 300_003])
-@pytest.mark.parametrize("variant", ["wp", "lean", "direct"])
+@pytest.mark.parametrize("variant", ["wp", "lean", "direct", pytest.param("bank", marks=pytest.mark.unverified)])
 def test_c2_sizes(n, variant):
     """ragged sizes around the 4-rows-per-lane / 128-rows-per-warp boundaries: warp-private, lean and general direct kernels"""
     cols = datagen.c2_table(0, n, n_groups=50)
-    opts = {"wp": {"use_wp": 1}, "lean": {}, "direct": {"no_lean": 1}}[variant]
+    opts = {"wp": {"use_wp": 1}, "lean": {}, "direct": {"no_lean": 1}, "bank": {"lean_bank": 1}}[variant]
     _, stats, _ = run_both(queries.c2_filter_groupby(), cols, keys=["0_1"], options=opts)
-    assert stats.main_kernel_name.decode() == {"wp": "k_agg_group_wp", "lean": "k_agg_group_lean", "direct": "k_agg_group_direct"}[variant]
+    assert stats.main_kernel_name.decode() == {"wp": "k_agg_group_wp", "lean": "k_agg_group_lean", "direct": "k_agg_group_direct", "bank": "k_agg_group_lean"}[variant]
 
 
 def test_lean_int64_key_and_integer_sums():
@@ -271,3 +271,13 @@ def test_literal_wider_than_the_column_keeps_its_value(variant):
                 {0: [(1, T.INT32), (2, T.INT32)], 1: [(1, T.INT64)]})
     got, _, _ = run_both(pl, cols, keys=["0_2"], options={"force_generic": 1} if variant == "generic" else None)
     assert sum({c.name: c for c in got}["1_1"].to_list()) == int(cols[0].valid.sum())
+
+
+@pytest.mark.unverified
+@pytest.mark.parametrize("n_groups", [7, 1000, 5000])
+def test_lean_bank_dealing_gives_the_same_groups(n_groups):
+    """option lean_bank: the drain deals each pass's entries to lanes by the bank group of their home slot (and lets the fifth entry of a
+    bank group be served by its own lane): same rows as the oracle at low, C2 and table-overflowing cardinalities, 0 % .. 100 % selectivity"""
+    for k in (0, 1 << 19, 1 << 21):
+        cols = datagen.c2_table(3, 250_003, n_groups=n_groups)
+        run_both(queries.c2_filter_groupby(k), cols, keys=["0_1"], options={"lean_bank": 1})
