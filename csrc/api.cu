@@ -24,11 +24,6 @@
 
 using namespace bk;
 
-// Paths written after the round's last GPU window stay off until they have run on a GPU: BKGPU_EXPERIMENTAL=1 turns them on (the pipelined fused
-// probe, the learned build range, the device-buffer cache); tests/conftest.py keys the tests that exercise them on the same variable.
-static bool experimental_on() { static const bool on = getenv("BKGPU_EXPERIMENTAL") && atoi(getenv("BKGPU_EXPERIMENTAL")) != 0; return on; }
-
-
 namespace {
 
 thread_local std::string g_thread_error;
@@ -109,7 +104,8 @@ struct bkgpu_plan {
     int64_t jb_rows = 0, jb_cap = 0;
     uint64_t* jt_keys = nullptr; uint32_t* jt_rows = nullptr; uint32_t jt_mask = 0; bool jt_built = false, jt_generic = false;
     JoinFast jf{}; uint32_t* jf_dense = nullptr; uint64_t* jf_packed = nullptr;   // FK -> PK fast path (unique build keys)
-    int join_pipeline = experimental_on() ? 1 : 0, join_learn_range = experimental_on() ? 1 : 0;   // options of the same names
+    int join_pipeline = 0;        // opt-in: the fused probe issues its lookups one drain ahead (measured equal: the kernel is shared-memory bound, profiles/r02_join_history.md)
+    int join_learn_range = 1;     // a re-run plan builds with the key range it saw before (checked by the build kernel): -0.05 ms per C3 request
     int lean_bank = 0;            // opt-in: bank-aware dealing of the lean kernel's drain (agg_direct.cuh, BANK)
     bool jf_learned = false; uint64_t jf_learn_min = 0, jf_learn_max = 0;   // key range of the plan's previous build (skips the min/max pass + round trip)
     JoinProbe jp{}; uint32_t* jp_attr = nullptr; uint64_t* jp_packed = nullptr; int jp_key_pos = 0;   // ... fused into the lean aggregate
@@ -186,7 +182,7 @@ struct DevCache {
     std::multimap<std::pair<int, size_t>, void*> free_;
     size_t held = 0;
     const size_t limit = (size_t)8 << 30;
-    const bool off = !experimental_on() || (getenv("BKGPU_NO_ALLOC_CACHE") && atoi(getenv("BKGPU_NO_ALLOC_CACHE")) != 0);
+    const bool off = getenv("BKGPU_NO_ALLOC_CACHE") && atoi(getenv("BKGPU_NO_ALLOC_CACHE")) != 0;
     void* take(int device, size_t sc) {
         std::lock_guard<std::mutex> g(mu);
         auto it = free_.find({device, sc});

@@ -116,8 +116,9 @@ int   bkgpu_init(bkgpu_plan** out, const uint8_t* plan_desc, size_t len,
  *   "scalar_tma"           0 = COUNT(*) WHERE int32 <cmp> c takes the LDG kernel instead of the TMA-staged one (csrc/scalar_tma.cu; default 1)
  *   "no_bounce"            pageable host input goes straight to cudaMemcpyAsync instead of the threaded pinned bounce buffers (A/B)
  *   "no_stream_copy"       the bounce copy uses memcpy instead of non-temporal stores (A/B)
- *   "join_pipeline"        the fused FK->PK probe issues its lookups one drain ahead; "join_learn_range": a re-run plan builds with the key range it saw
- *                          before (checked by the build kernel).  Both default to the BKGPU_EXPERIMENTAL environment switch. */
+ *   "join_learn_range"     (default 1) a re-run plan builds its join index with the key range it saw before, checked by the build kernel
+ *   "join_pipeline"        (default 0) the fused FK->PK probe issues its lookups one drain ahead (A/B: measured equal)
+ *   "lean_bank"            (default 0) the lean kernel deals each drained pass to lanes by shared-memory bank group (A/B: measured slower) */
 int   bkgpu_set_option(bkgpu_plan*, const char* key, int64_t value);
 /* ExecNode::open(RuntimeState*) (exec_node.h:140): allocate tables. */
 int   bkgpu_open(bkgpu_plan*);
@@ -147,7 +148,7 @@ int   bkgpu_get_stats(bkgpu_plan*, bkgpu_stats* out);
 
 /* Device buffers of closed plans are kept in a process-wide cache and handed to the next plan (a store opens one plan per request;
  * cudaMalloc / cudaFree of the group table would cost milliseconds each).  This returns the cached memory to the driver.
- * The cache is part of the BKGPU_EXPERIMENTAL=1 set (off otherwise); BKGPU_NO_ALLOC_CACHE=1 disables it there too. */
+ * Environment BKGPU_NO_ALLOC_CACHE=1 disables the cache. */
 void  bkgpu_release_cache(void);
 
 /* ---- date/time literals ----

@@ -1,5 +1,4 @@
 set -x
-export BKGPU_EXPERIMENTAL=1
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02_tests2.log 2>&1; tail -12 gpurun_out/r02_tests2.log
 timeout 300 python bench_configs.py c1 c3 c5 c5full --steps 10 > gpurun_out/r02_cfg2.json 2> gpurun_out/r02_cfg2.err
 timeout 300 ncu --set full --clock-control none --import-source on -f -k regex:k_rs_pass -s 5 -c 1 -o gpurun_out/r02_prof_rs_pass_v3 python bench_configs.py c5full --steps 1 --warmup 1 > gpurun_out/ncu2.log 2>&1

@@ -10,20 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    config.addinivalue_line("markers", "unverified: GPU test written after the round's last GPU window; runs only with BKGPU_EXPERIMENTAL=1 "
-                                       "(the same switch turns on the library paths it exercises)")
-
-
-EXPERIMENTAL = os.environ.get("BKGPU_EXPERIMENTAL", "0") not in ("", "0")
-
-
-def pytest_collection_modifyitems(config, items):
-    if EXPERIMENTAL:
-        return
-    skip = pytest.mark.skip(reason="not yet run on a GPU: set BKGPU_EXPERIMENTAL=1")
-    for item in items:
-        if "unverified" in item.keywords:
-            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session", autouse=True)

@@ -8,10 +8,7 @@ from baikaldb_b200 import plan as P
 from baikaldb_b200.column import make_column
 from baikaldb_b200.plan import PrimitiveType as T
 
-import os
-
 TUPLE0 = [(1, T.INT32), (2, T.INT64), (3, T.DOUBLE), (4, T.UINT32), (5, T.INT32)]
-WIDE = os.environ.get("BKGPU_EXPERIMENTAL", "0") not in ("", "0")
 
 
 def table(n, seed):
@@ -48,7 +45,7 @@ class Gen:
         """numeric-valued expression"""
         if d <= 0 or self.r.random() < 0.25:
             return self.col() if self.r.random() < 0.7 else self.lit()
-        k = int(self.r.integers(0, 17 if WIDE else 12))   # 12..16: the builtins added after the round's last GPU window (tests/conftest.py)
+        k = int(self.r.integers(0, 17))
         a, b = self.num(d - 1), self.num(d - 1)
         if k == 0: return P.add(a, b)
         if k == 1: return P.minus(a, b)

@@ -117,11 +117,8 @@ CASES = [
 ]
 
 
-NEW_THIS_ROUND = {"sqrt_ln", "pow_log", "fmod_greatest", "bit_count_pi", "trig", "tan_cot_acos"}   # (see tests/conftest.py: `unverified`)
-
-
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,build", [pytest.param(*c, marks=pytest.mark.unverified) if c[0] in NEW_THIS_ROUND else c for c in CASES], ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("name,build", CASES, ids=[c[0] for c in CASES])
 def test_gpu_matches_oracle(name, build):
     from tests.util import run_both
     key, kt, arg, at = build()

@@ -21,7 +21,7 @@ def test_c1_count_where():
 
 
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 127, 128, 129, 1000, 65537, 300_003])
-@pytest.mark.parametrize("variant", ["wp", "lean", "direct", pytest.param("bank", marks=pytest.mark.unverified)])
+@pytest.mark.parametrize("variant", ["wp", "lean", "direct", "bank"])
 def test_c2_sizes(n, variant):
     """ragged sizes around the 4-rows-per-lane / 128-rows-per-warp boundaries: warp-private, lean and general direct kernels"""
     cols = datagen.c2_table(0, n, n_groups=50)
@@ -273,7 +273,6 @@ def test_literal_wider_than_the_column_keeps_its_value(variant):
     assert sum({c.name: c for c in got}["1_1"].to_list()) == int(cols[0].valid.sum())
 
 
-@pytest.mark.unverified
 @pytest.mark.parametrize("n_groups", [7, 1000, 5000])
 def test_lean_bank_dealing_gives_the_same_groups(n_groups):
     """option lean_bank: the drain deals each pass's entries to lanes by the bank group of their home slot (and lets the fifth entry of a

@@ -113,7 +113,6 @@ def test_having_over_scalar_aggregate():
     assert not got or len(got[0]) == 0
 
 
-@pytest.mark.unverified
 def test_aggregate_over_a_filtered_join():
     """AGG -> FILTER -> JOIN (the store-side chain of `... FROM a JOIN b ON ... WHERE f(a, b) GROUP BY ...`): the filter sees the joined row;
     above an INNER join it joins the residual conditions, above an outer join it is refused"""

@@ -55,6 +55,7 @@ def test_join_fused_probe_dense_with_gaps_negative_keys_and_ragged_tail(nf):
     _, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact])
     if nf > 4:
         assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+    run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact], options={"join_pipeline": 1})   # the pipelined probe (opt-in)
 
 
 def test_c3_streamed_in_several_batches_host_and_build_first_rule():
@@ -119,6 +120,7 @@ def test_fused_probe_with_a_fact_side_filter(nf):
     _, stats, _ = run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact])
     assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
     run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact], options={"no_fused_probe": 1})
+    run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact], options={"join_pipeline": 1})
 
 
 def _outer_join_tables(seed, nd=2_500, nf=40_000):
@@ -190,7 +192,6 @@ def test_outer_join_with_an_empty_probe_side_and_unsupported_shapes():
     assert e.value.code == EUNSUPPORTED
 
 
-@pytest.mark.unverified
 def test_fused_build_reuses_the_learned_key_range_and_recovers_when_it_no_longer_fits():
     """prepared-statement reuse of C3's plan: the second build skips the min/max pass and trusts the first run's key range (checked by the
     build kernel); dimension keys that leave that range, and duplicate keys, must still give the oracle's rows"""
@@ -237,7 +238,6 @@ def _row_multiset(cols):
     return names, sorted((tuple(by[nm][i] for nm in names) for i in range(n)), key=key)
 
 
-@pytest.mark.unverified
 @pytest.mark.parametrize("jt", ["INNER_JOIN", "LEFT_JOIN", "RIGHT_JOIN"])
 @pytest.mark.parametrize("residual", [False, True])
 def test_join_that_returns_its_rows(jt, residual):
@@ -266,7 +266,6 @@ def test_join_that_returns_its_rows(jt, residual):
         assert any(r[fk] is None and r[gn.index("0_3")] is None for r in gr)          # NULL-extended rows exist
 
 
-@pytest.mark.unverified
 def test_join_rows_under_filter_sort_and_limit():
     from baikaldb_b200.exec_node import execute
     from oracle import oracle

@@ -99,7 +99,6 @@ def _distinct_case(seed=1, n=60_000, nk=9, nx=300):
 
 
 @pytest.mark.gpu
-@pytest.mark.unverified
 def test_distinct_aggregates_two_level_plan():
     import numpy as np
     from baikaldb_b200.exec_node import execute
