@@ -597,17 +597,20 @@ namespace {
 class CopyPool {
   public:
     explicit CopyPool(int n) { for (int i = 0; i < n; i++) th_.emplace_back([this] { run(); }); }
-    ~CopyPool() { { std::lock_guard<std::mutex> g(mu_); stop_ = true; } cv_.notify_all(); for (auto& t : th_) t.join(); }
+    ~CopyPool() { { std::lock_guard<std::mutex> g(mu_); stop_ = true; stop_pub_.store(true, std::memory_order_release); } cv_.notify_all(); for (auto& t : th_) t.join(); }
     int size() const { return (int)th_.size(); }
     // runs fn(0) .. fn(n - 1) on the workers and the caller; returns when all are done
     void parallel(int n, const std::function<void(int)>& fn) {
         if (n <= 0) return;
         {
             std::lock_guard<std::mutex> g(mu_);
-            fn_ = &fn; next_ = 0; total_ = n; done_ = 0; gen_++;
+            fn_ = &fn; next_ = 0; total_ = n; done_ = 0; done_pub_.store(0, std::memory_order_release); gen_++;
+            gen_pub_.store(gen_, std::memory_order_release);
         }
         cv_.notify_all();
         work();
+        for (const double t_end = HostClock::now() + 5.0; done_pub_.load(std::memory_order_acquire) < n && HostClock::now() < t_end;)   // (the last slices finish within microseconds)
+            for (int i = 0; i < 32; i++) __builtin_ia32_pause();
         std::unique_lock<std::mutex> g(mu_);
         done_cv_.wait(g, [this] { return done_ == total_; });
         fn_ = nullptr;
@@ -619,13 +622,26 @@ class CopyPool {
             const std::function<void(int)>* f;
             { std::lock_guard<std::mutex> g(mu_); if (!fn_ || next_ >= total_) return; i = next_++; f = fn_; }
             (*f)(i);
-            { std::lock_guard<std::mutex> g(mu_); if (++done_ == total_) done_cv_.notify_all(); }
+            { std::lock_guard<std::mutex> g(mu_); ++done_; done_pub_.store(done_, std::memory_order_release); if (done_ == total_) done_cv_.notify_all(); }
         }
     }
     void run() {
         uint64_t seen = 0;
         for (;;) {
-            { std::unique_lock<std::mutex> g(mu_); cv_.wait(g, [&] { return stop_ || gen_ != seen; }); if (stop_) return; seen = gen_; }
+            // a push hands over one chunk per millisecond: a worker that went to sleep on the condition variable after each chunk paid a futex
+            // wake-up (tens of microseconds, staggered over the threads) on a ~0.3 ms copy — it polls for the next chunk for a short while first
+            const double t_end = HostClock::now() + 2.0;   // ms
+            bool got = false;
+            while (HostClock::now() < t_end) {
+                if (gen_pub_.load(std::memory_order_acquire) != seen || stop_pub_.load(std::memory_order_acquire)) { got = true; break; }
+                for (int i = 0; i < 64; i++) __builtin_ia32_pause();
+            }
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                if (!got) cv_.wait(g, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
             work();
         }
     }
@@ -633,6 +649,7 @@ class CopyPool {
     std::mutex mu_; std::condition_variable cv_, done_cv_;
     const std::function<void(int)>* fn_ = nullptr;
     int next_ = 0, total_ = 0, done_ = 0; uint64_t gen_ = 0; bool stop_ = false;
+    std::atomic<uint64_t> gen_pub_{0}; std::atomic<bool> stop_pub_{false}; std::atomic<int> done_pub_{0};   // what the pollers read without the mutex
 };
 CopyPool& copy_pool() {
     static CopyPool pool(std::max(1, std::min(23, (int)std::thread::hardware_concurrency() / 2 - 1)));
