@@ -2,6 +2,7 @@
 // inverted into init/open/push/finish/get_next/close), batch staging, result materialisation.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -596,7 +597,7 @@ namespace bk { void stream_copy(void* dst, const void* src, size_t bytes); }   /
 namespace {
 class CopyPool {
   public:
-    explicit CopyPool(int n) { for (int i = 0; i < n; i++) th_.emplace_back([this] { run(); }); }
+    explicit CopyPool(int n, double poll_ms) : poll_ms_(poll_ms) { for (int i = 0; i < n; i++) th_.emplace_back([this] { run(); }); }
     ~CopyPool() { { std::lock_guard<std::mutex> g(mu_); stop_ = true; stop_pub_.store(true, std::memory_order_release); } cv_.notify_all(); for (auto& t : th_) t.join(); }
     int size() const { return (int)th_.size(); }
     // runs fn(0) .. fn(n - 1) on the workers and the caller; returns when all are done
@@ -609,8 +610,9 @@ class CopyPool {
         }
         cv_.notify_all();
         work();
-        for (const double t_end = HostClock::now() + 5.0; done_pub_.load(std::memory_order_acquire) < n && HostClock::now() < t_end;)   // (the last slices finish within microseconds)
-            for (int i = 0; i < 32; i++) __builtin_ia32_pause();
+        if (poll_ms_ > 0)
+            for (const double t_end = HostClock::now() + 5.0; done_pub_.load(std::memory_order_acquire) < n && HostClock::now() < t_end;)   // (the last slices finish within microseconds)
+                for (int i = 0; i < 32; i++) __builtin_ia32_pause();
         std::unique_lock<std::mutex> g(mu_);
         done_cv_.wait(g, [this] { return done_ == total_; });
         fn_ = nullptr;
@@ -630,9 +632,9 @@ class CopyPool {
         for (;;) {
             // a push hands over one chunk per millisecond: a worker that went to sleep on the condition variable after each chunk paid a futex
             // wake-up (tens of microseconds, staggered over the threads) on a ~0.3 ms copy — it polls for the next chunk for a short while first
-            const double t_end = HostClock::now() + 2.0;   // ms
+            const double t_end = HostClock::now() + poll_ms_;
             bool got = false;
-            while (HostClock::now() < t_end) {
+            while (poll_ms_ > 0 && HostClock::now() < t_end) {
                 if (gen_pub_.load(std::memory_order_acquire) != seen || stop_pub_.load(std::memory_order_acquire)) { got = true; break; }
                 for (int i = 0; i < 64; i++) __builtin_ia32_pause();
             }
@@ -649,10 +651,33 @@ class CopyPool {
     std::mutex mu_; std::condition_variable cv_, done_cv_;
     const std::function<void(int)>* fn_ = nullptr;
     int next_ = 0, total_ = 0, done_ = 0; uint64_t gen_ = 0; bool stop_ = false;
+    const double poll_ms_;   // > 0: a worker polls this long for the next chunk before it sleeps on the condition variable (BKGPU_COPY_POLL_US)
     std::atomic<uint64_t> gen_pub_{0}; std::atomic<bool> stop_pub_{false}; std::atomic<int> done_pub_{0};   // what the pollers read without the mutex
 };
+// CPUs this process may actually use: online CPUs, its affinity mask and its cgroup CPU quota (a container with a 16-CPU quota on a 128-CPU box
+// gets throttled for the rest of the scheduling period once its threads have burnt the quota — spinning or oversized pools make the copy SLOWER there)
+int cpu_budget() {
+    int n = (int)std::thread::hardware_concurrency();
+    cpu_set_t set; CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0) { const int a = CPU_COUNT(&set); if (a > 0 && a < n) n = a; }
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {   // cgroup v2: "<quota|max> <period>"
+        char q[32]; long long period = 0;
+        if (fscanf(f, "%31s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) { const long long c = atoll(q) / period; if (c > 0 && c < n) n = (int)c; }
+        fclose(f);
+    } else if (FILE* g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {   // cgroup v1
+        long long quota = -1, period = 100000;
+        if (fscanf(g, "%lld", &quota) != 1) quota = -1;
+        fclose(g);
+        if (FILE* h = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(h, "%lld", &period) != 1) period = 100000; fclose(h); }
+        if (quota > 0 && period > 0 && quota / period > 0 && quota / period < n) n = (int)(quota / period);
+    }
+    return n > 0 ? n : 1;
+}
 CopyPool& copy_pool() {
-    static CopyPool pool(std::max(1, std::min(23, (int)std::thread::hardware_concurrency() / 2 - 1)));
+    static CopyPool pool([] {
+        if (const char* e = getenv("BKGPU_COPY_THREADS")) { const int v = atoi(e); if (v > 0) return std::min(v, 64) - 1; }
+        return std::max(1, std::min(23, cpu_budget() / 2 - 1));
+    }(), [] { const char* e = getenv("BKGPU_COPY_POLL_US"); return e ? atof(e) / 1000.0 : 0.0; }());
     return pool;
 }
 bool is_pageable(const void* p) {
