@@ -22,6 +22,7 @@
 #include "plan.h"
 #include "sort.h"
 #include "nccl_dl.h"
+#include "build_id.h"
 
 using namespace bk;
 
@@ -153,7 +154,7 @@ static int thread_fail(int code, const char* fmt, ...) {
 }
 
 // ------------------------------------------------------------------ library
-extern "C" const char* bkgpu_version(void) { return "bkgpu 0.1 (sm_100a)"; }
+extern "C" const char* bkgpu_version(void) { return "bkgpu 0.2 (sm_100a) src=" BKGPU_SRC_DIGEST; }   // digest of csrc/ + include/ at compile time (csrc/Makefile)
 
 extern "C" int bkgpu_device_count(void) {
     int n = 0;

@@ -27,6 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_no_device_is_an_error_not_a_fallback():
     L = _lib.lib()
     assert L.bkgpu_version().startswith(b"bkgpu")
+
     n = L.bkgpu_device_count()
     if n > 0:
         pytest.skip("a GPU is visible here")
@@ -35,6 +36,28 @@ def test_version_and_no_device_is_an_error_not_a_fallback():
     rc = L.bkgpu_init(ctypes.byref(h), pb, len(pb), 0, None)
     assert rc == _lib.ENODEV
     assert b"no CPU fallback" in L.bkgpu_last_error(None)
+
+
+def test_library_was_built_from_the_sources_in_this_tree():
+    """provenance: libbkgpu.so is a git-ignored binary that travels to the GPU box; it reports a digest of csrc/ + include/ taken when it was
+    compiled (csrc/Makefile: build_id.h), which must equal the digest of the sources that are here now"""
+    import glob
+    import hashlib
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cs = os.path.join(root, "csrc")
+    mk = open(os.path.join(cs, "Makefile")).read()
+    names = []
+    for var in ("CU", "CPP"):
+        line = [l for l in mk.splitlines() if l.startswith(var + " :=")][0]
+        names += line.split(":=")[1].split()
+    names += [os.path.basename(p) for pat in ("*.h", "*.cuh", "*.inc") for p in glob.glob(os.path.join(cs, pat))]
+    names += ["../include/bkgpu.h", "../include/bkgpu_plan.h"]
+    h = hashlib.sha256()
+    for n in sorted(set(names)):
+        h.update(open(os.path.join(cs, n), "rb").read())
+    version = _lib.lib().bkgpu_version().decode()
+    assert version.endswith("src=" + h.hexdigest()[:16]), (version, h.hexdigest()[:16])
 
 
 def test_explain_c2_lowering():
