@@ -109,6 +109,7 @@ struct bkgpu_plan {
     int join_pipeline = 0;        // opt-in: the fused probe issues its lookups one drain ahead (measured equal: the kernel is shared-memory bound, profiles/r02_join_history.md)
     int join_learn_range = 1;     // a re-run plan builds with the key range it saw before (checked by the build kernel): -0.05 ms per C3 request
     int lean_bank = 0;            // opt-in: bank-aware dealing of the lean kernel's drain (agg_direct.cuh, BANK)
+    int blocking_sync = -1; bool blocking_wait = false; cudaEvent_t wait_event = nullptr;   // see agg_finish
     bool jf_learned = false; uint64_t jf_learn_min = 0, jf_learn_max = 0;   // key range of the plan's previous build (skips the min/max pass + round trip)
     JoinProbe jp{}; uint32_t* jp_attr = nullptr; uint64_t* jp_packed = nullptr; int jp_key_pos = 0;   // ... fused into the lean aggregate
     size_t jf_dense_cap = 0, jf_packed_cap = 0, jp_attr_cap = 0, jp_packed_cap = 0, j_scratch_cap = 0;
@@ -301,6 +302,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "no_stream_copy") p->no_stream_copy = v != 0;
     else if (k == "join_pipeline") p->join_pipeline = v != 0;
     else if (k == "lean_bank") p->lean_bank = v != 0;
+    else if (k == "blocking_sync") p->blocking_sync = (int)v;
     else if (k == "join_learn_range") p->join_learn_range = v != 0;
     else if (k == "no_lean") p->no_lean = v != 0;
     else if (k == "no_fused_probe") p->no_fused_probe = v != 0;
@@ -339,6 +341,8 @@ static int alloc_group_table(bkgpu_plan* p) {
     return BKGPU_OK;
 }
 
+namespace { int cpu_budget(); }   // CPUs this process may use (affinity, cgroup quota): defined with the copy pool
+
 extern "C" int bkgpu_open(bkgpu_plan* p) {
     if (!p) return thread_fail(BKGPU_EINVAL, "bkgpu_open: NULL plan");
     if (p->state != S_INIT) return p->fail(BKGPU_ESTATE, "bkgpu_open called twice");
@@ -350,6 +354,7 @@ extern "C" int bkgpu_open(bkgpu_plan* p) {
         CK(p, cudaEventCreateWithFlags(&p->stage_free[i], cudaEventDisableTiming));
         CK(p, cudaEventCreateWithFlags(&p->stage_ready[i], cudaEventDisableTiming));
     }
+    p->blocking_wait = p->blocking_sync >= 0 ? p->blocking_sync != 0 : (p->nranks > 1 && cpu_budget() < 4 * p->nranks);
     int rc = BKGPU_OK;
     if (p->c.kind == PK_AGG || p->c.kind == PK_JOIN_AGG) rc = alloc_group_table(p);
     if (!rc && (p->c.kind == PK_SORT || p->c.kind == PK_FILTER)) rc = sort_open(p->c, p->device, p->stream, p->region_base, &p->sort, p->last_error);
@@ -1401,7 +1406,17 @@ static int agg_finish(bkgpu_plan* p) {
             CK(p, cudaMemcpyAsync(hv, p->d_outv, n_words * 8, cudaMemcpyDeviceToHost, p->stream));
             CK(p, cudaMemcpyAsync(hn, p->d_outn, n_words, cudaMemcpyDeviceToHost, p->stream));
         }
-        { const double t0 = HostClock::now(); CK(p, cudaStreamSynchronize(p->stream)); p->hclk.extract_wait += HostClock::now() - t0; }
+        {   // the one wait of the request.  With several ranks on a host whose CPU budget is small (8 ranks under a 16-CPU cgroup quota: two CPUs per
+            // rank for the python thread, NCCL's proxy thread and this wait) a spinning wait burns the quota the other ranks' launches need:
+            // there the thread sleeps on a blocking-sync event instead (option blocking_sync: -1 auto, 0 spin, 1 sleep)
+            const double t0 = HostClock::now();
+            if (p->blocking_wait) {
+                if (!p->wait_event) CK(p, cudaEventCreateWithFlags(&p->wait_event, cudaEventBlockingSync | cudaEventDisableTiming));
+                CK(p, cudaEventRecord(p->wait_event, p->stream));
+                CK(p, cudaEventSynchronize(p->wait_event));
+            } else CK(p, cudaStreamSynchronize(p->stream));
+            p->hclk.extract_wait += HostClock::now() - t0;
+        }
         host_counts[0] = hc3[0]; host_counts[1] = hc3[1]; n_out = hc3[2]; merge_max = hc3[3];
         memcpy(&p->rows_passed_host, hc3 + 4, 8);
         if (p->peer_ready && p->h_pinned && p->h_pinned[6]) return p->fail(BKGPU_ENCCL, "peer merge: a rank did not publish its partial state within the time limit");
@@ -1602,6 +1617,7 @@ extern "C" void bkgpu_close(bkgpu_plan* p) {
     for (auto& q : p->dev_allocs) if (!dev_cache().put(p->device, q.second, q.first)) cudaFree(q.first);   // (both streams were drained above)
     for (int i = 0; i < 2; i++) { if (p->stage_free[i]) cudaEventDestroy(p->stage_free[i]); if (p->stage_ready[i]) cudaEventDestroy(p->stage_ready[i]); }
     for (int i = 0; i < 2; i++) { for (uint8_t* q : p->bounce[i]) if (q) cudaFreeHost(q); if (p->bounce_done[i]) cudaEventDestroy(p->bounce_done[i]); }
+    if (p->wait_event) cudaEventDestroy(p->wait_event);
     if (p->h_pinned) cudaFreeHost(p->h_pinned);
     if (p->h_outv) cudaFreeHost(p->h_outv);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);

@@ -118,6 +118,8 @@ int   bkgpu_init(bkgpu_plan** out, const uint8_t* plan_desc, size_t len,
  *   "no_stream_copy"       the bounce copy uses memcpy instead of non-temporal stores (A/B)
  *   "join_learn_range"     (default 1) a re-run plan builds its join index with the key range it saw before, checked by the build kernel
  *   "join_pipeline"        (default 0) the fused FK->PK probe issues its lookups one drain ahead (A/B: measured equal)
+ *   "blocking_sync"        the wait for a request's result: 0 spins (cudaStreamSynchronize), 1 sleeps on a blocking-sync event, -1 (default) sleeps only
+ *                          when several ranks share a small CPU budget (ranks > 1 and budget < 4 CPUs per rank)
  *   "lean_bank"            (default 0) the lean kernel deals each drained pass to lanes by shared-memory bank group (A/B: measured slower) */
 int   bkgpu_set_option(bkgpu_plan*, const char* key, int64_t value);
 /* ExecNode::open(RuntimeState*) (exec_node.h:140): allocate tables. */
