@@ -101,9 +101,11 @@ def host_cpu_info():
 # ----------------------------------------------------------------------------------------------
 # clocks: sampled DURING the timed region (B200_PROFILING.md)
 # ----------------------------------------------------------------------------------------------
+CLOCK_SAMPLE_S = float(os.environ.get("BKGPU_BENCH_CLOCK_MS", "10")) / 1e3   # NVML queries share the driver with the launches they sit beside: a sample per 10 ms
+
+
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region.  NVML in a background thread (one sample every ~2 ms: even a
-    10 ms region gets several); `nvidia-smi -lms` as a subprocess when pynvml is not importable."""
+    """SM clock + throttle reasons sampled DURING the timed region.  NVML in a background thread (the first sample at once, then one every BKGPU_BENCH_CLOCK_MS = 10 ms); `nvidia-smi -lms` as a subprocess when pynvml is not importable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
@@ -139,7 +141,7 @@ class ClockSampler:
                 self._sample()
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(CLOCK_SAMPLE_S)
 
     def start(self):
         if self.nvml:
