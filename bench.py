@@ -620,7 +620,8 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))
-        entry = prof.get(r["stats"].main_kernel_name.decode())
+        kname = r["stats"].main_kernel_name.decode()
+        entry = prof.get(kname) or prof.get(kname.replace("_fx", ""))   # (the FX variant reads the same columns once: no capture of its own yet -> the lean kernel's)
         if entry:  # DRAM bytes per launch, scaled from the committed ncu capture to this launch's row count
             traffic = entry["dram_bytes_per_row"] * rows
     except Exception:

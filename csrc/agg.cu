@@ -435,6 +435,9 @@ size_t direct_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2, int na) 
     return table + queue * warps;
 }
 
+// FX (agg_direct.cuh): one low-extension limb (4 bytes) per value column and slot, behind the queues
+size_t fx_ext_bytes(int na, int cap_log2) { return ((size_t)4 * (size_t)na) << cap_log2; }
+
 template <class K>
 static int occupancy_grid(K kernel, size_t smem, int sm_count) {
     int per_sm = 0;
@@ -451,7 +454,7 @@ cudaError_t launch_agg(const AggArgs& a, bool direct, int sm_count, cudaStream_t
         if (launch_count_where_tma(a, sm_count, s, &e)) { *kernel_name = "k_count_where_tma"; return e; }
     }
     if (direct) {
-        const size_t dsmem = grouped ? direct_smem_bytes(a.smem_keyw, a.n_smem_lanes, a.smem_cap_log2, a.direct.n_vals) : 0;
+        const size_t dsmem = grouped ? direct_smem_bytes(a.smem_keyw, a.n_smem_lanes, a.smem_cap_log2, a.direct.n_vals) + (a.lean_fx ? fx_ext_bytes(a.direct.n_vals, a.smem_cap_log2) : 0) : 0;
         *kernel_name = grouped ? "k_agg_group_direct" : "k_agg_scalar_direct";
         switch (a.direct.n_terms) {
             case 0: return launch_direct_np0(a, a.direct.n_vals, sm_count, dsmem, s, grouped);

@@ -62,6 +62,8 @@ struct AggArgs {
     int32_t scalar_tma;      // 1 = try the TMA-staged scalar kernel (scalar_tma.cu)
     int32_t jp_pipeline;     // 1 = the fused probe issues its dimension lookups one drain ahead (agg_direct.cuh)
     int32_t lean_bank;       // 1 = the lean kernel's drain deals entries to lanes by the bank group of their home slot (option lean_bank)
+    int32_t lean_fx;         // 1 = the lean kernel accumulates its double sums as fixed-point limbs with native 32-bit shared atomics (FX, agg_direct.cuh)
+    uint32_t fx_ext_off;     // FX: byte offset (in the CTA's dynamic shared memory) of the low-extension limb arrays [value column][slot]
     int32_t wp;              // 1 = launch k_agg_group_wp
     int32_t wp_gcap;         // dense group ids per warp table (multiple of 32)
     int32_t wp_kt_log2;      // log2 words of the CTA's key -> id table
@@ -85,6 +87,7 @@ cudaError_t launch_direct_np0(const AggArgs& a, int na, int sm_count, size_t sme
 cudaError_t launch_direct_np1(const AggArgs& a, int na, int sm_count, size_t smem, cudaStream_t s, bool grouped);
 cudaError_t launch_direct_np2(const AggArgs& a, int na, int sm_count, size_t smem, cudaStream_t s, bool grouped);
 size_t direct_smem_bytes(int smem_keyw, int n_smem_lanes, int cap_log2, int na);
+size_t fx_ext_bytes(int na, int cap_log2);
 cudaError_t launch_join_build(const DevCol& key, int from_prim, int cast_prim, int64_t nrows, uint64_t* keys, uint32_t* rows, uint32_t cap_mask, cudaStream_t s);
 // FK -> PK join fast path: unique build keys, looked up through a dense array (small key range) or a packed
 // (key32 << 32 | row) table; build-side columns are gathered to probe-row alignment

@@ -19,6 +19,7 @@
 // NULL keys wider than 32 bits ...) take out-of-line routines so the hot loop stays lean.
 #pragma once
 #include "agg_kernels.cuh"
+#include "fx.h"
 
 namespace bk {
 
@@ -242,8 +243,10 @@ static __device__ __noinline__ uint32_t direct_tail_row(const AggArgs& a, int64_
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t lds64(uint32_t a) { uint64_t v; asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_inc32(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
 __device__ __forceinline__ uint32_t atoms_add32(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
@@ -517,6 +520,56 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
     if (lane == 0 && passed) atomicAdd((unsigned long long*)a.rows_passed, (unsigned long long)passed);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// FX — double sums as fixed-point limbs (the lean kernel's default for SUM / AVG over DOUBLE columns)
+// Why: sm_100a's shared memory has native atomics for 32-bit integers only; a double add is LDS -> DADD -> ATOMS.CAS in a loop, and a
+// pass of 32 random group slots through `RED.u32 + LDS.128 + ATOMS.CAS.128` measures 71 SM-cycles (168 with 100 groups: the compare-and-
+// swap retries) against 50 for `RED.u32 + 2 x (ATOMS.ADD + RED)` at any cardinality (scripts/mb/mb_atoms.cu, profiles/r02_fx_history.md).
+// How: per CTA and value column a power-of-two scale 2^F is chosen from a sample of the batch (640 rows spread over the whole column),
+// so that the largest value seen has M - 3 significant bits above the quantum; M = 62 - ceil(log2(rows this CTA can add)) keeps the
+// 64-bit sum of one slot from overflowing whatever the key distribution.  A value x becomes y = x * 2^F (exact) and takes one of
+//   main  2^(M-15) <= |y| < 2^M : round(y) added to the slot's {mid, hi} limbs, ATOMS.ADD.32 with the carry folded into a RED.32;
+//                                 relative rounding error per value <= 2^-(M-14) (M = 42 at 100M rows: 3.7e-9, typically 1e-12),
+//   fine  2^(M-47) <= |y| < 2^(M-15) : round(y * 2^32) added to {ext, mid, hi} (three limbs, same per-value precision),
+//   zero  nothing to add,
+//   else  (beyond the sampled range, denormal, Inf, NaN): an exact double add into the global table.
+// The sum of a group is therefore the exact sum of values rounded to at least M-15 = 27 significant bits each: independent of the
+// order of the rows (bit-reproducible from run to run, unlike the CAS path), error <= 2^-28 relative to sum(|x|) in the worst case,
+// against north_star's 1e-6.  At flush time the limbs become one double per lane and the table is merged as before.
+// (AggFnCall::update's `add` is a sequential double add, agg_fn_call.cpp:496-555; any parallel order already differs from it in the
+// last bits.)
+// ------------------------------------------------------------------------------------------
+static __device__ __noinline__ void global_add_f64(const AggArgs& a, uint64_t k0, int glob_lane, double x) {
+    const AggPlan& ap = a.plan;
+    const GroupTable& gt = a.gt;
+    const uint32_t gcap = gt.cap_mask + 1;
+    uint64_t key[MAX_KEYW];
+    key[0] = k0;
+    for (int w = 1; w < MAX_KEYW; w++) key[w] = 0ull;
+    const int slot = table_upsert<false, 0>(gt.state, gt.keys, gt.cap_mask, key, ap.n_keyw, ap.n_keyw == 1 ? hash_key1(key[0]) : hash_key(key, ap.n_keyw), (int)gcap, gt.n_groups);
+    if (slot < 0) { atomicExch(gt.overflow, 1u); return; }
+    lane_atomic<false>(LN_ADD_F64, gt.lanes + (size_t)glob_lane * gcap + slot, f64_bits(x));
+}
+__device__ __forceinline__ void reds_add32(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// one value into the fixed-point limbs of `slot`: word = shared address of the slot's {mid, hi} pair, ext = of its low-extension limb
+__device__ __forceinline__ void fx_add(const AggArgs& a, uint32_t word, uint32_t ext, double scale, uint32_t fx_lo, uint64_t k0, int glob_lane, uint64_t vbits) {
+    uint32_t lo; uint64_t up;
+    const int kind = fx_split(bits_f64(vbits), scale, fx_lo, lo, up);
+    if (kind == FX_MAIN) {
+        const uint32_t old = atoms_add32(word, lo);
+        const uint32_t h = (uint32_t)up + ((old + lo) < old ? 1u : 0u);
+        if (h) reds_add32(word + 4u, h);
+    } else if (kind == FX_FINE) {
+        const uint32_t old = atoms_add32(ext, lo);
+        const uint64_t t = up + ((old + lo) < old ? 1u : 0u);   // sign-extended upper part + carry
+        const uint32_t m = (uint32_t)t;
+        const uint32_t old2 = atoms_add32(word, m);
+        const uint32_t h = (uint32_t)(t >> 32) + ((old2 + m) < old2 ? 1u : 0u);
+        if (h) reds_add32(word + 4u, h);
+    } else if (kind == FX_EXACT) global_add_f64(a, k0, glob_lane, bits_f64(vbits));
+}
+
 // ------------------------------------------------------------------------------------------
 // GROUP BY one column, LEAN shape — what the headline query (config C2/C4) and most star-schema
 // aggregations look like: no NULLs in this batch, every predicate term is `int32 column <cmp> int32
@@ -531,7 +584,8 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 // first rows of a group that is one LDS per row) and up to three lanes each (SUM + MIN + MAX over one column).
 // BANK (opt-in `lean_bank`, experimental): the drain re-deals the 32 entries of a pass so that lane L serves an entry whose home slot
 // is L mod 8 (mod the eight 16-byte bank groups): the 16-byte LDS / CAS of a quarter-warp then hit eight different bank groups.
-template <int NP, int NA, bool JOIN, bool NULLS = false, bool MM = false, bool BANK = false>
+// FX: double sums as fixed-point limbs updated with native 32-bit shared atomics (see above).
+template <int NP, int NA, bool JOIN, bool NULLS = false, bool MM = false, bool BANK = false, bool FX = false>
 __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid_constant__ AggArgs a) {
     constexpr int NS = NP + 1 + NA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -589,6 +643,35 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
     uint32_t passed = 0;
     const int64_t nquads = a.nrows >> 2;
     const int64_t stride = (int64_t)gridDim.x * LEAN_THREADS;
+    // ---- FX: per-CTA scale of every double sum, from a sample of 640 rows spread over the whole batch ----
+    double fx_scale[NA > 0 ? NA : 1]; uint32_t fx_lo = 0, fx_ext = 0;
+    __shared__ uint32_t fx_emax[4];
+    __shared__ int32_t fx_F[4];
+    if constexpr (FX) {
+        fx_ext = smem_addr(smem_raw) + a.fx_ext_off;
+        if (threadIdx.x < 4) fx_emax[threadIdx.x] = 0u;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)NA * tcap; i += LEAN_THREADS) sts32(fx_ext + i * 4u, 0u);
+        __syncthreads();
+        const int64_t srow = (int64_t)((uint64_t)(blockIdx.x + (uint64_t)threadIdx.x * gridDim.x) * (uint64_t)a.nrows / ((uint64_t)gridDim.x * LEAN_THREADS));
+#pragma unroll
+        for (int s = 0; s < NA; s++) {
+            if (!acc_f64[s]) continue;
+            uint32_t e = (uint32_t)(__ldg((const unsigned long long*)vptr[s] + srow) >> 52) & 0x7FFu;
+            if (e == 0x7FFu) e = 0u;   // Inf / NaN say nothing about the scale (they take the exact path anyway)
+            e = __reduce_max_sync(0xFFFFFFFFu, e);
+            if (lane == 0) atomicMax(&fx_emax[s], e);
+        }
+        __syncthreads();
+        const uint64_t rows_cta = (uint64_t)((nquads + stride - 1) / stride) * (LEAN_THREADS * 4u) + 4u;   // rows this CTA can add to one slot
+        const int M = fx_magnitude_bits(rows_cta);
+        fx_lo = fx_floor_exp(M);
+#pragma unroll
+        for (int s = 0; s < NA; s++) {
+            const int F = fx_scale_exp(M, fx_emax[s]);
+            fx_scale[s] = fx_pow2(F);
+            if (threadIdx.x == 0) fx_F[s] = F;
+        }
+    }
     int64_t q0 = (int64_t)blockIdx.x * LEAN_THREADS + warp * 32;
     uint32_t pr[NP > 0 ? NP : 1][4]; uint32_t kr[8]; uint64_t vr[NA > 0 ? NA : 1][4];
     auto issue_loads = [&](int64_t q) {
@@ -611,6 +694,22 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
 #pragma unroll
             for (int c = 0; c < NS; c++)
                 if (c != NP && valid[c]) nmask |= ((~((uint32_t)__ldg(valid[c] + (q >> 1)) >> ((q & 1) * 4))) & 0xFu) << (4 * c);
+        }
+    };
+    auto fx_finish = [&]() {   // FX: the limbs of every slot become the double the flush expects in the lane's word
+        if constexpr (FX) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < tcap; i += LEAN_THREADS) {
+#pragma unroll
+                for (int s = 0; s < NA; s++) {
+                    if (!acc_f64[s]) continue;
+                    const uint32_t word = acc_addr[s] + i * 16u;
+                    const long long top = (long long)lds64(word);                       // {mid, hi}: the sum in units of 2^-F
+                    const uint32_t ext = lds32(fx_ext + ((uint32_t)s * tcap + i) * 4u);   // units of 2^-(F+32)
+                    const double sum = fx_combine(top, ext, fx_F[s]);
+                    sts64(word, f64_bits(sum));
+                }
+            }
         }
     };
     if (q0 + lane < nquads) issue_loads(q0 + lane);
@@ -671,6 +770,14 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
                     int slot = -1;
                     if (k0 != EMPTY_KEY) slot = smem32_upsert1(keys_addr, cap_mask, k0, h >> hash_shift);
                     if (slot >= 0) {
+                      if constexpr (FX) {   // native 32-bit atomics only: row count, then two (rarely three) limbs per double sum
+                          reds_inc32(lanes_addr + slot * 16u);
+#pragma unroll
+                          for (int s = 0; s < NA; s++) {
+                              if (acc_f64[s]) fx_add(a, acc_addr[s] + slot * 16u, fx_ext + ((uint32_t)s * tcap + slot) * 4u, fx_scale[s], fx_lo, k0, a.vops[s].glob_lane[0], v[s]);
+                              else smem32_add_u64(acc_addr[s] + slot * 16u, v[s]);
+                          }
+                      } else {
                         reds_inc32(lanes_addr + slot * 16u);
                         int first = 0;
                         if (pair2) {
@@ -690,6 +797,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
                             if (s < first) continue;
                             if (acc_f64[s]) smem32_add_f64(acc_addr[s] + slot * 16u, bits_f64(v[s])); else smem32_add_u64(acc_addr[s] + slot * 16u, v[s]);
                         }
+                      }
                     } else {
                         uint64_t key[2] = {k0, 0ull};
                         uint64_t gv[NA > 0 ? NA : 1];
@@ -741,6 +849,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
             __syncwarp();
             q0 += stride;
         }
+        fx_finish();
         smem_table_flush(st, a);
         if (blockIdx.x == 0 && threadIdx.x < (a.nrows & 3)) passed += direct_tail_row<NP, NA, JOIN>(a, (a.nrows & ~(int64_t)3) + threadIdx.x);
 #pragma unroll
@@ -925,7 +1034,14 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
             int slot = -1;
             if (k0 != EMPTY_KEY) slot = smem32_upsert1(keys_addr, cap_mask, k0, h >> hash_shift);
             if (slot >= 0) {
-                {
+                if constexpr (FX) {   // native 32-bit atomics only: row count, then two (rarely three) limbs per double sum
+                    reds_inc32(lanes_addr + slot * 16u);
+#pragma unroll
+                    for (int s = 0; s < NA; s++) {
+                        if (acc_f64[s]) fx_add(a, acc_addr[s] + slot * 16u, fx_ext + ((uint32_t)s * tcap + slot) * 4u, fx_scale[s], fx_lo, k0, a.vops[s].glob_lane[0], v[s]);
+                        else smem32_add_u64(acc_addr[s] + slot * 16u, v[s]);
+                    }
+                } else {
                     reds_inc32(lanes_addr + slot * 16u);   // pair 0, half 0 = row count
                     if (NULLS) {
 #pragma unroll
@@ -976,6 +1092,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
         if (last) break;
         q0 += stride;
     }
+    fx_finish();
     smem_table_flush(st, a);
     if (blockIdx.x == 0 && threadIdx.x < (a.nrows & 3)) passed += direct_tail_row<NP, NA, JOIN>(a, (a.nrows & ~(int64_t)3) + threadIdx.x);
 #pragma unroll
@@ -1135,6 +1252,15 @@ static inline cudaError_t launch_direct(const AggArgs& a, int sm_count, size_t s
                 cudaError_t e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
                 k_agg_group_lean<NP, NA, false, true><<<direct_grid(k_agg_group_lean<NP, NA, false, true>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
+            }
+            else if (NA >= 1 && a.lean_fx) {   // double sums as fixed-point limbs (native 32-bit shared atomics)
+                if constexpr (NA >= 1) {
+                    cudaError_t e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_agg_group_lean<NP, NA, true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return e;
+                    if (a.jp.mode) k_agg_group_lean<NP, NA, true, false, false, false, true><<<direct_grid(k_agg_group_lean<NP, NA, true, false, false, false, true>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
+                    else k_agg_group_lean<NP, NA, false, false, false, false, true><<<direct_grid(k_agg_group_lean<NP, NA, false, false, false, false, true>, smem, sm_count, a.nrows, LEAN_THREADS), LEAN_THREADS, smem, s>>>(a);
+                }
             }
             else if (a.jp.mode) k_agg_group_lean<NP, NA, true><<<grid, LEAN_THREADS, smem, s>>>(a);
             else if (NA <= 2 && a.lean_bank) {

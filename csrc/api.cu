@@ -109,6 +109,7 @@ struct bkgpu_plan {
     int join_pipeline = 0;        // opt-in: the fused probe issues its lookups one drain ahead (measured equal: the kernel is shared-memory bound, profiles/r02_join_history.md)
     int join_learn_range = 1;     // a re-run plan builds with the key range it saw before (checked by the build kernel): -0.05 ms per C3 request
     int lean_bank = 0;            // opt-in: bank-aware dealing of the lean kernel's drain (agg_direct.cuh, BANK)
+    int lean_fx = [] { const char* e = getenv("BKGPU_LEAN_FX"); return e ? atoi(e) != 0 : BK_LEAN_FX_DEFAULT; }();   // double sums as fixed-point limbs with native shared atomics (agg_direct.cuh, FX); option lean_fx
     int blocking_sync = -1; bool blocking_wait = false; cudaEvent_t wait_event = nullptr;   // see agg_finish
     bool jf_learned = false; uint64_t jf_learn_min = 0, jf_learn_max = 0;   // key range of the plan's previous build (skips the min/max pass + round trip)
     JoinProbe jp{}; uint32_t* jp_attr = nullptr; uint64_t* jp_packed = nullptr; int jp_key_pos = 0;   // ... fused into the lean aggregate
@@ -302,6 +303,7 @@ extern "C" int bkgpu_set_option(bkgpu_plan* p, const char* key, int64_t v) {
     else if (k == "no_stream_copy") p->no_stream_copy = v != 0;
     else if (k == "join_pipeline") p->join_pipeline = v != 0;
     else if (k == "lean_bank") p->lean_bank = v != 0;
+    else if (k == "lean_fx") p->lean_fx = v != 0;
     else if (k == "blocking_sync") p->blocking_sync = (int)v;
     else if (k == "join_learn_range") p->join_learn_range = v != 0;
     else if (k == "no_lean") p->no_lean = v != 0;
@@ -489,6 +491,11 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
             if (a.n_smem_lanes < 2) a.n_smem_lanes = 2;
             a.smem_cap_log2 = pick_smem_log2(p, a.n_smem_lanes, true, na);
             if (a.smem_cap_log2 <= 0) { a.lean = 0; a.smem_paired = 0; return p->fail(BKGPU_ENOMEM, "lean kernel: shared table does not fit"); }
+            // FX: plain batches (no NULLs, no MIN / MAX) with at least one double sum, when the extension limbs fit beside table and queues
+            if (p->lean_fx && !p->lean_bank && !mm && !any_valid && nf64 >= 1 && nrows < ((int64_t)1 << 31)) {
+                const size_t base = direct_smem_bytes(a.smem_keyw, a.n_smem_lanes, a.smem_cap_log2, na);
+                if (base + fx_ext_bytes(na, a.smem_cap_log2) <= (size_t)226 * 1024) { a.lean_fx = 1; a.fx_ext_off = (uint32_t)base; }
+            }
 
         }
     }
@@ -538,7 +545,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
         cudaError_t e = launch_agg(b, direct, p->sm_count, p->stream, &name);
         timer_end(p, ep);
         if (e != cudaSuccess) return p->cuda_fail(e, "launch_agg");
-        snprintf(p->stats.main_kernel_name, sizeof p->stats.main_kernel_name, "%s", b.wp && direct ? "k_agg_group_wp" : (b.lean && direct ? "k_agg_group_lean" : name));
+        snprintf(p->stats.main_kernel_name, sizeof p->stats.main_kernel_name, "%s", b.wp && direct ? "k_agg_group_wp" : (b.lean && direct ? (b.lean_fx ? "k_agg_group_lean_fx" : "k_agg_group_lean") : name));
         p->stats.kernel_launches++;
     }
     return BKGPU_OK;

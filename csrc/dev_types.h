@@ -31,6 +31,9 @@ constexpr int DIRECT_THREADS = BK_DIRECT_THREADS;
 #define BK_LEAN_THREADS 640       // the lean kernel fits 96 registers: 20 warps per SM measured best (512: -2 %, 768: spills)
 #endif
 constexpr int LEAN_THREADS = BK_LEAN_THREADS;
+#ifndef BK_LEAN_FX_DEFAULT
+#define BK_LEAN_FX_DEFAULT 0      // 1 = the lean kernel's FX variant (fixed-point double sums) is the default; environment BKGPU_LEAN_FX and option lean_fx override
+#endif
 
 struct DevCol {
     const void* values;

@@ -5,7 +5,7 @@ import pytest
 from baikaldb_b200 import datagen, plan as P, queries
 from baikaldb_b200.column import make_column
 from baikaldb_b200.plan import PrimitiveType as T
-from tests.util import run_both
+from tests.util import LEAN_KERNELS, run_both
 
 pytestmark = pytest.mark.gpu
 
@@ -25,9 +25,9 @@ def test_c1_count_where():
 def test_c2_sizes(n, variant):
     """ragged sizes around the 4-rows-per-lane / 128-rows-per-warp boundaries: warp-private, lean and general direct kernels"""
     cols = datagen.c2_table(0, n, n_groups=50)
-    opts = {"wp": {"use_wp": 1}, "lean": {}, "direct": {"no_lean": 1}, "bank": {"lean_bank": 1}}[variant]
+    opts = {"wp": {"use_wp": 1}, "lean": {}, "direct": {"no_lean": 1}, "bank": {"lean_bank": 1, "lean_fx": 0}}[variant]
     _, stats, _ = run_both(queries.c2_filter_groupby(), cols, keys=["0_1"], options=opts)
-    assert stats.main_kernel_name.decode() == {"wp": "k_agg_group_wp", "lean": "k_agg_group_lean", "direct": "k_agg_group_direct", "bank": "k_agg_group_lean"}[variant]
+    assert stats.main_kernel_name.decode() in {"wp": ("k_agg_group_wp",), "lean": ("k_agg_group_lean", "k_agg_group_lean_fx"), "direct": ("k_agg_group_direct",), "bank": ("k_agg_group_lean",)}[variant]
 
 
 def test_lean_int64_key_and_integer_sums():
@@ -41,7 +41,7 @@ def test_lean_int64_key_and_integer_sums():
                  [P.slot_ref(0, 2, T.INT64)], aggs)
     pl = P.Plan(root, {0: [(1, T.INT32), (2, T.INT64), (3, T.DOUBLE), (4, T.INT64)], 1: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE, T.INT64, T.DOUBLE])})
     _, stats, _ = run_both(pl, cols, keys=["0_2"])
-    assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+    assert stats.main_kernel_name.decode() in LEAN_KERNELS
 
 
 @pytest.mark.parametrize("n", [3, 130, 70_001, 400_000])
@@ -61,7 +61,7 @@ def test_lean_kernel_with_null_predicate_and_value_columns(n, which):
         cols[3] = mk(cols[3], np.zeros(n, bool)); cols[2] = mk(cols[2], cols[0].values % 7 != 0)   # whole groups without a non-NULL input
     got, stats, _ = run_both(queries.c2_filter_groupby(), cols, keys=["0_1"])
     if n > 4:
-        assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+        assert stats.main_kernel_name.decode() in LEAN_KERNELS
     _, stats, _ = run_both(queries.c2_filter_groupby(), cols, keys=["0_1"], options={"no_lean_nulls": 1})
     if n > 4:
         assert stats.main_kernel_name.decode() == "k_agg_group_direct"
@@ -86,7 +86,7 @@ def test_lean_kernel_min_max_and_several_aggregates_per_column(n, nulls):
                        1: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE, T.DOUBLE, T.DOUBLE, T.INT64, T.INT64, T.UINT64, T.DOUBLE, T.DOUBLE])})
     _, stats, _ = run_both(pl, cols, keys=["0_1"])
     if n > 4:
-        assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+        assert stats.main_kernel_name.decode() in LEAN_KERNELS
     _, stats, _ = run_both(pl, cols, keys=["0_1"], options={"no_lean_mm": 1})
     if n > 4:
         assert stats.main_kernel_name.decode() == "k_agg_group_direct"

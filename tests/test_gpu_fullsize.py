@@ -4,6 +4,8 @@ is checked against an independent torch computation on the same columns — coun
 double sums within the north star's 1e-6 relative.  C1 100M rows, C2 100M, C3 100M x 10M, C5 125M (one GPU's region)."""
 import numpy as np
 import pytest
+
+from tests.util import LEAN_KERNELS
 import torch
 
 from baikaldb_b200 import _lib, datagen, queries
@@ -46,7 +48,7 @@ def test_c2_full_size_groupby():
     a, ca = _gen(0, 3, T.DOUBLE, 1, 2, 3, n)
     b, cb = _gen(0, 4, T.DOUBLE, 2, 2, 4, n, scale=datagen.NORMAL_SCALE_1E3)
     got, stats = execute(queries.c2_filter_groupby(), [ck, cf, ca, cb], options={"group_capacity_log2": 14})
-    assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+    assert stats.main_kernel_name.decode() in LEAN_KERNELS
     m = flt < (1 << 19)
     k64 = key[m].to(torch.int64)
     cnt = torch.bincount(k64, minlength=g)
@@ -70,7 +72,7 @@ def test_c3_full_size_join_groupby():
     pk, cpk = _gen(1, 1, T.INT32, datagen.DIST_PERMUTATION, 3, 11, nd, hi=nd)
     attr, cattr = _gen(1, 2, T.INT32, 0, 3, 12, nd, 0, g)
     got, stats = execute(queries.c3_join_groupby(), [[cpk, cattr], [cfk, cv]], options={"group_capacity_log2": 14})
-    assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")                                      # probe fused into the aggregate
+    assert stats.main_kernel_name.decode() in LEAN_KERNELS                                      # probe fused into the aggregate
     attr_of_key = torch.empty(nd, dtype=torch.int64, device="cuda")
     attr_of_key[pk.to(torch.int64)] = attr.to(torch.int64)                                            # pk is a permutation of [0, nd)
     grp = attr_of_key[fk.to(torch.int64)]

@@ -5,7 +5,7 @@ import pytest
 from baikaldb_b200 import datagen, plan as P, queries
 from baikaldb_b200.column import make_column
 from baikaldb_b200.plan import PrimitiveType as T
-from tests.util import run_both
+from tests.util import LEAN_KERNELS, run_both
 
 pytestmark = pytest.mark.gpu
 
@@ -15,10 +15,10 @@ def test_c3_join_groupby():
     got, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact])
     assert len(got[0]) == 100
     # unique build keys: the lean aggregate kernel looks the GROUP BY attribute up through the foreign key itself
-    assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+    assert stats.main_kernel_name.decode() in LEAN_KERNELS
     # ... or, with the fused probe switched off, reads build columns gathered to probe-row alignment
     _, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact], options={"no_fused_probe": 1})
-    assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+    assert stats.main_kernel_name.decode() in LEAN_KERNELS
     _, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact], options={"force_generic": 1})
     assert stats.main_kernel_name.decode() == "k_agg_interp"
 
@@ -33,11 +33,11 @@ def test_join_fast_path_sparse_keys_and_unmatched_rows():
     fk = pk[rng.integers(0, nd, nf)]
     fact_all = [make_column(0, 1, T.INT32, fk), make_column(0, 2, T.DOUBLE, rng.random(nf))]
     _, stats, _ = run_both(queries.c3_join_groupby(), fact_all + dim, keys=["1_2"], batches=[dim, fact_all])
-    assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+    assert stats.main_kernel_name.decode() in LEAN_KERNELS
     fk2 = fk.copy(); fk2[::1000] = 5                                   # 5 is not a build key
     fact_miss = [make_column(0, 1, T.INT32, fk2), make_column(0, 2, T.DOUBLE, fact_all[1].values)]
     _, stats, _ = run_both(queries.c3_join_groupby(), fact_miss + dim, keys=["1_2"], batches=[dim, fact_miss])
-    assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+    assert stats.main_kernel_name.decode() in LEAN_KERNELS
     _, stats, _ = run_both(queries.c3_join_groupby(), fact_miss + dim, keys=["1_2"], batches=[dim, fact_miss], options={"no_fused_probe": 1})
     assert stats.main_kernel_name.decode() == "k_agg_interp"
 
@@ -54,7 +54,7 @@ def test_join_fused_probe_dense_with_gaps_negative_keys_and_ragged_tail(nf):
     fact = [make_column(0, 1, T.INT32, fk), make_column(0, 2, T.DOUBLE, rng.random(nf))]
     _, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact])
     if nf > 4:
-        assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+        assert stats.main_kernel_name.decode() in LEAN_KERNELS
     run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], batches=[dim, fact], options={"join_pipeline": 1})   # the pipelined probe (opt-in)
 
 
@@ -118,7 +118,7 @@ def test_fused_probe_with_a_fact_side_filter(nf):
     pl = P.Plan(P.agg(j, 2, [P.slot_ref(1, 2, T.INT32)], aggs), {0: [(1, T.INT32), (2, T.DOUBLE), (3, T.INT32)], 1: [(1, T.INT32), (2, T.INT32)],
                                                                     2: P.agg_tuple_slots(aggs, [T.INT64, T.DOUBLE])})
     _, stats, _ = run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact])
-    assert stats.main_kernel_name.decode() in ("k_agg_group_lean", "k_agg_group_wp")
+    assert stats.main_kernel_name.decode() in LEAN_KERNELS
     run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact], options={"no_fused_probe": 1})
     run_both(pl, fact + dim, keys=["1_2"], batches=[dim, fact], options={"join_pipeline": 1})
 

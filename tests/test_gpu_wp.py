@@ -51,7 +51,7 @@ def test_wp_second_run_uses_learned_cardinality(n_groups):
             assert_same_rows(got, want.columns, ["0_1"])
             # (3000 groups x 8 warp tables do not fit 227 KB: once the cardinality is known a CTA-shared-table kernel takes over)
             name = node.stats().main_kernel_name.decode()
-            assert name == WP if (n_groups <= 1000 or run == 0) else name in ("k_agg_group_lean", "k_agg_group_direct")
+            assert name == WP if (n_groups <= 1000 or run == 0) else name in ("k_agg_group_lean", "k_agg_group_lean_fx", "k_agg_group_direct")
     finally:
         node.close(st)
 
