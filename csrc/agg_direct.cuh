@@ -569,6 +569,29 @@ __device__ __forceinline__ void fx_add(const AggArgs& a, uint32_t word, uint32_t
         if (h) reds_add32(word + 4u, h);
     } else if (kind == FX_EXACT) global_add_f64(a, k0, glob_lane, bits_f64(vbits));
 }
+#ifndef BK_FX_PAIR
+#define BK_FX_PAIR 1
+#endif
+// two double sums of one row: when both values are main values (the common case by construction of the scale) their two chains
+// DMUL -> F2I -> ATOMS.ADD -> carry -> RED run interleaved in ONE branch region; anything else takes fx_add per value
+__device__ __forceinline__ void fx_add2(const AggArgs& a, uint32_t word0, uint32_t word1, uint32_t ext0, uint32_t ext1, double scale0, double scale1, uint32_t fx_lo,
+                                        uint64_t k0, int glob_lane0, int glob_lane1, uint64_t v0, uint64_t v1) {
+    if (BK_FX_PAIR) {
+        const double y0 = bits_f64(v0) * scale0, y1 = bits_f64(v1) * scale1;
+        const uint32_t d0 = ((fx_hi_word(y0) >> 20) & 0x7FFu) - fx_lo - (uint32_t)FX_FINE_BINADES;
+        const uint32_t d1 = ((fx_hi_word(y1) >> 20) & 0x7FFu) - fx_lo - (uint32_t)FX_FINE_BINADES;
+        if ((d0 < (uint32_t)FX_MAIN_BINADES) & (d1 < (uint32_t)FX_MAIN_BINADES)) {
+            const long long f0 = fx_round(y0), f1 = fx_round(y1);
+            const uint32_t l0 = (uint32_t)f0, l1 = (uint32_t)f1;
+            const uint32_t o0 = atoms_add32(word0, l0), o1 = atoms_add32(word1, l1);
+            reds_add32(word0 + 4u, (uint32_t)((uint64_t)f0 >> 32) + ((o0 + l0) < o0 ? 1u : 0u));
+            reds_add32(word1 + 4u, (uint32_t)((uint64_t)f1 >> 32) + ((o1 + l1) < o1 ? 1u : 0u));
+            return;
+        }
+    }
+    fx_add(a, word0, ext0, scale0, fx_lo, k0, glob_lane0, v0);
+    fx_add(a, word1, ext1, scale1, fx_lo, k0, glob_lane1, v1);
+}
 
 // ------------------------------------------------------------------------------------------
 // GROUP BY one column, LEAN shape — what the headline query (config C2/C4) and most star-schema
@@ -645,6 +668,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
     const int64_t stride = (int64_t)gridDim.x * LEAN_THREADS;
     // ---- FX: per-CTA scale of every double sum, from a sample of 640 rows spread over the whole batch ----
     double fx_scale[NA > 0 ? NA : 1]; uint32_t fx_lo = 0, fx_ext = 0;
+    const bool fx_pair = FX && NA == 2 && acc_f64[0] && acc_f64[NA > 1 ? 1 : 0];   // both value columns feed double sums: fx_add2
     __shared__ uint32_t fx_emax[4];
     __shared__ int32_t fx_F[4];
     if constexpr (FX) {
@@ -772,6 +796,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
                     if (slot >= 0) {
                       if constexpr (FX) {   // native 32-bit atomics only: row count, then two (rarely three) limbs per double sum
                           reds_inc32(lanes_addr + slot * 16u);
+if (NA == 2 && fx_pair) fx_add2(a, acc_addr[0] + slot * 16u, acc_addr[NA > 1 ? 1 : 0] + slot * 16u, fx_ext + slot * 4u, fx_ext + (tcap + slot) * 4u,
+                                                          fx_scale[0], fx_scale[NA > 1 ? 1 : 0], fx_lo, k0, a.vops[0].glob_lane[0], a.vops[NA > 1 ? 1 : 0].glob_lane[0], v[0], v[NA > 1 ? 1 : 0]);
+                          else
 #pragma unroll
                           for (int s = 0; s < NA; s++) {
                               if (acc_f64[s]) fx_add(a, acc_addr[s] + slot * 16u, fx_ext + ((uint32_t)s * tcap + slot) * 4u, fx_scale[s], fx_lo, k0, a.vops[s].glob_lane[0], v[s]);
@@ -1036,6 +1063,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
             if (slot >= 0) {
                 if constexpr (FX) {   // native 32-bit atomics only: row count, then two (rarely three) limbs per double sum
                     reds_inc32(lanes_addr + slot * 16u);
+if (NA == 2 && fx_pair) fx_add2(a, acc_addr[0] + slot * 16u, acc_addr[NA > 1 ? 1 : 0] + slot * 16u, fx_ext + slot * 4u, fx_ext + (tcap + slot) * 4u,
+                                                    fx_scale[0], fx_scale[NA > 1 ? 1 : 0], fx_lo, k0, a.vops[0].glob_lane[0], a.vops[NA > 1 ? 1 : 0].glob_lane[0], v[0], v[NA > 1 ? 1 : 0]);
+                    else
 #pragma unroll
                     for (int s = 0; s < NA; s++) {
                         if (acc_f64[s]) fx_add(a, acc_addr[s] + slot * 16u, fx_ext + ((uint32_t)s * tcap + slot) * 4u, fx_scale[s], fx_lo, k0, a.vops[s].glob_lane[0], v[s]);

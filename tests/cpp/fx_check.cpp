@@ -119,7 +119,22 @@ int main() {
         for (int i = 0; i < 700000; i++) add(u, -big, sc, lo0);
         check(fabs(total(u, F) + 700000.0 * big) <= 700000.0 * big * 1e-9, "700k additions of the most negative value stay in range");
     }
+    check(fx_magnitude_bits(1) == FX_MAX_M && fx_magnitude_bits(2564) == FX_MAX_M && fx_magnitude_bits((uint64_t)1 << 40) == 21, "magnitude bits: capped for small launches");
+    {   // a small launch (few rows per CTA): the largest fine value times 2^32 must still round inside 63 bits
+        const int M = fx_magnitude_bits(2564); const int F = fx_scale_exp(M, 1022); const double sc = fx_pow2(F); const uint32_t lo0 = fx_floor_exp(M);
+        uint32_t lo; uint64_t up;
+        const double top_fine = ldexp(1.0 - ldexp(1.0, -53), M - FX_MAIN_BINADES - F);   // just below the main range's floor
+        check(fx_split(top_fine, sc, lo0, lo, up) == FX_FINE && fx_split(-top_fine, sc, lo0, lo, up) == FX_FINE, "largest fine value");
+        for (double x : {top_fine, -top_fine, top_fine / 3, -top_fine / 7}) {
+            Slot s; add(s, x, sc, lo0);
+            check(fabs(total(s, F) - x) <= ldexp(fabs(x), -40), "fine values of a small launch survive the second scaling");
+        }
+    }
     std::vector<double> v(N);
+    for (auto& x : v) x = nd(rng) * 1e3;
+    run_case("N(0, 1) * 1e3, small launch", v, 37, 2564, 20);
+    for (auto& x : v) x = exp(nd(rng) * 6.0) * ((rng() & 1) ? 1.0 : -1.0);
+    run_case("+-lognormal sigma 6, small launch", v, 37, 2564, 21);
     for (auto& x : v) x = ud(rng);
     run_case("uniform [0, 1)  (C2's 0_3)", v, 1000, 700000, 1);
     for (auto& x : v) x = nd(rng) * 1e3;
