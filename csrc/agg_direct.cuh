@@ -540,7 +540,15 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 // (AggFnCall::update's `add` is a sequential double add, agg_fn_call.cpp:496-555; any parallel order already differs from it in the
 // last bits.)
 // ------------------------------------------------------------------------------------------
-static __device__ __noinline__ void global_add_f64(const AggArgs& a, uint64_t k0, int glob_lane, double x) {
+#ifndef BK_FX_EXACT_INLINE
+#define BK_FX_EXACT_INLINE 1   // the rare exact path inlined: a call in the drain loop makes ptxas keep a loaded column in local memory (24-68 bytes of spills)
+#endif
+#if BK_FX_EXACT_INLINE
+static __device__ __forceinline__ void global_add_f64(const AggArgs& a, uint64_t k0, int glob_lane, double x)
+#else
+static __device__ __noinline__ void global_add_f64(const AggArgs& a, uint64_t k0, int glob_lane, double x)
+#endif
+{
     const AggPlan& ap = a.plan;
     const GroupTable& gt = a.gt;
     const uint32_t gcap = gt.cap_mask + 1;
@@ -552,6 +560,12 @@ static __device__ __noinline__ void global_add_f64(const AggArgs& a, uint64_t k0
     lane_atomic<false>(LN_ADD_F64, gt.lanes + (size_t)glob_lane * gcap + slot, f64_bits(x));
 }
 __device__ __forceinline__ void reds_add32(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+#ifndef BK_FX_PAIR
+#define BK_FX_PAIR 0      // 1 = fx_add2's interleaved pair path (measured SLOWER: 0.553 vs 0.462 ms on C2, its registers push a loaded column into local memory)
+#endif
+#ifndef BK_FX_HI_ALWAYS
+#define BK_FX_HI_ALWAYS 0
+#endif
 // one value into the fixed-point limbs of `slot`: word = shared address of the slot's {mid, hi} pair, ext = of its low-extension limb
 __device__ __forceinline__ void fx_add(const AggArgs& a, uint32_t word, uint32_t ext, double scale, uint32_t fx_lo, uint64_t k0, int glob_lane, uint64_t vbits) {
     uint32_t lo; uint64_t up;
@@ -559,7 +573,7 @@ __device__ __forceinline__ void fx_add(const AggArgs& a, uint32_t word, uint32_t
     if (kind == FX_MAIN) {
         const uint32_t old = atoms_add32(word, lo);
         const uint32_t h = (uint32_t)up + ((old + lo) < old ? 1u : 0u);
-        if (h) reds_add32(word + 4u, h);
+        if (BK_FX_HI_ALWAYS || h) reds_add32(word + 4u, h);
     } else if (kind == FX_FINE) {
         const uint32_t old = atoms_add32(ext, lo);
         const uint64_t t = up + ((old + lo) < old ? 1u : 0u);   // sign-extended upper part + carry
@@ -569,9 +583,6 @@ __device__ __forceinline__ void fx_add(const AggArgs& a, uint32_t word, uint32_t
         if (h) reds_add32(word + 4u, h);
     } else if (kind == FX_EXACT) global_add_f64(a, k0, glob_lane, bits_f64(vbits));
 }
-#ifndef BK_FX_PAIR
-#define BK_FX_PAIR 1
-#endif
 // two double sums of one row: when both values are main values (the common case by construction of the scale) their two chains
 // DMUL -> F2I -> ATOMS.ADD -> carry -> RED run interleaved in ONE branch region; anything else takes fx_add per value
 __device__ __forceinline__ void fx_add2(const AggArgs& a, uint32_t word0, uint32_t word1, uint32_t ext0, uint32_t ext1, double scale0, double scale1, uint32_t fx_lo,

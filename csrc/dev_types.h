@@ -32,7 +32,7 @@ constexpr int DIRECT_THREADS = BK_DIRECT_THREADS;
 #endif
 constexpr int LEAN_THREADS = BK_LEAN_THREADS;
 #ifndef BK_LEAN_FX_DEFAULT
-#define BK_LEAN_FX_DEFAULT 0      // 1 = the lean kernel's FX variant (fixed-point double sums) is the default; environment BKGPU_LEAN_FX and option lean_fx override
+#define BK_LEAN_FX_DEFAULT 1      // 1 = the lean kernel's FX variant (fixed-point double sums) is the default; environment BKGPU_LEAN_FX and option lean_fx override
 #endif
 
 struct DevCol {
