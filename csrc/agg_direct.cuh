@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 // last bits.)
 // ------------------------------------------------------------------------------------------
 #ifndef BK_FX_EXACT_INLINE
-#define BK_FX_EXACT_INLINE 1   // the rare exact path inlined: a call in the drain loop makes ptxas keep a loaded column in local memory (24-68 bytes of spills)
+#define BK_FX_EXACT_INLINE 0   // 1 = the rare exact path inlined: no spills (the call costs 24 bytes of them) but measured SLOWER, 0.607 vs 0.462 ms on C2: the loop outgrows the instruction cache
 #endif
 #if BK_FX_EXACT_INLINE
 static __device__ __forceinline__ void global_add_f64(const AggArgs& a, uint64_t k0, int glob_lane, double x)
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
     const int64_t stride = (int64_t)gridDim.x * LEAN_THREADS;
     // ---- FX: per-CTA scale of every double sum, from a sample of 640 rows spread over the whole batch ----
     double fx_scale[NA > 0 ? NA : 1]; uint32_t fx_lo = 0, fx_ext = 0;
-    const bool fx_pair = FX && NA == 2 && acc_f64[0] && acc_f64[NA > 1 ? 1 : 0];   // both value columns feed double sums: fx_add2
+    const bool fx_pair = BK_FX_PAIR && FX && NA == 2 && acc_f64[0] && acc_f64[NA > 1 ? 1 : 0];   // both value columns feed double sums: fx_add2
     __shared__ uint32_t fx_emax[4];
     __shared__ int32_t fx_F[4];
     if constexpr (FX) {
