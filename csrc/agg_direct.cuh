@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) k_agg_group_lean(const __grid
         }
         __syncthreads();
         const uint64_t rows_cta = (uint64_t)((nquads + stride - 1) / stride) * (LEAN_THREADS * 4u) + 4u;   // rows this CTA can add to one slot
-        const int M = fx_magnitude_bits(rows_cta);
+        const int M = fx_magnitude_bits(rows_cta | FX_MIN_ROWS);   // <= FX_MAX_M
         fx_lo = fx_floor_exp(M);
 #pragma unroll
         for (int s = 0; s < NA; s++) {

@@ -51,7 +51,7 @@ static void check(bool ok, const char* what) { if (!ok) { fails++; printf("FAIL 
 // one column of values summed into `groups` slots; reference = long double sum (64-bit mantissa) per group
 static void run_case(const char* name, std::vector<double> v, int groups, uint64_t rows_cta, unsigned seed) {
     std::mt19937_64 rng(seed);
-    const int M = fx_magnitude_bits(rows_cta);
+    const int M = fx_magnitude_bits(rows_cta | FX_MIN_ROWS);
     const uint32_t emax = sample_emax(v, std::min<size_t>(640, v.size()));
     const int F = fx_scale_exp(M, emax);
     const double scale = fx_pow2(F);
@@ -90,7 +90,7 @@ int main() {
     const size_t N = 2000000;
     // classification of the special values
     {
-        const int M = fx_magnitude_bits(700000); const int F = fx_scale_exp(M, 1022); const double sc = fx_pow2(F); const uint32_t lo0 = fx_floor_exp(M);
+        const int M = fx_magnitude_bits(700000 | FX_MIN_ROWS); const int F = fx_scale_exp(M, 1022); const double sc = fx_pow2(F); const uint32_t lo0 = fx_floor_exp(M);
         uint32_t lo; uint64_t up;
         check(M == 42, "700k rows per CTA leave 42 magnitude bits");
         check(fx_split(0.0, sc, lo0, lo, up) == FX_ZERO && fx_split(-0.0, sc, lo0, lo, up) == FX_ZERO, "zeros add nothing");
@@ -119,9 +119,9 @@ int main() {
         for (int i = 0; i < 700000; i++) add(u, -big, sc, lo0);
         check(fabs(total(u, F) + 700000.0 * big) <= 700000.0 * big * 1e-9, "700k additions of the most negative value stay in range");
     }
-    check(fx_magnitude_bits(1) == FX_MAX_M && fx_magnitude_bits(2564) == FX_MAX_M && fx_magnitude_bits((uint64_t)1 << 40) == 21, "magnitude bits: capped for small launches");
+    check(fx_magnitude_bits(1 | FX_MIN_ROWS) == FX_MAX_M && fx_magnitude_bits(2564 | FX_MIN_ROWS) == FX_MAX_M && fx_magnitude_bits(((uint64_t)1 << 40) | FX_MIN_ROWS) == 21, "magnitude bits: capped for small launches");
     {   // a small launch (few rows per CTA): the largest fine value times 2^32 must still round inside 63 bits
-        const int M = fx_magnitude_bits(2564); const int F = fx_scale_exp(M, 1022); const double sc = fx_pow2(F); const uint32_t lo0 = fx_floor_exp(M);
+        const int M = fx_magnitude_bits(2564 | FX_MIN_ROWS); const int F = fx_scale_exp(M, 1022); const double sc = fx_pow2(F); const uint32_t lo0 = fx_floor_exp(M);
         uint32_t lo; uint64_t up;
         const double top_fine = ldexp(1.0 - ldexp(1.0, -53), M - FX_MAIN_BINADES - F);   // just below the main range's floor
         check(fx_split(top_fine, sc, lo0, lo, up) == FX_FINE && fx_split(-top_fine, sc, lo0, lo, up) == FX_FINE, "largest fine value");
