@@ -108,6 +108,7 @@ struct bkgpu_plan {
     JoinFast jf{}; uint32_t* jf_dense = nullptr; uint64_t* jf_packed = nullptr;   // FK -> PK fast path (unique build keys)
     int join_pipeline = 0;        // opt-in: the fused probe issues its lookups one drain ahead (measured equal: the kernel is shared-memory bound, profiles/r02_join_history.md)
     int join_learn_range = 1;     // a re-run plan builds with the key range it saw before (checked by the build kernel): -0.05 ms per C3 request
+    int fx_off = 0;               // set when a finished request saw more than 1/64 of its surviving rows take FX's exact path (see agg_finish)
     int lean_bank = 0;            // opt-in: bank-aware dealing of the lean kernel's drain (agg_direct.cuh, BANK)
     int lean_fx = [] { const char* e = getenv("BKGPU_LEAN_FX"); return e ? atoi(e) != 0 : BK_LEAN_FX_DEFAULT; }();   // double sums as fixed-point limbs with native shared atomics (agg_direct.cuh, FX); option lean_fx
     int blocking_sync = -1; bool blocking_wait = false; cudaEvent_t wait_event = nullptr;   // see agg_finish
@@ -492,7 +493,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
             a.smem_cap_log2 = pick_smem_log2(p, a.n_smem_lanes, true, na);
             if (a.smem_cap_log2 <= 0) { a.lean = 0; a.smem_paired = 0; return p->fail(BKGPU_ENOMEM, "lean kernel: shared table does not fit"); }
             // FX: plain batches (no NULLs, no MIN / MAX) with at least one double sum, when the extension limbs fit beside table and queues
-            if (p->lean_fx && !p->lean_bank && !mm && !any_valid && nf64 >= 1 && nrows < ((int64_t)1 << 31)) {
+            if (p->lean_fx && !p->fx_off && !p->lean_bank && !mm && !any_valid && nf64 >= 1 && nrows < ((int64_t)1 << 31)) {
                 const size_t base = direct_smem_bytes(a.smem_keyw, a.n_smem_lanes, a.smem_cap_log2, na);
                 if (base + fx_ext_bytes(na, a.smem_cap_log2) <= (size_t)226 * 1024) { a.lean_fx = 1; a.fx_ext_off = (uint32_t)base; }
             }
@@ -1426,6 +1427,9 @@ static int agg_finish(bkgpu_plan* p) {
         }
         host_counts[0] = hc3[0]; host_counts[1] = hc3[1]; n_out = hc3[2]; merge_max = hc3[3];
         memcpy(&p->rows_passed_host, hc3 + 4, 8);
+        // FX: values beyond the sampled scale are added exactly, one global atomic each; a plan whose double columns keep producing many of them
+        // (a column spanning dozens of binades, outliers dominating the sample) goes back to the CAS kernel for its later launches
+        if (hc3[GT_FX_EXACT] > 4096 && (uint64_t)hc3[GT_FX_EXACT] * 64 > (uint64_t)std::max<int64_t>(p->rows_passed_host, 1)) p->fx_off = 1;
         if (p->peer_ready && p->h_pinned && p->h_pinned[6]) return p->fail(BKGPU_ENCCL, "peer merge: a rank did not publish its partial state within the time limit");
         if (rows_mode) {
             const uint32_t mx = merge_max;

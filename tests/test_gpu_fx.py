@@ -1,6 +1,8 @@
 """GPU parity of the lean kernel's FX variant (double sums as fixed-point limbs updated with native 32-bit shared atomics,
 csrc/agg_direct.cuh + csrc/fx.h) against the row-engine oracle, through the C ABI: value distributions that exercise the main / fine /
 exact classes, special values, group counts on both sides of the shared table's capacity, the fused join probe, and agreement with the CAS variant."""
+import os
+
 import numpy as np
 import pytest
 
@@ -149,3 +151,24 @@ def test_fx_fused_join_probe():
     fact = [make_column(0, 1, T.INT32, rng.integers(0, nd + 1000, nf)), make_column(0, 2, T.DOUBLE, rng.normal(size=nf) * 100)]
     _, stats, _ = run_both(queries.c3_join_groupby(), fact + dim, keys=["1_2"], options=FX, batches=[dim, fact])
     assert stats.main_kernel_name.decode() == NAME
+
+
+@pytest.mark.skipif(os.environ.get("BKGPU_UNVERIFIED") != "1", reason="written after round 2's last GPU window: not yet run on a GPU")
+def test_fx_plan_goes_back_to_cas_when_its_values_do_not_fit_one_scale():
+    """a reused plan (bkgpu_reset) whose double column puts most rows on FX's exact path — outliers 1e18 times the bulk dominate the
+    sample — launches the CAS kernel from its second request on (the exact-path counter comes back with the counter block)"""
+    from baikaldb_b200.exec_node import ColumnSource, GpuExecNode, RowBatch, RuntimeState
+    rng = np.random.default_rng(3)
+    n = 300_000
+    cols = table(rng, n, 20, DISTS["outliers"](rng, n), rng.random(n))
+    st = RuntimeState(device=0, options=dict(FX))
+    node = GpuExecNode(); node.init(sum_plan()); node.add_child(ColumnSource([cols]))
+    assert node.open(st) == 0, st.error_msg
+    rb = RowBatch()
+    eos = False
+    while not eos:
+        _, eos = node.get_next(st, rb)
+    assert node.stats().main_kernel_name.decode() == NAME
+    node.reset(); node.push(cols); node.finish()
+    assert node.stats().main_kernel_name.decode() == "k_agg_group_lean"
+    node.close()
