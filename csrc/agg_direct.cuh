@@ -534,9 +534,10 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 1) k_agg_group_direct(const __
 //   fine  2^(M-47) <= |y| < 2^(M-15) : round(y * 2^32) added to {ext, mid, hi} (three limbs, same per-value precision),
 //   zero  nothing to add,
 //   else  (beyond the sampled range, denormal, Inf, NaN): an exact double add into the global table.
-// The sum of a group is therefore the exact sum of values rounded to at least M-15 = 27 significant bits each: independent of the
-// order of the rows (bit-reproducible from run to run, unlike the CAS path), error <= 2^-28 relative to sum(|x|) in the worst case,
-// against north_star's 1e-6.  At flush time the limbs become one double per lane and the table is merged as before.
+// A CTA's partial sum of a group is therefore the exact sum of values rounded to at least M-15 = 27 significant bits each — it does not
+// depend on the order in which the atomics land — with an error <= 2^-28 relative to sum(|x|) in the worst case, against north_star's
+// 1e-6.  At flush time the limbs become one double per lane and the table is merged as before (the CTAs' partial sums meet as doubles
+// in the global table: RED.E.ADD.F64).
 // (AggFnCall::update's `add` is a sequential double add, agg_fn_call.cpp:496-555; any parallel order already differs from it in the
 // last bits.)
 // ------------------------------------------------------------------------------------------
