@@ -495,7 +495,7 @@ static int launch_agg_batch(bkgpu_plan* p, const Compiled& c, const DevCol* cols
             // FX: plain batches (no NULLs, no MIN / MAX) with at least one double sum, when the extension limbs fit beside table and queues
             if (p->lean_fx && !p->fx_off && !p->lean_bank && !mm && !any_valid && nf64 >= 1 && nrows < ((int64_t)1 << 31)) {
                 const size_t base = direct_smem_bytes(a.smem_keyw, a.n_smem_lanes, a.smem_cap_log2, na);
-                if (base + fx_ext_bytes(na, a.smem_cap_log2) <= (size_t)224 * 1024)   // (227 KB per CTA less the kernel's 1 KB of static shared memory) { a.lean_fx = 1; a.fx_ext_off = (uint32_t)base; }
+                if (base + fx_ext_bytes(na, a.smem_cap_log2) <= (size_t)224 * 1024) { a.lean_fx = 1; a.fx_ext_off = (uint32_t)base; }   // (227 KB per CTA less the kernel's 1 KB of static shared memory)
             }
 
         }
