@@ -65,6 +65,21 @@ def test_oracle_known_answers():
     assert ev(P.cast_to_double(i64), T.DOUBLE) == [10.0, 20.0, 30.0, 40.0]
 
 
+def test_round_matches_the_references_known_answers():
+    """test/test_internal_functions.cpp:34-166 (TEST(round, round)): the twelve (value, decimals) -> result vectors of the reference's own
+    unit test, through the oracle's restatement of `round` (internal_functions.cpp) — decimals beyond the double's digits leave the value,
+    negative decimals round left of the point, |decimals| past the range gives 0"""
+    vectors = [(3.1356, None, 3.0), (3.1356, 0, 3.0), (3.1356, 2, 3.14), (3.1356, 1, 3.1), (123456.1356, 30, 123456.1356), (123456.1356, -1, 123460.0),
+               (123456.1356, -3, 123000.0), (123456.1356, -300, 0.0), (-3.1356, 2, -3.14), (-3.1356, 3, -3.136), (-123456.1356, -2, -123500.0),
+               (-123456.1356, -30, 0.0)]
+    for x, dec, want in vectors:
+        cols = [make_column(0, 1, T.INT32, [0]), make_column(0, 2, T.DOUBLE, [x]), make_column(0, 3, T.INT64, [0]), make_column(0, 4, T.UINT64, [0])]
+        e = P.round_(_c(2)) if dec is None else P.round_(_c(2), P.int_lit(dec))
+        got, pl, _ = _scalar_rows(e, T.DOUBLE, cols)
+        assert got == [want], (x, dec, got, want)
+        _lib.explain(pl.serialize())   # the library lowers the same fragment (host side: parse, type inference, bytecode)
+
+
 def test_oracle_known_answers_of_the_remaining_numeric_builtins():
     """sqrt / sign / ln / log / pow / mod / greatest / least / bit_count / pi / trigonometry (internal_functions.cpp:101-350): NULL outside
     the domain, DOUBLE arithmetic on get_numberic<double>() of the arguments"""
