@@ -108,6 +108,28 @@ def main():
     got5, _ = run_plan(queries.c5_topk(1000), mine, comm, dev, {"region_base": rank * n_region})
     want5 = oracle.execute(queries.c5_topk(1000).serialize(), whole5)
     assert_same_rows(got5, want5.columns, None)
+    # ---- f3 beyond aggregates: a REPARTITIONED JOIN — both inputs hash-partitioned on the join key over NCCL (baikaldb_b200/exchange.py), every
+    #      rank runs the ordinary AGG -> JOIN fragment over what it received, bkgpu_finish merges the partial aggregates.  The exchange and the
+    #      decomposition run on the CPU under gloo (tests/test_exchange_gloo.py); this CUDA / NCCL run was written after round 2's last GPU window
+    if os.environ.get("BKGPU_UNVERIFIED") == "1":
+        from baikaldb_b200 import exchange as ex
+        from baikaldb_b200.plan import PrimitiveType as T
+        rng = np.random.default_rng(7)
+        nd, nf = 50_000, 600_000
+        dim_all = [make_column(1, 1, T.INT32, rng.permutation(nd)), make_column(1, 2, T.INT32, rng.integers(0, 500, nd))]
+        fact_all = [make_column(0, 1, T.INT32, rng.integers(0, nd + 1000, nf)), make_column(0, 2, T.DOUBLE, rng.normal(size=nf) * 100)]
+        shard = lambda cols: [make_column(c.tuple_id, c.slot_id, c.prim_type, c.values[rank::world]) for c in cols]
+        db, fb = ex.batch_from_columns(shard(dim_all), device="cuda"), ex.batch_from_columns(shard(fact_all), device="cuda")
+        dim_mine = ex.exchange(db, ex.destination(db, [(1, 1)], world))
+        fact_mine = ex.exchange(fb, ex.destination(fb, [(0, 1)], world))
+        st_j = RuntimeState(device=dev, nccl_comm=comm.value, options={})
+        node_j = GpuExecNode(); node_j.init(queries.c3_join_groupby())
+        node_j.add_child(ColumnSource([ex.device_columns(dim_mine), ex.device_columns(fact_mine)]))
+        assert node_j.open(st_j) == 0, st_j.error_msg
+        rbj = RowBatch(); rc, _ = node_j.get_next(st_j, rbj)
+        assert rc == 0, st_j.error_msg
+        assert_same_rows(rbj.columns, oracle.execute(queries.c3_join_groupby().serialize(), fact_all + dim_all).columns, ["1_2"])
+        node_j.close(st_j)
     dist.barrier()
     _lib.lib().bkgpu_nccl_comm_destroy(comm)
     dist.destroy_process_group()
