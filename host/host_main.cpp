@@ -7,6 +7,8 @@
 //   bkgpu_host explain <c1|c2|c3|c5>                       bkgpu_plan_explain of it (no GPU needed)
 //   bkgpu_host run     <c1|c2|c3|c5> <rows> [batch_rows]   executes on cuda:0 and prints one result row per line
 //   bkgpu_host chunk   - <rows> [capacity]                   CPU only: rows -> Chunk -> column batches -> rows, checked value by value
+//   bkgpu_host strings -  <rows>                             CPU only: two fragments over STRING columns rewritten to dictionary codes
+//                                                           (bkgpu_dictionary.hpp): plan bytes + a hash of every code column, compared with dictionary.py's
 //   bkgpu_host rows    c2 <rows> [capacity]                 the same table fed ROW by row (MemRow-style values with NULLs every
 //                                                           17th key) through Chunk -> column batches -> GPU -> Chunk::to_rows
 #include <cinttypes>
@@ -14,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "bkgpu_host.hpp"
+#include "bkgpu_dictionary.hpp"
 
 using namespace bkgpu;
 
@@ -137,9 +140,65 @@ static void print_value(const Column& c, int64_t i) {
     }
 }
 
+// ------------------------------------------------------------------ strings (tests/test_host_cpp.py builds the same data and plans in Python)
+static std::vector<std::optional<std::string>> gen_strings(uint64_t seed, int64_t n, int domain, int null_every) {
+    std::vector<std::optional<std::string>> v((size_t)n);
+    uint64_t x = seed;
+    for (int64_t i = 0; i < n; i++) {
+        x = x * 6364136223846793005ull + 1442695040888963407ull;
+        const int idx = (int)((x >> 33) % (uint64_t)domain);
+        if (null_every && (x >> 20) % (uint64_t)null_every == 0) continue;
+        v[(size_t)i] = "s" + std::to_string((idx * 7) % domain);
+    }
+    return v;
+}
+static void print_encoded(const EncodedStrings& enc) {
+    for (uint8_t b : enc.plan.serialize()) printf("%02x", b);
+    printf("\n");
+    for (const auto& c : enc.columns) {
+        uint64_t h = 1469598103934665603ull; int64_t nulls = 0;
+        for (int64_t r = 0; r < c.length; r++) {
+            if (c.is_null(r)) { nulls++; continue; }
+            const uint32_t code = (uint32_t)c.at<int32_t>(r);
+            for (int b = 0; b < 4; b++) { h ^= (code >> (8 * b)) & 0xFF; h *= 1099511628211ull; }
+        }
+        printf("%d_%d rows=%" PRId64 " nulls=%" PRId64 " hash=%016" PRIx64 " dict=%zu\n", c.tuple_id, c.slot_id, c.length, nulls, h, enc.dictionaries.at({c.tuple_id, c.slot_id})->size());
+    }
+}
+static int strings_mode(int64_t rows) {
+    auto S = [](int t, int s) { return Expr::slot_ref(t, s, BK_STRING); };
+    {   // A: SELECT `0_1`, COUNT(*), MIN(`0_2`), MAX(`0_2`), COUNT(`0_2`) WHERE `0_3` >= 's2' AND 's30' > `0_3` AND `0_2` != 'zzz' AND `0_1` IN ('s1', 's5', 'nope') GROUP BY `0_1`
+        Plan p;
+        PlanNode f = where(scan(0), cmp(BK_FT_GE, "ge", S(0, 3), Expr::string_literal("s2")));
+        f.conjuncts.push_back(cmp(BK_FT_GT, "gt", Expr::string_literal("s30"), S(0, 3)));
+        f.conjuncts.push_back(cmp(BK_FT_NE, "ne", S(0, 2), Expr::string_literal("zzz")));
+        f.conjuncts.push_back(Expr::predicate(BK_IN_PREDICATE, BK_FT_IN, "in", {S(0, 1), Expr::string_literal("s1"), Expr::string_literal("s5"), Expr::string_literal("nope")}));
+        p.root = agg(std::move(f), 1, {S(0, 1)}, {Expr::agg("count_star", 1, 1, 1, {}), Expr::agg("min", 1, 2, 2, {S(0, 2)}), Expr::agg("max", 1, 3, 3, {S(0, 2)}), Expr::agg("count", 1, 4, 4, {S(0, 2)})});
+        p.tuples = {{0, {{1, BK_STRING}, {2, BK_STRING}, {3, BK_STRING}}}, {1, {{1, BK_INT64}, {2, BK_STRING}, {3, BK_STRING}, {4, BK_INT64}}}};
+        std::vector<StringColumn> cols = {{0, 1, gen_strings(11, rows, 37, 0)}, {0, 2, gen_strings(12, rows, 23, 9)}, {0, 3, gen_strings(13, rows, 41, 0)}};
+        print_encoded(encode_strings(p, cols));
+    }
+    {   // B: SELECT `1_2`, COUNT(*) FROM fact JOIN dim ON `1_1` = `0_1` GROUP BY `1_2`  (string join keys: one dictionary for both sides)
+        Plan p; PlanNode j; j.node_type = BK_JOIN_NODE; j.join_type = BK_INNER_JOIN;
+        j.children.push_back(scan(1)); j.children.push_back(scan(0));
+        j.conjuncts.push_back(cmp(BK_FT_EQ, "eq", S(1, 1), S(0, 1)));
+        p.root = agg(std::move(j), 2, {Expr::slot_ref(1, 2, BK_INT32)}, {Expr::agg("count_star", 2, 1, 1, {})});
+        p.tuples = {{0, {{1, BK_STRING}}}, {1, {{1, BK_STRING}, {2, BK_INT32}}}, {2, {{1, BK_INT64}}}};
+        std::vector<StringColumn> cols = {{0, 1, gen_strings(21, rows, 53, 13)}, {1, 1, gen_strings(22, rows / 4 + 1, 61, 0)}};
+        print_encoded(encode_strings(p, cols));
+    }
+    try {   // refused: SUM over a string
+        Plan p; p.root = agg(scan(0), 1, {}, {Expr::agg("sum", 1, 1, 1, {S(0, 1)})}); p.tuples = {{0, {{1, BK_STRING}}}, {1, {{1, BK_DOUBLE}}}};
+        encode_strings(p, {{0, 1, gen_strings(1, 4, 3, 0)}});
+        printf("NOT REFUSED\n"); return 1;
+    } catch (const Unsupported& e) { printf("refused: %s\n", e.what()); }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s plan|explain|run c1|c2|c3|c5 [rows] [batch_rows]\n", argv[0]); return 2; }
     std::string mode = argv[1], cfg = argv[2];
+    if (mode == "strings") return strings_mode(argc > 3 ? atoll(argv[3]) : 1000);
     Plan plan = cfg == "c1" ? plan_c1() : cfg == "c2" ? plan_c2() : cfg == "c3" ? plan_c3() : plan_c5();
     if (mode == "chunk") {   // CPU-only: rows -> Chunk -> column batches of `capacity` rows -> rows again (f1 adapter round trip)
         const int64_t rows = argc > 3 ? atoll(argv[3]) : 1000, capacity = argc > 4 ? atoll(argv[4]) : 64;

@@ -7,6 +7,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 from baikaldb_b200 import datagen, queries
@@ -136,3 +137,53 @@ def test_stream_copy_is_a_byte_exact_copy(tmp_path):
     subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "cpp", "stream_copy_check.cpp"), os.path.join(ROOT, "csrc", "hostcopy.cpp"), "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout + r.stderr
+
+
+def _gen_strings(seed, n, domain, null_every):
+    out, x = [], seed
+    for _ in range(n):
+        x = (x * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        idx = (x >> 33) % domain
+        if null_every and (x >> 20) % null_every == 0:
+            out.append(None)
+            continue
+        out.append(b"s" + str((idx * 7) % domain).encode())
+    return out
+
+
+def test_cpp_dictionary_adapter_matches_python(host_bin):
+    """host/bkgpu_dictionary.hpp (STRING columns as order-preserving dictionary codes, C++ side of the adapter) produces the same rewritten
+    plan bytes and the same code columns as baikaldb_b200/dictionary.py — whose rewrite tests/test_dictionary.py checks against pyarrow's
+    string kernels — on two fragments: filters + IN + GROUP BY + MIN / MAX / COUNT over strings, and a join on string keys"""
+    from baikaldb_b200 import dictionary as D, plan as P
+    from baikaldb_b200.plan import PrimitiveType as T
+    rows = 3000
+    out = subprocess.run([host_bin, "strings", "-", str(rows)], capture_output=True, text=True, check=True).stdout.splitlines()
+    S = lambda t, s: P.slot_ref(t, s, T.STRING)
+
+    def fnv(col):
+        h = 1469598103934665603
+        ok = np.ones(len(col), bool) if col.valid is None else col.valid
+        for code in np.asarray(col.values, dtype=np.uint32)[ok].tolist():
+            for b in range(4):
+                h = ((h ^ ((code >> (8 * b)) & 0xFF)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    def lines(enc):
+        res = [enc.plan.serialize().hex()]
+        for c in enc.columns:
+            nulls = 0 if c.valid is None else int((~c.valid).sum())
+            res.append(f"{c.name} rows={len(c)} nulls={nulls} hash={fnv(c):016x} dict={len(enc.dictionaries[(c.tuple_id, c.slot_id)])}")
+        return res
+
+    aggs = [P.agg_expr("count_star", 1, 1), P.agg_expr("min", 1, 2, None, S(0, 2)), P.agg_expr("max", 1, 3, None, S(0, 2)), P.agg_expr("count", 1, 4, None, S(0, 2))]
+    f = P.where(P.scan(0), P.ge(S(0, 3), P.str_lit("s2")), P.gt(P.str_lit("s30"), S(0, 3)), P.ne(S(0, 2), P.str_lit("zzz")),
+                P.in_(S(0, 1), P.str_lit("s1"), P.str_lit("s5"), P.str_lit("nope")))
+    pa_ = P.Plan(P.agg(f, 1, [S(0, 1)], aggs), {0: [(1, T.STRING), (2, T.STRING), (3, T.STRING)], 1: [(1, T.INT64), (2, T.STRING), (3, T.STRING), (4, T.INT64)]})
+    ea = D.encode_strings(pa_, [D.StringColumn(0, 1, _gen_strings(11, rows, 37, 0)), D.StringColumn(0, 2, _gen_strings(12, rows, 23, 9)), D.StringColumn(0, 3, _gen_strings(13, rows, 41, 0))])
+    j = P.join(P.scan(1), P.scan(0), [P.eq(S(1, 1), S(0, 1))])
+    pb_ = P.Plan(P.agg(j, 2, [P.slot_ref(1, 2, T.INT32)], [P.agg_expr("count_star", 2, 1)]), {0: [(1, T.STRING)], 1: [(1, T.STRING), (2, T.INT32)], 2: [(1, T.INT64)]})
+    eb = D.encode_strings(pb_, [D.StringColumn(0, 1, _gen_strings(21, rows, 53, 13)), D.StringColumn(1, 1, _gen_strings(22, rows // 4 + 1, 61, 0))])
+    want = lines(ea) + lines(eb)
+    assert out[:len(want)] == want
+    assert out[len(want)].startswith("refused:")
