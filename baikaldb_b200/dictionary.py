@@ -12,7 +12,8 @@ include/common/expr_value.h:892-943; ``MutTableKey`` keys are memcomparable).  L
     s >  'x'  ->  code >= bisect_right('x')     s >= 'x'  ->  code >= bisect_left('x')
     s IN (..) ->  code IN (ranks of the members that exist)
 
-Everything else on a string (LIKE, concat, length, SUM ...) is refused here exactly as the library refuses it (``Unsupported``): nothing is
+``s LIKE 'pat'`` is matched against the DICTIONARY on the host with the reference's own matcher (``LikePredicate::like``) and becomes an OR of
+rank ranges (one range for a prefix pattern).  Everything else on a string (concat, length, SUM ...) is refused here exactly as the library refuses it (``Unsupported``): nothing is
 ever answered differently.  The kernels that run are the verified INT32 ones; this module is host code and is checked on the CPU against
 pyarrow's own string kernels (tests/test_dictionary.py).
 """
@@ -86,7 +87,75 @@ def _walk_exprs(e: P.Expr):
         yield from _walk_exprs(c)
 
 
-def encode_strings(plan: P.Plan, string_cols: Sequence[StringColumn]) -> Encoded:
+def _code_point(s: bytes, i: int, charset: str) -> int:
+    """bytes of the character that starts at s[i]: 1 for the Binary charset, the UTF-8 sequence length otherwise (LikePredicate::Binary /
+    UTF8Charset::next_code_point, include/expr/predicate.h:348-360; 0 = malformed)"""
+    if charset != "utf8":
+        return 1
+    b = s[i]
+    n = 1 if b < 0x80 else 2 if b >> 5 == 0b110 else 3 if b >> 4 == 0b1110 else 4 if b >> 3 == 0b11110 else 0
+    return n if n and i + n <= len(s) else 0
+
+
+def like_match(target: bytes, pattern: bytes, charset: str = "binary", escape: bytes = b"\\") -> Optional[bool]:
+    """the reference's LIKE matcher, LikePredicate::like<Charset> (include/expr/predicate.h:503-573): `%` any run of characters, `_` one
+    character, the escape character takes the next pattern character literally; greedy with one backtrack point.  None = a malformed
+    character (the reference then retries with the Binary charset, like_one, src/expr/predicate.cpp:509-547 — so does `like_one` below)."""
+    tx = px = ntx = npx = 0
+    while tx < len(target) or px < len(pattern):
+        if px < len(pattern):
+            pn = _code_point(pattern, px, charset)
+            if pn == 0:
+                return None
+            pc = pattern[px:px + pn]
+            if pc == b"_":
+                if tx < len(target):
+                    tn = _code_point(target, tx, charset)
+                    px += 1
+                    tx += tn if tn > 0 else 1
+                    continue
+            elif pc == b"%":
+                off = 1
+                if tx < len(target):
+                    tn = _code_point(target, tx, charset)
+                    if tn > 0:
+                        off = tn
+                npx, ntx = px, tx + off
+                px += 1
+                continue
+            else:
+                if pc == escape and px + len(escape) < len(pattern):
+                    px += len(escape)
+                    pn = _code_point(pattern, px, charset)
+                    if pn == 0:
+                        return None
+                    pc = pattern[px:px + pn]
+                if tx < len(target):
+                    tn = _code_point(target, tx, charset)
+                    if tn == 0:
+                        return None
+                    if pc == target[tx:tx + tn]:
+                        px += pn
+                        tx += tn
+                        continue
+        if 0 < ntx <= len(target):
+            px, tx = npx, ntx
+            continue
+        return False
+    return True
+
+
+def like_one(target: bytes, pattern: bytes, charset: str = "utf8") -> bool:
+    r = like_match(target, pattern, charset)
+    if r is None:
+        r = like_match(target, pattern, "binary")
+    return bool(r)
+
+
+MAX_LIKE_RANGES = 16   # a LIKE becomes an OR of at most this many code ranges
+
+
+def encode_strings(plan: P.Plan, string_cols: Sequence[StringColumn], charset: str = "utf8") -> Encoded:
     strings = {(c.tuple_id, c.slot_id): c for c in string_cols}
     is_str = lambda e: e.node_type == E.SLOT_REF and (e.tuple_id, e.slot_id) in strings
     as_bytes = lambda v: v if isinstance(v, bytes) else str(v).encode()
@@ -149,6 +218,31 @@ def encode_strings(plan: P.Plan, string_cols: Sequence[StringColumn]) -> Encoded
                 return P.ge(col, code_lit(lo))
             if is_str(a) or is_str(b):
                 raise Unsupported(f"'{e.name}' between a STRING column and something that is neither a STRING column nor a string literal")
+        if nt == E.LIKE_PREDICATE and len(e.children) == 2 and is_str(e.children[0]):
+            # the pattern is matched against the DICTIONARY on the host (D strings, not N rows); the codes that match form ranges of ranks —
+            # one range for a prefix pattern — and the predicate becomes an OR of those ranges
+            if e.children[1].node_type != E.STRING_LITERAL:
+                raise Unsupported("LIKE takes a literal pattern")
+            d = dictionary[(e.children[0].tuple_id, e.children[0].slot_id)]
+            pat = as_bytes(e.children[1].value)
+            hit = [like_one(v, pat, charset) for v in d]
+            ranges, i = [], 0
+            while i < len(d):
+                if hit[i]:
+                    j = i
+                    while j < len(d) and hit[j]:
+                        j += 1
+                    ranges.append((i, j))
+                    i = j
+                else:
+                    i += 1
+            if len(ranges) > MAX_LIKE_RANGES:
+                raise Unsupported(f"LIKE '{pat.decode(errors='replace')}' selects {len(ranges)} separate ranges of the dictionary (more than {MAX_LIKE_RANGES})")
+            col = lambda: rewrite(e.children[0])
+            if not ranges:
+                return P.eq(col(), code_lit(-1))
+            terms = [P.and_(P.ge(col(), code_lit(a)), P.lt(col(), code_lit(b))) for a, b in ranges]
+            return terms[0] if len(terms) == 1 else P.or_(*terms)
         if nt == E.IN_PREDICATE and e.children and is_str(e.children[0]):
             d = dictionary[(e.children[0].tuple_id, e.children[0].slot_id)]
             codes = []

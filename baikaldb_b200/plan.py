@@ -326,6 +326,7 @@ def not_(a: Expr) -> Expr: return _pred(ExprNodeType.NOT_PREDICATE, FuncType.LOG
 def is_null(a: Expr) -> Expr: return _pred(ExprNodeType.IS_NULL_PREDICATE, FuncType.IS_NULL, "is_null", a)
 def is_true(a: Expr) -> Expr: return _pred(ExprNodeType.IS_TRUE_PREDICATE, FuncType.IS_TRUE, "is_true", a)
 def in_(x: Expr, *lits: Expr) -> Expr: return _pred(ExprNodeType.IN_PREDICATE, FuncType.IN, "in", x, *lits)
+def like(x: Expr, pattern: Expr) -> Expr: return _pred(ExprNodeType.LIKE_PREDICATE, FuncType.LIKE, "like", x, pattern)   # only over dictionary-coded STRING columns (dictionary.py)
 
 
 def agg_expr(name: str, agg_tuple_id: int, final_slot_id: int, intermediate_slot_id: Optional[int] = None,

@@ -2,7 +2,7 @@
 // (the Python mirror, with the reasoning and the checks against pyarrow's string kernels: baikaldb_b200/dictionary.py, tests/test_dictionary.py;
 // tests/test_host_cpp.py checks that this rewrite produces the SAME plan bytes and the SAME codes).
 //
-// A fragment whose STRING slots are only compared (= != < <= > >=, IN, IS NULL), grouped, joined, ordered, counted or MIN / MAX-ed needs
+// A fragment whose STRING slots are only compared (= != < <= > >=, IN, IS NULL, LIKE 'literal'), grouped, joined, ordered, counted or MIN / MAX-ed needs
 // only the ORDER of the strings: GpuExecNode's child hands the strings over, this builds one sorted dictionary per comparison domain
 // (string slots compared with each other share one), replaces every string by its rank (INT32, NULL stays NULL), rewrites the fragment —
 // literals become rank thresholds — and maps the codes of the result's key / MIN / MAX columns back.  Byte order is the reference's string
@@ -37,6 +37,53 @@ struct EncodedStrings {
         return out;
     }
 };
+
+// LikePredicate::like<Charset> (include/expr/predicate.h:503-573) restated: `%` any run of characters, `_` one character, the escape character
+// takes the next pattern character literally; one backtrack point.  utf8 = false: the Binary charset (one byte per character).
+// Returns -1 for a malformed character (like_one then retries as Binary, src/expr/predicate.cpp:509-547), else 0 / 1.
+inline int like_code_point(const std::string& s, size_t i, bool utf8) {
+    if (!utf8) return 1;
+    const uint8_t b = (uint8_t)s[i];
+    const int n = b < 0x80 ? 1 : (b >> 5) == 0x6 ? 2 : (b >> 4) == 0xE ? 3 : (b >> 3) == 0x1E ? 4 : 0;
+    return n && i + (size_t)n <= s.size() ? n : 0;
+}
+inline int like_match(const std::string& target, const std::string& pattern, bool utf8, char escape = '\\') {
+    size_t tx = 0, px = 0, ntx = 0, npx = 0;
+    while (tx < target.size() || px < pattern.size()) {
+        if (px < pattern.size()) {
+            int pn = like_code_point(pattern, px, utf8);
+            if (pn == 0) return -1;
+            if (pn == 1 && pattern[px] == '_') {
+                if (tx < target.size()) { const int tn = like_code_point(target, tx, utf8); px++; tx += tn > 0 ? (size_t)tn : 1; continue; }
+            } else if (pn == 1 && pattern[px] == '%') {
+                size_t off = 1;
+                if (tx < target.size()) { const int tn = like_code_point(target, tx, utf8); if (tn > 0) off = (size_t)tn; }
+                npx = px; ntx = tx + off; px++;
+                continue;
+            } else {
+                if (pn == 1 && pattern[px] == escape && px + 1 < pattern.size()) {
+                    px++;
+                    pn = like_code_point(pattern, px, utf8);
+                    if (pn == 0) return -1;
+                }
+                if (tx < target.size()) {
+                    const int tn = like_code_point(target, tx, utf8);
+                    if (tn == 0) return -1;
+                    if (tn == pn && target.compare(tx, (size_t)tn, pattern, px, (size_t)pn) == 0) { px += (size_t)pn; tx += (size_t)tn; continue; }
+                }
+            }
+        }
+        if (ntx > 0 && ntx <= target.size()) { px = npx; tx = ntx; continue; }
+        return 0;
+    }
+    return 1;
+}
+inline bool like_one(const std::string& target, const std::string& pattern, bool utf8 = true) {
+    int r = like_match(target, pattern, utf8);
+    if (r < 0) r = like_match(target, pattern, false);
+    return r > 0;
+}
+constexpr size_t MAX_LIKE_RANGES = 16;   // a LIKE becomes an OR of at most this many code ranges
 
 inline EncodedStrings encode_strings(const Plan& plan, const std::vector<StringColumn>& string_cols) {
     using Key = std::pair<int, int>;
@@ -109,6 +156,27 @@ inline EncodedStrings encode_strings(const Plan& plan, const std::vector<StringC
                 }
             }
             if (is_str(a) || is_str(b)) throw Unsupported("'" + e.name + "' between a STRING column and something that is neither a STRING column nor a string literal");
+        }
+        if (e.node_type == BK_LIKE_PREDICATE && e.children.size() == 2 && is_str(e.children[0])) {
+            // the pattern is matched against the DICTIONARY on the host; the ranks that match form ranges (one for a prefix pattern)
+            if (e.children[1].node_type != BK_STRING_LITERAL) throw Unsupported("LIKE takes a literal pattern");
+            const auto& d = *enc.dictionaries[{e.children[0].tuple_id, e.children[0].slot_id}];
+            std::vector<std::pair<int64_t, int64_t>> ranges;
+            for (size_t i = 0; i < d.size();) {
+                if (!like_one(d[i], e.children[1].name)) { i++; continue; }
+                size_t j = i;
+                while (j < d.size() && like_one(d[j], e.children[1].name)) j++;
+                ranges.push_back({(int64_t)i, (int64_t)j});
+                i = j;
+            }
+            if (ranges.size() > MAX_LIKE_RANGES) throw Unsupported("LIKE '" + e.children[1].name + "' selects " + std::to_string(ranges.size()) + " separate ranges of the dictionary");
+            if (ranges.empty()) return cmp(BK_FT_EQ, "eq", rewrite(e.children[0]), Expr::int_literal(-1));
+            std::vector<Expr> terms;
+            for (auto& r : ranges)
+                terms.push_back(Expr::predicate(BK_AND_PREDICATE, BK_FT_LOGIC_AND, "logic_and", {cmp(BK_FT_GE, "ge", rewrite(e.children[0]), Expr::int_literal(r.first)),
+                                                                                               cmp(BK_FT_LT, "lt", rewrite(e.children[0]), Expr::int_literal(r.second))}));
+            if (terms.size() == 1) return terms[0];
+            return Expr::predicate(BK_OR_PREDICATE, BK_FT_LOGIC_OR, "logic_or", std::move(terms));
         }
         if (e.node_type == BK_IN_PREDICATE && !e.children.empty() && is_str(e.children[0])) {
             const auto& d = *enc.dictionaries[{e.children[0].tuple_id, e.children[0].slot_id}];

@@ -167,12 +167,14 @@ static void print_encoded(const EncodedStrings& enc) {
 }
 static int strings_mode(int64_t rows) {
     auto S = [](int t, int s) { return Expr::slot_ref(t, s, BK_STRING); };
-    {   // A: SELECT `0_1`, COUNT(*), MIN(`0_2`), MAX(`0_2`), COUNT(`0_2`) WHERE `0_3` >= 's2' AND 's30' > `0_3` AND `0_2` != 'zzz' AND `0_1` IN ('s1', 's5', 'nope') GROUP BY `0_1`
+    {   // A: SELECT `0_1`, COUNT(*), MIN(`0_2`), MAX(`0_2`), COUNT(`0_2`) WHERE `0_3` >= 's2' AND 's30' > `0_3` AND `0_2` != 'zzz' AND `0_1` IN ('s1', 's5', 'nope') AND `0_2` LIKE 's1%' AND `0_3` LIKE '%2_' GROUP BY `0_1`
         Plan p;
         PlanNode f = where(scan(0), cmp(BK_FT_GE, "ge", S(0, 3), Expr::string_literal("s2")));
         f.conjuncts.push_back(cmp(BK_FT_GT, "gt", Expr::string_literal("s30"), S(0, 3)));
         f.conjuncts.push_back(cmp(BK_FT_NE, "ne", S(0, 2), Expr::string_literal("zzz")));
         f.conjuncts.push_back(Expr::predicate(BK_IN_PREDICATE, BK_FT_IN, "in", {S(0, 1), Expr::string_literal("s1"), Expr::string_literal("s5"), Expr::string_literal("nope")}));
+        f.conjuncts.push_back(Expr::predicate(BK_LIKE_PREDICATE, BK_FT_LIKE, "like", {S(0, 2), Expr::string_literal("s1%")}));
+        f.conjuncts.push_back(Expr::predicate(BK_LIKE_PREDICATE, BK_FT_LIKE, "like", {S(0, 3), Expr::string_literal("%2_")}));
         p.root = agg(std::move(f), 1, {S(0, 1)}, {Expr::agg("count_star", 1, 1, 1, {}), Expr::agg("min", 1, 2, 2, {S(0, 2)}), Expr::agg("max", 1, 3, 3, {S(0, 2)}), Expr::agg("count", 1, 4, 4, {S(0, 2)})});
         p.tuples = {{0, {{1, BK_STRING}, {2, BK_STRING}, {3, BK_STRING}}}, {1, {{1, BK_INT64}, {2, BK_STRING}, {3, BK_STRING}, {4, BK_INT64}}}};
         std::vector<StringColumn> cols = {{0, 1, gen_strings(11, rows, 37, 0)}, {0, 2, gen_strings(12, rows, 23, 9)}, {0, 3, gen_strings(13, rows, 41, 0)}};
@@ -199,6 +201,11 @@ int main(int argc, char** argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s plan|explain|run c1|c2|c3|c5 [rows] [batch_rows]\n", argv[0]); return 2; }
     std::string mode = argv[1], cfg = argv[2];
     if (mode == "strings") return strings_mode(argc > 3 ? atoll(argv[3]) : 1000);
+    if (mode == "like") {   // bkgpu_host like - <hex target> <hex pattern> <utf8 0|1> ... (triples): the matcher of bkgpu_dictionary.hpp, one result per line
+        auto unhex = [](const char* h) { std::string o; for (size_t i = 0; h[i] && h[i + 1]; i += 2) o.push_back((char)strtol(std::string(h + i, 2).c_str(), nullptr, 16)); return o; };
+        for (int i = 3; i + 2 < argc; i += 3) printf("%d\n", like_match(unhex(argv[i]), unhex(argv[i + 1]), atoi(argv[i + 2]) != 0));
+        return 0;
+    }
     Plan plan = cfg == "c1" ? plan_c1() : cfg == "c2" ? plan_c2() : cfg == "c3" ? plan_c3() : plan_c5();
     if (mode == "chunk") {   // CPU-only: rows -> Chunk -> column batches of `capacity` rows -> rows again (f1 adapter round trip)
         const int64_t rows = argc > 3 ? atoll(argv[3]) : 1000, capacity = argc > 4 ? atoll(argv[4]) : 64;

@@ -133,3 +133,47 @@ def test_gpu_runs_the_rewritten_fragment():
     w = {k: (c, mn, mx) for k, c, mn, mx in zip(want["s1"], want["count_all"], want["s2_min"], want["s2_max"])}
     g = {k: (c, mn, mx) for k, c, mn, mx in zip(dec["0_1"], dec["1_1"], dec["1_3"], dec["1_4"])}
     assert g == w
+
+
+def test_like_matcher_equals_the_references_known_answers():
+    """test/test_predicate.cpp:33-66 (TEST(test_covent_pattern, case_all)): the Binary-charset vectors and the charset-independent ASCII ones of
+    LikePredicate::like<Charset>, through the restatement in dictionary.like_match (the GBK vectors need a GBK decoder and are not restated)"""
+    binary = [(b"www.bad/aca?bd_vid", b"www.bad/aca?bd_vid", True), (b"abc", b"a_c", True), (b"abc", b"%", True), (b"axxx", b"a%x%x", True),
+              (b"test", b"te%st", True), (b"test", b"te%%st", True), (b"test", b"%test%", True), (b"3hello", b"3%hello", True),
+              (b"aaaaaaaaaaaaaaaaaaaaaaaaaaa", b"a%a%a%a%a%a%a%a%b", False)]
+    for t, p, want in binary:
+        assert D.like_match(t, p, "binary") is want, (t, p)
+    for t, p, want in [(b"", b"", True), (b"test", b"_%_%_%_", True), (b"test", b"_%_%st", True), (b"axxx", b"a%x%x", True)] + binary:
+        assert D.like_match(t, p, "utf8") is want, (t, p)
+    # the escape character takes `%` and `_` literally (the reference's GBK vectors "x\\%y" / "x\\_y", here with ASCII and UTF-8 text)
+    assert D.like_match("中%文".encode(), "中\\%文".encode(), "utf8") is True and D.like_match("中间文".encode(), "中\\%文".encode(), "utf8") is False
+    assert D.like_match("中f文".encode(), "中\\_文".encode(), "utf8") is False and D.like_match("中f文".encode(), "中_文".encode(), "utf8") is True
+    assert D.like_match("中aaa文".encode(), "中%文".encode(), "utf8") is True
+    # `_` is one CHARACTER in a charset, one BYTE in Binary
+    assert D.like_match("中".encode(), b"_", "utf8") is True and D.like_match("中".encode(), b"_", "binary") is False and D.like_match("中".encode(), b"___", "binary") is True
+    assert D.like_match(b"\xffa", b"\xffa", "utf8") is None and D.like_one(b"\xffa", b"\xffa", "utf8") is True   # a malformed character: retried as Binary (like_one)
+    assert D.like_match(b"\xff\xfe", b"_", "utf8") is False                                                       # ... but `_` steps over a malformed byte
+
+
+def test_like_becomes_ranges_of_the_dictionary():
+    rng = np.random.default_rng(8)
+    words = [b"", b"a", b"ab", b"abc", b"abd", b"b", b"ba", b"bab", b"cab", b"k", b"zebra", "中文".encode(), "中间".encode(), b"a%c", b"a_c"]
+    n = 8000
+    s = _strings(rng, n, 0.1, words)
+    tbl = pa.table({"s": pa.array(s, pa.binary())})
+    for pat, n_ranges in [("ab%", 1), ("%", 1), ("a_", 1), ("%ab%", 2), ("b%b", 1), ("nomatch%", 0), ("中_", 1), ("a\\%c", 1), ("%a%", None), ("_", None)]:
+        plan = P.Plan(P.agg(P.where(P.scan(0), P.like(P.slot_ref(0, 1, T.STRING), P.str_lit(pat))), 1, [P.slot_ref(0, 1, T.STRING)], [P.agg_expr("count_star", 1, 1)]),
+                      {0: [(1, T.STRING)], 1: [(1, T.INT64)]})
+        enc, got = _run(plan, [D.StringColumn(0, 1, s)], [])
+        g = dict(zip(got[0].values, got[1].to_list()))
+        mask = pc.match_like(tbl["s"].cast(pa.string()), pat)     # (utf8 type: `_` is one character, as in the reference's UTF8Charset; on binary pyarrow counts bytes)
+        w = tbl.filter(pc.fill_null(mask, False)).group_by("s", use_threads=False).aggregate([([], "count_all")]).to_pydict()
+        assert g == dict(zip(w["s"], w["count_all"])), pat
+        if n_ranges is not None:   # the shape of the rewritten predicate: no range -> `code = -1`, one -> AND, several -> OR of ANDs
+            pred = enc.plan.root.children[0].conjuncts[0]
+            shape = 0 if pred.node_type == P.ExprNodeType.FUNCTION_CALL else 1 if pred.node_type == P.ExprNodeType.AND_PREDICATE else len(pred.children)
+            assert shape == n_ranges, (pat, shape)
+    many = [f"{c}x".encode() for c in "abcdefghijklmnopqrstuvwxyz"] + [f"{c}y".encode() for c in "abcdefghijklmnopqrstuvwxyz"]
+    with pytest.raises(D.Unsupported):   # 26 separate ranges: refused, the caller keeps its CPU engine for this fragment
+        D.encode_strings(P.Plan(P.agg(P.where(P.scan(0), P.like(P.slot_ref(0, 1, T.STRING), P.str_lit("%x"))), 1, [], [P.agg_expr("count_star", 1, 1)]),
+                                {0: [(1, T.STRING)], 1: [(1, T.INT64)]}), [D.StringColumn(0, 1, many)])

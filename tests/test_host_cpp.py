@@ -154,7 +154,7 @@ def _gen_strings(seed, n, domain, null_every):
 def test_cpp_dictionary_adapter_matches_python(host_bin):
     """host/bkgpu_dictionary.hpp (STRING columns as order-preserving dictionary codes, C++ side of the adapter) produces the same rewritten
     plan bytes and the same code columns as baikaldb_b200/dictionary.py — whose rewrite tests/test_dictionary.py checks against pyarrow's
-    string kernels — on two fragments: filters + IN + GROUP BY + MIN / MAX / COUNT over strings, and a join on string keys"""
+    string kernels — on two fragments: filters + IN + LIKE (one and several dictionary ranges) + GROUP BY + MIN / MAX / COUNT over strings, and a join on string keys"""
     from baikaldb_b200 import dictionary as D, plan as P
     from baikaldb_b200.plan import PrimitiveType as T
     rows = 3000
@@ -178,7 +178,7 @@ def test_cpp_dictionary_adapter_matches_python(host_bin):
 
     aggs = [P.agg_expr("count_star", 1, 1), P.agg_expr("min", 1, 2, None, S(0, 2)), P.agg_expr("max", 1, 3, None, S(0, 2)), P.agg_expr("count", 1, 4, None, S(0, 2))]
     f = P.where(P.scan(0), P.ge(S(0, 3), P.str_lit("s2")), P.gt(P.str_lit("s30"), S(0, 3)), P.ne(S(0, 2), P.str_lit("zzz")),
-                P.in_(S(0, 1), P.str_lit("s1"), P.str_lit("s5"), P.str_lit("nope")))
+                P.in_(S(0, 1), P.str_lit("s1"), P.str_lit("s5"), P.str_lit("nope")), P.like(S(0, 2), P.str_lit("s1%")), P.like(S(0, 3), P.str_lit("%2_")))
     pa_ = P.Plan(P.agg(f, 1, [S(0, 1)], aggs), {0: [(1, T.STRING), (2, T.STRING), (3, T.STRING)], 1: [(1, T.INT64), (2, T.STRING), (3, T.STRING), (4, T.INT64)]})
     ea = D.encode_strings(pa_, [D.StringColumn(0, 1, _gen_strings(11, rows, 37, 0)), D.StringColumn(0, 2, _gen_strings(12, rows, 23, 9)), D.StringColumn(0, 3, _gen_strings(13, rows, 41, 0))])
     j = P.join(P.scan(1), P.scan(0), [P.eq(S(1, 1), S(0, 1))])
@@ -187,3 +187,27 @@ def test_cpp_dictionary_adapter_matches_python(host_bin):
     want = lines(ea) + lines(eb)
     assert out[:len(want)] == want
     assert out[len(want)].startswith("refused:")
+
+
+def test_cpp_like_matcher_matches_python(host_bin):
+    """the C++ restatement of LikePredicate::like (host/bkgpu_dictionary.hpp) agrees with dictionary.like_match — which tests/test_dictionary.py pins
+    to the reference's own vectors (test/test_predicate.cpp:33-66) — on those vectors, on escapes, on multi-byte characters and on malformed bytes"""
+    from baikaldb_b200 import dictionary as D
+    cases = [(b"www.bad/aca?bd_vid", b"www.bad/aca?bd_vid"), (b"abc", b"a_c"), (b"abc", b"%"), (b"axxx", b"a%x%x"), (b"test", b"te%st"), (b"test", b"te%%st"),
+             (b"test", b"%test%"), (b"test", b"_%_%_%_"), (b"test", b"_%_%st"), (b"3hello", b"3%hello"), (b"aaaaaaaaaaaaaaaaaaaaaaaaaaa", b"a%a%a%a%a%a%a%a%b"),
+             (b"", b""), (b"", b"%"), (b"a", b""), (b"", b"_"), ("中%文".encode(), "中\\%文".encode()), ("中间文".encode(), "中\\%文".encode()), ("中f文".encode(), "中\\_文".encode()),
+             ("中f文".encode(), "中_文".encode()), ("中aaa文".encode(), "中%文".encode()), ("中".encode(), b"_"), ("中".encode(), b"___"), (b"\xffa", b"\xffa"), (b"\xff\xfe", b"_"),
+             (b"a\\", b"a\\"), (b"a%", b"a\\%"), (b"ab", b"a\\b"), (b"abcabc", b"%abc"), (b"abcab", b"%abc"), (b"x", b"%%%"), (b"xyz", b"x%y%z%")]
+    args = []
+    for t, p in cases:
+        for utf8 in (0, 1):
+            args += [t.hex() or "", p.hex() or "", str(utf8)]
+    # (an empty string has no hex digits: pass a placeholder the binary un-hexes to "")
+    args = [a if a else "" for a in args]
+    out = subprocess.run([host_bin, "like", "-"] + args, capture_output=True, text=True, check=True).stdout.split()
+    want = []
+    for t, p in cases:
+        for utf8 in (0, 1):
+            r = D.like_match(t, p, "utf8" if utf8 else "binary")
+            want.append("-1" if r is None else "1" if r else "0")
+    assert out == want
