@@ -25,6 +25,8 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
 
 from . import plan as P
 from .column import Column, make_column
@@ -39,7 +41,7 @@ class Unsupported(Exception):
 class StringColumn:
     tuple_id: int
     slot_id: int
-    values: List[Optional[bytes]]      # None = NULL
+    values: object                     # list of bytes (None = NULL), or a pyarrow binary / string array
 
     @property
     def name(self) -> str:
@@ -176,16 +178,20 @@ def encode_strings(plan: P.Plan, string_cols: Sequence[StringColumn], charset: s
     members: Dict[Tuple[int, int], List[Tuple[int, int]]] = {}
     for k in strings:
         members.setdefault(find(k), []).append(k)
+    # the columns as Arrow binary arrays: distinct values, byte-wise sort and the value -> rank lookup below are Arrow's vectorised kernels
+    arrays = {k: (c.values if isinstance(c.values, (pa.Array, pa.ChunkedArray)) else pa.array(c.values, pa.large_binary())) for k, c in strings.items()}
+    arrays = {k: (a.combine_chunks() if isinstance(a, pa.ChunkedArray) else a).cast(pa.large_binary()) for k, a in arrays.items()}
     dictionary: Dict[Tuple[int, int], List[bytes]] = {}
+    dict_arrays: Dict[Tuple[int, int], pa.Array] = {}
     for root, ks in members.items():
-        vals = set()
-        for k in ks:
-            vals.update(v for v in strings[k].values if v is not None)
-        d = sorted(vals)                                  # bytes order = the reference's string order
-        if len(d) >= 1 << 31:
+        distinct = pc.unique(pa.concat_arrays([arrays[k] for k in ks])).drop_null()
+        distinct = distinct.take(pc.sort_indices(distinct))      # binary arrays sort by unsigned bytes = the reference's string order
+        if len(distinct) >= 1 << 31:
             raise Unsupported("more than 2^31 distinct strings in one comparison domain")
+        d = distinct.to_pylist()
         for k in ks:
             dictionary[k] = d
+            dict_arrays[k] = distinct
 
     enc = Encoded(plan=None, columns=[], dictionaries=dictionary)
 
@@ -300,9 +306,9 @@ def encode_strings(plan: P.Plan, string_cols: Sequence[StringColumn], charset: s
 
     # ---- columns: string -> rank in its domain's dictionary ----
     for c in string_cols:
-        d = dictionary[(c.tuple_id, c.slot_id)]
-        index = {v: i for i, v in enumerate(d)}
-        ok = np.array([v is not None for v in c.values], dtype=bool)
-        codes = np.array([index[v] if v is not None else 0 for v in c.values], dtype=np.int32)
+        k = (c.tuple_id, c.slot_id)
+        ranks = pc.index_in(arrays[k], value_set=dict_arrays[k])           # int32, NULL where the string is NULL
+        ok = np.asarray(ranks.is_valid())
+        codes = np.asarray(ranks.fill_null(0)).astype(np.int32)
         enc.columns.append(make_column(c.tuple_id, c.slot_id, T.INT32, codes, None if ok.all() else ok))
     return enc
