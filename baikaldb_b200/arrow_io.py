@@ -114,3 +114,42 @@ def execute_ipc(plan: Plan, schema_bytes: bytes, rows_bytes: bytes, device: int 
     got, stats = execute(plan, cols, device=device, options=options)
     s, r = encode(got)
     return s, r, stats
+
+
+def execute_ipc_with_strings(plan: Plan, schema_bytes: bytes, rows_bytes: bytes, device: int = 0, options: Optional[Dict[str, int]] = None, runner=None):
+    """``execute_ipc`` for fragments over STRING columns: the binary / utf8 fields of the SCAN tuples (the Chunk map sends STRING as
+    ``large_binary``, src/expr/arrow_function.cpp:69-96) become order-preserving dictionary codes (``dictionary.encode_strings``), the rewritten
+    INT32 fragment runs, and the string-valued result columns (GROUP BY keys, MIN / MAX, returned rows) leave as ``large_binary`` again.
+    ``runner(plan, columns) -> columns`` defaults to the GPU path; tests pass the oracle.  Returns (schema bytes, rows bytes)."""
+    from . import dictionary as D
+    from .plan import PlanNodeType
+    schema = pa.ipc.read_schema(pa.py_buffer(schema_bytes))
+    rb = pa.ipc.read_record_batch(pa.py_buffer(rows_bytes), schema)
+    scan_tuples, stack = set(), [plan.root]
+    while stack:
+        n = stack.pop()
+        if n.node_type == PlanNodeType.SCAN_NODE:
+            scan_tuples.add(n.tuple_id)
+        stack.extend(n.children)
+    stringy = (pa.large_binary(), pa.binary(), pa.string(), pa.large_string())
+    string_cols, keep = [], []
+    for i, f in enumerate(schema):
+        tid, sid = _field_ids(f.name)
+        if f.type in stringy and tid in scan_tuples:
+            string_cols.append(D.StringColumn(tid, sid, rb.column(i).cast(pa.large_binary())))
+        else:
+            keep.append(i)
+    rest = columns_from_record_batch(rb.select(keep), plan.tuples) if keep else []
+    enc = D.encode_strings(plan, string_cols)
+    if runner is None:
+        from .exec_node import execute
+        runner = lambda p, c: execute(p, c, device=device, options=options)[0]
+    arrays, fields = [], []
+    for c in enc.decode(runner(enc.plan, enc.columns + rest)):
+        if isinstance(c, D.StringColumn):
+            arrays.append(pa.array(c.values, pa.large_binary())); fields.append(pa.field(c.name, pa.large_binary()))
+        else:
+            one = record_batch_from_columns([c])
+            arrays.append(one.column(0)); fields.append(one.schema.field(0))
+    out = pa.RecordBatch.from_arrays(arrays, schema=pa.schema(fields))
+    return out.schema.serialize().to_pybytes(), out.serialize().to_pybytes()

@@ -177,3 +177,31 @@ def test_like_becomes_ranges_of_the_dictionary():
     with pytest.raises(D.Unsupported):   # 26 separate ranges: refused, the caller keeps its CPU engine for this fragment
         D.encode_strings(P.Plan(P.agg(P.where(P.scan(0), P.like(P.slot_ref(0, 1, T.STRING), P.str_lit("%x"))), 1, [], [P.agg_expr("count_star", 1, 1)]),
                                 {0: [(1, T.STRING)], 1: [(1, T.INT64)]}), [D.StringColumn(0, 1, many)])
+
+
+def test_ipc_in_and_out_with_string_columns():
+    """the store <-> db wire with STRING fields (large_binary, the Chunk map): strings in, dictionary-coded fragment (run by the oracle here),
+    strings out — equal to pyarrow's own group-by over the same batch"""
+    from baikaldb_b200 import arrow_io
+    rng = np.random.default_rng(6)
+    n = 12_000
+    city = pa.array(_strings(rng, n, 0.05, [b"beijing", b"shanghai", b"shenzhen", "杭州".encode(), b"chengdu", b"xi'an"]), pa.large_binary())
+    tag = pa.array(_strings(rng, n, 0.3), pa.large_binary())
+    amount = rng.random(n) * 100
+    rb = pa.RecordBatch.from_arrays([city, tag, pa.array(amount)], names=["0_1", "0_2", "0_3"])
+    S = lambda s: P.slot_ref(0, s, T.STRING)
+    aggs = [P.agg_expr("count_star", 1, 1), P.agg_expr("sum", 1, 2, None, P.slot_ref(0, 3, T.DOUBLE)), P.agg_expr("max", 1, 3, None, S(2))]
+    plan = P.Plan(P.agg(P.where(P.scan(0), P.like(S(1), P.str_lit("s%")), P.ne(S(1), P.str_lit("shenzhen"))), 1, [S(1)], aggs),
+                  {0: [(1, T.STRING), (2, T.STRING), (3, T.DOUBLE)], 1: [(1, T.INT64), (2, T.DOUBLE), (3, T.STRING)]})
+    s, d = arrow_io.execute_ipc_with_strings(plan, rb.schema.serialize().to_pybytes(), rb.serialize().to_pybytes(),
+                                             runner=lambda p, c: oracle.execute(p.serialize(), c).columns)
+    out = pa.ipc.read_record_batch(pa.py_buffer(d), pa.ipc.read_schema(pa.py_buffer(s))).to_pydict()
+    assert pa.ipc.read_schema(pa.py_buffer(s)).field("0_1").type == pa.large_binary() and pa.ipc.read_schema(pa.py_buffer(s)).field("1_3").type == pa.large_binary()
+    tbl = pa.table({"city": city, "tag": tag, "amount": amount})
+    m = pc.and_kleene(pc.match_like(tbl["city"].cast(pa.string()), "s%"), pc.not_equal(tbl["city"], b"shenzhen"))
+    want = tbl.filter(pc.fill_null(m, False)).group_by("city", use_threads=False).aggregate([([], "count_all"), ("amount", "sum"), ("tag", "max")]).to_pydict()
+    g = {k: (c, mx) for k, c, mx in zip(out["0_1"], out["1_1"], out["1_3"])}
+    assert g == {k: (c, mx) for k, c, mx in zip(want["city"], want["count_all"], want["tag_max"])} and set(g) == {b"shanghai"}
+    sums = dict(zip(out["0_1"], out["1_2"]))
+    for k, v in zip(want["city"], want["amount_sum"]):
+        assert abs(sums[k] - v) <= 1e-9 * abs(v)
