@@ -205,3 +205,63 @@ def test_ipc_in_and_out_with_string_columns():
     sums = dict(zip(out["0_1"], out["1_2"]))
     for k, v in zip(want["city"], want["amount_sum"]):
         assert abs(sums[k] - v) <= 1e-9 * abs(v)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_string_predicates_against_pyarrow(seed):
+    """random predicate trees (AND / OR / NOT over = != < <= > >= with literals in and out of the dictionary, IN, LIKE, IS NULL, and
+    column-to-column comparisons) over three nullable STRING columns: rewritten to codes and run by the oracle == pyarrow's Kleene logic"""
+    rng = np.random.default_rng(1000 + seed)
+    n = 3000
+    words = [b"", b"a", b"aa", b"ab", b"abc", b"b", b"bb", b"c", b"ca", b"cab", b"d", b"x", b"xy", b"xyz", b"y"]
+    cols = {i: _strings(rng, n, 0.15, words) for i in (1, 2, 3)}
+    tbl = pa.table({f"s{i}": pa.array(v, pa.binary()) for i, v in cols.items()})
+    lits = words + [b"0", b"ab0", b"bz", b"zz"]
+    S = lambda i: P.slot_ref(0, i, T.STRING)
+
+    def leaf():
+        i = int(rng.integers(1, 4))
+        kind = rng.integers(0, 10)
+        f = tbl[f"s{i}"]
+        if kind < 5:
+            op = ["eq", "ne", "lt", "le", "gt", "ge"][int(rng.integers(0, 6))]
+            lit = lits[int(rng.integers(0, len(lits)))]
+            pcf = {"eq": pc.equal, "ne": pc.not_equal, "lt": pc.less, "le": pc.less_equal, "gt": pc.greater, "ge": pc.greater_equal}[op]
+            if rng.random() < 0.25:   # literal on the left
+                mirror = {"eq": "eq", "ne": "ne", "lt": "gt", "le": "ge", "gt": "lt", "ge": "le"}[op]
+                return getattr(P, mirror)(P.str_lit(lit.decode()), S(i)), pcf(f, lit)
+            return getattr(P, op)(S(i), P.str_lit(lit.decode())), pcf(f, lit)
+        if kind == 5:
+            j = int(rng.integers(1, 4))
+            return P.lt(S(i), S(j)), pc.less(f, tbl[f"s{j}"])
+        if kind == 6:
+            members = [lits[int(k)] for k in rng.integers(0, len(lits), 3)]
+            # (pyarrow's is_in answers FALSE for a NULL input; SQL's IN — InPredicate, include/expr/predicate.h:281-345 — answers NULL, which matters under NOT)
+            return P.in_(S(i), *[P.str_lit(m.decode()) for m in members]), pc.if_else(pc.is_null(f), pa.scalar(None, pa.bool_()), pc.is_in(f, value_set=pa.array(members, pa.binary())))
+        if kind == 7:
+            pat = ["a%", "%b", "_", "%a%", "x_z", "c%b", "%"][int(rng.integers(0, 7))]
+            return P.like(S(i), P.str_lit(pat)), pc.match_like(f.cast(pa.string()), pat)
+        if kind == 8:
+            return P.is_null(S(i)), pc.is_null(f)
+        return P.eq(S(i), S(int(rng.integers(1, 4)))), None
+
+    def tree(depth):
+        if depth == 0 or rng.random() < 0.3:
+            e, m = leaf()
+            while m is None:
+                e, m = leaf()
+            return e, m
+        k = rng.integers(0, 3)
+        if k == 0:
+            e, m = tree(depth - 1)
+            return P.not_(e), pc.invert(m)
+        (a, ma), (b, mb) = tree(depth - 1), tree(depth - 1)
+        return (P.and_(a, b), pc.and_kleene(ma, mb)) if k == 1 else (P.or_(a, b), pc.or_kleene(ma, mb))
+
+    pred, mask = tree(3)
+    plan = P.Plan(P.agg(P.where(P.scan(0), pred), 1, [S(1)], [P.agg_expr("count_star", 1, 1), P.agg_expr("max", 1, 2, None, S(2))]),
+                  {0: [(1, T.STRING), (2, T.STRING), (3, T.STRING)], 1: [(1, T.INT64), (2, T.STRING)]})
+    enc, got = _run(plan, [D.StringColumn(0, i, cols[i]) for i in (1, 2, 3)], [])
+    g = {k: (c, m) for k, c, m in zip(got[0].values, got[1].to_list(), got[2].values)} if got and len(got[0].values) else {}
+    want = tbl.filter(pc.fill_null(mask, False)).group_by("s1", use_threads=False).aggregate([([], "count_all"), ("s2", "max")]).to_pydict()
+    assert g == {k: (c, m) for k, c, m in zip(want["s1"], want["count_all"], want["s2_max"])}
